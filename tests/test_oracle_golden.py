@@ -1,0 +1,85 @@
+"""The oracle (oracle/pearson_oracle.py) against outputs of the unmodified
+reference stored in tests/golden (generator: tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_case_names, load_case, load_coo
+from oracle import pearson_oracle as po
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_normxcorr2_oracle_matches_reference(name):
+    signal, kernel, kw, dense, corr_ref, pval_ref = load_case(name)
+    mask = kw.pop("missing_mask", None)
+    pval = kw.pop("pval", False)
+    r, p = po.normxcorr2_dense(
+        signal.toarray(), kernel,
+        missing_mask=None if mask is None else mask.toarray(), pval=pval, **kw)
+    assert r.shape == corr_ref.shape
+    # tolerance: fp64 round-off of two different summation orders.  Windows of
+    # exactly constant signal have a variance that is pure round-off in the
+    # reference (|r| ~ 1e-8 noise, e.g. the zoomed 0.5/1.5 hairpin template):
+    # there only the magnitude is comparable.
+    d = np.abs(r - corr_ref)
+    sig = (np.abs(corr_ref) > 1e-6) | (np.abs(r) > 1e-6)
+    assert d.max() < 1e-6
+    assert d[sig].max() < 1e-8
+    if pval_ref is not None:
+        nz = (corr_ref != 0) & sig
+        fin = nz & np.isfinite(pval_ref)
+        assert np.array_equal(np.isneginf(p[nz]), np.isneginf(pval_ref[nz]))
+        assert np.allclose(p[fin], pval_ref[fin], rtol=1e-6, atol=1e-7)
+
+
+def test_xcorr2_oracle_matches_reference():
+    import json
+    z = np.load(os.path.join(GOLDEN, "xcorr2_cases.npz"))
+    for nm in ("gauss", "band", "band_const", "band_tsvd", "band_rect"):
+        sig = load_coo(z, f"{nm}_signal").toarray()
+        kw = json.loads(str(z[f"{nm}_kwargs"]))
+        out = po.xcorr2_dense(sig, z[f"{nm}_kernel"], **kw)
+        ref = load_coo(z, f"{nm}_out").toarray()
+        assert np.max(np.abs(out - ref)) < 1e-9, nm
+
+
+def test_preprocessing_oracle_matches_reference():
+    z = np.load(os.path.join(GOLDEN, "preproc_cases.npz"))
+    for i in range(2):
+        for tag in ("upper", "sym"):
+            raw = load_coo(z, f"d{i}_{tag}_raw").toarray()
+            det = z[f"d{i}_{tag}_detect"]
+            D = int(z[f"d{i}_{tag}_max_dist"])
+            law = po.distance_law_dense(raw, det, D)
+            assert np.allclose(law, z[f"d{i}_{tag}_law"], rtol=1e-12, equal_nan=True)
+            out = po.detrend_dense(raw, det, D, max_val=10)
+            ref = load_coo(z, f"d{i}_{tag}_out").toarray()
+            assert np.allclose(out, ref, rtol=1e-12, atol=0)
+            out = po.detrend_dense(raw, det, D, max_val=None)
+            ref = load_coo(z, f"d{i}_{tag}_out_nomax").toarray()
+            assert np.allclose(out, ref, rtol=1e-12, atol=0)
+    vr = z["mask_valid_rows"]
+    m1 = po.make_missing_mask_dense((12, 12), vr, vr, max_dist=3, sym_upper=True)
+    assert np.array_equal(m1, z["mask_m1"])
+    assert np.array_equal(po.frame_missing_mask_dense(m1, (5, 5), True, 3), z["mask_f1"])
+    m2 = po.make_missing_mask_dense((12, 9), vr, np.array([0, 2, 3, 4, 6, 8]), sym_upper=False)
+    assert np.array_equal(m2, z["mask_m2"])
+    assert np.array_equal(po.frame_missing_mask_dense(m2, (5, 3), False, None), z["mask_f2"])
+    m3 = po.make_missing_mask_dense((12, 12), vr, vr, max_dist=None, sym_upper=True)
+    assert np.array_equal(m3, z["mask_m3"])
+    assert np.array_equal(po.frame_missing_mask_dense(m3, (3, 5), True, None), z["mask_f3"])
+    assert np.array_equal(po.frame_missing_mask_dense(m1, (3, 7), True, 2), z["mask_f4"])
+    assert np.allclose(po.truncate_kernel(__import__("chromosight_b200.kernels", fromlist=["x"]).loops["kernels"][0], 0.999),
+                       z["fact_loops_uv"], atol=1e-12)
+
+
+def test_reference_known_answers():
+    """Known answers of the reference's own tests: distance law of the docstring
+    example (pre:162-171, tests/test_preprocessing.py:202-213) and
+    make_missing_mask's worked example (pre:578-585)."""
+    m = np.ones((3, 3)) + np.array([1, 2, 3])
+    assert np.allclose(po.distance_law_dense(m), [3.0, 3.5, 4.0])
+    valid = np.array([0, 2, 4])
+    exp = np.array([[0, 1, 0, 0, 0], [0, 1, 1, 0, 0], [0, 0, 0, 1, 0], [0, 0, 0, 1, 1], [0, 0, 0, 0, 0]], bool)
+    assert np.array_equal(po.make_missing_mask_dense((5, 5), valid, valid, max_dist=1, sym_upper=True), exp)
