@@ -1,0 +1,46 @@
+"""Device-memory plumbing on top of PyTorch (tensors as raw device buffers, the
+current CUDA stream as the launch stream).  PyTorch is only the allocator and
+stream provider here; all arithmetic happens in libchromosight_b200.so."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+def require_cuda():
+    t = torch()
+    if not t.cuda.is_available():
+        raise _lib.BackendError(
+            "chromosight_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    _lib.load()
+    return t
+
+
+def stream_ptr():
+    return C.c_void_p(torch().cuda.current_stream().cuda_stream)
+
+
+def to_device(arr, dtype=None, device=None):
+    """numpy array -> contiguous CUDA tensor (pageable source, synchronous copy)."""
+    t = torch()
+    a = np.ascontiguousarray(arr, dtype=dtype)
+    return t.from_numpy(a).to(device or "cuda")
+
+
+def empty(n, dtype, device=None):
+    return torch().empty(int(n), dtype=dtype, device=device or "cuda")
+
+
+def ptr(tensor):
+    return C.c_void_p(tensor.data_ptr()) if tensor is not None else C.c_void_p(0)

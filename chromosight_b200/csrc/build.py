@@ -1,0 +1,65 @@
+#!/usr/bin/env python3
+"""Build libchromosight_b200.so (sm_100a) in-tree with nvcc.
+
+    python chromosight_b200/csrc/build.py [--force] [--verbose]
+
+The shared library lands next to the package (chromosight_b200/libchromosight_b200.so)
+so that it travels with the repository snapshot to the GPU box.
+"""
+import concurrent.futures as cf
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+SOURCES = ["image.cu", "pearson.cu", "scores.cu", "detrend.cu", "host_api.cu"]
+HEADERS = ["common.cuh", os.path.join("..", "..", "include", "chromosight_b200.h")]
+LIB = os.path.join(PKG, "libchromosight_b200.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
+]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(src, verbose):
+    obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+    deps = [os.path.join(HERE, src)] + [os.path.join(HERE, h) for h in HEADERS]
+    if not _stale(obj, deps):
+        return obj, ""
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(HERE, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    return obj, r.stderr
+
+
+def build(force=False, verbose=False):
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    if force:
+        for f in os.listdir(os.path.join(HERE, "build")):
+            os.remove(os.path.join(HERE, "build", f))
+    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
+    objs = [o for o, _ in results]
+    if verbose:
+        for _, log in results:
+            sys.stderr.write(log)
+    if force or _stale(LIB, objs):
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,230 @@
+// K0b: framing + densification of a CSR signal (and its missing mask) into the
+// float32 band / dense image consumed by the Pearson kernel.
+//   detection.py:979-991      zero frame of (mk-1, nk-1) pixels around the signal
+//   preprocessing.py:404-498  frame_missing_mask (margins + sub-diagonals)
+//   preprocessing.py:501-532  check_missing_mask (signal must be 0 under the mask)
+// Missing pixels are stored as NaN sentinels in the image itself, so the Pearson
+// kernel reads ONE array (4 B / pixel) whatever the mask looks like.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace cs {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct FillParams {
+    int rows, cols, dlo, dhi, pitch, dense;
+    int row_off, col_off;
+};
+
+__device__ __forceinline__ bool stored(const FillParams &F, int Y, int X) {
+    if (Y < 0 || Y >= F.rows || X < 0 || X >= F.cols) return false;
+    if (F.dense) return true;
+    const int d = X - Y;
+    return d >= F.dlo && d <= F.dhi;
+}
+__device__ __forceinline__ long long at(const FillParams &F, int Y, int X) {
+    return (long long)Y * F.pitch + (X - (F.dense ? 0 : F.dlo));
+}
+
+// one warp per CSR row
+__global__ void scatter_signal(FillParams F, const int64_t *__restrict__ indptr,
+                               const int32_t *__restrict__ indices,
+                               const double *__restrict__ data, int n_rows, float *img,
+                               int *err) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += gridDim.x * wpb) {
+        const int64_t b = indptr[r], e = indptr[r + 1];
+        const int Y = r + F.row_off;
+        for (int64_t k = b + lane; k < e; k += 32) {
+            const int X = indices[k] + F.col_off;
+            const double v = data[k];
+            if (stored(F, Y, X)) {
+                // duplicates of a non-canonical CSR would need atomics; scipy sums them
+                // before we get here (host side calls sum_duplicates)
+                img[at(F, Y, X)] = (float)v;
+            } else if (v != 0.0) {
+                atomicAdd(err + 1, 1);
+            }
+        }
+    }
+}
+
+// user mask pixels -> NaN; counts signal pixels that are non-zero under the mask
+__global__ void scatter_mask(FillParams F, const int64_t *__restrict__ indptr,
+                             const int32_t *__restrict__ indices, int n_rows, int trim_lo,
+                             int trim_hi, int do_trim, float *img, int *err) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += gridDim.x * wpb) {
+        const int64_t b = indptr[r], e = indptr[r + 1];
+        const int Y = r + F.row_off;
+        for (int64_t k = b + lane; k < e; k += 32) {
+            const int c = indices[k];
+            const int X = c + F.col_off;
+            if (!stored(F, Y, X)) continue;
+            const long long i = at(F, Y, X);
+            const float v = img[i];
+            if (v != 0.f && v == v) atomicAdd(err, 1);  // pre:516-523
+            // pre:452-454: the mask is diag-trimmed before framing
+            if (do_trim && (c - r < trim_lo || c - r > trim_hi)) continue;
+            img[i] = quiet_nan_f();
+        }
+    }
+}
+
+// NaN over a rectangle of the framed image (margins of frame_missing_mask)
+__global__ void nan_rect(FillParams F, int y0, int y1, int x0, int x1, float *img) {
+    const long long w = x1 - x0;
+    const long long n = (long long)(y1 - y0) * w;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int Y = y0 + (int)(i / w), X = x0 + (int)(i % w);
+        if (stored(F, Y, X)) img[at(F, Y, X)] = quiet_nan_f();
+    }
+}
+
+// pre:483-497: big_k diagonals below the main diagonal of the framed image
+__global__ void nan_subdiag(FillParams F, int big_k, float *img, int *err) {
+    const long long n = (long long)F.rows * big_k;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int Y = (int)(i / big_k), X = Y - 1 - (int)(i % big_k);
+        if (!stored(F, Y, X)) continue;
+        const long long k = at(F, Y, X);
+        const float v = img[k];
+        if (v != 0.f && v == v) atomicAdd(err, 1);
+        img[k] = quiet_nan_f();
+    }
+}
+
+}  // namespace cs
+
+using namespace cs;
+
+extern "C" int cs_version(void) { return CS_ABI_VERSION; }
+extern "C" const char *cs_last_error(void) { return cs::g_err; }
+extern "C" int64_t cs_launch_count(void) { return (int64_t)cs::g_launches.load(); }
+
+extern "C" int cs_layout_band(cs_layout *L, int32_t rows, int32_t cols, int32_t dlo, int32_t dhi) {
+    CS_REQUIRE(L && rows > 0 && cols > 0 && dhi >= dlo, "cs_layout_band: bad arguments");
+    if (dlo < -(rows - 1)) dlo = -(rows - 1);
+    if (dhi > cols - 1) dhi = cols - 1;
+    CS_REQUIRE(dhi >= dlo, "cs_layout_band: empty band");
+    L->rows = rows;
+    L->cols = cols;
+    L->dlo = dlo;
+    L->dhi = dhi;
+    L->dense = 0;
+    int pitch = round_up(dhi - dlo, 4);
+    if (pitch < 4) pitch = 4;
+    L->pitch = pitch;
+    int64_t n = (int64_t)(rows - 1) * pitch + ((int64_t)cols - dlo);
+    int64_t n2 = (int64_t)rows * (pitch + 1);
+    if (n2 > n) n = n2;
+    L->n_elems = (n + 3 + 64) / 4 * 4;
+    return CS_OK;
+}
+
+extern "C" int cs_layout_dense(cs_layout *L, int32_t rows, int32_t cols) {
+    CS_REQUIRE(L && rows > 0 && cols > 0, "cs_layout_dense: bad arguments");
+    L->rows = rows;
+    L->cols = cols;
+    L->dlo = 0;
+    L->dhi = 0;
+    L->dense = 1;
+    L->pitch = round_up(cols, 4);
+    L->n_elems = (int64_t)rows * L->pitch + 64;
+    return CS_OK;
+}
+
+extern "C" int cs_image_fill_f32(const cs_layout *L, float *d_img, const int64_t *d_sig_indptr,
+                                 const int32_t *d_sig_indices, const double *d_sig_data,
+                                 int32_t n_rows, int32_t n_cols, int32_t row_off, int32_t col_off,
+                                 int32_t mask_mode, const int64_t *d_mask_indptr,
+                                 const int32_t *d_mask_indices, int32_t sym_upper,
+                                 int32_t max_dist, int32_t frame_mk, int32_t frame_nk,
+                                 int32_t *d_err, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CS_REQUIRE(L && d_img && d_err, "cs_image_fill_f32: null argument");
+    CS_REQUIRE(n_rows + row_off <= L->rows && n_cols + col_off <= L->cols,
+               "signal does not fit in the image");
+    FillParams F;
+    F.rows = L->rows;
+    F.cols = L->cols;
+    F.dlo = L->dlo;
+    F.dhi = L->dhi;
+    F.pitch = L->pitch;
+    F.dense = L->dense;
+    F.row_off = row_off;
+    F.col_off = col_off;
+    CS_CUDA(cudaMemsetAsync(d_img, 0, (size_t)L->n_elems * sizeof(float), st));
+    CS_CUDA(cudaMemsetAsync(d_err, 0, 2 * sizeof(int32_t), st));
+    const int threads = 256;
+    const int wpb = threads / 32;
+    if (d_sig_indptr && n_rows > 0) {
+        int grid = (n_rows + wpb - 1) / wpb;
+        if (grid > 148 * 16) grid = 148 * 16;
+        scatter_signal<<<grid, threads, 0, st>>>(F, d_sig_indptr, d_sig_indices, d_sig_data,
+                                                 n_rows, d_img, d_err);
+        CS_LAUNCHED();
+    }
+    if (mask_mode == 1) {
+        CS_REQUIRE(d_mask_indptr && d_mask_indices, "mask arrays missing");
+        const bool framed = frame_mk > 0;
+        const bool banded = sym_upper && max_dist >= 0;
+        const int big_k = frame_mk > frame_nk ? frame_mk : frame_nk;
+        int grid = (n_rows + wpb - 1) / wpb;
+        if (grid > 148 * 16) grid = 148 * 16;
+        scatter_mask<<<grid, threads, 0, st>>>(F, d_mask_indptr, d_mask_indices, n_rows, 0,
+                                               max_dist + big_k, (framed && banded) ? 1 : 0, d_img,
+                                               d_err);
+        CS_LAUNCHED();
+        if (framed) {
+            const int H = L->rows, W = L->cols, mk = frame_mk, nk = frame_nk;
+            const int ns = n_cols;
+            struct R {
+                int y0, y1, x0, x1;
+            } rc[4];
+            int nr = 0;
+            if (banded) {
+                const int max_m = max_dist + mk, max_n = max_dist + nk;
+                const int tn = max_n < ns ? max_n : ns;
+                rc[nr++] = {0, mk - 1, nk - 1, nk - 1 + tn};                           // pre:461-463
+                rc[nr++] = {H - (max_m + 1) > 0 ? H - (max_m + 1) : 0, H, W - (nk - 1), W};  // pre:475
+                rc[nr++] = {0, mk - 1, 0, nk - 1};                                     // pre:477
+            } else {
+                rc[nr++] = {0, mk - 1, 0, W};
+                rc[nr++] = {H - (mk - 1), H, 0, W};
+                rc[nr++] = {0, H, 0, nk - 1};
+                rc[nr++] = {0, H, W - (nk - 1), W};
+            }
+            for (int i = 0; i < nr; ++i) {
+                const long long n = (long long)(rc[i].y1 - rc[i].y0) * (rc[i].x1 - rc[i].x0);
+                if (n <= 0) continue;
+                int g = (int)((n + threads - 1) / threads);
+                if (g > 148 * 8) g = 148 * 8;
+                nan_rect<<<g, threads, 0, st>>>(F, rc[i].y0, rc[i].y1, rc[i].x0, rc[i].x1, d_img);
+                CS_LAUNCHED();
+            }
+            if (sym_upper) {
+                const long long n = (long long)H * big_k;
+                int g = (int)((n + threads - 1) / threads);
+                if (g > 148 * 16) g = 148 * 16;
+                nan_subdiag<<<g, threads, 0, st>>>(F, big_k, d_img, d_err);
+                CS_LAUNCHED();
+            }
+        }
+    }
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}

@@ -1,0 +1,227 @@
+// K2: score image -> what the reference hands back.
+//   detection.py:1098-1131   non-zero scores as CSR float64 + log10 p-values
+//   stats.py:43-81           corr_to_pval (Fisher z, two-sided, log10)
+//   detection.py:417-421     pick_foci's thresholding, fused as a candidate list
+#include "common.cuh"
+
+namespace cs {
+
+struct ScoreView {
+    int rows, cols, dlo, dhi, pitch, dense;
+    int dmin, dmax;  // keep dmin <= col - row <= dmax
+};
+
+__device__ __forceinline__ void row_range(const ScoreView &S, int y, int &x0, int &x1) {
+    long long lo = (long long)y + S.dmin, hi = (long long)y + S.dmax;
+    if (!S.dense) {
+        if (lo < (long long)y + S.dlo) lo = (long long)y + S.dlo;
+        if (hi > (long long)y + S.dhi) hi = (long long)y + S.dhi;
+    }
+    if (lo < 0) lo = 0;
+    if (hi > S.cols - 1) hi = S.cols - 1;
+    x0 = (int)lo;
+    x1 = (int)hi + 1;  // exclusive; may be <= x0
+}
+__device__ __forceinline__ long long sidx(const ScoreView &S, int y, int x) {
+    return (long long)y * S.pitch + (x - (S.dense ? 0 : S.dlo));
+}
+
+// stats.py:74-81.  2*Phi(-|z|) = erfc(|z|/sqrt 2); scipy's ndtr underflows to exactly
+// 0 once (|z|/sqrt 2)^2 > log(DBL_MAX).
+__device__ __forceinline__ double log10_pval(double r, double n_obs) {
+    const double z = fabs(atanh(r) * sqrt(n_obs - 3.0));
+    if (z != z) return z;
+    const double a = z * 0.70710678118654752440;
+    if (a * a > 7.09782712893383996843e2) return -INFINITY;
+    return log10(erfc(a));
+}
+
+__global__ void count_rows(ScoreView S, const float *__restrict__ sc, int64_t *counts) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int y = blockIdx.x * wpb + (threadIdx.x >> 5); y < S.rows; y += gridDim.x * wpb) {
+        int x0, x1;
+        row_range(S, y, x0, x1);
+        int c = 0;
+        for (int x = x0 + lane; x < x1; x += 32) c += (sc[sidx(S, y, x)] != 0.f);
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) counts[y + 1] = c;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = 0;
+}
+
+// in-place inclusive scan of a[1..n] (a[0] = 0) by a single block
+__global__ void scan_inplace(int64_t *a, int n) {
+    __shared__ long long wsum[32];
+    __shared__ long long carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 1; base <= n; base += blockDim.x) {
+        const int i = base + tid;
+        long long v = (i <= n) ? a[i] : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            long long t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (lane == 31) wsum[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            long long w = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                long long t = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += t;
+            }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const long long pre = (wid > 0 ? wsum[wid - 1] : 0) + carry_s;
+        if (i <= n) a[i] = v + pre;
+        __syncthreads();
+        if (tid == blockDim.x - 1) carry_s = v + pre;
+        __syncthreads();
+    }
+}
+
+__global__ void emit_rows(ScoreView S, const float *__restrict__ sc,
+                          const unsigned short *__restrict__ nobs, int nobs_const,
+                          const int64_t *__restrict__ indptr, int32_t *indices, double *data,
+                          double *log10p) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int y = blockIdx.x * wpb + (threadIdx.x >> 5); y < S.rows; y += gridDim.x * wpb) {
+        int x0, x1;
+        row_range(S, y, x0, x1);
+        int64_t pos = indptr[y];
+        for (int xb = x0; xb < x1; xb += 32) {
+            const int x = xb + lane;
+            float v = 0.f;
+            long long i = 0;
+            if (x < x1) {
+                i = sidx(S, y, x);
+                v = sc[i];
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, v != 0.f);
+            if (v != 0.f) {
+                const int64_t o = pos + __popc(m & ((1u << lane) - 1u));
+                indices[o] = x;
+                data[o] = (double)v;
+                if (log10p) {
+                    const double n = nobs ? (double)nobs[i] : (double)nobs_const;
+                    log10p[o] = log10_pval((double)v, n);
+                }
+            }
+            pos += __popc(m);
+        }
+    }
+}
+
+__global__ void emit_candidates(ScoreView S, const float *__restrict__ sc,
+                                const unsigned short *__restrict__ nobs, int nobs_const,
+                                float threshold, cs_candidate *out, long long cap,
+                                unsigned long long *count) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int y = blockIdx.x * wpb + (threadIdx.x >> 5); y < S.rows; y += gridDim.x * wpb) {
+        int x0, x1;
+        row_range(S, y, x0, x1);
+        for (int xb = x0; xb < x1; xb += 32) {
+            const int x = xb + lane;
+            float v = 0.f;
+            long long i = 0;
+            bool hit = false;
+            if (x < x1) {
+                i = sidx(S, y, x);
+                v = sc[i];
+                hit = (v != 0.f) && (v >= threshold);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m == 0) continue;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit) {
+                const unsigned long long o = base + __popc(m & ((1u << lane) - 1u));
+                if ((long long)o < cap) {
+                    cs_candidate c;
+                    c.row = y;
+                    c.col = x;
+                    c.score = v;
+                    const double n = nobs ? (double)nobs[i] : (double)nobs_const;
+                    c.log10p = (float)log10_pval((double)v, n);
+                    out[o] = c;
+                }
+            }
+        }
+    }
+}
+
+static ScoreView make_view(const cs_layout *L, int dmin, int dmax) {
+    ScoreView S;
+    S.rows = L->rows;
+    S.cols = L->cols;
+    S.dlo = L->dlo;
+    S.dhi = L->dhi;
+    S.pitch = L->pitch;
+    S.dense = L->dense;
+    S.dmin = dmin;
+    S.dmax = dmax;
+    return S;
+}
+
+}  // namespace cs
+
+using namespace cs;
+
+extern "C" int cs_scores_count(const cs_layout *Lo, const float *d_out, int32_t dmin, int32_t dmax,
+                               int64_t *d_indptr, int64_t *nnz_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CS_REQUIRE(Lo && d_out && d_indptr && nnz_host, "cs_scores_count: null argument");
+    ScoreView S = make_view(Lo, dmin, dmax);
+    int grid = (S.rows + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    count_rows<<<grid, 256, 0, st>>>(S, d_out, d_indptr);
+    CS_LAUNCHED();
+    scan_inplace<<<1, 1024, 0, st>>>(d_indptr, S.rows);
+    CS_LAUNCHED();
+    CS_CUDA(cudaGetLastError());
+    CS_CUDA(cudaMemcpyAsync(nnz_host, d_indptr + S.rows, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                            st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    return CS_OK;
+}
+
+extern "C" int cs_scores_emit(const cs_layout *Lo, const float *d_out, const uint16_t *d_nobs,
+                              int32_t nobs_const, int32_t dmin, int32_t dmax,
+                              const int64_t *d_indptr, int32_t *d_indices, double *d_data,
+                              double *d_log10p, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CS_REQUIRE(Lo && d_out && d_indptr && d_indices && d_data, "cs_scores_emit: null argument");
+    ScoreView S = make_view(Lo, dmin, dmax);
+    int grid = (S.rows + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    emit_rows<<<grid, 256, 0, st>>>(S, d_out, d_nobs, nobs_const, d_indptr, d_indices, d_data,
+                                    d_log10p);
+    CS_LAUNCHED();
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+extern "C" int cs_scores_candidates(const cs_layout *Lo, const float *d_out, const uint16_t *d_nobs,
+                                    int32_t nobs_const, int32_t dmin, int32_t dmax, float threshold,
+                                    cs_candidate *d_cand, int64_t cap, int64_t *d_count,
+                                    int64_t *n_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CS_REQUIRE(Lo && d_out && d_cand && d_count && n_host, "cs_scores_candidates: null argument");
+    ScoreView S = make_view(Lo, dmin, dmax);
+    CS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    int grid = (S.rows + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    emit_candidates<<<grid, 256, 0, st>>>(S, d_out, d_nobs, nobs_const, threshold, d_cand,
+                                          (long long)cap, (unsigned long long *)d_count);
+    CS_LAUNCHED();
+    CS_CUDA(cudaGetLastError());
+    CS_CUDA(cudaMemcpyAsync(n_host, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    return CS_OK;
+}

@@ -1,0 +1,286 @@
+"""Drop-in mirror of chromosight.utils.detection for the hot path.
+
+`normxcorr2` and `xcorr2` keep the reference's signatures, return types and
+error behaviour (det:595-624, det:807-914) but run on a B200 through
+libchromosight_b200.so: the CSR signal is densified into a float32 band in HBM,
+one fused CUDA kernel evaluates every window, and the non-zero scores come
+back as the same scipy CSR objects the reference returns.  There is no CPU
+implementation behind these functions.
+
+The callers of the hot path (pick_foci & co, det:387-592) are host code, as in
+the reference.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from .. import _lib
+from . import preprocessing as preproc
+
+# statistics of the last hot-path call (device-side timings, windows evaluated)
+last_call_stats = {}
+
+
+def _device_index():
+    from .. import _cuda
+    t = _cuda.require_cuda()
+    return int(t.cuda.current_device())
+
+
+def _as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _diag_extent(csr):
+    """Smallest and largest stored diagonal (col - row) of a CSR matrix."""
+    if csr.nnz == 0:
+        return 0, -1
+    counts = np.diff(csr.indptr)
+    rows = np.flatnonzero(counts)
+    if csr.has_sorted_indices:
+        first = csr.indices[csr.indptr[rows]]
+        last = csr.indices[csr.indptr[rows + 1] - 1]
+        return int((first - rows).min()), int((last - rows).max())
+    r = np.repeat(np.arange(csr.shape[0]), counts)
+    d = csr.indices - r
+    return int(d.min()), int(d.max())
+
+
+def _canonical_csr(mat, dtype):
+    csr = mat.tocsr() if sp.issparse(mat) else sp.csr_matrix(mat)
+    if csr.dtype != dtype:
+        csr = csr.astype(dtype)
+    if not csr.has_canonical_format:
+        csr = csr.copy()
+        csr.sum_duplicates()
+    return csr
+
+
+def _kernel_desc(kernel, tsvd, keep):
+    """Fill a cs_kernel_desc; `keep` collects the arrays that must outlive the call."""
+    K = _as_f64(kernel)
+    if tsvd is not None:
+        k_corr = _as_f64(preproc.truncate_kernel(K, tsvd))
+        k2_mask = _as_f64(preproc.truncate_kernel(K ** 2, tsvd))
+    else:
+        k_corr = K
+        k2_mask = _as_f64(K ** 2)
+    keep.extend([K, k_corr, k2_mask])
+    d = _lib.KernelDesc()
+    d.kh, d.kw = K.shape
+    d.k_corr = k_corr.ctypes.data
+    d.k_mask = k_corr.ctypes.data
+    d.k2_mask = k2_mask.ctypes.data
+    d.k_sum = float(K.sum())
+    d.k2_sum = float((K ** 2).sum())
+    d.k_mean = float(K.mean())
+    d.k_std = float(K.std())
+    return d
+
+
+def _run_host(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsvd, pval,
+              raw_xcorr=False, threshold=1e-4, trim_to_max_dist=False):
+    """One call of cs_normxcorr2_host -> (corr csr, log10 p csr or None)."""
+    lib = _lib.load()
+    keep = []
+    a = _lib.Normxcorr2Args()
+    a.rows, a.cols = csr.shape
+    indptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
+    data = _as_f64(csr.data)
+    keep.extend([indptr, indices, data])
+    a.indptr, a.indices, a.data = indptr.ctypes.data, indices.ctypes.data, data.ctypes.data
+    a.has_mask = 0
+    if mask_csr is not None:
+        m_indptr = np.ascontiguousarray(mask_csr.indptr, dtype=np.int64)
+        m_indices = np.ascontiguousarray(mask_csr.indices, dtype=np.int32)
+        keep.extend([m_indptr, m_indices])
+        a.has_mask = 1
+        a.mask_indptr, a.mask_indices = m_indptr.ctypes.data, m_indices.ctypes.data
+    a.sym_upper = int(bool(sym_upper))
+    a.max_dist = -1 if max_dist is None else int(max_dist)
+    a.full = int(bool(full))
+    a.pval = int(bool(pval))
+    a.trim_to_max_dist = int(bool(trim_to_max_dist))
+    a.sig_dmin, a.sig_dmax = _diag_extent(csr)
+    a.kernel = _kernel_desc(kernel, tsvd, keep)
+    a.missing_tol = float(missing_tol)
+    a.device = _device_index()
+    a.raw_xcorr = int(bool(raw_xcorr))
+    a.xcorr_threshold = float(threshold)
+    res = _lib.CsrResult()
+    _lib.check(lib.cs_normxcorr2_host(C.byref(a), C.byref(res)))
+    try:
+        n = int(res.nnz)
+        indptr_o = np.ctypeslib.as_array(C.cast(res.indptr, C.POINTER(C.c_int64)),
+                                         shape=(a.rows + 1,)).copy()
+        if n:
+            idx = np.ctypeslib.as_array(C.cast(res.indices, C.POINTER(C.c_int32)), shape=(n,)).copy()
+            val = np.ctypeslib.as_array(C.cast(res.data, C.POINTER(C.c_double)), shape=(n,)).copy()
+        else:
+            idx = np.zeros(0, dtype=np.int32)
+            val = np.zeros(0, dtype=np.float64)
+        corr = sp.csr_matrix((val, idx, indptr_o), shape=csr.shape)
+        pvals = None
+        if pval:
+            if n:
+                pv = np.ctypeslib.as_array(C.cast(res.log10p, C.POINTER(C.c_double)), shape=(n,)).copy()
+            else:
+                pv = np.zeros(0, dtype=np.float64)
+            pvals = sp.csr_matrix((pv, idx.copy(), indptr_o.copy()), shape=csr.shape)
+        last_call_stats.clear()
+        last_call_stats.update(ms_h2d=res.ms_h2d, ms_kernels=res.ms_kernels, ms_d2h=res.ms_d2h,
+                               n_windows=int(res.n_windows), nnz=n)
+    finally:
+        lib.cs_result_free(C.byref(res))
+    return corr, pvals
+
+
+def _check_kernel_shape(kernel):
+    km, kn = kernel.shape
+    if km % 2 == 0 or kn % 2 == 0:
+        # even kernels break the reference too (inconsistent shapes after zero_pad_sparse,
+        # det:720-722); fail early with a clear message
+        raise ValueError("kernel dimensions must be odd")
+
+
+def xcorr2(signal, kernel, threshold=1e-4, tsvd=None):
+    """Cross-correlation of a 2-D signal with a dense kernel (det:595-624).
+
+    Same shape as the signal, zero margins of half a kernel, values below
+    `threshold` in magnitude set to zero.  Sparse in -> csr_matrix out, dense in
+    -> ndarray out."""
+    if isinstance(kernel, tuple):
+        left, right = kernel
+        if left.shape[1] != right.shape[0]:
+            raise ValueError("Kernel factorisation is invalid")
+        kernel = np.asarray(left) @ np.asarray(right)
+        tsvd = None
+    if sp.issparse(kernel):
+        raise ValueError("cannot handle kernel in sparse format")
+    kernel = np.asarray(kernel, dtype=np.float64)
+    _check_kernel_shape(kernel)
+    dense_in = not sp.issparse(signal)
+    csr = _canonical_csr(np.asarray(signal) if dense_in else signal, np.float64)
+    out, _ = _run_host(csr, kernel, None, None, False, False, 0.75, tsvd, False,
+                       raw_xcorr=True, threshold=threshold)
+    return out.toarray() if dense_in else out
+
+
+def normxcorr2(
+    signal,
+    kernel,
+    max_dist=None,
+    sym_upper=False,
+    full=False,
+    missing_mask=None,
+    missing_tol=0.75,
+    tsvd=None,
+    pval=False,
+    *,
+    trim_to_max_dist=False,
+):
+    """Pearson correlation of every window of `signal` with `kernel`
+    (det:807-914).  Arguments, return values and ValueErrors follow the
+    reference; `trim_to_max_dist` is an extension that skips the scores beyond
+    `max_dist` which pattern_detector throws away anyway (det:270).
+
+    Returns (corr, log10_pvals): csr_matrix for a sparse signal, ndarray for a
+    dense one; log10_pvals is None unless pval=True."""
+    if missing_mask is not None:
+        if not sp.issparse(missing_mask):
+            raise ValueError("Missing mask must be a sparse matrix.")
+        if not signal.shape == missing_mask.shape:
+            raise ValueError("Signal and missing mask do not have the same shape")
+        if missing_mask.dtype != bool:
+            raise ValueError(f"Missing mask dtype is {missing_mask.dtype}. Should be bool.")
+        if min(kernel.shape) >= max(signal.shape):
+            raise ValueError("cannot have kernel bigger than signal")
+    if sp.issparse(kernel):
+        raise ValueError("cannot handle kernel in sparse format")
+    kernel = np.asarray(kernel, dtype=np.float64)
+    if not (kernel.std() > 0):
+        raise ValueError("Cannot have flat kernel.")
+    _check_kernel_shape(kernel)
+    dense_in = not sp.issparse(signal)
+    csr = _canonical_csr(np.asarray(signal) if dense_in else signal, np.float64)
+    mask_csr = None
+    if missing_mask is not None:
+        mask_csr = missing_mask.tocsr()
+        if mask_csr.nnz and not mask_csr.data.all():
+            mask_csr = mask_csr.copy()
+            mask_csr.eliminate_zeros()
+    corr, pvals = _run_host(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsvd,
+                            pval, trim_to_max_dist=trim_to_max_dist)
+    if dense_in:
+        return corr.toarray(), (pvals.toarray() if pvals is not None else None)
+    return corr, pvals
+
+
+# --------------------------------------------------------------------------- foci (host)
+def label_foci(matrix):
+    """4-connected component labelling of the non-zero pixels (det:459-554).
+    Labels start at 1 and are numbered by the first pixel of each focus in
+    row-major order."""
+    coo = sp.coo_matrix(sp.csr_matrix(matrix))
+    n = coo.nnz
+    order = np.lexsort((coo.col, coo.row))
+    row, col = coo.row[order].astype(np.int64), coo.col[order].astype(np.int64)
+    width = int(coo.shape[1]) + 1
+    key = row * width + col
+    idx = np.arange(n)
+    # right neighbours are adjacent in row-major order; lower neighbours by key lookup
+    right = np.flatnonzero((row[1:] == row[:-1]) & (col[1:] == col[:-1] + 1))
+    below_pos = np.searchsorted(key, key + width)
+    below_ok = (below_pos < n)
+    below_ok[below_ok] = key[below_pos[below_ok]] == (key + width)[below_ok]
+    a = np.concatenate([right, idx[below_ok]])
+    b = np.concatenate([right + 1, below_pos[below_ok]])
+    graph = sp.coo_matrix((np.ones(len(a), dtype=np.int8), (a, b)), shape=(n, n))
+    num, comp = sp.csgraph.connected_components(graph, directed=False)
+    # number components by first appearance in row-major order
+    first = np.full(num, n, dtype=np.int64)
+    np.minimum.at(first, comp, idx)
+    rank = np.empty(num, dtype=np.int64)
+    rank[np.argsort(first)] = np.arange(num)
+    labels = rank[comp] + 1
+    out = sp.coo_matrix((labels, (row, col)), shape=coo.shape)
+    return num, out
+
+
+def filter_foci(foci_mat, min_size=2):
+    """Drop foci of fewer than min_size pixels (det:557-592)."""
+    data = foci_mat.data
+    ids, sizes = np.unique(data, return_counts=True)
+    small = ids[sizes < min_size]
+    data = np.where(np.isin(data, small), 0, data)
+    out = foci_mat.copy()
+    out.data = data
+    out.eliminate_zeros()
+    return int((sizes >= min_size).sum()), out
+
+
+def pick_foci(mat_conv, pearson, min_size=2):
+    """Local maxima of the thresholded correlation map, one per focus
+    (det:387-456).  Returns (coords, labelled matrix) or (None, None)."""
+    cand = sp.coo_matrix(mat_conv).copy()
+    keep = (cand.data >= pearson) & (cand.data != 0)
+    cand = sp.coo_matrix((np.ones(keep.sum()), (cand.row[keep], cand.col[keep])), shape=cand.shape)
+    if cand.nnz == 0:
+        return None, None
+    _, labelled = label_foci(cand)
+    num, labelled = filter_foci(labelled, min_size=min_size)
+    if num == 0:
+        return None, None
+    scores = np.asarray(sp.csr_matrix(mat_conv)[labelled.row, labelled.col]).ravel()
+    coords = np.zeros((num, 2), dtype=int)
+    order = np.argsort(labelled.data, kind="stable")
+    lab_sorted = labelled.data[order]
+    starts = np.flatnonzero(np.r_[True, lab_sorted[1:] != lab_sorted[:-1]])
+    ends = np.r_[starts[1:], len(order)]
+    for k, (s, e) in enumerate(zip(starts, ends)):
+        members = order[s:e]                       # row-major order within the focus
+        best = members[np.argmax(scores[members])]  # first maximum, as np.argmax
+        coords[k] = labelled.row[best], labelled.col[best]
+    return coords, labelled

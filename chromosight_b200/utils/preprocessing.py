@@ -1,0 +1,249 @@
+"""Mirror of the parts of chromosight.utils.preprocessing that sit on the hot
+path: same names, same arguments, same error
+behaviour.  The O(nnz) arithmetic of the distance law and of detrending runs in
+CUDA (csrc/detrend.cu); masks, trimming and padding are host bookkeeping on
+scipy.sparse objects, as in the reference.
+"""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from .. import _cuda, _lib
+
+
+# --------------------------------------------------------------------------- host helpers
+def valid_to_missing(valid, size):
+    """Complement of an index list within range(size) (pre:850-875)."""
+    flags = np.ones(size, dtype=bool)
+    try:
+        flags[valid] = False
+    except IndexError:
+        pass
+    return np.flatnonzero(flags)
+
+
+def diag_trim(mat, n):
+    """Keep diagonals 0..n (inclusive) of the upper triangle (pre:93-126)."""
+    if sp.issparse(mat):
+        if mat.format != "csr":
+            raise ValueError("input type must be scipy.sparse.csr_matrix")
+        coo = mat.tocoo()
+        d = coo.col - coo.row
+        keep = (d >= 0) & (d <= n)
+        return sp.csr_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=mat.shape)
+    out = np.array(mat, copy=True)
+    rows = np.arange(out.shape[0])[:, None]
+    cols = np.arange(out.shape[1])[None, :]
+    # the dense variant of the reference blanks diagonals n.. of the upper part
+    # only and leaves the lower triangle untouched (pre:119-124)
+    out[(cols - rows) >= n] = 0
+    return out
+
+
+def zero_pad_sparse(mat, margin_h, margin_v, fmt="coo"):
+    """Zero margins around a sparse matrix (pre:636-676)."""
+    coo = sp.coo_matrix(mat)
+    sm, sn = coo.shape
+    out = sp.coo_matrix(
+        (coo.data, (coo.row + margin_v, coo.col + margin_h)),
+        shape=(sm + 2 * margin_v, sn + 2 * margin_h),
+    )
+    # the reference always hands back CSR, whatever fmt says (pre:671-676)
+    return out.tocsr()
+
+
+def make_missing_mask(shape, valid_rows, valid_cols, max_dist=None, sym_upper=False):
+    """Sparse boolean mask of the pixels that belong to missing bins (pre:535-633)."""
+    sm, sn = shape
+    if sym_upper and (sm != sn or len(valid_rows) != len(valid_cols)):
+        raise ValueError("Rectangular matrices cannot be upper symmetric")
+    miss_r = valid_to_missing(valid_rows, sm)
+    if sym_upper:
+        if max_dist is None:
+            max_dist = min(shape)
+        shifts = np.arange(max_dist + 1)
+        # pixels above each missing bin (same column) and to its right (same row)
+        rows = np.concatenate([(miss_r[:, None] - shifts[None, :]).ravel(),
+                               np.repeat(miss_r, max_dist + 1)])
+        cols = np.concatenate([np.repeat(miss_r, max_dist + 1),
+                               (miss_r[:, None] + shifts[None, :]).ravel()])
+        ok = (rows >= 0) & (rows < sm) & (cols >= 0) & (cols < sm)
+        mask = sp.coo_matrix((np.ones(ok.sum(), dtype=bool), (rows[ok], cols[ok])),
+                             shape=shape, dtype=bool).tocsr()
+        return mask
+    miss_c = valid_to_missing(valid_cols, sn)
+    fr = np.zeros(sm, dtype=bool)
+    fr[miss_r] = True
+    fc = np.zeros(sn, dtype=bool)
+    fc[miss_c] = True
+    # whole rows, then the remaining pixels of whole columns
+    r1 = np.repeat(miss_r, sn)
+    c1 = np.tile(np.arange(sn), len(miss_r))
+    good_rows = np.flatnonzero(~fr)
+    r2 = np.tile(good_rows, len(miss_c))
+    c2 = np.repeat(miss_c, len(good_rows))
+    rows = np.concatenate([r1, r2])
+    cols = np.concatenate([c1, c2])
+    return sp.coo_matrix((np.ones(len(rows), dtype=bool), (rows, cols)), shape=shape,
+                         dtype=bool).tocsr()
+
+
+def frame_missing_mask(mask, kernel_shape, sym_upper=False, max_dist=None):
+    """Missing mask of the framed signal (pre:404-498).  The CUDA path builds this
+    frame itself (csrc/image.cu); this host version exists for API parity."""
+    if mask.dtype != bool:
+        raise ValueError("Mask must contain boolean values")
+    if not sp.issparse(mask):
+        raise ValueError("Mask must be a sparse matrix")
+    ms, ns = mask.shape
+    mk, nk = kernel_shape
+    banded = sym_upper and (max_dist is not None)
+    coo = mask.tocoo()
+    keep = coo.data != 0
+    r, c = coo.row[keep], coo.col[keep]
+    if banded:
+        d = c - r
+        ok = (d >= 0) & (d <= max_dist + max(nk, mk))
+        r, c = r[ok], c[ok]
+    H, W = ms + 2 * (mk - 1), ns + 2 * (nk - 1)
+    framed = sp.coo_matrix((np.ones(len(r), dtype=bool), (r + mk - 1, c + nk - 1)),
+                           shape=(H, W), dtype=bool).tolil()
+    if banded:
+        max_m, max_n = max_dist + mk, max_dist + nk
+        framed[: mk - 1, nk - 1: nk - 1 + min(max_n, ns)] = True
+        if nk > 1:
+            framed[max(0, H - (max_m + 1)):, W - (nk - 1):] = True
+        framed[: mk - 1, : nk - 1] = True
+    else:
+        framed[: mk - 1, :] = True
+        framed[H - (mk - 1):, :] = True
+        framed[:, : nk - 1] = True
+        framed[:, W - (nk - 1):] = True
+    framed = framed.tocsr()
+    if sym_upper:
+        big_k = max(nk, mk)
+        framed = framed + sp.diags(np.ones(big_k), -np.arange(1, big_k + 1), shape=(H, W),
+                                   format="csr", dtype=bool)
+        framed = framed.astype(bool)
+    return framed.tocsr()
+
+
+def check_missing_mask(signal, mask):
+    """Raise ValueError when the signal is non-zero under the mask (pre:501-532)."""
+    if sp.issparse(mask):
+        m = mask.tocoo()
+        r, c = m.row[m.data != 0], m.col[m.data != 0]
+        vals = np.asarray(signal[r, c]).ravel() if len(r) else np.zeros(0)
+        n_bad = int(np.count_nonzero(np.abs(vals) > 0))
+        if n_bad:
+            raise ValueError("There are", n_bad, "non-zero elements reported as missing.")
+    else:
+        tot = np.sum(np.abs(np.asarray(signal)[np.asarray(mask) > 0]))
+        if tot > 1e-10:
+            raise ValueError("There are", str(tot), "non-zero elements reported as missing.")
+
+
+def factorise_kernel(kernel, prop_info=0.999):
+    """Truncated SVD factors (U sqrt(s), sqrt(s) V) keeping `prop_info` of the
+    squared singular values (pre:810-847)."""
+    u, s, vt = np.linalg.svd(np.asarray(kernel, dtype=float))
+    keep = int(np.flatnonzero(np.cumsum(s ** 2) > prop_info * np.sum(s ** 2))[0]) + 1
+    root = np.sqrt(s[:keep])
+    return u[:, :keep] * root[None, :], vt[:keep, :] * root[:, None]
+
+
+def truncate_kernel(kernel, prop_info):
+    """U @ V of factorise_kernel: the dense kernel the factorised convolution is
+    equivalent to (det:648-665)."""
+    left, right = factorise_kernel(kernel, prop_info)
+    return left @ right
+
+
+def ztransform(matrix):
+    """Global z-score of the stored values (pre:313-334)."""
+    out = matrix.copy()
+    out.data = (out.data - np.mean(out.data)) / np.std(out.data)
+    return out
+
+
+# --------------------------------------------------------------------------- CUDA path
+def _csr_device(csr):
+    indptr = _cuda.to_device(csr.indptr, np.int64)
+    indices = _cuda.to_device(csr.indices, np.int32)
+    data = _cuda.to_device(csr.data, np.float64)
+    return indptr, indices, data
+
+
+def _law_device(csr, d_csr, detectable_bins, max_dist):
+    """Distance law of a CSR matrix already on the device -> (torch tensor of
+    length n, float64)."""
+    t = _cuda.require_cuda()
+    lib = _lib.load()
+    n = csr.shape[0]
+    if max_dist is None:
+        max_dist = n
+    n_diags = int(min(n, max_dist + 1))
+    if detectable_bins is None:
+        d_detect = None
+    else:
+        flags = np.zeros(n, dtype=np.uint8)
+        flags[np.asarray(detectable_bins)] = 1
+        d_detect = _cuda.to_device(flags)
+    d_sum = _cuda.empty(n_diags, t.float64)
+    d_cnt = _cuda.empty(n_diags, t.int64)
+    d_law = _cuda.empty(n, t.float64)
+    indptr, indices, data = d_csr
+    _lib.check(lib.cs_distance_law(_cuda.ptr(indptr), _cuda.ptr(indices), _cuda.ptr(data), n,
+                                   _cuda.ptr(d_detect), n_diags, _cuda.ptr(d_sum),
+                                   _cuda.ptr(d_cnt), _cuda.ptr(d_law), _cuda.stream_ptr()))
+    return d_law, d_cnt, n_diags
+
+
+def distance_law(matrix, detectable_bins=None, max_dist=None, smooth=True, fun=np.nanmean):
+    """Average contact value per upper diagonal (pre:129-197)."""
+    if fun is not np.nanmean:
+        raise NotImplementedError("the CUDA distance law implements fun=np.nanmean only")
+    csr = sp.csr_matrix(matrix)
+    if not csr.has_canonical_format:
+        csr = csr.copy()
+        csr.sum_duplicates()
+    n = csr.shape[0]
+    d_law, d_cnt, n_diags = _law_device(csr, _csr_device(csr), detectable_bins, max_dist)
+    law = d_law.cpu().numpy()
+    cnt = d_cnt.cpu().numpy()
+    # the reference reports NaN for diagonals without any usable pixel (nanmean of
+    # an empty slice); the device array already holds the 0 that detrend needs
+    law[:n_diags][cnt == 0] = np.nan
+    if smooth and n > 2:
+        from sklearn.isotonic import IsotonicRegression
+        law[~np.isfinite(law)] = 0
+        law = IsotonicRegression(increasing=False).fit_transform(range(len(law)), law)
+    return law
+
+
+def detrend(matrix, detectable_bins=None, max_dist=None, smooth=False, fun=np.nanmean, max_val=10):
+    """Divide each pixel by the distance law of its diagonal (pre:256-310)."""
+    if fun is not np.nanmean:
+        raise NotImplementedError("the CUDA detrend implements fun=np.nanmean only")
+    t = _cuda.require_cuda()
+    lib = _lib.load()
+    csr = sp.csr_matrix(matrix, dtype=np.float64)
+    if not csr.has_canonical_format:
+        csr = csr.copy()
+        csr.sum_duplicates()
+    n = csr.shape[0]
+    d_csr = _csr_device(csr)
+    if smooth:
+        law = distance_law(csr, detectable_bins, max_dist, smooth=True)
+        law[np.isnan(law)] = 0.0
+        d_law = _cuda.to_device(law, np.float64)
+    else:
+        d_law, _, _ = _law_device(csr, d_csr, detectable_bins, max_dist)
+    out = _cuda.empty(csr.nnz, t.float64)
+    if csr.nnz:
+        _lib.check(lib.cs_detrend_apply(_cuda.ptr(d_csr[0]), _cuda.ptr(d_csr[1]), _cuda.ptr(d_csr[2]),
+                                        _cuda.ptr(out), n, _cuda.ptr(d_law), n,
+                                        C.c_double(-1.0 if max_val is None else float(max_val)),
+                                        _cuda.stream_ptr()))
+    return sp.csr_matrix((out.cpu().numpy(), csr.indices.copy(), csr.indptr.copy()), shape=csr.shape)

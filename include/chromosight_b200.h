@@ -1,0 +1,210 @@
+/*
+ * chromosight_b200 -- C ABI of the B200 (sm_100a) hot path of koszullab/chromosight.
+ *
+ * The reference is pure Python (no FFI exists in it); each entry point below
+ * names the reference function it stands in for (file:line relative to the
+ * reference tree, v1.6.3 @ ecb32c5).  All sizes are in elements, all pointers
+ * are plain C pointers; `d_` prefixed arguments are DEVICE pointers owned by
+ * the caller, everything else is HOST memory.  Every function returns 0 on
+ * success or a negative cs_status; cs_last_error() gives the message of the
+ * last failure on the calling thread.  `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream).
+ */
+#ifndef CHROMOSIGHT_B200_H
+#define CHROMOSIGHT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_ABI_VERSION 1
+
+typedef enum cs_status {
+    CS_OK = 0,
+    CS_ERR_INVALID = -1,      /* bad argument (the Python layer raises ValueError) */
+    CS_ERR_CUDA = -2,         /* CUDA runtime / driver failure */
+    CS_ERR_NOMEM = -3,
+    CS_ERR_MASKED_SIGNAL = -4 /* signal non-zero under the missing mask (pre:501-532) */
+} cs_status;
+
+int cs_version(void);
+const char *cs_last_error(void);
+/* Number of kernels launched by this library since process start (bench.py's gpu_launches). */
+int64_t cs_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Band layout.  A (framed) image of rows x cols pixels of which only the
+ * diagonals dlo <= X - Y <= dhi are stored.  Pixel (Y, X) lives at element
+ *      Y * pitch + (X - dlo)          with pitch % 4 == 0,
+ * i.e. the classic skewed band of pitch + 1 diagonals per row, addressed so
+ * that a TMA tensor map of row stride `pitch` presents it as an ordinary
+ * matrix.  A dense image is the same formula with dlo = 0 and
+ * pitch = roundup4(cols); set dense = 1.
+ * ------------------------------------------------------------------------ */
+typedef struct cs_layout {
+    int32_t rows, cols;
+    int32_t dlo, dhi; /* stored diagonals (ignored when dense) */
+    int32_t pitch;
+    int32_t dense;
+    int64_t n_elems; /* allocation size in elements (floats) */
+} cs_layout;
+
+int cs_layout_band(cs_layout *L, int32_t rows, int32_t cols, int32_t dlo, int32_t dhi);
+int cs_layout_dense(cs_layout *L, int32_t rows, int32_t cols);
+
+/* ------------------------------------------------------------------------
+ * Framing + densification: detection.py:979-991 (zero frame around the
+ * signal), preprocessing.py:404-498 (frame_missing_mask) and
+ * preprocessing.py:501-532 (check_missing_mask).
+ *
+ * Scatters the CSR signal (n_rows x n_cols, float64 values, int32 column
+ * indices, int64 row pointers) into the float32 image `d_img` (layout L) at
+ * offset (row_off, col_off), writes the missing mask as NaN sentinels
+ * (user mask pixels from a CSR pattern, then the geometric frame of
+ * frame_missing_mask when frame_mk > 0), and counts signal pixels that are
+ * non-zero under the mask into *d_err (int32, device).
+ *   mask_mode: 0 no mask, 1 mask given.
+ *   sym_upper / max_dist (-1 = None): as in frame_missing_mask.
+ *   frame_mk, frame_nk: kernel shape when the image is framed (full=True), 0 otherwise.
+ * ------------------------------------------------------------------------ */
+int cs_image_fill_f32(const cs_layout *L, float *d_img,
+                      const int64_t *d_sig_indptr, const int32_t *d_sig_indices,
+                      const double *d_sig_data, int32_t n_rows, int32_t n_cols,
+                      int32_t row_off, int32_t col_off,
+                      int32_t mask_mode, const int64_t *d_mask_indptr,
+                      const int32_t *d_mask_indices,
+                      int32_t sym_upper, int32_t max_dist,
+                      int32_t frame_mk, int32_t frame_nk,
+                      int32_t *d_err, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Pearson map: detection.py:917-1131 (_normxcorr2_sparse; the no-mask branch
+ * det:1002-1020 and the masked branch det:1021-1092) for every window centred
+ * on an output pixel.  detection.py:595-723 (xcorr2) when raw_xcorr = 1.
+ *
+ * Output pixel set (image coordinates): oy0 <= Y < oy1, ox0 <= X < ox1 and
+ * odlo <= X - Y <= odhi.  Results go to the float32 image `d_out` with layout
+ * Lout, whose pixel (Y - out_row_shift, X - out_col_shift) receives the score of
+ * window (Y, X) (the shifts undo the frame, det:1124-1129).  `d_nobs` (uint16, same
+ * layout, may be NULL) receives the number of observations of each window
+ * (det:1110-1116).
+ * ------------------------------------------------------------------------ */
+typedef struct cs_kernel_desc {
+    int32_t kh, kw;          /* kernel shape (mk, nk), both odd */
+    const double *k_corr;    /* kh*kw, kernel correlated with the signal (truncated when tsvd) */
+    const double *k_mask;    /* kh*kw, kernel correlated with the mask (det:1035-1040) */
+    const double *k2_mask;   /* kh*kw, squared kernel correlated with the mask (det:1041-1046) */
+    double k_sum, k2_sum;    /* sums of the ORIGINAL kernel and of its square (det:1024-1027) */
+    double k_mean, k_std;    /* mean / std of the original kernel (det:1003-1004) */
+} cs_kernel_desc;
+
+typedef struct cs_pearson_opts {
+    int32_t has_mask;        /* image carries NaN sentinels (masked branch) */
+    double missing_tol;      /* det:1069-1072 */
+    double xcorr_threshold;  /* 1e-4, det:595 */
+    int32_t raw_xcorr;       /* 1: write thresholded raw cross-correlation instead of Pearson */
+    int32_t nobs_full;       /* 1: n_obs = present pixels (full=True & mask), det:1110 */
+    int32_t tile_rows;       /* 0 = auto */
+    int32_t out_row_shift;   /* score of window (Y, X) is written to pixel           */
+    int32_t out_col_shift;   /* (Y - out_row_shift, X - out_col_shift) of the output */
+} cs_pearson_opts;
+
+int cs_pearson_f32(const cs_layout *Limg, const float *d_img,
+                   const cs_kernel_desc *K, const cs_pearson_opts *opts,
+                   int32_t oy0, int32_t oy1, int32_t ox0, int32_t ox1,
+                   int32_t odlo, int32_t odhi,
+                   const cs_layout *Lout, float *d_out, uint16_t *d_nobs,
+                   void *stream);
+
+/* ------------------------------------------------------------------------
+ * Score map -> CSR (what normxcorr2 returns, det:1098-1131): non-zero scores
+ * as float64 CSR, plus log10 p-values (stats.py:43-81) at the same pattern.
+ * Two calls: count (fills d_indptr[0..rows], returns nnz in *nnz_host after
+ * synchronising the stream) then emit.
+ * ------------------------------------------------------------------------ */
+int cs_scores_count(const cs_layout *Lout, const float *d_out,
+                    int32_t dmin, int32_t dmax, /* keep only dmin <= col-row <= dmax */
+                    int64_t *d_indptr, int64_t *nnz_host, void *stream);
+int cs_scores_emit(const cs_layout *Lout, const float *d_out, const uint16_t *d_nobs,
+                   int32_t nobs_const, int32_t dmin, int32_t dmax,
+                   const int64_t *d_indptr, int32_t *d_indices, double *d_data,
+                   double *d_log10p /* may be NULL */, void *stream);
+
+/* Candidate pixels (score >= threshold) as (row, col, score, log10p) records:
+ * the thresholding of pick_foci (det:417-421) fused with the p-value lookup
+ * (det:337-339). Returns the number found in *n_host (capped at cap). */
+typedef struct cs_candidate {
+    int32_t row, col;
+    float score;
+    float log10p;
+} cs_candidate;
+int cs_scores_candidates(const cs_layout *Lout, const float *d_out, const uint16_t *d_nobs,
+                         int32_t nobs_const, int32_t dmin, int32_t dmax, float threshold,
+                         cs_candidate *d_cand, int64_t cap, int64_t *d_count,
+                         int64_t *n_host, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Distance-law detrending: preprocessing.py:129-197 (distance_law, smooth=False,
+ * fun=nanmean) and preprocessing.py:256-310 (detrend).
+ * cs_distance_law: per upper diagonal d <= max_dist, mean of the strictly
+ * positive pixels whose bins are both detectable (d_detect: uint8[n], 1 = ok).
+ * d_sum/d_cnt: double[n_diags] / int64[n_diags] workspaces (zeroed inside),
+ * d_law: double[n] output (0 beyond n_diags and where no pixel qualifies,
+ * as after pre:289).
+ * cs_detrend_apply: data[i] /= law[|row-col|]; values >= max_val -> 1
+ * (max_val < 0 disables), pre:303-309.
+ * ------------------------------------------------------------------------ */
+int cs_distance_law(const int64_t *d_indptr, const int32_t *d_indices, const double *d_data,
+                    int32_t n, const uint8_t *d_detect, int32_t n_diags,
+                    double *d_sum, int64_t *d_cnt, double *d_law, void *stream);
+int cs_detrend_apply(const int64_t *d_indptr, const int32_t *d_indices, const double *d_data_in,
+                     double *d_data_out, int32_t n_rows, const double *d_law, int32_t n_law,
+                     double max_val, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Host-buffer, whole-call entry point: what chromosight.utils.detection.
+ * normxcorr2 (det:807-914) does for a sparse signal, from host CSR arrays to
+ * host CSR arrays, including host<->device copies through pinned staging.
+ * The result buffers are owned by the library until cs_result_free().
+ * ------------------------------------------------------------------------ */
+typedef struct cs_csr_result {
+    int64_t nnz;
+    int32_t rows, cols;
+    int64_t *indptr;  /* rows + 1 */
+    int32_t *indices; /* nnz */
+    double *data;     /* nnz */
+    double *log10p;   /* nnz or NULL */
+    double ms_h2d, ms_kernels, ms_d2h; /* device-side timings of the call */
+    int64_t n_windows;
+} cs_csr_result;
+
+typedef struct cs_normxcorr2_args {
+    int32_t rows, cols;
+    const int64_t *indptr;
+    const int32_t *indices;
+    const double *data;
+    int32_t has_mask;
+    const int64_t *mask_indptr;
+    const int32_t *mask_indices;
+    int32_t sym_upper;
+    int32_t max_dist; /* -1 = None */
+    int32_t full;
+    int32_t pval;
+    int32_t trim_to_max_dist; /* extension: drop scores beyond max_dist (det:270) */
+    int32_t sig_dmin, sig_dmax; /* diagonal extent of the stored signal (col-row) */
+    cs_kernel_desc kernel;
+    double missing_tol;
+    int32_t device;
+    int32_t raw_xcorr;       /* 1: xcorr2 (det:595-723) instead of normxcorr2 */
+    double xcorr_threshold;  /* threshold of xcorr2 when raw_xcorr (normxcorr2 always uses 1e-4) */
+} cs_normxcorr2_args;
+
+int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *res);
+void cs_result_free(cs_csr_result *res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHROMOSIGHT_B200_H */

@@ -1,0 +1,170 @@
+"""CUDA path vs the reference's golden outputs and vs the oracle (run on a B200:
+`pytest -m gpu`).  Everything goes through the C ABI (cs_normxcorr2_host & co).
+
+Tolerances (BASELINE.json north_star): Pearson scores within 1e-5 absolute;
+log10 p-values within 1e-4 relative where the score itself is significant.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GOLDEN, golden_case_names, load_case, load_coo
+
+pytestmark = pytest.mark.gpu
+
+SCORE_TOL = 1e-5
+
+
+def _compare(r, p, corr_ref, pval_ref):
+    r = r.toarray() if sp.issparse(r) else np.asarray(r)
+    assert r.shape == corr_ref.shape
+    d = np.abs(r - corr_ref)
+    assert d.max() <= SCORE_TOL, f"max |dr| = {d.max():.3e}"
+    if pval_ref is not None:
+        assert p is not None
+        p = p.toarray() if sp.issparse(p) else np.asarray(p)
+        sel = (np.abs(corr_ref) > 1e-3) & (r != 0)
+        fin = sel & np.isfinite(pval_ref)
+        assert np.array_equal(np.isneginf(p[sel]), np.isneginf(pval_ref[sel]))
+        # d(log10 p)/dr is large: a 1e-5 change of r moves log10 p by up to ~1e-3
+        assert np.allclose(p[fin], pval_ref[fin], rtol=1e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_normxcorr2_golden(name):
+    from chromosight_b200.utils import detection as cud
+    signal, kernel, kw, dense, corr_ref, pval_ref = load_case(name)
+    sig = signal.toarray() if dense else signal
+    r, p = cud.normxcorr2(sig, kernel, **kw)
+    if dense:
+        assert isinstance(r, np.ndarray)
+    else:
+        assert sp.issparse(r) and r.format == "csr" and r.dtype == np.float64
+        assert r.nnz == 0 or np.all(r.data != 0)
+    _compare(r, p, corr_ref, pval_ref)
+
+
+def test_xcorr2_golden():
+    from chromosight_b200.utils import detection as cud
+    z = np.load(os.path.join(GOLDEN, "xcorr2_cases.npz"))
+    for nm in ("gauss", "band", "band_const", "band_tsvd", "band_rect"):
+        sig = load_coo(z, f"{nm}_signal").tocsr()
+        kw = json.loads(str(z[f"{nm}_kwargs"]))
+        out = cud.xcorr2(sig, z[f"{nm}_kernel"], **kw)
+        ref = load_coo(z, f"{nm}_out").toarray()
+        scale = max(1.0, np.abs(ref).max())
+        # raw sums of up to 289 products: relative tolerance on the map's scale
+        assert np.abs(out.toarray() - ref).max() <= 2e-5 * scale, nm
+
+
+def test_detrend_golden():
+    from chromosight_b200.utils import preprocessing as cup
+    z = np.load(os.path.join(GOLDEN, "preproc_cases.npz"))
+    for i in range(2):
+        for tag in ("upper", "sym"):
+            raw = load_coo(z, f"d{i}_{tag}_raw").tocsr()
+            det = z[f"d{i}_{tag}_detect"]
+            D = int(z[f"d{i}_{tag}_max_dist"])
+            law = cup.distance_law(raw, detectable_bins=det, max_dist=D, smooth=False)
+            assert np.allclose(law, z[f"d{i}_{tag}_law"], rtol=1e-12, equal_nan=True)
+            out = cup.detrend(raw, detectable_bins=det, max_dist=D, max_val=10)
+            ref = load_coo(z, f"d{i}_{tag}_out").toarray()
+            assert sp.issparse(out) and out.format == "csr"
+            assert np.allclose(out.toarray(), ref, rtol=1e-12)
+            out = cup.detrend(raw, detectable_bins=det, max_dist=D, max_val=None)
+            ref = load_coo(z, f"d{i}_{tag}_out_nomax").toarray()
+            assert np.allclose(out.toarray(), ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("seed,n,D,kname,tol", [
+    (21, 700, 60, "loops", 0.5), (22, 513, 25, "loops_small", 0.5),
+    (23, 400, 90, "hairpins", 0.75), (24, 333, 40, "borders", 0.75),
+])
+def test_production_call_vs_oracle(seed, n, D, kname, tol, presets):
+    """pattern_detector's call (det:242-263) on seeded synthetic maps, checked
+    against the oracle on every window."""
+    from chromosight_b200 import synthetic
+    from chromosight_b200.utils import detection as cud, preprocessing as cup
+    from oracle import pearson_oracle as po
+    kernel = getattr(presets, kname)["kernels"][0]
+    k = kernel.shape[0]
+    raw, detect = synthetic.band_counts(n, D + k, seed=seed, missing_frac=0.04, max_dist=D)
+    mat = cup.detrend(raw, detectable_bins=detect, max_dist=D + k, max_val=10)
+    mat = cup.diag_trim(mat.tocsr(), D + k)
+    mat.data[np.isnan(mat.data)] = 0
+    mat.eliminate_zeros()
+    mask = cup.make_missing_mask(mat.shape, detect, detect, max_dist=D, sym_upper=True)
+    kw = dict(max_dist=D, sym_upper=True, full=True, missing_tol=tol, pval=True)
+    r, p = cud.normxcorr2(mat, kernel, missing_mask=mask, **kw)
+    r0, p0 = po.normxcorr2_dense(mat.toarray(), kernel, missing_mask=mask.toarray(), **kw)
+    _compare(r, p, r0, p0)
+    # the extension that skips scores beyond max_dist equals a diag_trim of the full result
+    rt, _ = cud.normxcorr2(mat, kernel, missing_mask=mask, trim_to_max_dist=True, **kw)
+    assert np.array_equal(rt.toarray(), cup.diag_trim(r.tocsr(), D).toarray())
+
+
+def test_inter_and_odd_shapes_vs_oracle(presets):
+    from chromosight_b200 import synthetic
+    from chromosight_b200.utils import detection as cud, preprocessing as cup
+    from oracle import pearson_oracle as po
+    kernel = presets.loops["kernels"][0][3:14, :]           # 11 x 17 rectangle
+    imat, (vr, vc) = synthetic.inter_counts(301, 187, seed=31, density=0.2, missing_frac=0.05)
+    mask = cup.make_missing_mask(imat.shape, vr, vc, sym_upper=False)
+    for full in (True, False):
+        kw = dict(max_dist=None, sym_upper=False, full=full, missing_tol=0.6, pval=True)
+        r, p = cud.normxcorr2(imat, kernel, missing_mask=mask, **kw)
+        r0, p0 = po.normxcorr2_dense(imat.toarray(), kernel, missing_mask=mask.toarray(), **kw)
+        _compare(r, p, r0, p0)
+    r, p = cud.normxcorr2(imat, kernel, full=True, pval=True)
+    r0, p0 = po.normxcorr2_dense(imat.toarray(), kernel, full=True, pval=True)
+    _compare(r, p, r0, p0)
+
+
+def test_error_behaviour(presets):
+    """ValueErrors of det:871-889 and pre:520-532."""
+    from chromosight_b200.utils import detection as cud
+    k = presets.loops_small["kernels"][0]
+    sig = sp.random(50, 50, density=0.3, random_state=1, format="csr")
+    with pytest.raises(ValueError):
+        cud.normxcorr2(sig, sp.csr_matrix(k))
+    with pytest.raises(ValueError):
+        cud.normxcorr2(sig, np.ones((7, 7)))
+    with pytest.raises(ValueError):
+        cud.normxcorr2(sig, k, missing_mask=np.zeros((50, 50), bool))
+    with pytest.raises(ValueError):
+        cud.normxcorr2(sig, k, missing_mask=sp.csr_matrix((50, 50), dtype=float))
+    with pytest.raises(ValueError):
+        cud.normxcorr2(sig, k, missing_mask=sp.csr_matrix((40, 50), dtype=bool))
+    with pytest.raises(ValueError):
+        cud.normxcorr2(sp.csr_matrix(np.ones((5, 5))), k, missing_mask=sp.csr_matrix((5, 5), dtype=bool))
+    bad = sp.csr_matrix(np.ones((50, 50), dtype=bool))      # everything missing, signal non-zero
+    with pytest.raises(ValueError):
+        cud.normxcorr2(sig, k, missing_mask=bad, full=True)
+    # empty signal -> empty result, not an error
+    r, p = cud.normxcorr2(sp.csr_matrix((50, 50)), k, pval=True)
+    assert r.nnz == 0 and p.nnz == 0
+
+
+def test_scale_and_shift_properties_large(presets):
+    """Size-independent properties on a map far larger than the oracle can take:
+    Pearson scores are invariant to a positive rescaling of the signal, and a map
+    made of two identical halves yields identical scores in both halves."""
+    from chromosight_b200 import synthetic
+    from chromosight_b200.utils import detection as cud
+    kernel = presets.loops["kernels"][0]
+    n, D = 20000, 120
+    raw, _ = synthetic.band_counts(n, D, seed=5, missing_frac=0.0)
+    half = raw[: n // 2, : n // 2]
+    two = sp.block_diag([half, half], format="csr")
+    r, _ = cud.normxcorr2(two, kernel, max_dist=D, sym_upper=True, full=True)
+    r2, _ = cud.normxcorr2(two * 8.0, kernel, max_dist=D, sym_upper=True, full=True)
+    assert r.nnz > 1e6
+    # x8 is exact in floating point except through the 1e-4 thresholds of xcorr2
+    assert np.abs((r - r2)).max() <= 1e-6
+    h = n // 2
+    a = r[: h, : h].toarray() if False else r[200: h - 200, :][:, 200: h - 200]
+    b = r[h + 200: n - 200, :][:, h + 200: n - 200]
+    assert np.abs((a - b)).max() <= 2e-6

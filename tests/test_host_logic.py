@@ -1,0 +1,136 @@
+"""CPU-side tests: host bookkeeping that mirrors the reference, and the C ABI
+surface (the library must load and export every symbol of include/*.h)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GOLDEN, REPO, load_coo
+
+
+def test_library_exports_every_declared_symbol():
+    from chromosight_b200 import _lib
+    header = open(os.path.join(REPO, "include", "chromosight_b200.h")).read()
+    declared = set(re.findall(r"\b(cs_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.cs_version() == 1
+    assert lib.cs_launch_count() == 0
+
+
+def test_layout_arithmetic():
+    from chromosight_b200 import _lib
+    lib = _lib.load()
+    L = _lib.Layout()
+    assert lib.cs_layout_band(ctypes.byref(L), 1000, 1000, -32, 233) == 0
+    assert L.pitch % 4 == 0 and L.pitch >= 233 + 32
+    assert L.n_elems >= 999 * L.pitch + 1000 + 32
+    assert lib.cs_layout_dense(ctypes.byref(L), 10, 13) == 0
+    assert L.pitch == 16 and L.dense == 1
+    assert lib.cs_layout_band(ctypes.byref(L), 10, 10, 5, 2) != 0
+    assert b"band" in lib.cs_last_error()
+
+
+def test_no_silent_cpu_fallback():
+    """Without a GPU the hot path must raise, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from chromosight_b200 import _lib
+    from chromosight_b200.utils import detection as cud
+    sig = sp.random(40, 40, density=0.3, random_state=0, format="csr")
+    with pytest.raises(_lib.BackendError):
+        cud.normxcorr2(sig, np.arange(9.0).reshape(3, 3))
+
+
+def test_masks_match_reference():
+    from chromosight_b200.utils import preprocessing as cup
+    z = np.load(os.path.join(GOLDEN, "preproc_cases.npz"))
+    vr = z["mask_valid_rows"]
+    m1 = cup.make_missing_mask((12, 12), vr, vr, max_dist=3, sym_upper=True)
+    assert m1.dtype == bool and np.array_equal(m1.toarray(), z["mask_m1"])
+    assert np.array_equal(cup.frame_missing_mask(m1, (5, 5), True, 3).toarray(), z["mask_f1"])
+    m2 = cup.make_missing_mask((12, 9), vr, np.array([0, 2, 3, 4, 6, 8]), sym_upper=False)
+    assert np.array_equal(m2.toarray(), z["mask_m2"])
+    assert np.array_equal(cup.frame_missing_mask(m2, (5, 3), False, None).toarray(), z["mask_f2"])
+    m3 = cup.make_missing_mask((12, 12), vr, vr, max_dist=None, sym_upper=True)
+    assert np.array_equal(m3.toarray(), z["mask_m3"])
+    assert np.array_equal(cup.frame_missing_mask(m3, (3, 5), True, None).toarray(), z["mask_f3"])
+    assert np.array_equal(cup.frame_missing_mask(m1, (3, 7), True, 2).toarray(), z["mask_f4"])
+    with pytest.raises(ValueError):
+        cup.make_missing_mask((12, 9), vr, vr, sym_upper=True)
+    with pytest.raises(ValueError):
+        cup.frame_missing_mask(m1.astype(float), (3, 3))
+    # reference's worked example (pre:578-585)
+    valid = np.array([0, 2, 4])
+    exp = np.array([[0, 1, 0, 0, 0], [0, 1, 1, 0, 0], [0, 0, 0, 1, 0], [0, 0, 0, 1, 1], [0, 0, 0, 0, 0]], bool)
+    assert np.array_equal(cup.make_missing_mask((5, 5), valid, valid, max_dist=1, sym_upper=True).toarray(), exp)
+
+
+def test_small_preprocessing_helpers():
+    from chromosight_b200.utils import preprocessing as cup
+    z = np.load(os.path.join(GOLDEN, "preproc_cases.npz"))
+    raw = load_coo(z, "d1_upper_raw").tocsr()
+    assert np.array_equal(cup.diag_trim(raw, 17).toarray(), load_coo(z, "trim_out").toarray())
+    assert np.allclose(cup.ztransform(raw.tocoo()).toarray(), load_coo(z, "zt_out").toarray())
+    from chromosight_b200 import kernels
+    u, v = cup.factorise_kernel(kernels.loops["kernels"][0], 0.999)
+    assert np.allclose(u @ v, z["fact_loops_uv"], atol=1e-12)
+    # zero_pad_sparse docstring example (pre:655-661)
+    m = sp.csr_matrix(np.array([[1, 2], [10, 20]]))
+    exp = np.array([[0, 0, 0, 0, 0, 0], [0, 0, 1, 2, 0, 0], [0, 0, 10, 20, 0, 0], [0, 0, 0, 0, 0, 0]])
+    assert np.array_equal(cup.zero_pad_sparse(m, 2, 1).toarray(), exp)
+    assert np.array_equal(cup.valid_to_missing(np.array([0, 2]), 4), [1, 3])
+    with pytest.raises(ValueError):
+        cup.check_missing_mask(sp.csr_matrix(np.eye(3)), sp.csr_matrix(np.eye(3, dtype=bool)))
+    cup.check_missing_mask(sp.csr_matrix(np.eye(3)), sp.csr_matrix(np.eye(3, k=1, dtype=bool)))
+
+
+def test_stats_known_answers():
+    """BH q-values vs R's p.adjust (reference tests/test_stats.py)."""
+    from chromosight_b200.utils import stats as cus
+    from oracle import pearson_oracle as po
+    assert np.allclose(cus.fdr_correction(np.array([0.1, 0.1, 0.05, 0.01])), [0.1, 0.1, 0.1, 0.04])
+    r = np.array([0.0, 0.3, -0.7, 1.0])
+    assert np.allclose(cus.corr_to_pval(r, 289), po.corr_to_log10_pval(r, 289))
+    assert cus.corr_to_pval(np.array([1.0]), 49)[0] == -np.inf
+
+
+def test_foci_match_reference():
+    from chromosight_b200.utils import detection as cud
+    z = np.load(os.path.join(GOLDEN, "foci_cases.npz"))
+    corr = load_coo(z, "corr")
+    for thr in (20, 30):
+        coords, lab = cud.pick_foci(corr.copy(), thr / 100)
+        assert np.array_equal(coords, z[f"thr{thr}_coords"])
+        assert np.array_equal(lab.toarray(), load_coo(z, f"thr{thr}_labels").toarray())
+    assert cud.pick_foci(corr, 2.0) == (None, None)
+
+
+def test_label_foci_known_answer():
+    """Exact labels of the reference's test_label_spec (tests/test_detection.py:204-238)."""
+    from chromosight_b200.utils import detection as cud
+    m = np.array([
+        [1, 0, 1, 1, 0],
+        [1, 0, 0, 0, 1],
+        [1, 0, 1, 0, 1],
+        [0, 0, 1, 1, 0],
+        [1, 0, 0, 0, 1],
+    ])
+    num, lab = cud.label_foci(sp.coo_matrix(m))
+    assert num == 6
+    exp = np.array([
+        [1, 0, 2, 2, 0],
+        [1, 0, 0, 0, 3],
+        [1, 0, 4, 0, 3],
+        [0, 0, 4, 4, 0],
+        [5, 0, 0, 0, 6],
+    ])
+    assert np.array_equal(lab.toarray(), exp)
+    n2, filt = cud.filter_foci(lab.copy(), min_size=3)
+    assert n2 == 2 and set(np.unique(filt.data)) == {1, 4}
