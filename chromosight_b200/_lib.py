@@ -85,6 +85,15 @@ class Normxcorr2Args(C.Structure):
     ]
 
 
+class RunStats(C.Structure):
+    _fields_ = [
+        ("ms_fill", C.c_double), ("ms_pearson", C.c_double),
+        ("ms_compact", C.c_double), ("ms_total", C.c_double),
+        ("n_windows", C.c_int64), ("nnz", C.c_int64), ("launches", C.c_int64),
+        ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+    ]
+
+
 # name -> (restype, argtypes); also the list of symbols the header declares
 _P = C.c_void_p
 _PROTOS = {
@@ -109,6 +118,13 @@ _PROTOS = {
     "cs_detrend_apply": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_double, _P]),
     "cs_normxcorr2_host": (C.c_int, [C.POINTER(Normxcorr2Args), C.POINTER(CsrResult)]),
     "cs_result_free": (None, [C.POINTER(CsrResult)]),
+    "cs_session_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
+    "cs_session_destroy": (None, [C.c_void_p]),
+    "cs_session_upload": (C.c_int, [C.c_void_p, C.POINTER(Normxcorr2Args)]),
+    "cs_session_run": (C.c_int, [C.c_void_p, C.POINTER(RunStats)]),
+    "cs_session_candidates": (C.c_int, [C.c_void_p, C.c_float, C.c_int32, C.c_int32, _P, C.c_int64,
+                                         _P, C.POINTER(C.c_int64)]),
+    "cs_session_download": (C.c_int, [C.c_void_p, C.POINTER(CsrResult)]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
 

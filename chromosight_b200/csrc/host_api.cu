@@ -141,33 +141,87 @@ extern "C" void cs_result_free(cs_csr_result *r) {
     r->log10p = nullptr;
 }
 
-extern "C" int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *res) {
-    CS_REQUIRE(a && res, "cs_normxcorr2_host: null argument");
-    CS_REQUIRE(a->rows > 0 && a->cols > 0 && a->indptr && a->indices && a->data,
-               "cs_normxcorr2_host: bad signal");
-    memset(res, 0, sizeof(*res));
+
+// ---------------------------------------------------------------------------
+// session: plan + device-resident inputs of one normxcorr2 call
+// ---------------------------------------------------------------------------
+struct cs_session {
     HostCtx *c = nullptr;
-    int rc = get_ctx(a->device, &c);
+    bool uploaded = false, ran = false, empty = false;
+    cs_normxcorr2_args a;
+    std::vector<double> k_corr, k_mask, k2_mask;
+    cs_layout Li, Lo;
+    int oy0 = 0, oy1 = 0, ox0 = 0, ox1 = 0, od_lo = 0, od_hi = 0, pr = 0, pc = 0;
+    bool want_nobs = false;
+    int64_t nnz_in = 0, nnz_m = 0, nnz_out = 0, n_windows = 0;
+    size_t h2d_bytes = 0;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+extern "C" int cs_session_create(int32_t device, cs_session **out) {
+    CS_REQUIRE(out, "cs_session_create: null argument");
+    HostCtx *c = nullptr;
+    int rc = get_ctx(device, &c);
     if (rc) return rc;
+    cs_session *s = new cs_session();
+    s->c = c;
+    for (int i = 0; i < 6; ++i) CS_CUDA(cudaEventCreate(&s->ev[i]));
+    *out = s;
+    return CS_OK;
+}
+
+extern "C" void cs_session_destroy(cs_session *s) {
+    if (!s) return;
+    for (int i = 0; i < 6; ++i)
+        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    delete s;
+}
+
+// Plan the call and copy its inputs to the device (through pinned staging).
+extern "C" int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a) {
+    CS_REQUIRE(s && a, "cs_session_upload: null argument");
+    CS_REQUIRE(a->rows > 0 && a->cols > 0 && a->indptr && a->indices && a->data,
+               "cs_session_upload: bad signal");
+    HostCtx *c = s->c;
     std::lock_guard<std::mutex> lk(c->mu);
-    CS_CUDA(cudaSetDevice(a->device));
+    CS_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->st;
+    s->uploaded = s->ran = false;
+    s->a = *a;
     const cs_kernel_desc &K = a->kernel;
+    CS_REQUIRE(K.kh >= 1 && K.kw >= 1 && K.k_corr, "cs_session_upload: bad kernel");
+    const int nk2 = K.kh * K.kw;
+    s->k_corr.assign(K.k_corr, K.k_corr + nk2);
+    s->k_mask.assign(K.k_mask ? K.k_mask : K.k_corr, (K.k_mask ? K.k_mask : K.k_corr) + nk2);
+    if (K.k2_mask)
+        s->k2_mask.assign(K.k2_mask, K.k2_mask + nk2);
+    else {
+        s->k2_mask.resize(nk2);
+        for (int i = 0; i < nk2; ++i) s->k2_mask[i] = K.k_corr[i] * K.k_corr[i];
+    }
+    s->a.kernel.k_corr = s->k_corr.data();
+    s->a.kernel.k_mask = s->k_mask.data();
+    s->a.kernel.k2_mask = s->k2_mask.data();
+    s->a.indptr = nullptr;  // host arrays are not kept
+    s->a.indices = nullptr;
+    s->a.data = nullptr;
+    s->a.mask_indptr = nullptr;
+    s->a.mask_indices = nullptr;
+
     const int mk = K.kh, nk = K.kw;
     const int kh = (mk - 1) / 2, kw = (nk - 1) / 2;
-    const int pr = a->full ? mk - 1 : 0, pc = a->full ? nk - 1 : 0;
+    s->pr = a->full ? mk - 1 : 0;
+    s->pc = a->full ? nk - 1 : 0;
+    const int pr = s->pr, pc = s->pc;
     const int H = a->rows + 2 * pr, W = a->cols + 2 * pc;
-    int oy0, oy1, ox0, ox1;
     if (a->full) {
-        oy0 = pr, oy1 = pr + a->rows, ox0 = pc, ox1 = pc + a->cols;
+        s->oy0 = pr, s->oy1 = pr + a->rows, s->ox0 = pc, s->ox1 = pc + a->cols;
     } else {
-        oy0 = kh, oy1 = a->rows - kh, ox0 = kw, ox1 = a->cols - kw;
+        s->oy0 = kh, s->oy1 = a->rows - kh, s->ox0 = kw, s->ox1 = a->cols - kw;
     }
-    res->rows = a->rows;
-    res->cols = a->cols;
-    const int64_t nnz_in = a->indptr[a->rows];
-    const bool empty = (oy1 <= oy0) || (ox1 <= ox0) || nnz_in == 0 || a->sig_dmax < a->sig_dmin;
-
+    s->nnz_in = a->indptr[a->rows];
+    s->empty = (s->oy1 <= s->oy0) || (s->ox1 <= s->ox0) || s->nnz_in == 0 ||
+               a->sig_dmax < a->sig_dmin;
     // diagonal ranges in image coordinates
     const int sh = pc - pr;
     long long od_lo = (long long)a->sig_dmin + sh - (kh + kw);
@@ -175,161 +229,269 @@ extern "C" int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *re
     if (a->sym_upper && od_lo < sh) od_lo = sh;  // det:1098-1099 (triu of the cropped map)
     if (a->trim_to_max_dist && a->max_dist >= 0 && od_hi > (long long)a->max_dist + sh)
         od_hi = (long long)a->max_dist + sh;
-    if (!empty) {
-        const long long dmin_poss = (long long)ox0 - (oy1 - 1), dmax_poss = (long long)(ox1 - 1) - oy0;
+    if (!s->empty) {
+        const long long dmin_poss = (long long)s->ox0 - (s->oy1 - 1);
+        const long long dmax_poss = (long long)(s->ox1 - 1) - s->oy0;
         if (od_lo < dmin_poss) od_lo = dmin_poss;
         if (od_hi > dmax_poss) od_hi = dmax_poss;
     }
-    if (empty || od_hi < od_lo) {
-        void *ip = nullptr;
-        rc = pin_alloc(c, (size_t)(a->rows + 1) * sizeof(int64_t), &ip);
-        if (rc) return rc;
-        memset(ip, 0, (size_t)(a->rows + 1) * sizeof(int64_t));
-        res->indptr = (int64_t *)ip;
+    if (od_hi < od_lo) s->empty = true;
+    s->n_windows = 0;
+    s->nnz_out = 0;
+    s->h2d_bytes = 0;
+    if (s->empty) {
+        s->uploaded = true;
         return CS_OK;
     }
+    s->od_lo = (int)od_lo;
+    s->od_hi = (int)od_hi;
     const int id_lo = (int)(od_lo - (kh + kw)), id_hi = (int)(od_hi + (kh + kw));
-
-    cs_layout Li, Lo;
+    int rc;
     const bool band_img = (long long)(id_hi - id_lo + 1) * 2 < (long long)W;
-    if (band_img)
-        rc = cs_layout_band(&Li, H, W, id_lo, id_hi);
-    else
-        rc = cs_layout_dense(&Li, H, W);
+    rc = band_img ? cs_layout_band(&s->Li, H, W, id_lo, id_hi) : cs_layout_dense(&s->Li, H, W);
     if (rc) return rc;
     // scores live in original coordinates: diagonal = image diagonal - sh
     const bool band_out = (od_hi - od_lo + 1) * 2 < (long long)a->cols;
-    if (band_out)
-        rc = cs_layout_band(&Lo, a->rows, a->cols, (int)(od_lo - sh), (int)(od_hi - sh));
-    else
-        rc = cs_layout_dense(&Lo, a->rows, a->cols);
+    rc = band_out ? cs_layout_band(&s->Lo, a->rows, a->cols, (int)(od_lo - sh), (int)(od_hi - sh))
+                  : cs_layout_dense(&s->Lo, a->rows, a->cols);
     if (rc) return rc;
+    for (int Y = s->oy0; Y < s->oy1; ++Y) {
+        long long lo = (long long)Y + od_lo, hi = (long long)Y + od_hi;
+        if (lo < s->ox0) lo = s->ox0;
+        if (hi > s->ox1 - 1) hi = s->ox1 - 1;
+        if (hi >= lo) s->n_windows += hi - lo + 1;
+    }
 
     // ---- device buffers ---------------------------------------------------------
     const size_t n_ip = (size_t)a->rows + 1;
     if ((rc = c->sig_indptr.ensure(n_ip * sizeof(int64_t)))) return rc;
-    if ((rc = c->sig_indices.ensure((size_t)nnz_in * sizeof(int32_t)))) return rc;
-    if ((rc = c->sig_data.ensure((size_t)nnz_in * sizeof(double)))) return rc;
-    int64_t nnz_m = 0;
+    if ((rc = c->sig_indices.ensure((size_t)s->nnz_in * sizeof(int32_t)))) return rc;
+    if ((rc = c->sig_data.ensure((size_t)s->nnz_in * sizeof(double)))) return rc;
+    s->nnz_m = 0;
     if (a->has_mask) {
         CS_REQUIRE(a->mask_indptr && a->mask_indices, "mask arrays missing");
-        nnz_m = a->mask_indptr[a->rows];
+        s->nnz_m = a->mask_indptr[a->rows];
         if ((rc = c->m_indptr.ensure(n_ip * sizeof(int64_t)))) return rc;
-        if ((rc = c->m_indices.ensure((size_t)(nnz_m > 0 ? nnz_m : 1) * sizeof(int32_t)))) return rc;
+        if ((rc = c->m_indices.ensure((size_t)(s->nnz_m > 0 ? s->nnz_m : 1) * sizeof(int32_t))))
+            return rc;
     }
-    if ((rc = c->img.ensure((size_t)Li.n_elems * sizeof(float)))) return rc;
-    if ((rc = c->out.ensure((size_t)Lo.n_elems * sizeof(float)))) return rc;
-    const bool want_nobs = a->pval && a->has_mask && a->full;
-    if (want_nobs)
-        if ((rc = c->nobs.ensure((size_t)Lo.n_elems * sizeof(uint16_t)))) return rc;
+    if ((rc = c->img.ensure((size_t)s->Li.n_elems * sizeof(float)))) return rc;
+    if ((rc = c->out.ensure((size_t)s->Lo.n_elems * sizeof(float)))) return rc;
+    s->want_nobs = a->pval && a->has_mask && a->full && !a->raw_xcorr;
+    if (s->want_nobs)
+        if ((rc = c->nobs.ensure((size_t)s->Lo.n_elems * sizeof(uint16_t)))) return rc;
     if ((rc = c->r_indptr.ensure(n_ip * sizeof(int64_t)))) return rc;
     if ((rc = c->err.ensure(64))) return rc;
 
     // ---- H2D ----------------------------------------------------------------------
-    CS_CUDA(cudaEventRecord(c->ev[0], st));
+    CS_CUDA(cudaEventRecord(s->ev[0], st));
     if ((rc = h2d_staged(c, c->sig_indptr.p, a->indptr, n_ip * sizeof(int64_t)))) return rc;
-    if ((rc = h2d_staged(c, c->sig_indices.p, a->indices, (size_t)nnz_in * sizeof(int32_t)))) return rc;
-    if ((rc = h2d_staged(c, c->sig_data.p, a->data, (size_t)nnz_in * sizeof(double)))) return rc;
+    if ((rc = h2d_staged(c, c->sig_indices.p, a->indices, (size_t)s->nnz_in * sizeof(int32_t))))
+        return rc;
+    if ((rc = h2d_staged(c, c->sig_data.p, a->data, (size_t)s->nnz_in * sizeof(double)))) return rc;
+    s->h2d_bytes = n_ip * sizeof(int64_t) + (size_t)s->nnz_in * (sizeof(int32_t) + sizeof(double));
     if (a->has_mask) {
         if ((rc = h2d_staged(c, c->m_indptr.p, a->mask_indptr, n_ip * sizeof(int64_t)))) return rc;
-        if (nnz_m > 0)
-            if ((rc = h2d_staged(c, c->m_indices.p, a->mask_indices, (size_t)nnz_m * sizeof(int32_t))))
+        if (s->nnz_m > 0)
+            if ((rc = h2d_staged(c, c->m_indices.p, a->mask_indices,
+                                 (size_t)s->nnz_m * sizeof(int32_t))))
                 return rc;
+        s->h2d_bytes += n_ip * sizeof(int64_t) + (size_t)s->nnz_m * sizeof(int32_t);
     }
-    CS_CUDA(cudaEventRecord(c->ev[1], st));
+    CS_CUDA(cudaEventRecord(s->ev[1], st));
+    s->uploaded = true;
+    return CS_OK;
+}
 
-    // ---- kernels --------------------------------------------------------------------
-    rc = cs_image_fill_f32(&Li, (float *)c->img.p, (const int64_t *)c->sig_indptr.p,
-                           (const int32_t *)c->sig_indices.p, (const double *)c->sig_data.p,
-                           a->rows, a->cols, pr, pc, a->has_mask ? 1 : 0,
-                           (const int64_t *)c->m_indptr.p, (const int32_t *)c->m_indices.p,
-                           a->sym_upper, a->max_dist, a->full ? mk : 0, a->full ? nk : 0,
-                           (int32_t *)c->err.p, st);
+// fill -> Pearson -> CSR compaction, all on the device, inputs already resident.
+extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
+    CS_REQUIRE(s && s->uploaded, "cs_session_run: nothing uploaded");
+    HostCtx *c = s->c;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->st;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    s->ran = false;
+    if (s->empty) {
+        s->nnz_out = 0;
+        s->ran = true;
+        return CS_OK;
+    }
+    const cs_normxcorr2_args &a = s->a;
+    const cs_kernel_desc &K = a.kernel;
+    const long long l0 = g_launches.load();
+    CS_CUDA(cudaEventRecord(s->ev[2], st));
+    int rc = cs_image_fill_f32(&s->Li, (float *)c->img.p, (const int64_t *)c->sig_indptr.p,
+                               (const int32_t *)c->sig_indices.p, (const double *)c->sig_data.p,
+                               a.rows, a.cols, s->pr, s->pc, a.has_mask ? 1 : 0,
+                               (const int64_t *)c->m_indptr.p, (const int32_t *)c->m_indices.p,
+                               a.sym_upper, a.max_dist, a.full ? K.kh : 0, a.full ? K.kw : 0,
+                               (int32_t *)c->err.p, st);
     if (rc) return rc;
     // scores outside the computed set must read as 0
-    CS_CUDA(cudaMemsetAsync(c->out.p, 0, (size_t)Lo.n_elems * sizeof(float), st));
+    CS_CUDA(cudaMemsetAsync(c->out.p, 0, (size_t)s->Lo.n_elems * sizeof(float), st));
     cs_pearson_opts po;
     memset(&po, 0, sizeof(po));
-    po.has_mask = a->has_mask;
-    po.missing_tol = a->missing_tol;
-    po.xcorr_threshold = a->raw_xcorr ? a->xcorr_threshold : 1e-4;
-    po.raw_xcorr = a->raw_xcorr;
-    po.nobs_full = want_nobs ? 1 : 0;
-    po.out_row_shift = pr;
-    po.out_col_shift = pc;
-    rc = cs_pearson_f32(&Li, (const float *)c->img.p, &K, &po, oy0, oy1, ox0, ox1, (int)od_lo,
-                        (int)od_hi, &Lo, (float *)c->out.p, want_nobs ? (uint16_t *)c->nobs.p : nullptr,
-                        st);
+    po.has_mask = a.has_mask;
+    po.missing_tol = a.missing_tol;
+    po.xcorr_threshold = a.raw_xcorr ? a.xcorr_threshold : 1e-4;
+    po.raw_xcorr = a.raw_xcorr;
+    po.nobs_full = s->want_nobs ? 1 : 0;
+    po.out_row_shift = s->pr;
+    po.out_col_shift = s->pc;
+    CS_CUDA(cudaEventRecord(s->ev[3], st));
+    rc = cs_pearson_f32(&s->Li, (const float *)c->img.p, &K, &po, s->oy0, s->oy1, s->ox0, s->ox1,
+                        s->od_lo, s->od_hi, &s->Lo, (float *)c->out.p,
+                        s->want_nobs ? (uint16_t *)c->nobs.p : nullptr, st);
     if (rc) return rc;
-    // windows evaluated (the metric's unit)
-    {
-        long long nw = 0;
-        for (int Y = oy0; Y < oy1; ++Y) {
-            long long lo = (long long)Y + od_lo, hi = (long long)Y + od_hi;
-            if (lo < ox0) lo = ox0;
-            if (hi > ox1 - 1) hi = ox1 - 1;
-            if (hi >= lo) nw += hi - lo + 1;
-        }
-        res->n_windows = nw;
-    }
+    CS_CUDA(cudaEventRecord(s->ev[4], st));
     int64_t nnz = 0;
-    rc = cs_scores_count(&Lo, (const float *)c->out.p, -(1 << 30), (1 << 30),
+    rc = cs_scores_count(&s->Lo, (const float *)c->out.p, -(1 << 30), (1 << 30),
                          (int64_t *)c->r_indptr.p, &nnz, st);
     if (rc) return rc;
     int32_t herr[2] = {0, 0};
     CS_CUDA(cudaMemcpyAsync(herr, c->err.p, sizeof(herr), cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaStreamSynchronize(st));
-    if (herr[0] > 0 && a->has_mask) {
+    if (herr[0] > 0 && a.has_mask) {
         set_error("There are %d non-zero elements reported as missing.", herr[0]);
         return CS_ERR_MASKED_SIGNAL;
     }
-    if (herr[1] > 0) {
+    // with trim_to_max_dist the band is deliberately narrower than the signal
+    if (herr[1] > 0 && !a.trim_to_max_dist) {
         set_error("internal: %d signal pixels fell outside the stored band", herr[1]);
         return CS_ERR_INVALID;
     }
     if ((rc = c->r_indices.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t)))) return rc;
     if ((rc = c->r_data.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(double)))) return rc;
-    if (a->pval)
+    if (a.pval)
         if ((rc = c->r_p.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(double)))) return rc;
     if (nnz > 0) {
-        rc = cs_scores_emit(&Lo, (const float *)c->out.p, want_nobs ? (const uint16_t *)c->nobs.p : nullptr,
-                            mk * nk, -(1 << 30), (1 << 30), (const int64_t *)c->r_indptr.p,
+        rc = cs_scores_emit(&s->Lo, (const float *)c->out.p,
+                            s->want_nobs ? (const uint16_t *)c->nobs.p : nullptr, K.kh * K.kw,
+                            -(1 << 30), (1 << 30), (const int64_t *)c->r_indptr.p,
                             (int32_t *)c->r_indices.p, (double *)c->r_data.p,
-                            a->pval ? (double *)c->r_p.p : nullptr, st);
+                            a.pval ? (double *)c->r_p.p : nullptr, st);
         if (rc) return rc;
     }
-    CS_CUDA(cudaEventRecord(c->ev[2], st));
+    CS_CUDA(cudaEventRecord(s->ev[5], st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    s->nnz_out = nnz;
+    s->ran = true;
+    if (stats) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]);
+        stats->ms_fill = ms;
+        cudaEventElapsedTime(&ms, s->ev[3], s->ev[4]);
+        stats->ms_pearson = ms;
+        cudaEventElapsedTime(&ms, s->ev[4], s->ev[5]);
+        stats->ms_compact = ms;
+        cudaEventElapsedTime(&ms, s->ev[2], s->ev[5]);
+        stats->ms_total = ms;
+        stats->n_windows = s->n_windows;
+        stats->nnz = nnz;
+        stats->launches = g_launches.load() - l0;
+        stats->h2d_bytes = (int64_t)s->h2d_bytes;
+        stats->d2h_bytes = (int64_t)(((size_t)a.rows + 1) * sizeof(int64_t) +
+                                     (size_t)nnz * (sizeof(int32_t) + sizeof(double) +
+                                                    (a.pval ? sizeof(double) : 0)));
+    }
+    return CS_OK;
+}
 
-    // ---- D2H into pooled pinned buffers ------------------------------------------------
+// Candidate pixels (score >= threshold) of the last run, written to a caller-owned
+// device buffer (e.g. the send buffer of the final all-gather).
+extern "C" int cs_session_candidates(cs_session *s, float threshold, int32_t dmin, int32_t dmax,
+                                     cs_candidate *d_cand, int64_t cap, int64_t *d_count,
+                                     int64_t *n_host) {
+    CS_REQUIRE(s && s->ran && d_cand && d_count && n_host, "cs_session_candidates: bad arguments");
+    HostCtx *c = s->c;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CS_CUDA(cudaSetDevice(c->device));
+    if (s->empty) {
+        *n_host = 0;
+        return CS_OK;
+    }
+    return cs_scores_candidates(&s->Lo, (const float *)c->out.p,
+                                s->want_nobs ? (const uint16_t *)c->nobs.p : nullptr,
+                                s->a.kernel.kh * s->a.kernel.kw, dmin, dmax, threshold, d_cand, cap,
+                                d_count, n_host, c->st);
+}
+
+// D2H of the CSR result of the last run into pooled pinned buffers.
+extern "C" int cs_session_download(cs_session *s, cs_csr_result *res) {
+    CS_REQUIRE(s && res && s->ran, "cs_session_download: run first");
+    HostCtx *c = s->c;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->st;
+    memset(res, 0, sizeof(*res));
+    const cs_normxcorr2_args &a = s->a;
+    res->rows = a.rows;
+    res->cols = a.cols;
+    res->n_windows = s->n_windows;
+    const size_t n_ip = (size_t)a.rows + 1;
+    int rc;
     void *h_ip = nullptr, *h_ix = nullptr, *h_d = nullptr, *h_p = nullptr;
     if ((rc = pin_alloc(c, n_ip * sizeof(int64_t), &h_ip))) return rc;
+    res->indptr = (int64_t *)h_ip;
+    if (s->empty) {
+        memset(h_ip, 0, n_ip * sizeof(int64_t));
+        return CS_OK;
+    }
+    const int64_t nnz = s->nnz_out;
     if ((rc = pin_alloc(c, (size_t)nnz * sizeof(int32_t), &h_ix))) return rc;
     if ((rc = pin_alloc(c, (size_t)nnz * sizeof(double), &h_d))) return rc;
-    if (a->pval)
+    if (a.pval)
         if ((rc = pin_alloc(c, (size_t)nnz * sizeof(double), &h_p))) return rc;
+    CS_CUDA(cudaEventRecord(s->ev[0], st));
     CS_CUDA(cudaMemcpyAsync(h_ip, c->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     if (nnz > 0) {
         CS_CUDA(cudaMemcpyAsync(h_ix, c->r_indices.p, (size_t)nnz * sizeof(int32_t),
                                 cudaMemcpyDeviceToHost, st));
         CS_CUDA(cudaMemcpyAsync(h_d, c->r_data.p, (size_t)nnz * sizeof(double),
                                 cudaMemcpyDeviceToHost, st));
-        if (a->pval)
+        if (a.pval)
             CS_CUDA(cudaMemcpyAsync(h_p, c->r_p.p, (size_t)nnz * sizeof(double),
                                     cudaMemcpyDeviceToHost, st));
     }
-    CS_CUDA(cudaEventRecord(c->ev[3], st));
+    CS_CUDA(cudaEventRecord(s->ev[1], st));
     CS_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-    res->ms_h2d = ms;
-    cudaEventElapsedTime(&ms, c->ev[1], c->ev[2]);
-    res->ms_kernels = ms;
-    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]);
     res->ms_d2h = ms;
     res->nnz = nnz;
-    res->indptr = (int64_t *)h_ip;
     res->indices = (int32_t *)h_ix;
     res->data = (double *)h_d;
     res->log10p = (double *)h_p;
+    return CS_OK;
+}
+
+// One-shot: upload + run + download on a per-device cached session.
+extern "C" int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *res) {
+    CS_REQUIRE(a && res, "cs_normxcorr2_host: null argument");
+    static std::mutex mu;
+    static std::vector<cs_session *> cache;
+    cs_session *s = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (cs_session *x : cache)
+            if (x->c->device == a->device) s = x;
+        if (!s) {
+            int rc = cs_session_create(a->device, &s);
+            if (rc) return rc;
+            cache.push_back(s);
+        }
+    }
+    int rc = cs_session_upload(s, a);
+    if (rc) return rc;
+    float ms_h2d = 0.f;
+    cs_run_stats stt;
+    rc = cs_session_run(s, &stt);
+    if (rc) return rc;
+    if (!s->empty) cudaEventElapsedTime(&ms_h2d, s->ev[0], s->ev[1]);
+    rc = cs_session_download(s, res);
+    if (rc) return rc;
+    res->ms_h2d = ms_h2d;
+    res->ms_kernels = stt.ms_total;
     return CS_OK;
 }

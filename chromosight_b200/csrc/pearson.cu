@@ -37,6 +37,8 @@ struct PearsonParams {
     // kernel matrices [nmat][KH][KWp] float (device)
     const float *kmat;
     double q, sumKp, ksum, k2sum, kmean, kstd, thr;
+    double sumKp2;   // sum K'^2
+    double qm, qm2;  // pivots of the two mask kernels (their sums are accumulated centred)
     int min_present, kmean_zero, has_mask, raw_xcorr, nobs_full;
     // shared memory carve-up (bytes)
     int off_V, off_Vm, off_K, off_red, off_bar;
@@ -97,6 +99,70 @@ __device__ __forceinline__ void load_krow(float *kk, const float *src) {
         kk[4 * qd + 2] = v.z;
         kk[4 * qd + 3] = v.w;
     }
+}
+
+// Squared error amplification above which a window is recomputed in float64: the
+// float32 sums carry ~1e-6 relative error on well-conditioned windows, and the score
+// error grows like amp = f * rms(S') * rms(K') / (sigma_S * sigma_K).
+constexpr double kAmpLimit2 = 9.0;
+
+// The reference's formulas (det:1002-1020 no mask, det:1021-1092 masked) from the
+// window sums of the shifted signal S' = S - p and shifted kernels.
+//   h1, h2   : sum S', sum S'^2 over the N window pixels (missing pixels count as S = 0)
+//   s3       : sum S' * K'            (K' = K_corr - q)
+//   sKm,sKm2 : sums of the centred mask kernels over the missing pixels
+template <bool MASK>
+__device__ __forceinline__ float score_from_sums(const PearsonParams &P, double p, double h1,
+                                                 double h2, int nmiss, double s3, double sKm_c,
+                                                 double sKm2_c, int &nobs, double &amp2) {
+    const double dN = (double)P.N;
+    const double invN = 1.0 / dN;
+    const double m1 = h1 * invN;
+    double A1 = m1 + p;
+    double A2 = h2 * invN + 2.0 * p * m1 + p * p;
+    double A3 = (s3 + P.q * h1 + p * P.sumKp) * invN + p * P.q;
+    nobs = P.N;
+    amp2 = 0.0;
+    if (P.raw_xcorr) return (float)thr0(A3 * dN, P.thr);
+    A1 = thr0(A1, P.thr);
+    A2 = thr0(A2, P.thr);
+    A3 = thr0(A3, P.thr);
+    double cov, den2, f = 1.0;
+    bool ok = true;
+    if (!MASK) {
+        const double vS = A2 - A1 * A1;
+        cov = A3 - A1 * P.kmean;
+        den2 = vS * P.kstd * P.kstd;
+        ok = vS >= 0.0;
+    } else if (nmiss == 0) {
+        const double vS = A2 - A1 * A1;
+        const double k2mean = P.k2sum * invN;
+        cov = A3 - A1 * P.kmean;
+        den2 = vS * (k2mean - P.kmean * P.kmean);
+    } else {
+        const int npres = P.N - nmiss;
+        f = dN / (double)npres;
+        // mask kernels are stored centred (K - qm): add the pivot back
+        const double sKm = thr0(sKm_c + P.qm * nmiss, P.thr);
+        const double sKm2 = thr0(sKm2_c + P.qm2 * nmiss, P.thr);
+        const double mK = (P.ksum - sKm) / (double)npres;
+        const double m2K = (P.k2sum - sKm2) / (double)npres;
+        const double mS = A1 * f;
+        const double vS = A2 * f - mS * mS;
+        cov = (A3 - A1 * mK) * f;
+        den2 = vS * (m2K - mK * mK);
+        ok = (npres > 0) && (npres >= P.min_present) && !P.kmean_zero;
+        if (P.nobs_full && npres != 0) nobs = npres;
+    }
+    // det:1066,1088-1091: denom = sqrt(den2); |denom| < 1e-10 or NaN -> 0
+    float r = 0.f;
+    if (ok && den2 >= 1e-20 && den2 < 1e300) {
+        amp2 = (h2 * P.sumKp2 * invN * invN) * f * f / den2;
+        r = (float)cov * rsqrtf((float)den2);
+        if (!(fabsf(r) <= 3.0e38f)) r = 0.f;
+        r = fminf(1.f, fmaxf(-1.f, r));
+    }
+    return r;
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -264,9 +330,6 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     const float *Kc = Ks;
     const float *Km = Ks + P.KH * P.KWp;
     const float *Km2 = Ks + 2 * P.KH * P.KWp;
-    const double invN = 1.0 / (double)P.N;
-    const double dN = (double)P.N;
-
     for (int item = tid; item < nitems; item += kThreads) {
         const int g = item / P.NBc, m = item - g * P.NBc;
         const int Xp0 = xb + 4 * g * P.skew + 4 * m;  // X' of output column t=0
@@ -374,55 +437,31 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 const int X = Xp0 + t + P.dlo;
                 const int d = X - Y;
                 if (X < P.ox0 || X >= P.ox1 || d < P.odlo || d > P.odhi) continue;
-                // un-shift: sums of the zero-filled signal S = S' + p, K = K' + q
-                const double s3 = (double)acc[u][t];
-                const double m1 = h1 * invN;
-                double A1 = m1 + p;
-                double A2 = h2 * invN + 2.0 * p * m1 + p * p;
-                double A3 = (s3 + P.q * h1 + p * P.sumKp) * invN + p * P.q;
-                float r = 0.f;
+                int nmiss = 0;
+                if (MASK) nmiss = (int)(hm + 0.5f);
                 int nobs = P.N;
-                if (P.raw_xcorr) {
-                    r = (float)thr0(A3 * dN, P.thr);
-                } else {
-                    A1 = thr0(A1, P.thr);
-                    A2 = thr0(A2, P.thr);
-                    A3 = thr0(A3, P.thr);
-                    double cov, den2;
-                    bool ok = true;
-                    if (!MASK) {
-                        const double vS = A2 - A1 * A1;
-                        cov = A3 - A1 * P.kmean;
-                        den2 = vS * P.kstd * P.kstd;
-                        ok = vS >= 0.0;
-                    } else {
-                        const int nmiss = (int)(hm + 0.5f);
-                        if (nmiss == 0) {
-                            const double vS = A2 - A1 * A1;
-                            const double k2mean = P.k2sum * invN;
-                            cov = A3 - A1 * P.kmean;
-                            den2 = vS * (k2mean - P.kmean * P.kmean);
-                        } else {
-                            const int npres = P.N - nmiss;
-                            const double f = dN / (double)npres;
-                            const double sKm = thr0((double)accm[u][t], P.thr);
-                            const double sKm2 = thr0((double)accm2[u][t], P.thr);
-                            const double mK = (P.ksum - sKm) / (double)npres;
-                            const double m2K = (P.k2sum - sKm2) / (double)npres;
-                            const double mS = A1 * f;
-                            const double vS = A2 * f - mS * mS;
-                            cov = (A3 - A1 * mK) * f;
-                            den2 = vS * (m2K - mK * mK);
-                            ok = (npres > 0) && (npres >= P.min_present) && !P.kmean_zero;
-                            if (P.nobs_full && npres != 0) nobs = npres;
+                double amp2 = 0.0;
+                float r = score_from_sums<MASK>(P, p, h1, h2, nmiss, (double)acc[u][t],
+                                                (double)accm[u][t], (double)accm2[u][t], nobs, amp2);
+                if (amp2 > kAmpLimit2) {
+                    // ill-conditioned window (flat signal or mostly missing): the float32
+                    // accumulators are not accurate enough, redo the three sums in float64
+                    double s3 = 0.0, sm = 0.0, sm2 = 0.0;
+                    const float *wp = tile + (4 * g + u) * IC + cxa + off + t;
+                    for (int i = 0; i < P.KH; ++i) {
+                        const float *wr = wp + i * IC;
+                        const float *kr = Kc + i * P.KWp;
+                        for (int j = 0; j < KW; ++j) {
+                            float sv = wr[j];
+                            if (MASK && !(sv == sv)) {
+                                sv = -pv;
+                                sm += (double)Km[i * P.KWp + j];
+                                sm2 += (double)Km2[i * P.KWp + j];
+                            }
+                            s3 = fma((double)sv, (double)kr[j], s3);
                         }
                     }
-                    // det:1066,1088-1091: denom = sqrt(den2); |denom| < 1e-10 or NaN -> 0
-                    if (ok && den2 >= 1e-20 && den2 < 1e300) {
-                        r = (float)cov * rsqrtf((float)den2);
-                        if (!(fabsf(r) <= 3.0e38f)) r = 0.f;
-                        r = fminf(1.f, fmaxf(-1.f, r));
-                    }
+                    r = score_from_sums<MASK>(P, p, h1, h2, nmiss, s3, sm, sm2, nobs, amp2);
                 }
                 const long long oi =
                     (long long)(Y - P.osy) * P.out_pitch + ((X - P.osx) - P.out_dlo);
@@ -617,19 +656,31 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
     for (int i = 0; i < nk; ++i) qd += K->k_corr[i];
     qd /= nk;
     const float qf = (float)qd;
+    float qmf = 0.f, qm2f = 0.f;
+    if (opts->has_mask) {
+        CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < nk; ++i) {
+            a += K->k_mask[i];
+            b += K->k2_mask[i];
+        }
+        qmf = (float)(a / nk);
+        qm2f = (float)(b / nk);
+    }
     const size_t kbytes = (size_t)nmat * K->kh * P.KWp * sizeof(float);
     float *hk = (float *)malloc(kbytes);
     if (!hk) return CS_ERR_NOMEM;
     memset(hk, 0, kbytes);
-    double sumKp = 0.0;
+    double sumKp = 0.0, sumKp2 = 0.0;
     for (int i = 0; i < K->kh; ++i)
         for (int j = 0; j < K->kw; ++j) {
             const float v = (float)(K->k_corr[i * K->kw + j] - (double)qf);
             hk[i * P.KWp + j] = v;
             sumKp += (double)v;
+            sumKp2 += (double)v * (double)v;
             if (opts->has_mask) {
-                hk[(K->kh + i) * P.KWp + j] = (float)K->k_mask[i * K->kw + j];
-                hk[(2 * K->kh + i) * P.KWp + j] = (float)K->k2_mask[i * K->kw + j];
+                hk[(K->kh + i) * P.KWp + j] = (float)(K->k_mask[i * K->kw + j] - (double)qmf);
+                hk[(2 * K->kh + i) * P.KWp + j] = (float)(K->k2_mask[i * K->kw + j] - (double)qm2f);
             }
         }
     KmatRing &ring = g_ring;
@@ -649,6 +700,9 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
     P.kmat = ring.buf[slot];
     P.q = (double)qf;
     P.sumKp = sumKp;
+    P.sumKp2 = sumKp2;
+    P.qm = (double)qmf;
+    P.qm2 = (double)qm2f;
     P.ksum = K->k_sum;
     P.k2sum = K->k2_sum;
     P.kmean = K->k_mean;

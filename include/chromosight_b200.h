@@ -204,6 +204,26 @@ typedef struct cs_normxcorr2_args {
 int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *res);
 void cs_result_free(cs_csr_result *res);
 
+/* The same call split in phases, so that a caller can keep the inputs resident in
+ * HBM and re-run the device part (bench.py's `value` leg; iterated detection,
+ * cli:730-792, re-runs the same sub-matrix with a new kernel):
+ *   upload   : plan + host CSR -> HBM through pinned staging
+ *   run      : K0b fill -> K1 Pearson -> K2 CSR compaction, device only
+ *   download : CSR result -> pinned host buffers (free with cs_result_free)
+ *   candidates: pixels with score >= threshold into a caller-owned DEVICE buffer. */
+typedef struct cs_session cs_session;
+typedef struct cs_run_stats {
+    double ms_fill, ms_pearson, ms_compact, ms_total; /* CUDA-event times of the run */
+    int64_t n_windows, nnz, launches, h2d_bytes, d2h_bytes;
+} cs_run_stats;
+int cs_session_create(int32_t device, cs_session **out);
+void cs_session_destroy(cs_session *s);
+int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a);
+int cs_session_run(cs_session *s, cs_run_stats *stats);
+int cs_session_candidates(cs_session *s, float threshold, int32_t dmin, int32_t dmax,
+                          cs_candidate *d_cand, int64_t cap, int64_t *d_count, int64_t *n_host);
+int cs_session_download(cs_session *s, cs_csr_result *res);
+
 #ifdef __cplusplus
 }
 #endif

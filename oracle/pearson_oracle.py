@@ -141,6 +141,8 @@ def normxcorr2_dense(
     missing_tol=0.75,
     tsvd=None,
     pval=False,
+    return_nobs=False,
+    return_cond=False,
 ):
     """det:917-1131 (`_normxcorr2_sparse`) restated on dense float64 arrays.
 
@@ -175,6 +177,7 @@ def normxcorr2_dense(
             bad = ~(np.abs(denom) >= DENOM_EPS)                 # det:1011 (NaN -> dropped later)
             r = np.where(bad, 0.0, num / denom)
             n_obs = np.full(F.shape, float(N))
+            cond = np.sqrt(mean_s2 / (mean_s2 - mean_s ** 2))
         else:
             k_sum, k2_sum = K.sum(), (K ** 2).sum()
             k_mean, k2_mean = k_sum / N, k2_sum / N
@@ -201,6 +204,7 @@ def normxcorr2_dense(
             num = np.where(has, cov_miss, cov_plain)
             bad = ~(np.abs(denom) >= DENOM_EPS)                 # det:1088-1091
             r = np.where(bad, 0.0, num / denom)
+            cond = np.sqrt(m_s2 / (m_s2 - m_s ** 2))
             if full:
                 n_obs = np.where(has & (n_pres != 0), n_pres, float(N))  # det:1110-1116
             else:
@@ -218,6 +222,14 @@ def normxcorr2_dense(
         r = r[mk - 1:mk - 1 + ms, nk - 1:nk - 1 + ns]           # det:1124-1129
         if p is not None:
             p = p[mk - 1:mk - 1 + ms, nk - 1:nk - 1 + ns]
+        n_obs = n_obs[mk - 1:mk - 1 + ms, nk - 1:nk - 1 + ns]
+        cond = cond[mk - 1:mk - 1 + ms, nk - 1:nk - 1 + ns]
+    if return_cond:
+        # rms / std of the present pixels of each window: how much a relative
+        # perturbation of the signal (e.g. float32 storage) is amplified in r
+        return r, p, n_obs, np.where(np.isfinite(cond), cond, np.inf)
+    if return_nobs:
+        return r, p, n_obs
     return r, p
 
 
