@@ -1,0 +1,393 @@
+#!/usr/bin/env python3
+"""Benchmark of the chromosight hot path on B200 (BASELINE.json metric:
+Pearson-windows/s, 17x17 loops kernel, 200k x 200k synthetic intra map).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over one sub-matrix, issued exactly as
+pattern_detector does (det:253-263): normxcorr2(matrix, kernel, max_dist=D,
+sym_upper=True, full=True, missing_mask=mask, missing_tol=0.5, pval=True),
+followed by the candidate thresholding of pick_foci (det:417-421) and, for
+N > 1, the all-gather of the candidate records.
+
+Legs of the default arm (one JSON line on rank 0):
+  value        windows/s with the CSR inputs already resident in HBM (Session.run:
+               image fill -> Pearson tiles -> CSR compaction + p-values), CUDA events
+               on the launch stream, max over ranks;
+  e2e          the same call through chromosight_b200.utils.detection.normxcorr2 with
+               host scipy matrices in and out (pinned staging, H2D and D2H inside the
+               timed region);
+  roofline     the Pearson kernel against the measured HBM peak, 8 B per window;
+  cpu_baseline oracle/sparse_port.py (scipy.sparse port of the reference's algorithm)
+               on a bounded row-slab of the same map, 1 core.
+`--impl reference` times that port on all host cores (one slab per worker per step).
+Windows are counted by the metric's definition, sum_{d<=D}(n-d), although the
+reference call (and therefore this one) also evaluates the k+(k-1) diagonals
+beyond D that pattern_detector trims afterwards (det:270).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "pearson_windows_per_s"
+UNIT = "windows/s"
+BYTES_PER_WINDOW = 8  # one fp32 pixel in + one fp32 score out
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=200_000, help="bins of the synthetic chromosome")
+    ap.add_argument("--max-dist", type=int, default=200, help="scan distance in bins (2 Mb @ 10 kb)")
+    ap.add_argument("--kernel", default="loops")
+    ap.add_argument("--pearson", type=float, default=0.3)
+    ap.add_argument("--cpu-rows", type=int, default=12_000, help="rows of the CPU-baseline slab")
+    ap.add_argument("--ref-rows", type=int, default=2_000, help="rows per worker per step (--impl reference)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 8)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- workload
+def raw_map(n, D, k, seed):
+    from chromosight_b200 import synthetic
+    return synthetic.band_counts(n, D + k, seed=seed, missing_frac=0.02, max_dist=D)
+
+
+def finish_map(mat, detect, D, k, trim, mask_fn):
+    """What ContactMap.create_mat does after detrending (cm:618-624, cm:539-548) and the
+    mask pattern_detector builds (det:242-248)."""
+    mat = trim(mat.tocsr(), D + k)
+    mat.data[np.isnan(mat.data)] = 0
+    mat.eliminate_zeros()
+    mask = mask_fn(mat.shape, detect, detect, max_dist=D, sym_upper=True)
+    return mat, mask
+
+
+def call_kwargs(D):
+    return dict(max_dist=D, sym_upper=True, full=True, missing_tol=0.5, pval=True)
+
+
+# --------------------------------------------------------------------------- CPU arms
+def _cpu_slab(args):
+    """One CPU unit of work: detrended slab-map -> Pearson map with the scipy.sparse port."""
+    rows, D, kernel, seed, reps = args
+    from chromosight_b200.utils import preprocessing as hostpre  # host-only helpers (no CUDA)
+    from oracle import sparse_port as spt
+    k = kernel.shape[0]
+    raw, detect = raw_map(rows, D, k, seed)
+    mat = spt.detrend_sparse(raw, detect, D + k, 10)
+    mat, mask = finish_map(mat, detect, D, k, hostpre.diag_trim, hostpre.make_missing_mask)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r, p = spt.normxcorr2_sparse(mat, kernel, missing_mask=mask, **call_kwargs(D))
+    dt = (time.perf_counter() - t0) / reps
+    return dt, int(r.nnz)
+
+
+def cpu_baseline(rows, D, kernel):
+    from chromosight_b200 import synthetic
+    dt, _ = _cpu_slab((rows, D, kernel, 0, 1))
+    nwin = synthetic.n_windows(rows, D)
+    return {"value": nwin / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"first-principles slab of the same generator: {rows} rows x D={D}, "
+                      f"{nwin} windows, {dt:.2f} s, oracle/sparse_port.normxcorr2_sparse "
+                      f"(scipy.sparse port of det:917-1131), host has {os.cpu_count()} cpus"}
+
+
+def run_reference(a, kernel):
+    """--impl reference: the scipy.sparse port on every host core; a step = one slab of
+    `ref_rows` rows per worker."""
+    import multiprocessing as mp
+    from chromosight_b200 import synthetic
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    D, rows = a.max_dist, a.ref_rows
+    nwin_slab = synthetic.n_windows(rows, D)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        jobs = [(rows, D, kernel, 1000 + i, 1) for i in range(cores)]
+        for _ in range(a.warmup):
+            pool.map(_cpu_slab, jobs)
+        t0 = time.perf_counter()
+        per_step = []
+        for _ in range(a.steps):
+            # input generation runs in the workers but outside the port's own timer: a step
+            # costs the slowest worker's normxcorr2 time
+            res = pool.map(_cpu_slab, jobs)
+            per_step.append(max(r[0] for r in res))
+        wall = time.perf_counter() - t0
+    t = float(np.sum(per_step))
+    value = cores * nwin_slab * a.steps / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": workload_config(a, kernel, sample=f"{cores} slabs of {rows} rows per step"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} workers x {rows}-row slab ({nwin_slab} windows each) per "
+                                   f"step, max-over-workers time per step, wall {wall:.1f} s incl. input generation"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, kernel, sample=None):
+    from chromosight_b200 import synthetic
+    k = kernel.shape[0]
+    cfg = {
+        "workload": f"intra {a.n}x{a.n} synthetic band map (10 kb bins), max_dist {a.max_dist} bins, "
+                    f"{a.kernel} kernel {k}x{k}, masked full-mode normxcorr2 as issued by pattern_detector",
+        "n_bins": a.n, "max_dist_bins": a.max_dist, "kernel": f"{a.kernel} {k}x{k}",
+        "windows_per_map": synthetic.n_windows(a.n, a.max_dist),
+        "missing_bins": "2%", "seed": 0,
+        "l2": "inputs_exceed_l2 (CSR input, fp32 band and score band are each > 126 MB)",
+        "parallelism": f"{a.gpus} x one chromosome per GPU (independent sub-matrices)",
+    }
+    if sample:
+        cfg["sample"] = sample
+    return cfg
+
+
+# --------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.f = None
+
+    def start(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def run_b200(a, kernel):
+    import torch
+    import torch.distributed as dist
+    from chromosight_b200 import _lib, synthetic
+    from chromosight_b200.session import Session
+    from chromosight_b200.utils import detection as cud, preprocessing as cup
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the hot path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, D, k = a.n, a.max_dist, kernel.shape[0]
+    kw = call_kwargs(D)
+    nwin = synthetic.n_windows(n, D)
+
+    # ---- inputs: one chromosome per rank (weak scaling), detrended with the CUDA path (a8)
+    raw, detect = raw_map(n, D, k, seed=rank)
+    mat = cup.detrend(raw, detectable_bins=detect, max_dist=D + k, max_val=10)
+    mat, mask = finish_map(mat, detect, D, k, cup.diag_trim, cup.make_missing_mask)
+    del raw
+
+    sess = Session(local)
+    sess.upload(mat, kernel, missing_mask=mask, **kw)
+    cap = 1 << 22
+    cand_buf = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    state = {"ncand": 0, "gathered": 0}
+
+    def step():
+        st = sess.run()
+        _, nc = sess.candidates(a.pearson, 0, D, out=cand_buf)
+        state["ncand"] = nc
+        if world > 1:
+            # the one collective of the path: candidate records of every sub-matrix
+            counts = torch.zeros(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(counts, torch.tensor([nc], dtype=torch.int64, device=dev))
+            mx = int(counts.max().item())
+            allc = torch.empty((world, max(mx, 1), 4), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(allc, cand_buf[:max(mx, 1)].contiguous())
+            state["gathered"] = int(counts.sum().item())
+        return st
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        st = step()
+    launches_per_step = None
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_pearson, ms_fill, ms_compact = [], [], []
+    ev0.record()
+    for _ in range(a.steps):
+        st = step()
+        ms_pearson.append(st["ms_pearson"])
+        ms_fill.append(st["ms_fill"])
+        ms_compact.append(st["ms_compact"])
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / a.steps
+    value = world * nwin / (ms_step * 1e-3)
+    n_eval = int(st["n_windows"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    t_k = float(np.mean(ms_pearson)) * 1e-3
+    achieved = BYTES_PER_WINDOW * n_eval / t_k / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "pearson_tiles", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+        "traffic": traffic_from_profile(),
+        "bytes_per_window": BYTES_PER_WINDOW, "windows_per_launch": n_eval,
+        "kernel_ms": t_k * 1e3,
+        "fp32_fma_per_window": int(kernel.size),
+        "note": "CUDA-core stencil: k*k FMAs per window bound it well below the HBM roof (DESIGN.md)",
+    }
+
+    # ---- e2e: the reference-facing call, host matrices in and out
+    e2e = None
+    if not a.no_e2e:
+        ke = a.e2e_steps or min(a.steps, 8)
+        for _ in range(2):
+            r, p = cud.normxcorr2(mat, kernel, missing_mask=mask, **kw)
+        del r, p
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            r, p = cud.normxcorr2(mat, kernel, missing_mask=mask, **kw)
+            checksum = float(r.data[:: max(1, r.nnz // 1024)].sum())  # touch the result on the host
+        torch.cuda.synchronize()
+        te = (time.perf_counter() - t0) / ke
+        t = torch.tensor([te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t.item())
+        s = cud.last_call_stats
+        e2e = {"value": world * nwin / te, "unit": UNIT,
+               "h2d_bytes_per_step": int(s.get("h2d_bytes", 0)), "d2h_bytes_per_step": int(s.get("d2h_bytes", 0)),
+               "ms_per_step": te * 1e3, "steps": ke, "timer": "host wall clock around the API call, max over ranks",
+               "breakdown_ms": {"h2d": s.get("ms_h2d"), "kernels": s.get("ms_kernels"), "d2h": s.get("ms_d2h")},
+               "result_nnz": int(r.nnz), "checksum": checksum}
+        del r, p
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 storage, f32 FMA + f64 window statistics",
+        "data": "synthetic", "config": workload_config(a, kernel),
+        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "step_breakdown_ms": {"fill": float(np.mean(ms_fill)), "pearson": float(np.mean(ms_pearson)),
+                              "compact_csr_pvalues": float(np.mean(ms_compact))},
+        "candidates_per_map": state["ncand"], "result_nnz": int(st["nnz"]),
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a.cpu_rows, D, kernel)
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def traffic_from_profile():
+    """DRAM bytes per launch of the Pearson kernel from the committed ncu capture
+    (profiles/pearson_traffic.json, written by scripts/summarize_ncu.py), else null."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "pearson_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def main():
+    a = parse_args()
+    from chromosight_b200 import kernels
+    kernel = np.asarray(getattr(kernels, a.kernel)["kernels"][0], dtype=np.float64)
+    if a.impl == "reference":
+        run_reference(a, kernel)
+    else:
+        run_b200(a, kernel)
+
+
+if __name__ == "__main__":
+    main()

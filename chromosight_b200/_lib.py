@@ -62,8 +62,10 @@ class CsrResult(C.Structure):
         ("rows", C.c_int32), ("cols", C.c_int32),
         ("indptr", C.c_void_p), ("indices", C.c_void_p),
         ("data", C.c_void_p), ("log10p", C.c_void_p),
+        ("p_indptr", C.c_void_p), ("p_indices", C.c_void_p),
         ("ms_h2d", C.c_double), ("ms_kernels", C.c_double), ("ms_d2h", C.c_double),
         ("n_windows", C.c_int64),
+        ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
     ]
 
 
@@ -120,6 +122,7 @@ _PROTOS = {
     "cs_result_free": (None, [C.POINTER(CsrResult)]),
     "cs_session_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
     "cs_session_destroy": (None, [C.c_void_p]),
+    "cs_session_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cs_session_upload": (C.c_int, [C.c_void_p, C.POINTER(Normxcorr2Args)]),
     "cs_session_run": (C.c_int, [C.c_void_p, C.POINTER(RunStats)]),
     "cs_session_candidates": (C.c_int, [C.c_void_p, C.c_float, C.c_int32, C.c_int32, _P, C.c_int64,

@@ -39,8 +39,6 @@ constexpr size_t kStageBytes = 32u << 20;
 struct HostCtx {
     int device = -1;
     cudaStream_t st = nullptr;
-    DevBuf sig_indptr, sig_indices, sig_data, m_indptr, m_indices, img, out, nobs, r_indptr,
-        r_indices, r_data, r_p, err;
     void *stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -74,15 +72,15 @@ static int get_ctx(int device, HostCtx **out) {
 
 // pageable host -> device through the two pinned staging buffers (CPU memcpy of chunk
 // i+1 overlaps the DMA of chunk i)
-static int h2d_staged(HostCtx *c, void *dst, const void *src, size_t bytes) {
+static int h2d_staged(HostCtx *c, cudaStream_t st, void *dst, const void *src, size_t bytes) {
     size_t done = 0;
     int k = 0;
     while (done < bytes) {
         const size_t n = bytes - done < kStageBytes ? bytes - done : kStageBytes;
         CS_CUDA(cudaEventSynchronize(c->stage_ev[k]));
         memcpy(c->stage[k], (const char *)src + done, n);
-        CS_CUDA(cudaMemcpyAsync((char *)dst + done, c->stage[k], n, cudaMemcpyHostToDevice, c->st));
-        CS_CUDA(cudaEventRecord(c->stage_ev[k], c->st));
+        CS_CUDA(cudaMemcpyAsync((char *)dst + done, c->stage[k], n, cudaMemcpyHostToDevice, st));
+        CS_CUDA(cudaEventRecord(c->stage_ev[k], st));
         done += n;
         k ^= 1;
     }
@@ -135,6 +133,10 @@ extern "C" void cs_result_free(cs_csr_result *r) {
     pin_release(r->indices);
     pin_release(r->data);
     pin_release(r->log10p);
+    pin_release(r->p_indptr);
+    pin_release(r->p_indices);
+    r->p_indptr = nullptr;
+    r->p_indices = nullptr;
     r->indptr = nullptr;
     r->indices = nullptr;
     r->data = nullptr;
@@ -147,6 +149,12 @@ extern "C" void cs_result_free(cs_csr_result *r) {
 // ---------------------------------------------------------------------------
 struct cs_session {
     HostCtx *c = nullptr;
+    cudaStream_t user_st = nullptr;
+    bool use_user_st = false;
+    cudaStream_t stream() const { return use_user_st ? user_st : c->st; }
+    // device-resident inputs, images and results of this session
+    DevBuf sig_indptr, sig_indices, sig_data, m_indptr, m_indices, img, out, nobs, r_indptr,
+        r_indices, r_data, r_p, err;
     bool uploaded = false, ran = false, empty = false;
     cs_normxcorr2_args a;
     std::vector<double> k_corr, k_mask, k2_mask;
@@ -174,7 +182,20 @@ extern "C" void cs_session_destroy(cs_session *s) {
     if (!s) return;
     for (int i = 0; i < 6; ++i)
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    DevBuf *bufs[] = {&s->sig_indptr, &s->sig_indices, &s->sig_data, &s->m_indptr, &s->m_indices,
+                      &s->img,        &s->out,         &s->nobs,     &s->r_indptr, &s->r_indices,
+                      &s->r_data,     &s->r_p,         &s->err};
+    cudaSetDevice(s->c->device);
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
     delete s;
+}
+
+extern "C" int cs_session_set_stream(cs_session *s, void *stream) {
+    CS_REQUIRE(s, "cs_session_set_stream: null session");
+    s->user_st = (cudaStream_t)stream;
+    s->use_user_st = stream != nullptr;
+    return CS_OK;
 }
 
 // Plan the call and copy its inputs to the device (through pinned staging).
@@ -185,7 +206,7 @@ extern "C" int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a) {
     HostCtx *c = s->c;
     std::lock_guard<std::mutex> lk(c->mu);
     CS_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = c->st;
+    cudaStream_t st = s->stream();
     s->uploaded = s->ran = false;
     s->a = *a;
     const cs_kernel_desc &K = a->kernel;
@@ -264,36 +285,36 @@ extern "C" int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a) {
 
     // ---- device buffers ---------------------------------------------------------
     const size_t n_ip = (size_t)a->rows + 1;
-    if ((rc = c->sig_indptr.ensure(n_ip * sizeof(int64_t)))) return rc;
-    if ((rc = c->sig_indices.ensure((size_t)s->nnz_in * sizeof(int32_t)))) return rc;
-    if ((rc = c->sig_data.ensure((size_t)s->nnz_in * sizeof(double)))) return rc;
+    if ((rc = s->sig_indptr.ensure(n_ip * sizeof(int64_t)))) return rc;
+    if ((rc = s->sig_indices.ensure((size_t)s->nnz_in * sizeof(int32_t)))) return rc;
+    if ((rc = s->sig_data.ensure((size_t)s->nnz_in * sizeof(double)))) return rc;
     s->nnz_m = 0;
     if (a->has_mask) {
         CS_REQUIRE(a->mask_indptr && a->mask_indices, "mask arrays missing");
         s->nnz_m = a->mask_indptr[a->rows];
-        if ((rc = c->m_indptr.ensure(n_ip * sizeof(int64_t)))) return rc;
-        if ((rc = c->m_indices.ensure((size_t)(s->nnz_m > 0 ? s->nnz_m : 1) * sizeof(int32_t))))
+        if ((rc = s->m_indptr.ensure(n_ip * sizeof(int64_t)))) return rc;
+        if ((rc = s->m_indices.ensure((size_t)(s->nnz_m > 0 ? s->nnz_m : 1) * sizeof(int32_t))))
             return rc;
     }
-    if ((rc = c->img.ensure((size_t)s->Li.n_elems * sizeof(float)))) return rc;
-    if ((rc = c->out.ensure((size_t)s->Lo.n_elems * sizeof(float)))) return rc;
+    if ((rc = s->img.ensure((size_t)s->Li.n_elems * sizeof(float)))) return rc;
+    if ((rc = s->out.ensure((size_t)s->Lo.n_elems * sizeof(float)))) return rc;
     s->want_nobs = a->pval && a->has_mask && a->full && !a->raw_xcorr;
     if (s->want_nobs)
-        if ((rc = c->nobs.ensure((size_t)s->Lo.n_elems * sizeof(uint16_t)))) return rc;
-    if ((rc = c->r_indptr.ensure(n_ip * sizeof(int64_t)))) return rc;
-    if ((rc = c->err.ensure(64))) return rc;
+        if ((rc = s->nobs.ensure((size_t)s->Lo.n_elems * sizeof(uint16_t)))) return rc;
+    if ((rc = s->r_indptr.ensure(n_ip * sizeof(int64_t)))) return rc;
+    if ((rc = s->err.ensure(64))) return rc;
 
     // ---- H2D ----------------------------------------------------------------------
     CS_CUDA(cudaEventRecord(s->ev[0], st));
-    if ((rc = h2d_staged(c, c->sig_indptr.p, a->indptr, n_ip * sizeof(int64_t)))) return rc;
-    if ((rc = h2d_staged(c, c->sig_indices.p, a->indices, (size_t)s->nnz_in * sizeof(int32_t))))
+    if ((rc = h2d_staged(c, st, s->sig_indptr.p, a->indptr, n_ip * sizeof(int64_t)))) return rc;
+    if ((rc = h2d_staged(c, st, s->sig_indices.p, a->indices, (size_t)s->nnz_in * sizeof(int32_t))))
         return rc;
-    if ((rc = h2d_staged(c, c->sig_data.p, a->data, (size_t)s->nnz_in * sizeof(double)))) return rc;
+    if ((rc = h2d_staged(c, st, s->sig_data.p, a->data, (size_t)s->nnz_in * sizeof(double)))) return rc;
     s->h2d_bytes = n_ip * sizeof(int64_t) + (size_t)s->nnz_in * (sizeof(int32_t) + sizeof(double));
     if (a->has_mask) {
-        if ((rc = h2d_staged(c, c->m_indptr.p, a->mask_indptr, n_ip * sizeof(int64_t)))) return rc;
+        if ((rc = h2d_staged(c, st, s->m_indptr.p, a->mask_indptr, n_ip * sizeof(int64_t)))) return rc;
         if (s->nnz_m > 0)
-            if ((rc = h2d_staged(c, c->m_indices.p, a->mask_indices,
+            if ((rc = h2d_staged(c, st, s->m_indices.p, a->mask_indices,
                                  (size_t)s->nnz_m * sizeof(int32_t))))
                 return rc;
         s->h2d_bytes += n_ip * sizeof(int64_t) + (size_t)s->nnz_m * sizeof(int32_t);
@@ -309,7 +330,7 @@ extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
     HostCtx *c = s->c;
     std::lock_guard<std::mutex> lk(c->mu);
     CS_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = c->st;
+    cudaStream_t st = s->stream();
     if (stats) memset(stats, 0, sizeof(*stats));
     s->ran = false;
     if (s->empty) {
@@ -321,15 +342,15 @@ extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
     const cs_kernel_desc &K = a.kernel;
     const long long l0 = g_launches.load();
     CS_CUDA(cudaEventRecord(s->ev[2], st));
-    int rc = cs_image_fill_f32(&s->Li, (float *)c->img.p, (const int64_t *)c->sig_indptr.p,
-                               (const int32_t *)c->sig_indices.p, (const double *)c->sig_data.p,
+    int rc = cs_image_fill_f32(&s->Li, (float *)s->img.p, (const int64_t *)s->sig_indptr.p,
+                               (const int32_t *)s->sig_indices.p, (const double *)s->sig_data.p,
                                a.rows, a.cols, s->pr, s->pc, a.has_mask ? 1 : 0,
-                               (const int64_t *)c->m_indptr.p, (const int32_t *)c->m_indices.p,
+                               (const int64_t *)s->m_indptr.p, (const int32_t *)s->m_indices.p,
                                a.sym_upper, a.max_dist, a.full ? K.kh : 0, a.full ? K.kw : 0,
-                               (int32_t *)c->err.p, st);
+                               (int32_t *)s->err.p, st);
     if (rc) return rc;
     // scores outside the computed set must read as 0
-    CS_CUDA(cudaMemsetAsync(c->out.p, 0, (size_t)s->Lo.n_elems * sizeof(float), st));
+    CS_CUDA(cudaMemsetAsync(s->out.p, 0, (size_t)s->Lo.n_elems * sizeof(float), st));
     cs_pearson_opts po;
     memset(&po, 0, sizeof(po));
     po.has_mask = a.has_mask;
@@ -340,17 +361,17 @@ extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
     po.out_row_shift = s->pr;
     po.out_col_shift = s->pc;
     CS_CUDA(cudaEventRecord(s->ev[3], st));
-    rc = cs_pearson_f32(&s->Li, (const float *)c->img.p, &K, &po, s->oy0, s->oy1, s->ox0, s->ox1,
-                        s->od_lo, s->od_hi, &s->Lo, (float *)c->out.p,
-                        s->want_nobs ? (uint16_t *)c->nobs.p : nullptr, st);
+    rc = cs_pearson_f32(&s->Li, (const float *)s->img.p, &K, &po, s->oy0, s->oy1, s->ox0, s->ox1,
+                        s->od_lo, s->od_hi, &s->Lo, (float *)s->out.p,
+                        s->want_nobs ? (uint16_t *)s->nobs.p : nullptr, st);
     if (rc) return rc;
     CS_CUDA(cudaEventRecord(s->ev[4], st));
     int64_t nnz = 0;
-    rc = cs_scores_count(&s->Lo, (const float *)c->out.p, -(1 << 30), (1 << 30),
-                         (int64_t *)c->r_indptr.p, &nnz, st);
+    rc = cs_scores_count(&s->Lo, (const float *)s->out.p, -(1 << 30), (1 << 30),
+                         (int64_t *)s->r_indptr.p, &nnz, st);
     if (rc) return rc;
     int32_t herr[2] = {0, 0};
-    CS_CUDA(cudaMemcpyAsync(herr, c->err.p, sizeof(herr), cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaMemcpyAsync(herr, s->err.p, sizeof(herr), cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaStreamSynchronize(st));
     if (herr[0] > 0 && a.has_mask) {
         set_error("There are %d non-zero elements reported as missing.", herr[0]);
@@ -361,16 +382,16 @@ extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
         set_error("internal: %d signal pixels fell outside the stored band", herr[1]);
         return CS_ERR_INVALID;
     }
-    if ((rc = c->r_indices.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t)))) return rc;
-    if ((rc = c->r_data.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(double)))) return rc;
+    if ((rc = s->r_indices.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t)))) return rc;
+    if ((rc = s->r_data.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(double)))) return rc;
     if (a.pval)
-        if ((rc = c->r_p.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(double)))) return rc;
+        if ((rc = s->r_p.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(double)))) return rc;
     if (nnz > 0) {
-        rc = cs_scores_emit(&s->Lo, (const float *)c->out.p,
-                            s->want_nobs ? (const uint16_t *)c->nobs.p : nullptr, K.kh * K.kw,
-                            -(1 << 30), (1 << 30), (const int64_t *)c->r_indptr.p,
-                            (int32_t *)c->r_indices.p, (double *)c->r_data.p,
-                            a.pval ? (double *)c->r_p.p : nullptr, st);
+        rc = cs_scores_emit(&s->Lo, (const float *)s->out.p,
+                            s->want_nobs ? (const uint16_t *)s->nobs.p : nullptr, K.kh * K.kw,
+                            -(1 << 30), (1 << 30), (const int64_t *)s->r_indptr.p,
+                            (int32_t *)s->r_indices.p, (double *)s->r_data.p,
+                            a.pval ? (double *)s->r_p.p : nullptr, st);
         if (rc) return rc;
     }
     CS_CUDA(cudaEventRecord(s->ev[5], st));
@@ -411,10 +432,10 @@ extern "C" int cs_session_candidates(cs_session *s, float threshold, int32_t dmi
         *n_host = 0;
         return CS_OK;
     }
-    return cs_scores_candidates(&s->Lo, (const float *)c->out.p,
-                                s->want_nobs ? (const uint16_t *)c->nobs.p : nullptr,
+    return cs_scores_candidates(&s->Lo, (const float *)s->out.p,
+                                s->want_nobs ? (const uint16_t *)s->nobs.p : nullptr,
                                 s->a.kernel.kh * s->a.kernel.kw, dmin, dmax, threshold, d_cand, cap,
-                                d_count, n_host, c->st);
+                                d_count, n_host, s->stream());
 }
 
 // D2H of the CSR result of the last run into pooled pinned buffers.
@@ -423,7 +444,7 @@ extern "C" int cs_session_download(cs_session *s, cs_csr_result *res) {
     HostCtx *c = s->c;
     std::lock_guard<std::mutex> lk(c->mu);
     CS_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = c->st;
+    cudaStream_t st = s->stream();
     memset(res, 0, sizeof(*res));
     const cs_normxcorr2_args &a = s->a;
     res->rows = a.rows;
@@ -431,29 +452,43 @@ extern "C" int cs_session_download(cs_session *s, cs_csr_result *res) {
     res->n_windows = s->n_windows;
     const size_t n_ip = (size_t)a.rows + 1;
     int rc;
-    void *h_ip = nullptr, *h_ix = nullptr, *h_d = nullptr, *h_p = nullptr;
+    void *h_ip = nullptr, *h_ix = nullptr, *h_d = nullptr, *h_p = nullptr, *h_ip2 = nullptr,
+         *h_ix2 = nullptr;
     if ((rc = pin_alloc(c, n_ip * sizeof(int64_t), &h_ip))) return rc;
     res->indptr = (int64_t *)h_ip;
+    if (a.pval) {
+        if ((rc = pin_alloc(c, n_ip * sizeof(int64_t), &h_ip2))) return rc;
+        res->p_indptr = (int64_t *)h_ip2;
+    }
     if (s->empty) {
         memset(h_ip, 0, n_ip * sizeof(int64_t));
+        if (h_ip2) memset(h_ip2, 0, n_ip * sizeof(int64_t));
         return CS_OK;
     }
     const int64_t nnz = s->nnz_out;
     if ((rc = pin_alloc(c, (size_t)nnz * sizeof(int32_t), &h_ix))) return rc;
     if ((rc = pin_alloc(c, (size_t)nnz * sizeof(double), &h_d))) return rc;
-    if (a.pval)
+    if (a.pval) {
         if ((rc = pin_alloc(c, (size_t)nnz * sizeof(double), &h_p))) return rc;
-    CS_CUDA(cudaEventRecord(s->ev[0], st));
-    CS_CUDA(cudaMemcpyAsync(h_ip, c->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    if (nnz > 0) {
-        CS_CUDA(cudaMemcpyAsync(h_ix, c->r_indices.p, (size_t)nnz * sizeof(int32_t),
-                                cudaMemcpyDeviceToHost, st));
-        CS_CUDA(cudaMemcpyAsync(h_d, c->r_data.p, (size_t)nnz * sizeof(double),
-                                cudaMemcpyDeviceToHost, st));
-        if (a.pval)
-            CS_CUDA(cudaMemcpyAsync(h_p, c->r_p.p, (size_t)nnz * sizeof(double),
-                                    cudaMemcpyDeviceToHost, st));
+        if ((rc = pin_alloc(c, (size_t)nnz * sizeof(int32_t), &h_ix2))) return rc;
     }
+    CS_CUDA(cudaEventRecord(s->ev[0], st));
+    CS_CUDA(cudaMemcpyAsync(h_ip, s->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (nnz > 0) {
+        CS_CUDA(cudaMemcpyAsync(h_ix, s->r_indices.p, (size_t)nnz * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaMemcpyAsync(h_d, s->r_data.p, (size_t)nnz * sizeof(double),
+                                cudaMemcpyDeviceToHost, st));
+        if (a.pval) {
+            CS_CUDA(cudaMemcpyAsync(h_p, s->r_p.p, (size_t)nnz * sizeof(double),
+                                    cudaMemcpyDeviceToHost, st));
+            CS_CUDA(cudaMemcpyAsync(h_ix2, s->r_indices.p, (size_t)nnz * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (a.pval)
+        CS_CUDA(cudaMemcpyAsync(h_ip2, s->r_indptr.p, n_ip * sizeof(int64_t),
+                                cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaEventRecord(s->ev[1], st));
     CS_CUDA(cudaStreamSynchronize(st));
     float ms = 0.f;
@@ -463,6 +498,10 @@ extern "C" int cs_session_download(cs_session *s, cs_csr_result *res) {
     res->indices = (int32_t *)h_ix;
     res->data = (double *)h_d;
     res->log10p = (double *)h_p;
+    res->p_indices = (int32_t *)h_ix2;
+    res->d2h_bytes = (int64_t)(n_ip * sizeof(int64_t) * (a.pval ? 2 : 1) +
+                               (size_t)nnz * (sizeof(int32_t) * (a.pval ? 2 : 1) + sizeof(double) *
+                                                                                      (a.pval ? 2 : 1)));
     return CS_OK;
 }
 
@@ -493,5 +532,6 @@ extern "C" int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *re
     if (rc) return rc;
     res->ms_h2d = ms_h2d;
     res->ms_kernels = stt.ms_total;
+    res->h2d_bytes = stt.h2d_bytes;
     return CS_OK;
 }

@@ -1,0 +1,102 @@
+"""Device-resident form of the hot-path call (cs_session_* of the C ABI).
+
+`chromosight.utils.detection.normxcorr2` is one synchronous host-to-host call;
+iterated detection (cli:730-792) and quantify re-run the same sub-matrix with a
+new kernel, and a benchmark wants the inputs resident in HBM.  A Session splits
+the call into upload / run / download (+ candidates: the thresholding of
+pick_foci, det:417-421, on the device)."""
+import ctypes as C
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _cuda, _lib
+from .utils import detection as _det
+
+
+class Session:
+    def __init__(self, device=None, use_torch_stream=True):
+        t = _cuda.require_cuda()
+        self._lib = _lib.load()
+        self.device = int(t.cuda.current_device() if device is None else device)
+        self._h = C.c_void_p()
+        _lib.check(self._lib.cs_session_create(self.device, C.byref(self._h)))
+        self._use_torch_stream = use_torch_stream
+        self.shape = None
+        self.pval = False
+        self.stats = {}
+
+    def close(self):
+        if self._h:
+            self._lib.cs_session_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _bind_stream(self):
+        if self._use_torch_stream:
+            t = _cuda.torch()
+            with t.cuda.device(self.device):
+                st = t.cuda.current_stream().cuda_stream
+            # stream 0 is the legacy default stream: a valid choice, but NULL means
+            # "library stream" in the ABI, so only bind real streams
+            _lib.check(self._lib.cs_session_set_stream(self._h, C.c_void_p(st) if st else None))
+
+    def upload(self, signal, kernel, max_dist=None, sym_upper=False, full=False, missing_mask=None,
+               missing_tol=0.75, tsvd=None, pval=False, trim_to_max_dist=False):
+        """Plan a normxcorr2 call (same arguments, det:807-817) and copy its inputs to HBM."""
+        kernel = np.asarray(kernel, dtype=np.float64)
+        _det._validate(signal, kernel, missing_mask)
+        csr = _det._canonical_csr(signal, np.float64)
+        mask_csr = _det._mask_csr(missing_mask)
+        a, keep = _det._build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol,
+                                   tsvd, pval, trim_to_max_dist=trim_to_max_dist, device=self.device)
+        self._bind_stream()
+        _lib.check(self._lib.cs_session_upload(self._h, C.byref(a)))
+        del keep
+        self.shape = csr.shape
+        self.pval = bool(pval)
+        return self
+
+    def run(self):
+        """fill -> Pearson -> CSR compaction on the device; returns the run statistics."""
+        self._bind_stream()
+        st = _lib.RunStats()
+        _lib.check(self._lib.cs_session_run(self._h, C.byref(st)))
+        self.stats = {f: getattr(st, f) for f, _ in _lib.RunStats._fields_}
+        return self.stats
+
+    def download(self):
+        """(corr, log10 p-values or None) of the last run as scipy CSR matrices."""
+        self._bind_stream()
+        res = _lib.CsrResult()
+        _lib.check(self._lib.cs_session_download(self._h, C.byref(res)))
+        self.stats["ms_d2h"] = res.ms_d2h
+        return _det._result_to_csr(res, self.shape, self.pval)
+
+    def candidates(self, threshold, dmin=0, dmax=2 ** 30, cap=1 << 22, out=None):
+        """Pixels with score >= threshold on diagonals dmin..dmax of the last run as a
+        DEVICE tensor of (row, col, score, log10p) records (16 B each, _lib.CANDIDATE_DTYPE)
+        -- the send buffer of the final all-gather.  Returns (tensor, count)."""
+        t = _cuda.torch()
+        self._bind_stream()
+        dev = t.device("cuda", self.device)
+        if out is None:
+            out = t.empty((cap, 4), dtype=t.int32, device=dev)
+        cap = out.shape[0]
+        cnt = t.zeros(1, dtype=t.int64, device=dev)
+        n = C.c_int64(0)
+        _lib.check(self._lib.cs_session_candidates(self._h, C.c_float(threshold), int(dmin),
+                                                   int(min(dmax, 2 ** 30)), _cuda.ptr(out), cap,
+                                                   _cuda.ptr(cnt), C.byref(n)))
+        return out, int(min(n.value, cap))
+
+
+def records_to_numpy(tensor, count):
+    """Candidate records (device or host int32[*, 4] tensor) -> structured numpy array."""
+    a = tensor[:count].cpu().numpy()
+    return a.view(_lib.CANDIDATE_DTYPE).reshape(-1)

@@ -79,10 +79,9 @@ def _kernel_desc(kernel, tsvd, keep):
     return d
 
 
-def _run_host(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsvd, pval,
-              raw_xcorr=False, threshold=1e-4, trim_to_max_dist=False):
-    """One call of cs_normxcorr2_host -> (corr csr, log10 p csr or None)."""
-    lib = _lib.load()
+def _build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsvd, pval,
+                raw_xcorr=False, threshold=1e-4, trim_to_max_dist=False, device=None):
+    """cs_normxcorr2_args of one call; the second value keeps the host arrays alive."""
     keep = []
     a = _lib.Normxcorr2Args()
     a.rows, a.cols = csr.shape
@@ -106,35 +105,73 @@ def _run_host(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsv
     a.sig_dmin, a.sig_dmax = _diag_extent(csr)
     a.kernel = _kernel_desc(kernel, tsvd, keep)
     a.missing_tol = float(missing_tol)
-    a.device = _device_index()
+    a.device = _device_index() if device is None else int(device)
     a.raw_xcorr = int(bool(raw_xcorr))
     a.xcorr_threshold = float(threshold)
+    return a, keep
+
+
+class _PinnedOwner:
+    """Keeps the library's pinned result buffers alive for as long as a numpy view of
+    them is (zero-copy hand-over to scipy); returns them to the pool afterwards."""
+
+    def __init__(self, res):
+        self._res = res
+
+    def __del__(self):
+        try:
+            _lib.load().cs_result_free(C.byref(self._res))
+        except Exception:
+            pass
+
+
+def _view(owner, ptr, ctype, dtype, n):
+    """numpy view of n elements of a library-owned pinned buffer."""
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    buf = (ctype * n).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=n)
+    # frombuffer keeps `buf` alive; tie the owner to it as well
+    buf._owner = owner
+    return arr
+
+
+def _result_to_csr(res, shape, pval):
+    """cs_csr_result -> (corr, pvals) scipy CSR matrices.  The value arrays are
+    zero-copy views of the pinned buffers the device wrote into; the buffers go
+    back to the library's pool when the matrices are garbage collected."""
+    n = int(res.nnz)
+    owner = _PinnedOwner(res)
+    indptr_o = _view(owner, res.indptr, C.c_int64, np.int64, shape[0] + 1)
+    idx = _view(owner, res.indices, C.c_int32, np.int32, n)
+    val = _view(owner, res.data, C.c_double, np.float64, n)
+    corr = sp.csr_matrix(shape, dtype=np.float64)
+    corr.indptr, corr.indices, corr.data = indptr_o, idx, val
+    pvals = None
+    if pval:
+        pv = _view(owner, res.log10p, C.c_double, np.float64, n)
+        # own structure arrays: callers compact the two matrices independently (det:267)
+        p_indptr = _view(owner, res.p_indptr, C.c_int64, np.int64, shape[0] + 1)
+        p_idx = _view(owner, res.p_indices, C.c_int32, np.int32, n)
+        pvals = sp.csr_matrix(shape, dtype=np.float64)
+        pvals.indptr, pvals.indices, pvals.data = p_indptr, p_idx, pv
+    return corr, pvals
+
+
+def _run_host(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsvd, pval,
+              raw_xcorr=False, threshold=1e-4, trim_to_max_dist=False):
+    """One call of cs_normxcorr2_host -> (corr csr, log10 p csr or None)."""
+    lib = _lib.load()
+    a, keep = _build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsvd,
+                          pval, raw_xcorr, threshold, trim_to_max_dist)
     res = _lib.CsrResult()
     _lib.check(lib.cs_normxcorr2_host(C.byref(a), C.byref(res)))
-    try:
-        n = int(res.nnz)
-        indptr_o = np.ctypeslib.as_array(C.cast(res.indptr, C.POINTER(C.c_int64)),
-                                         shape=(a.rows + 1,)).copy()
-        if n:
-            idx = np.ctypeslib.as_array(C.cast(res.indices, C.POINTER(C.c_int32)), shape=(n,)).copy()
-            val = np.ctypeslib.as_array(C.cast(res.data, C.POINTER(C.c_double)), shape=(n,)).copy()
-        else:
-            idx = np.zeros(0, dtype=np.int32)
-            val = np.zeros(0, dtype=np.float64)
-        corr = sp.csr_matrix((val, idx, indptr_o), shape=csr.shape)
-        pvals = None
-        if pval:
-            if n:
-                pv = np.ctypeslib.as_array(C.cast(res.log10p, C.POINTER(C.c_double)), shape=(n,)).copy()
-            else:
-                pv = np.zeros(0, dtype=np.float64)
-            pvals = sp.csr_matrix((pv, idx.copy(), indptr_o.copy()), shape=csr.shape)
-        last_call_stats.clear()
-        last_call_stats.update(ms_h2d=res.ms_h2d, ms_kernels=res.ms_kernels, ms_d2h=res.ms_d2h,
-                               n_windows=int(res.n_windows), nnz=n)
-    finally:
-        lib.cs_result_free(C.byref(res))
-    return corr, pvals
+    last_call_stats.clear()
+    last_call_stats.update(ms_h2d=res.ms_h2d, ms_kernels=res.ms_kernels, ms_d2h=res.ms_d2h,
+                           n_windows=int(res.n_windows), nnz=int(res.nnz),
+                           h2d_bytes=int(res.h2d_bytes), d2h_bytes=int(res.d2h_bytes))
+    del keep
+    return _result_to_csr(res, csr.shape, pval)
 
 
 def _check_kernel_shape(kernel):
@@ -143,6 +180,39 @@ def _check_kernel_shape(kernel):
         # even kernels break the reference too (inconsistent shapes after zero_pad_sparse,
         # det:720-722); fail early with a clear message
         raise ValueError("kernel dimensions must be odd")
+
+
+def _validate(signal, kernel, missing_mask):
+    """The argument checks of det:871-889, in the reference's order."""
+    if missing_mask is not None:
+        if not sp.issparse(missing_mask):
+            raise ValueError("Missing mask must be a sparse matrix.")
+        if not signal.shape == missing_mask.shape:
+            raise ValueError("Signal and missing mask do not have the same shape")
+        if missing_mask.dtype != bool:
+            raise ValueError(f"Missing mask dtype is {missing_mask.dtype}. Should be bool.")
+        if min(kernel.shape) >= max(signal.shape):
+            raise ValueError("cannot have kernel bigger than signal")
+    if sp.issparse(kernel):
+        raise ValueError("cannot handle kernel in sparse format")
+    kernel = np.asarray(kernel, dtype=np.float64)
+    if not (kernel.std() > 0):
+        raise ValueError("Cannot have flat kernel.")
+    _check_kernel_shape(kernel)
+    return kernel
+
+
+def _mask_csr(missing_mask):
+    if missing_mask is None:
+        return None
+    mask_csr = missing_mask.tocsr()
+    if mask_csr.nnz and not mask_csr.data.all():
+        mask_csr = mask_csr.copy()
+        mask_csr.eliminate_zeros()
+    if not mask_csr.has_canonical_format:
+        mask_csr = mask_csr.copy()
+        mask_csr.sum_duplicates()
+    return mask_csr
 
 
 def xcorr2(signal, kernel, threshold=1e-4, tsvd=None):
@@ -188,29 +258,10 @@ def normxcorr2(
 
     Returns (corr, log10_pvals): csr_matrix for a sparse signal, ndarray for a
     dense one; log10_pvals is None unless pval=True."""
-    if missing_mask is not None:
-        if not sp.issparse(missing_mask):
-            raise ValueError("Missing mask must be a sparse matrix.")
-        if not signal.shape == missing_mask.shape:
-            raise ValueError("Signal and missing mask do not have the same shape")
-        if missing_mask.dtype != bool:
-            raise ValueError(f"Missing mask dtype is {missing_mask.dtype}. Should be bool.")
-        if min(kernel.shape) >= max(signal.shape):
-            raise ValueError("cannot have kernel bigger than signal")
-    if sp.issparse(kernel):
-        raise ValueError("cannot handle kernel in sparse format")
-    kernel = np.asarray(kernel, dtype=np.float64)
-    if not (kernel.std() > 0):
-        raise ValueError("Cannot have flat kernel.")
-    _check_kernel_shape(kernel)
+    kernel = _validate(signal, kernel, missing_mask)
     dense_in = not sp.issparse(signal)
     csr = _canonical_csr(np.asarray(signal) if dense_in else signal, np.float64)
-    mask_csr = None
-    if missing_mask is not None:
-        mask_csr = missing_mask.tocsr()
-        if mask_csr.nnz and not mask_csr.data.all():
-            mask_csr = mask_csr.copy()
-            mask_csr.eliminate_zeros()
+    mask_csr = _mask_csr(missing_mask)
     corr, pvals = _run_host(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsvd,
                             pval, trim_to_max_dist=trim_to_max_dist)
     if dense_in:

@@ -176,8 +176,11 @@ typedef struct cs_csr_result {
     int32_t *indices; /* nnz */
     double *data;     /* nnz */
     double *log10p;   /* nnz or NULL */
+    int64_t *p_indptr;  /* second copy of indptr / indices for the p-value matrix, so   */
+    int32_t *p_indices; /* that the two returned matrices share no storage (NULL if !pval) */
     double ms_h2d, ms_kernels, ms_d2h; /* device-side timings of the call */
     int64_t n_windows;
+    int64_t h2d_bytes, d2h_bytes; /* bytes copied host<->device by the call */
 } cs_csr_result;
 
 typedef struct cs_normxcorr2_args {
@@ -218,6 +221,9 @@ typedef struct cs_run_stats {
 } cs_run_stats;
 int cs_session_create(int32_t device, cs_session **out);
 void cs_session_destroy(cs_session *s);
+/* Launch on the caller's stream (e.g. PyTorch's current stream) instead of the library's
+ * own; NULL restores the library stream.  SURVEY 8b: one CUDA stream per call. */
+int cs_session_set_stream(cs_session *s, void *stream);
 int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a);
 int cs_session_run(cs_session *s, cs_run_stats *stats);
 int cs_session_candidates(cs_session *s, float threshold, int32_t dmin, int32_t dmax,
