@@ -2,23 +2,30 @@
 // banded / dense float32 image (detection.py:917-1131 of the reference).
 //
 // One CTA = one output tile of TR rows that follows the band (a parallelogram in
-// matrix coordinates).  The input tile (TR+KH-1 rows x IC columns, matrix
-// coordinates) is fetched with ONE TMA box load out of the skewed band (the row
-// stride of the tensor map is pitch, see cs_layout), fixed up in shared memory
-// (out-of-band aliases -> 0, NaN sentinels = missing), shifted by a tile pivot,
-// then:
-//   phase A  per-column sliding sums over KH rows in float64 (sum S', sum S'^2,
-//            missing count) -> V in shared memory;
-//   main     each thread owns a 4x4 block of windows: for every input row it
-//            loads its row segment once (LDS.128) and feeds 4 x 4 x KW FFMAs;
-//   epilogue horizontal KW-sums of V per window, the reference's formulas in
-//            float64, one float32 score per window.
+// matrix coordinates), possibly one of several column chunks.  The input tile
+// ((TR+KH-1) rows x IC columns, matrix coordinates) is fetched with ONE TMA box
+// load out of the skewed band (the row stride of the tensor map is `pitch`, see
+// cs_layout).  Then, all in shared memory:
+//   pivot    sampled mean of the tile (any pivot is algebraically exact; a good one
+//            keeps the float32 products small);
+//   phase A  one thread per column walks down the tile: band fix-up (out-of-band
+//            aliases -> 0), NaN sentinels -> bit array (warp ballot) + value 0, shift by
+//            the pivot, vertical sliding sums over KH rows in float64 (sum S', sum S'^2,
+//            missing count) -> V;
+//   main     each thread owns an 8x4 block of windows: per input row one conflict-free
+//            LDS.128 sweep of its 20-pixel segment feeds up to 8 x 4 x KW FMAs issued as
+//            packed fma.rn.f32x2 (two windows per instruction, kernel taps pre-duplicated
+//            in shared memory) -- no mask work in this loop;
+//   epilogue per window: horizontal KW-sums of V, the masked kernel sums from the bit
+//            array (full columns / row runs through prefix tables of K and K^2, float64,
+//            exact), the reference's formulas in float64, one float32 score.
 // No tensor cores: this is a CUDA-core stencil (BASELINE.json north_star).
 #include "common.cuh"
 
 namespace cs {
 
-constexpr int kThreads = 256;
+constexpr int RU = 8;  // window rows per thread
+constexpr int RT = 4;  // window columns per thread
 
 struct PearsonParams {
     // image
@@ -27,21 +34,21 @@ struct PearsonParams {
     int oy0, oy1, ox0, ox1, odlo, odhi;
     // tiling
     int TR, G, NBc, nchunks, skew;
-    int IC, IR, ICq;
+    int IC, IR, VQ, NW;
     // kernel geometry
-    int KH, KW, KWp, N;
+    int KH, KW, KWP, N;
     // output image
     float *out;
     unsigned short *nobs;
     int out_pitch, out_dlo, osy, osx;
-    // kernel matrices [nmat][KH][KWp] float (device)
-    const float *kmat;
-    double q, sumKp, ksum, k2sum, kmean, kstd, thr;
-    double sumKp2;   // sum K'^2
-    double qm, qm2;  // pivots of the two mask kernels (their sums are accumulated centred)
+    // tables (device): float part then double part, copied to shared memory by every CTA
+    const float *ftab;
+    const double *dtab;
+    int n_ftab, n_dtab;
+    double q, sumKp, sumKp2, ksum, k2sum, kmean, kstd, thr;
     int min_present, kmean_zero, has_mask, raw_xcorr, nobs_full;
     // shared memory carve-up (bytes)
-    int off_V, off_Vm, off_K, off_red, off_bar;
+    int off_V, off_Vm, off_bits, off_K, off_D, off_acc, off_red, off_bar;
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -83,23 +90,21 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
         : "memory");
 }
+// two float32 FMAs per instruction (FFMA2): acc.{lo,hi} += a.{lo,hi} * b.{lo,hi}
+__device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long a,
+                                     unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
 
 __device__ __forceinline__ double thr0(double v, double t) { return fabs(v) < t ? 0.0 : v; }
-
-// one kernel row (padded to a multiple of 4 floats, 16-byte aligned) -> registers;
-// every lane reads the same address: a shared-memory broadcast
-template <int KWQ>
-__device__ __forceinline__ void load_krow(float *kk, const float *src) {
-    const float4 *s4 = reinterpret_cast<const float4 *>(src);
-#pragma unroll
-    for (int qd = 0; qd < KWQ; ++qd) {
-        const float4 v = s4[qd];
-        kk[4 * qd + 0] = v.x;
-        kk[4 * qd + 1] = v.y;
-        kk[4 * qd + 2] = v.z;
-        kk[4 * qd + 3] = v.w;
-    }
-}
 
 // Squared error amplification above which a window is recomputed in float64: the
 // float32 sums carry ~1e-6 relative error on well-conditioned windows, and the score
@@ -107,14 +112,14 @@ __device__ __forceinline__ void load_krow(float *kk, const float *src) {
 constexpr double kAmpLimit2 = 9.0;
 
 // The reference's formulas (det:1002-1020 no mask, det:1021-1092 masked) from the
-// window sums of the shifted signal S' = S - p and shifted kernels.
-//   h1, h2   : sum S', sum S'^2 over the N window pixels (missing pixels count as S = 0)
-//   s3       : sum S' * K'            (K' = K_corr - q)
-//   sKm,sKm2 : sums of the centred mask kernels over the missing pixels
+// window sums of the shifted signal S' = S - p and the shifted kernel K' = K_corr - q.
+//   h1, h2    : sum S', sum S'^2 over the N window pixels (missing pixels count as S = 0)
+//   s3        : sum S' * K'
+//   sKm, sKm2 : sums of the mask kernels (K and K^2) over the missing pixels
 template <bool MASK>
-__device__ __forceinline__ float score_from_sums(const PearsonParams &P, double p, double h1,
-                                                 double h2, int nmiss, double s3, double sKm_c,
-                                                 double sKm2_c, int &nobs, double &amp2) {
+__device__ __forceinline__ float score_from_sums(const PearsonParams &P, double p, double h1, double h2,
+                                              int nmiss, double s3, double sKm, double sKm2,
+                                              int &nobs, double &amp2) {
     const double dN = (double)P.N;
     const double invN = 1.0 / dN;
     const double m1 = h1 * invN;
@@ -142,9 +147,8 @@ __device__ __forceinline__ float score_from_sums(const PearsonParams &P, double 
     } else {
         const int npres = P.N - nmiss;
         f = dN / (double)npres;
-        // mask kernels are stored centred (K - qm): add the pivot back
-        const double sKm = thr0(sKm_c + P.qm * nmiss, P.thr);
-        const double sKm2 = thr0(sKm2_c + P.qm2 * nmiss, P.thr);
+        sKm = thr0(sKm, P.thr);
+        sKm2 = thr0(sKm2, P.thr);
         const double mK = (P.ksum - sKm) / (double)npres;
         const double m2K = (P.k2sum - sKm2) / (double)npres;
         const double mS = A1 * f;
@@ -161,46 +165,61 @@ __device__ __forceinline__ float score_from_sums(const PearsonParams &P, double 
         r = (float)cov * rsqrtf((float)den2);
         if (!(fabsf(r) <= 3.0e38f)) r = 0.f;
         r = fminf(1.f, fmaxf(-1.f, r));
+    } else if (ok && A2 != 0.0 && den2 < 1e-20) {
+        // a non-zero window whose variance vanished: exactly flat, or flat up to the
+        // float32 rounding of the column sums -- let the float64 pass decide
+        amp2 = 1e300;
     }
     return r;
 }
 
+// bits [c0, c0 + 64) of one row of the missing-pixel bit array
+__device__ __forceinline__ unsigned long long row_bits(const uint32_t *brow, int c0) {
+    const int w = c0 >> 5, sh = c0 & 31;
+    const uint32_t a = brow[w], b = brow[w + 1], c = brow[w + 2];
+    const uint32_t lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
 // ---------------------------------------------------------------- the kernel
 template <int KW, bool MASK>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(256, 1)
 pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     constexpr int kw = (KW - 1) / 2;
     constexpr int kwa = (kw + 3) / 4 * 4;
     constexpr int off = kwa - kw;
-    constexpr int NQ = (2 * kwa + 4) / 4;
-    constexpr int KWQ = (KW + 3) / 4;
+    constexpr int XW = RT + KW - 1;           // pixels of one footprint row
+    constexpr int NQ = (off + XW + 3) / 4;    // float4 loads per footprint row
+    constexpr int KWP = (KW + 1) / 2 * 2;     // taps padded to an even count
+    constexpr unsigned KWMASK = (KW == 32) ? 0xffffffffu : ((1u << KW) - 1u);
 
     extern __shared__ __align__(1024) unsigned char smem[];
     float *tile = reinterpret_cast<float *>(smem);
-    double2 *V = reinterpret_cast<double2 *>(smem + P.off_V);
-    float *Vm = reinterpret_cast<float *>(smem + P.off_Vm);
-    float *Ks = reinterpret_cast<float *>(smem + P.off_K);
+    float2 *V = reinterpret_cast<float2 *>(smem + P.off_V);
+    unsigned char *Vm = smem + P.off_Vm;
+    uint32_t *bits = reinterpret_cast<uint32_t *>(smem + P.off_bits);
+    const float2 *Kdup = reinterpret_cast<const float2 *>(smem + P.off_K);
+    const double *Dt = reinterpret_cast<const double *>(smem + P.off_D);
+    float *accS = reinterpret_cast<float *>(smem + P.off_acc);
     float *red = reinterpret_cast<float *>(smem + P.off_red);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + P.off_bar);
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
     const int rb = blockIdx.x / P.nchunks;
     const int ch = blockIdx.x - rb * P.nchunks;
-    const int kh = (P.KH - 1) / 2;
+    const int KH = P.KH;
+    const int kh = (KH - 1) / 2;
     const int Y0 = P.oy0 + rb * P.TR;
     // aligned X' (= X - dlo) of the first block of row group 0
     int xb;
-    if (P.skew) {
-        int v = Y0 + P.odlo - P.dlo;
-        xb = (v >= 0 ? v / 4 : -((-v + 3) / 4)) * 4;
-    } else {
-        int v = P.ox0 - P.dlo;
+    {
+        const int v = P.skew ? (Y0 + P.odlo - P.dlo) : (P.ox0 - P.dlo);
         xb = (v >= 0 ? v / 4 : -((-v + 3) / 4)) * 4;
     }
     xb += 4 * ch * P.NBc;
     const int TXp = xb - kwa;  // X' of tile column 0
     const int TY = Y0 - kh;    // image row of tile row 0
-    const int IC = P.IC, IR = P.IR;
+    const int IC = P.IC, IR = P.IR, NW = P.NW, VQ = P.VQ;
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -209,69 +228,116 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         mbar_expect_tx(bar, (uint32_t)(IC * IR * sizeof(float)));
         tma_load_2d(tile, &tmap, bar, TXp, TY);
     }
-    // kernel matrices -> shared memory while the tile is in flight
+    // tables -> shared memory while the tile is in flight
     {
-        const int nk = (MASK ? 3 : 1) * P.KH * P.KWp;
-        for (int i = tid; i < nk; i += kThreads) Ks[i] = P.kmat[i];
+        float *Kf = reinterpret_cast<float *>(smem + P.off_K);
+        for (int i = tid; i < P.n_ftab; i += nthr) Kf[i] = P.ftab[i];
+        double *Dd = reinterpret_cast<double *>(smem + P.off_D);
+        for (int i = tid; i < P.n_dtab; i += nthr) Dd[i] = P.dtab[i];
+        if (MASK)
+            for (int i = tid; i < IR * NW; i += nthr) bits[i] = 0u;
     }
     __syncthreads();
     mbar_wait(bar, 0);
 
-    // ---- pass 1: band fix-up, tile statistics ---------------------------------
-    float lsum = 0.f;
-    int lnz = 0;
-    for (int iy = tid / 64; iy < IR; iy += kThreads / 64) {
-        const int Y = TY + iy;
-        float *row = tile + iy * IC;
-        for (int ix = tid % 64; ix < IC; ix += 64) {
-            const int X = TXp + ix + P.dlo;
-            const int d = X - Y;
-            float v = row[ix];
-            const bool inside = P.dense ? true : (d >= P.dlo && d <= P.dhi);
-            if (!inside) {
-                v = 0.f;
-                row[ix] = 0.f;
+    // ---- pivot: mean of the in-band, non-missing pixels of every 4th tile row ----
+    float pv;
+    {
+        float lsum = 0.f, lcnt = 0.f;
+        const int ICq4 = IC >> 2;
+        const int nrow_s = (IR + 3) >> 2;
+        for (int i = tid; i < nrow_s * ICq4; i += nthr) {
+            const int iy = (i / ICq4) << 2, c4 = (i - (i / ICq4) * ICq4) << 2;
+            const float4 v = *reinterpret_cast<const float4 *>(tile + iy * IC + c4);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            const int d0 = (TXp + c4 + P.dlo) - (TY + iy);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool inside = P.dense ? true : (d0 + e >= P.dlo && d0 + e <= P.dhi);
+                if (inside && vv[e] == vv[e]) {
+                    lsum += vv[e];
+                    lcnt += 1.f;
+                }
             }
-            if (v == v) {
-                lsum += v;
-                lnz |= (v != 0.f);
-            } else if (!MASK) {
-                row[ix] = 0.f;  // no-mask mode never sees sentinels; be safe
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+            lcnt += __shfl_xor_sync(0xffffffffu, lcnt, o);
+        }
+        if (lane == 0) {
+            red[tid >> 5] = lsum;
+            red[8 + (tid >> 5)] = lcnt;
+        }
+        __syncthreads();
+        float ts = 0.f, tc = 0.f;
+        for (int w = 0; w < (nthr >> 5); ++w) {
+            ts += red[w];
+            tc += red[8 + w];
+        }
+        pv = tc > 0.f ? ts / tc : 0.f;
+    }
+    const double p = (double)pv;
+
+    // ---- phase A: fix-up + bit array + vertical sliding sums --------------------------
+    int anynz = 0;
+    {
+        const int ICr = (IC + 31) & ~31;
+        for (int cb = (tid >> 5) << 5; cb < ICr; cb += nthr) {
+            const int ix = cb + lane;
+            const bool live = ix < IC;
+            const int slot = (ix & 3) * VQ + (ix >> 2);
+            const int X = TXp + ix + P.dlo;
+            double r1 = 0.0, r2 = 0.0;
+            int rm = 0;
+            for (int iy = 0; iy < IR; ++iy) {
+                float v = live ? tile[iy * IC + ix] : 0.f;
+                const int d = X - (TY + iy);
+                const bool inside = P.dense ? true : (d >= P.dlo && d <= P.dhi);
+                if (!inside) v = 0.f;
+                bool miss = false;
+                if (MASK) {
+                    miss = !(v == v);
+                    const unsigned word = __ballot_sync(0xffffffffu, miss);
+                    if (lane == 0) bits[iy * NW + (cb >> 5)] = word;
+                    rm += miss ? 1 : 0;
+                }
+                if (!(v == v)) v = 0.f;  // missing pixels count as S = 0
+                anynz |= (v != 0.f);
+                const float vs = v - pv;
+                if (live) tile[iy * IC + ix] = vs;
+                const double a = (double)vs;
+                r1 += a;
+                r2 = fma(a, a, r2);
+                const int yo = iy - (KH - 1);
+                if (yo >= 0) {
+                    if (live) {
+                        V[yo * 4 * VQ + slot] = make_float2((float)r1, (float)r2);
+                        if (MASK) Vm[yo * 4 * VQ + slot] = (unsigned char)rm;
+                    }
+                    const float w = live ? tile[yo * IC + ix] : -pv;
+                    if (MASK) {
+                        __syncwarp();
+                        rm -= (bits[yo * NW + (cb >> 5)] >> lane) & 1u;
+                    }
+                    const double b = (double)w;
+                    r1 -= b;
+                    r2 = fma(-b, b, r2);
+                }
             }
         }
     }
-    // block reduction of (sum, any non-zero)
-    for (int o = 16; o > 0; o >>= 1) {
-        lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-        lnz |= __shfl_xor_sync(0xffffffffu, lnz, o);
-    }
-    if ((tid & 31) == 0) {
-        red[tid >> 5] = lsum;
-        red[8 + (tid >> 5)] = __int_as_float(lnz);
-    }
-    __syncthreads();
-    float tsum = 0.f;
-    int tnz = 0;
-#pragma unroll
-    for (int w = 0; w < kThreads / 32; ++w) {
-        tsum += red[w];
-        tnz |= __float_as_int(red[8 + w]);
-    }
-    const float pv = tsum / (float)(IC * IR);  // tile pivot
-    const double p = (double)pv;
+    const int tnz = __syncthreads_or(anynz);
 
-    // item decode ---------------------------------------------------------------
     const int nitems = P.G * P.NBc;
-
     if (!tnz) {
         // all-zero signal: every score of the tile is 0 (variance 0 -> det:1088-1091)
-        for (int item = tid; item < nitems; item += kThreads) {
+        for (int item = tid; item < nitems; item += nthr) {
             const int g = item / P.NBc, m = item - g * P.NBc;
-            const int Xp0 = xb + 4 * g * P.skew + 4 * m;
-            for (int u = 0; u < 4; ++u) {
-                const int Y = Y0 + 4 * g + u;
+            const int Xp0 = xb + RU * g * P.skew + RT * m;
+            for (int u = 0; u < RU; ++u) {
+                const int Y = Y0 + RU * g + u;
                 if (Y >= P.oy1) continue;
-                for (int t = 0; t < 4; ++t) {
+                for (int t = 0; t < RT; ++t) {
                     const int X = Xp0 + t + P.dlo;
                     const int d = X - Y;
                     if (X < P.ox0 || X >= P.ox1 || d < P.odlo || d > P.odhi) continue;
@@ -285,183 +351,200 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         return;
     }
 
-    // ---- pass 2: shift by the pivot (missing pixels keep their NaN) -----------
-    for (int i = tid; i < IC * IR; i += kThreads) {
-        float v = tile[i];
-        tile[i] = v - pv;  // NaN stays NaN
-    }
-    __syncthreads();
+    // double tables (mask branch): prefix sums of the mask kernels along rows, column sums
+    const double *PK = Dt;                        // [KH][KW + 1]
+    const double *PK2 = Dt + KH * (KW + 1);       // [KH][KW + 1]
+    const double *Kcol = Dt + 2 * KH * (KW + 1);  // [KW]
+    const double *K2col = Kcol + KW;              // [KW]
 
-    // ---- phase A: vertical sliding sums in float64 ------------------------------
-    const int Vpitch = 4 * P.ICq;  // entries per output row
-    for (int ix = tid; ix < IC; ix += kThreads) {
-        const int slot = (ix & 3) * P.ICq + (ix >> 2);
-        double r1 = 0.0, r2 = 0.0;
-        float rm = 0.f;
-        for (int iy = 0; iy < IR; ++iy) {
-            float v = tile[iy * IC + ix];
-            if (MASK) {
-                const bool miss = !(v == v);
-                rm += miss ? 1.f : 0.f;
-                v = miss ? -pv : v;
-            }
-            const double a = (double)v;
-            r1 += a;
-            r2 = fma(a, a, r2);
-            const int yo = iy - (P.KH - 1);
-            if (yo >= 0) {
-                V[yo * Vpitch + slot] = make_double2(r1, r2);
-                if (MASK) Vm[yo * Vpitch + slot] = rm;
-                float w = tile[yo * IC + ix];
-                if (MASK) {
-                    const bool miss = !(w == w);
-                    rm -= miss ? 1.f : 0.f;
-                    w = miss ? -pv : w;
-                }
-                const double b = (double)w;
-                r1 -= b;
-                r2 = fma(-b, b, r2);
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- main loop + epilogue ---------------------------------------------------
-    const float *Kc = Ks;
-    const float *Km = Ks + P.KH * P.KWp;
-    const float *Km2 = Ks + 2 * P.KH * P.KWp;
-    for (int item = tid; item < nitems; item += kThreads) {
+    // ---- main loop + epilogue -----------------------------------------------------------
+    for (int item = tid; item < nitems; item += nthr) {
         const int g = item / P.NBc, m = item - g * P.NBc;
-        const int Xp0 = xb + 4 * g * P.skew + 4 * m;  // X' of output column t=0
-        const int cxa = 4 * g * P.skew + 4 * m;       // aligned tile column of x[0]
-        const int Yg = Y0 + 4 * g;
+        const int Xp0 = xb + RU * g * P.skew + RT * m;  // X' of output column t = 0
+        const int cxa = RU * g * P.skew + RT * m;       // aligned tile column of x[0]
+        const int Yg = Y0 + RU * g;
         // skip blocks without any valid output pixel
         {
             bool any = false;
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < RU; ++u) {
                 const int Y = Yg + u;
                 if (Y >= P.oy1) continue;
                 const int Xlo = max(P.ox0, Y + P.odlo), Xhi = min(P.ox1 - 1, Y + P.odhi);
                 const int Xa = Xp0 + P.dlo;
-                if (Xa + 3 >= Xlo && Xa <= Xhi) any = true;
+                if (Xa + RT - 1 >= Xlo && Xa <= Xhi) any = true;
             }
             if (!any) continue;
         }
 
-        float acc[4][4], accm[4][4], accm2[4][4];
+        unsigned long long acc[RU][RT / 2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < RU; ++u)
 #pragma unroll
-            for (int t = 0; t < 4; ++t) acc[u][t] = accm[u][t] = accm2[u][t] = 0.f;
+            for (int t = 0; t < RT / 2; ++t) acc[u][t] = 0ull;
 
-        const int nrow = P.KH + 3;
+        const int nrow = KH + RU - 1;
+#pragma unroll 1
         for (int iy = 0; iy < nrow; ++iy) {
-            const float4 *rp = reinterpret_cast<const float4 *>(tile + (4 * g + iy) * IC + cxa);
-            float x[4 * NQ];
-            float mk[MASK ? 4 * NQ : 1];
+            const ulonglong2 *rp =
+                reinterpret_cast<const ulonglong2 *>(tile + (RU * g + iy) * IC + cxa);
+            // xe[q] = (x[2q], x[2q+1]), xo[q] = (x[2q+1], x[2q+2])
+            unsigned long long xe[2 * NQ], xo[2 * NQ];
 #pragma unroll
             for (int qd = 0; qd < NQ; ++qd) {
-                const float4 v = rp[qd];
-                x[4 * qd + 0] = v.x;
-                x[4 * qd + 1] = v.y;
-                x[4 * qd + 2] = v.z;
-                x[4 * qd + 3] = v.w;
-            }
-            if (MASK) {
-#pragma unroll
-                for (int e = 0; e < 4 * NQ; ++e) {
-                    const bool miss = !(x[e] == x[e]);
-                    mk[e] = miss ? 1.f : 0.f;
-                    x[e] = miss ? -pv : x[e];
-                }
+                const ulonglong2 v = rp[qd];
+                xe[2 * qd] = v.x;
+                xe[2 * qd + 1] = v.y;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int qd = 0; qd < 2 * NQ - 1; ++qd) {
+                float a0, a1, b0, b1;
+                unpack2(xe[qd], a0, a1);
+                unpack2(xe[qd + 1], b0, b1);
+                xo[qd] = pack2(a1, b0);
+            }
+            xo[2 * NQ - 1] = 0ull;
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
                 const int i = iy - u;
-                if (i < 0 || i >= P.KH) continue;
-                float kk[4 * KWQ];
-                load_krow<KWQ>(kk, Kc + i * P.KWp);
+                if (i < 0 || i >= KH) continue;  // uniform across the block
+                const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(Kdup + i * KWP);
+                unsigned long long kd[KWP];
+#pragma unroll
+                for (int qd = 0; qd < KWP / 2; ++qd) {
+                    const ulonglong2 v = kp[qd];
+                    kd[2 * qd] = v.x;
+                    kd[2 * qd + 1] = v.y;
+                }
 #pragma unroll
                 for (int j = 0; j < KW; ++j) {
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) acc[u][t] = fmaf(x[off + t + j], kk[j], acc[u][t]);
-                }
-                if (MASK) {
-                    load_krow<KWQ>(kk, Km + i * P.KWp);
-#pragma unroll
-                    for (int j = 0; j < KW; ++j) {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t)
-                            accm[u][t] = fmaf(mk[off + t + j], kk[j], accm[u][t]);
-                    }
-                    load_krow<KWQ>(kk, Km2 + i * P.KWp);
-#pragma unroll
-                    for (int j = 0; j < KW; ++j) {
-#pragma unroll
-                        for (int t = 0; t < 4; ++t)
-                            accm2[u][t] = fmaf(mk[off + t + j], kk[j], accm2[u][t]);
+                    for (int tp = 0; tp < RT / 2; ++tp) {
+                        const int e = off + 2 * tp + j;  // compile-time
+                        fma2(acc[u][tp], (e & 1) ? xo[e >> 1] : xe[e >> 1], kd[j]);
                     }
                 }
             }
         }
 
-        // epilogue: one output row at a time
+        // park the accumulators in shared memory: the epilogue runs as compact loops
+        float *myacc = accS + tid;
+#pragma unroll
+        for (int u = 0; u < RU; ++u)
+#pragma unroll
+            for (int tp = 0; tp < RT / 2; ++tp) {
+                float lo, hi;
+                unpack2(acc[u][tp], lo, hi);
+                myacc[(u * RT + 2 * tp) * nthr] = lo;
+                myacc[(u * RT + 2 * tp + 1) * nthr] = hi;
+            }
+
+        // footprint mask summary: columns missing on every footprint row, rows with other
+        // missing pixels
+        const int fc0 = cxa + off;  // tile column of footprint column 0
+        unsigned long long colfull = 0ull;
+        unsigned long long rowsel = 0ull;
+        bool anymiss = false;
+        if (MASK) {
+            constexpr unsigned long long FWMASK = (XW >= 64) ? ~0ull : ((1ull << XW) - 1ull);
+            unsigned long long band = FWMASK, bor = 0ull;
+            const int fr = KH + RU - 1;
+            for (int r = 0; r < fr; ++r) {
+                const unsigned long long b = row_bits(bits + (RU * g + r) * NW, fc0) & FWMASK;
+                band &= b;
+                bor |= b;
+            }
+            anymiss = bor != 0ull;
+            if (anymiss) {
+                colfull = band;
+                if (bor & ~band)
+                    for (int r = 0; r < fr; ++r) {
+                        const unsigned long long b =
+                            row_bits(bits + (RU * g + r) * NW, fc0) & FWMASK;
+                        if (b & ~band) rowsel |= 1ull << r;
+                    }
+            }
+        }
+
         const int qbase = cxa >> 2;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
+#pragma unroll 1
+        for (int u = 0; u < RU; ++u) {
             const int Y = Yg + u;
-            if (Y >= P.oy1) continue;
-            const double2 *Vr = V + (4 * g + u) * Vpitch;
-            const float *Vmr = Vm + (4 * g + u) * Vpitch;
+            if (Y >= P.oy1) break;
+            const float2 *Vr = V + (RU * g + u) * 4 * VQ;
+            const unsigned char *Vmr = Vm + (RU * g + u) * 4 * VQ;
             double h1 = 0.0, h2 = 0.0;
-            float hm = 0.f;
-#pragma unroll
+            int hm = 0;
+#pragma unroll 1
             for (int e = off; e < off + KW; ++e) {
-                const int s = (e & 3) * P.ICq + qbase + (e >> 2);
-                const double2 v = Vr[s];
-                h1 += v.x;
-                h2 += v.y;
+                const int s = (e & 3) * VQ + qbase + (e >> 2);
+                const float2 v = Vr[s];
+                h1 += (double)v.x;
+                h2 += (double)v.y;
                 if (MASK) hm += Vmr[s];
             }
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
+#pragma unroll 1
+            for (int t = 0; t < RT; ++t) {
                 if (t > 0) {
                     const int e0 = off + t - 1, e1 = off + t - 1 + KW;
-                    const int s0 = (e0 & 3) * P.ICq + qbase + (e0 >> 2);
-                    const int s1 = (e1 & 3) * P.ICq + qbase + (e1 >> 2);
-                    const double2 a = Vr[s0], b = Vr[s1];
-                    h1 += b.x - a.x;
-                    h2 += b.y - a.y;
-                    if (MASK) hm += Vmr[s1] - Vmr[s0];
+                    const int s0 = (e0 & 3) * VQ + qbase + (e0 >> 2);
+                    const int s1 = (e1 & 3) * VQ + qbase + (e1 >> 2);
+                    const float2 a = Vr[s0], b = Vr[s1];
+                    h1 += (double)b.x - (double)a.x;
+                    h2 += (double)b.y - (double)a.y;
+                    if (MASK) hm += (int)Vmr[s1] - (int)Vmr[s0];
                 }
                 const int X = Xp0 + t + P.dlo;
                 const int d = X - Y;
                 if (X < P.ox0 || X >= P.ox1 || d < P.odlo || d > P.odhi) continue;
-                int nmiss = 0;
-                if (MASK) nmiss = (int)(hm + 0.5f);
-                int nobs = P.N;
-                double amp2 = 0.0;
-                float r = score_from_sums<MASK>(P, p, h1, h2, nmiss, (double)acc[u][t],
-                                                (double)accm[u][t], (double)accm2[u][t], nobs, amp2);
-                if (amp2 > kAmpLimit2) {
-                    // ill-conditioned window (flat signal or mostly missing): the float32
-                    // accumulators are not accurate enough, redo the three sums in float64
-                    double s3 = 0.0, sm = 0.0, sm2 = 0.0;
-                    const float *wp = tile + (4 * g + u) * IC + cxa + off + t;
-                    for (int i = 0; i < P.KH; ++i) {
-                        const float *wr = wp + i * IC;
-                        const float *kr = Kc + i * P.KWp;
-                        for (int j = 0; j < KW; ++j) {
-                            float sv = wr[j];
-                            if (MASK && !(sv == sv)) {
-                                sv = -pv;
-                                sm += (double)Km[i * P.KWp + j];
-                                sm2 += (double)Km2[i * P.KWp + j];
-                            }
-                            s3 = fma((double)sv, (double)kr[j], s3);
+                const int nmiss = MASK ? hm : 0;
+                double sKm = 0.0, sKm2 = 0.0;
+                if (MASK && nmiss > 0) {
+                    // columns missing over the whole footprint: whole kernel columns
+                    const unsigned cbw = (unsigned)(colfull >> t) & KWMASK;
+                    for (unsigned c = cbw; c; c &= c - 1) {
+                        const int j = __ffs(c) - 1;
+                        sKm += Kcol[j];
+                        sKm2 += K2col[j];
+                    }
+                    // remaining missing pixels, row by row, as runs [a, b) of kernel taps
+                    const unsigned KHMASK = (KH >= 32) ? 0xffffffffu : ((1u << KH) - 1u);
+                    for (unsigned rs = (unsigned)(rowsel >> u) & KHMASK; rs; rs &= rs - 1) {
+                        const int i = __ffs(rs) - 1;
+                        unsigned wb = (unsigned)(row_bits(bits + (RU * g + u + i) * NW, fc0) >> t);
+                        wb &= KWMASK & ~cbw;
+                        const double *pk = PK + i * (KW + 1), *pk2 = PK2 + i * (KW + 1);
+                        while (wb) {
+                            const int a = __ffs(wb) - 1;
+                            const unsigned rest = ~(wb >> a);  // first zero above a ends the run
+                            const int len = __ffs(rest) - 1;   // rest != 0: wb has < 32 bits
+                            const int b = a + len;
+                            sKm += pk[b] - pk[a];
+                            sKm2 += pk2[b] - pk2[a];
+                            wb = (b >= 32) ? 0u : (wb >> b) << b;
                         }
                     }
-                    r = score_from_sums<MASK>(P, p, h1, h2, nmiss, s3, sm, sm2, nobs, amp2);
+                }
+                double s3 = (double)myacc[(u * RT + t) * nthr];
+                int nobs = P.N;
+                double amp2 = 0.0;
+                float r = score_from_sums<MASK>(P, p, h1, h2, nmiss, s3, sKm, sKm2, nobs, amp2);
+                if (amp2 > kAmpLimit2) {
+                    // ill-conditioned window (flat signal or mostly missing): redo the window
+                    // sums in float64 from the tile (the V entries were rounded to float32)
+                    s3 = 0.0;
+                    double g1 = 0.0, g2 = 0.0;
+                    const float *wp = tile + (RU * g + u) * IC + fc0 + t;
+                    for (int i = 0; i < KH; ++i) {
+                        const float *wr = wp + i * IC;
+                        const float2 *kr = Kdup + i * KWP;
+                        for (int j = 0; j < KW; ++j) {
+                            const double sv = (double)wr[j];
+                            g1 += sv;
+                            g2 = fma(sv, sv, g2);
+                            s3 = fma(sv, (double)kr[j].x, s3);
+                        }
+                    }
+                    r = score_from_sums<MASK>(P, p, g1, g2, nmiss, s3, sKm, sKm2, nobs, amp2);
                 }
                 const long long oi =
                     (long long)(Y - P.osy) * P.out_pitch + ((X - P.osx) - P.out_dlo);
@@ -492,11 +575,11 @@ static PFN_encodeTiled get_encode() {
 }
 
 template <int KW, bool MASK>
-static int launch_kw(const CUtensorMap &tmap, const PearsonParams &P, int grid, size_t smem,
-                     cudaStream_t st) {
+static int launch_kw(const CUtensorMap &tmap, const PearsonParams &P, int grid, int threads,
+                     size_t smem, cudaStream_t st) {
     auto kern = pearson_tiles<KW, MASK>;
     CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(tmap, P);
+    kern<<<grid, threads, smem, st>>>(tmap, P);
     CS_LAUNCHED();
     CS_CUDA(cudaGetLastError());
     return CS_OK;
@@ -504,11 +587,11 @@ static int launch_kw(const CUtensorMap &tmap, const PearsonParams &P, int grid, 
 
 template <bool MASK>
 static int launch_mask(int KW, const CUtensorMap &tmap, const PearsonParams &P, int grid,
-                       size_t smem, cudaStream_t st) {
+                       int threads, size_t smem, cudaStream_t st) {
     switch (KW) {
 #define CS_CASE(n) \
     case n:        \
-        return launch_kw<n, MASK>(tmap, P, grid, smem, st);
+        return launch_kw<n, MASK>(tmap, P, grid, threads, smem, st);
         CS_CASE(3) CS_CASE(5) CS_CASE(7) CS_CASE(9) CS_CASE(11) CS_CASE(13) CS_CASE(15) CS_CASE(17)
         CS_CASE(19) CS_CASE(21) CS_CASE(23) CS_CASE(25) CS_CASE(27) CS_CASE(29) CS_CASE(31)
 #undef CS_CASE
@@ -518,14 +601,14 @@ static int launch_mask(int KW, const CUtensorMap &tmap, const PearsonParams &P, 
     }
 }
 
-// device scratch holding the float kernel matrices of one launch; kept per stream-agnostic
-// small ring so that back-to-back launches do not race on it.
-struct KmatRing {
-    float *buf[8] = {nullptr};
+// device scratch holding the kernel tables of one launch; a small ring so that
+// back-to-back launches do not race on it.
+struct KtabRing {
+    void *buf[8] = {nullptr};
     size_t cap[8] = {0};
     int next = 0;
 };
-static thread_local KmatRing g_ring;
+static thread_local KtabRing g_ring;
 
 }  // namespace cs
 
@@ -539,7 +622,7 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
     CS_REQUIRE(Li && d_img && K && opts && Lo && d_out, "cs_pearson_f32: null argument");
     CS_REQUIRE(K->kh >= 1 && K->kw >= 3 && (K->kh & 1) && (K->kw & 1),
                "kernel shape must be odd (got %dx%d)", K->kh, K->kw);
-    CS_REQUIRE(K->kh * K->kw < 65535, "kernel too large");
+    CS_REQUIRE(K->kh <= 31 && K->kw <= 31, "kernel %dx%d too large (31x31 at most)", K->kh, K->kw);
     CS_REQUIRE(oy1 > oy0 && ox1 > ox0, "empty output region");
     const int kh = (K->kh - 1) / 2, kw = (K->kw - 1) / 2;
     CS_REQUIRE(oy0 - kh >= 0 && oy1 + kh <= Li->rows && ox0 - kw >= 0 && ox1 + kw <= Li->cols,
@@ -568,141 +651,176 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
     CS_REQUIRE(odhi >= odlo, "empty output diagonal range");
     P.odlo = odlo;
     P.odhi = odhi;
-    if (!Li->dense) {
-        // every pixel read by a window must be stored or be a true zero: windows of
-        // outputs on diagonal d read diagonals d-(kw+kh) .. d+(kw+kh); pixels outside
-        // the stored band count as zeros, which is what the caller asserts.
-    }
     P.KH = K->kh;
     P.KW = K->kw;
-    P.KWp = round_up(K->kw, 4);
+    P.KWP = (K->kw + 1) / 2 * 2;
     P.N = K->kh * K->kw;
     const int kwa = round_up(kw, 4);
+    const int nrows_out = oy1 - oy0;
 
-    // ---- tiling ---------------------------------------------------------------
-    const int Wo = odhi - odlo + 1;  // output diagonals
-    const int ncols_out = ox1 - ox0;
-    // banded traversal when the output band is narrow relative to the region
-    P.skew = (Wo + 8 < ncols_out) ? 1 : 0;
-    int TR = opts->tile_rows > 0 ? round_up(opts->tile_rows, 4) : 16;
-    const int nmat = opts->has_mask ? 3 : 1;
-    size_t smem = 0;
-    int NBc = 0, nchunks = 0, IC = 0, IR = 0, ICq = 0;
-    for (;; TR -= 4) {
-        CS_REQUIRE(TR >= 4, "kernel %dx%d does not fit in shared memory", K->kh, K->kw);
-        const int G = TR / 4;
-        const int span = P.skew ? (Wo + 6) : (ncols_out + 3);
-        const int nblk_total = (span + 3) / 4;
-        const int nb_max = (256 - 2 * kwa - 4 * (G - 1) * P.skew) / 4;
-        if (nb_max < 1) continue;
-        // aim at ~kThreads items per tile
-        int nb_want = kThreads / G;
-        if (nb_want > nb_max) nb_want = nb_max;
-        nchunks = (nblk_total + nb_want - 1) / nb_want;
-        NBc = (nblk_total + nchunks - 1) / nchunks;
-        IC = 4 * NBc + 4 * (G - 1) * P.skew + 2 * kwa;
-        IR = TR + K->kh - 1;
-        if (IR > 256) continue;
-        ICq = (IC / 4) | 1;
-        size_t o = (size_t)IC * IR * sizeof(float);
-        o = (o + 15) / 16 * 16;
-        P.off_V = (int)o;
-        o += (size_t)TR * 4 * ICq * sizeof(double2);
-        P.off_Vm = (int)o;
-        if (opts->has_mask) o += (size_t)TR * 4 * ICq * sizeof(float);
-        o = (o + 15) / 16 * 16;
-        P.off_K = (int)o;
-        o += (size_t)nmat * K->kh * P.KWp * sizeof(float);
-        o = (o + 15) / 16 * 16;
-        P.off_red = (int)o;
-        o += 64 * sizeof(float);
-        P.off_bar = (int)o;
-        o += 16;
-        smem = o;
-        if (smem <= 112 * 1024 || (TR == 4 && smem <= 227 * 1024)) break;
-    }
-    P.TR = TR;
-    P.G = TR / 4;
-    P.NBc = NBc;
-    P.nchunks = nchunks;
-    P.IC = IC;
-    P.IR = IR;
-    P.ICq = ICq;
-    const int nrb = (oy1 - oy0 + TR - 1) / TR;
-    const long long grid_ll = (long long)nrb * nchunks;
-    CS_REQUIRE(grid_ll < (1ll << 31), "grid too large");
-
-    // ---- output -----------------------------------------------------------------
-    P.osy = opts->out_row_shift;
-    P.osx = opts->out_col_shift;
-    CS_REQUIRE(oy0 - P.osy >= 0 && ox0 - P.osx >= 0 && Lo->rows >= oy1 - P.osy &&
-                   Lo->cols >= ox1 - P.osx,
-               "output image too small");
-    P.out = d_out;
-    P.nobs = d_nobs;
-    P.out_pitch = Lo->pitch;
-    P.out_dlo = Lo->dense ? 0 : Lo->dlo;
-    if (!Lo->dense) {
-        // output pixel (y, x) = (Y - osy, X - osx); its diagonal is d - (osx - osy)
-        const int sh = P.osx - P.osy;
-        CS_REQUIRE(Lo->dlo <= odlo - sh && Lo->dhi >= odhi - sh,
-                   "output band [%d,%d] does not cover scores on diagonals [%d,%d]", Lo->dlo,
-                   Lo->dhi, odlo - sh, odhi - sh);
-    }
-
-    // ---- kernel matrices ----------------------------------------------------------
+    // ---- tables -------------------------------------------------------------------
+    // float: K' = K_corr - q, every tap duplicated (k, k) for the packed FMAs, [KH][KWP]
+    // double (mask): row prefix sums of K_mask and K2_mask [KH][KW+1] each, column sums [KW] each
     const int nk = K->kh * K->kw;
     double qd = 0.0;
     for (int i = 0; i < nk; ++i) qd += K->k_corr[i];
     qd /= nk;
     const float qf = (float)qd;
-    float qmf = 0.f, qm2f = 0.f;
-    if (opts->has_mask) {
-        CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
-        double a = 0.0, b = 0.0;
-        for (int i = 0; i < nk; ++i) {
-            a += K->k_mask[i];
-            b += K->k2_mask[i];
-        }
-        qmf = (float)(a / nk);
-        qm2f = (float)(b / nk);
-    }
-    const size_t kbytes = (size_t)nmat * K->kh * P.KWp * sizeof(float);
-    float *hk = (float *)malloc(kbytes);
+    P.n_ftab = 2 * K->kh * P.KWP;
+    P.n_dtab = opts->has_mask ? (2 * K->kh * (K->kw + 1) + 2 * K->kw) : 0;
+    if (opts->has_mask) CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
+    const size_t fbytes = (size_t)round_up(P.n_ftab, 4) * sizeof(float);
+    const size_t kbytes = fbytes + (size_t)P.n_dtab * sizeof(double);
+    unsigned char *hk = (unsigned char *)malloc(kbytes);
     if (!hk) return CS_ERR_NOMEM;
     memset(hk, 0, kbytes);
+    float *hf = (float *)hk;
+    double *hd = (double *)(hk + fbytes);
     double sumKp = 0.0, sumKp2 = 0.0;
     for (int i = 0; i < K->kh; ++i)
         for (int j = 0; j < K->kw; ++j) {
             const float v = (float)(K->k_corr[i * K->kw + j] - (double)qf);
-            hk[i * P.KWp + j] = v;
+            hf[2 * (i * P.KWP + j)] = v;
+            hf[2 * (i * P.KWP + j) + 1] = v;
             sumKp += (double)v;
             sumKp2 += (double)v * (double)v;
-            if (opts->has_mask) {
-                hk[(K->kh + i) * P.KWp + j] = (float)(K->k_mask[i * K->kw + j] - (double)qmf);
-                hk[(2 * K->kh + i) * P.KWp + j] = (float)(K->k2_mask[i * K->kw + j] - (double)qm2f);
+        }
+    if (opts->has_mask) {
+        double *pk = hd, *pk2 = hd + K->kh * (K->kw + 1);
+        double *kc = hd + 2 * K->kh * (K->kw + 1), *k2c = kc + K->kw;
+        for (int i = 0; i < K->kh; ++i) {
+            double a = 0.0, b = 0.0;
+            pk[i * (K->kw + 1)] = 0.0;
+            pk2[i * (K->kw + 1)] = 0.0;
+            for (int j = 0; j < K->kw; ++j) {
+                a += K->k_mask[i * K->kw + j];
+                b += K->k2_mask[i * K->kw + j];
+                pk[i * (K->kw + 1) + j + 1] = a;
+                pk2[i * (K->kw + 1) + j + 1] = b;
+                kc[j] += K->k_mask[i * K->kw + j];
+                k2c[j] += K->k2_mask[i * K->kw + j];
             }
         }
-    KmatRing &ring = g_ring;
+    }
+
+    // ---- tiling ---------------------------------------------------------------
+    const int Wo = odhi - odlo + 1;  // output diagonals
+    const int ncols_out = ox1 - ox0;
+    // banded traversal when the output band is narrow relative to the region
+    P.skew = (Wo + 16 < ncols_out) ? 1 : 0;
+    int TR = opts->tile_rows > 0 ? round_up(opts->tile_rows, RU) : 32;
+    if (TR > round_up(nrows_out, RU)) TR = round_up(nrows_out, RU);
+    size_t smem = 0;
+    int NBc = 0, nchunks = 0, IC = 0, IR = 0, VQ = 0, NW = 0, threads = 0;
+    for (;; TR -= RU) {
+        if (TR < RU) {
+            free(hk);
+            set_error("kernel %dx%d does not fit in shared memory", K->kh, K->kw);
+            return CS_ERR_INVALID;
+        }
+        const int G = TR / RU;
+        const int span = P.skew ? (Wo + RU - 1 + 3) : (ncols_out + 3);
+        const int nblk_total = (span + RT - 1) / RT;
+        const int nb_max = (256 - 2 * kwa - RU * (G - 1) * P.skew) / RT;
+        if (nb_max < 1) continue;
+        // aim at <= 256 items per tile and a box of at most 256 columns
+        int nb_want = 256 / G;
+        if (nb_want > nb_max) nb_want = nb_max;
+        if (nb_want < 1) nb_want = 1;
+        nchunks = (nblk_total + nb_want - 1) / nb_want;
+        NBc = (nblk_total + nchunks - 1) / nchunks;
+        IC = RT * NBc + RU * (G - 1) * P.skew + 2 * kwa;
+        IR = TR + K->kh - 1;
+        if (IR > 256 || IC > 256) continue;
+        threads = round_up(G * NBc, 32);
+        if (threads > 256) threads = 256;
+        if (threads < 64) threads = 64;
+        VQ = (IC / 4 + 1) | 1;
+        NW = (IC + 31) / 32 + 3;
+        size_t o = (size_t)IC * IR * sizeof(float);
+        o = (o + 15) / 16 * 16;
+        P.off_V = (int)o;
+        o += (size_t)TR * 4 * VQ * sizeof(float2);
+        P.off_Vm = (int)o;
+        if (opts->has_mask) o += (size_t)TR * 4 * VQ;
+        o = (o + 15) / 16 * 16;
+        P.off_bits = (int)o;
+        if (opts->has_mask) o += (size_t)IR * NW * sizeof(uint32_t);
+        o = (o + 15) / 16 * 16;
+        P.off_K = (int)o;
+        o += fbytes;
+        P.off_D = (int)o;
+        o += (size_t)P.n_dtab * sizeof(double);
+        o = (o + 15) / 16 * 16;
+        P.off_acc = (int)o;
+        o += (size_t)RU * RT * threads * sizeof(float);
+        P.off_red = (int)o;
+        o += 64 * sizeof(float);
+        P.off_bar = (int)o;
+        o += 16;
+        smem = o;
+        if (smem <= 110 * 1024 || (TR == RU && smem <= 227 * 1024)) break;
+    }
+    P.TR = TR;
+    P.G = TR / RU;
+    P.NBc = NBc;
+    P.nchunks = nchunks;
+    P.IC = IC;
+    P.IR = IR;
+    P.VQ = VQ;
+    P.NW = NW;
+    const int nrb = (nrows_out + TR - 1) / TR;
+    const long long grid_ll = (long long)nrb * nchunks;
+    if (grid_ll >= (1ll << 31)) {
+        free(hk);
+        set_error("grid too large");
+        return CS_ERR_INVALID;
+    }
+
+    // ---- output -----------------------------------------------------------------
+    P.osy = opts->out_row_shift;
+    P.osx = opts->out_col_shift;
+    P.out = d_out;
+    P.nobs = d_nobs;
+    P.out_pitch = Lo->pitch;
+    P.out_dlo = Lo->dense ? 0 : Lo->dlo;
+    {
+        bool ok = oy0 - P.osy >= 0 && ox0 - P.osx >= 0 && Lo->rows >= oy1 - P.osy &&
+                  Lo->cols >= ox1 - P.osx;
+        const int sh = P.osx - P.osy;
+        // output pixel (y, x) = (Y - osy, X - osx); its diagonal is d - (osx - osy)
+        if (ok && !Lo->dense) ok = Lo->dlo <= odlo - sh && Lo->dhi >= odhi - sh;
+        if (!ok) {
+            free(hk);
+            set_error("output image does not cover scores on diagonals [%d,%d]", odlo - sh,
+                      odhi - sh);
+            return CS_ERR_INVALID;
+        }
+    }
+
+    KtabRing &ring = g_ring;
     const int slot = ring.next;
     ring.next = (ring.next + 1) % 8;
     if (ring.cap[slot] < kbytes) {
         if (ring.buf[slot]) cudaFree(ring.buf[slot]);
         ring.buf[slot] = nullptr;
         ring.cap[slot] = 0;
-        CS_CUDA(cudaMalloc(&ring.buf[slot], kbytes));
+        if (cudaMalloc(&ring.buf[slot], kbytes) != cudaSuccess) {
+            free(hk);
+            set_error("cudaMalloc of the kernel tables failed");
+            return CS_ERR_NOMEM;
+        }
         ring.cap[slot] = kbytes;
     }
     // pageable source: the copy is staged by the runtime before the call returns
     cudaError_t ce = cudaMemcpyAsync(ring.buf[slot], hk, kbytes, cudaMemcpyHostToDevice, st);
     free(hk);
     CS_CUDA(ce);
-    P.kmat = ring.buf[slot];
+    P.ftab = (const float *)ring.buf[slot];
+    P.dtab = (const double *)((const unsigned char *)ring.buf[slot] + fbytes);
     P.q = (double)qf;
     P.sumKp = sumKp;
     P.sumKp2 = sumKp2;
-    P.qm = (double)qmf;
-    P.qm2 = (double)qm2f;
     P.ksum = K->k_sum;
     P.k2sum = K->k2_sum;
     P.kmean = K->k_mean;
@@ -735,6 +853,6 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
         }
     }
     if (opts->has_mask)
-        return launch_mask<true>(K->kw, tmap, P, (int)grid_ll, smem, st);
-    return launch_mask<false>(K->kw, tmap, P, (int)grid_ll, smem, st);
+        return launch_mask<true>(K->kw, tmap, P, (int)grid_ll, threads, smem, st);
+    return launch_mask<false>(K->kw, tmap, P, (int)grid_ll, threads, smem, st);
 }

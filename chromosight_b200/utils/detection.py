@@ -145,6 +145,11 @@ def _result_to_csr(res, shape, pval):
     indptr_o = _view(owner, res.indptr, C.c_int64, np.int64, shape[0] + 1)
     idx = _view(owner, res.indices, C.c_int32, np.int32, n)
     val = _view(owner, res.data, C.c_double, np.float64, n)
+    # scipy wants one index dtype for both structure arrays
+    if n < 2 ** 31:
+        indptr_o = indptr_o.astype(np.int32)
+    else:
+        idx = idx.astype(np.int64)
     corr = sp.csr_matrix(shape, dtype=np.float64)
     corr.indptr, corr.indices, corr.data = indptr_o, idx, val
     pvals = None
@@ -153,6 +158,10 @@ def _result_to_csr(res, shape, pval):
         # own structure arrays: callers compact the two matrices independently (det:267)
         p_indptr = _view(owner, res.p_indptr, C.c_int64, np.int64, shape[0] + 1)
         p_idx = _view(owner, res.p_indices, C.c_int32, np.int32, n)
+        if n < 2 ** 31:
+            p_indptr = p_indptr.astype(np.int32)
+        else:
+            p_idx = p_idx.astype(np.int64)
         pvals = sp.csr_matrix(shape, dtype=np.float64)
         pvals.indptr, pvals.indices, pvals.data = p_indptr, p_idx, pv
     return corr, pvals
