@@ -46,6 +46,7 @@ class PearsonOpts(C.Structure):
         ("tile_rows", C.c_int32),
         ("out_row_shift", C.c_int32),
         ("out_col_shift", C.c_int32),
+        ("strip_dlo", C.c_int32), ("strip_dhi", C.c_int32),
     ]
 
 

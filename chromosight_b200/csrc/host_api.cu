@@ -360,6 +360,14 @@ extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
     po.nobs_full = s->want_nobs ? 1 : 0;
     po.out_row_shift = s->pr;
     po.out_col_shift = s->pc;
+    po.strip_dlo = 0;
+    po.strip_dhi = -1;
+    if (a.has_mask && a.full && a.sym_upper) {
+        // nan_subdiag (image.cu) blanks the big_k diagonals below the main one (pre:483-497)
+        const int big_k = K.kh > K.kw ? K.kh : K.kw;
+        po.strip_dlo = -big_k;
+        po.strip_dhi = -1;
+    }
     CS_CUDA(cudaEventRecord(s->ev[3], st));
     rc = cs_pearson_f32(&s->Li, (const float *)s->img.p, &K, &po, s->oy0, s->oy1, s->ox0, s->ox1,
                         s->od_lo, s->od_hi, &s->Lo, (float *)s->out.p,

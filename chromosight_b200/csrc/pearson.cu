@@ -45,8 +45,9 @@ struct PearsonParams {
     const float *ftab;
     const double *dtab;
     int n_ftab, n_dtab;
-    double q, sumKp, sumKp2, ksum, k2sum, kmean, kstd, thr;
+    double q, sumKp, sumKp2, ksum, k2sum, kmean, kstd, thr, invN, vK0;
     int min_present, kmean_zero, has_mask, raw_xcorr, nobs_full;
+    int sdlo, sdhi, st_base, st_n;  // declared-missing diagonal strip and its tables
     // shared memory carve-up (bytes)
     int off_V, off_Vm, off_bits, off_K, off_D, off_acc, off_red, off_bar;
 };
@@ -116,59 +117,58 @@ constexpr double kAmpLimit2 = 9.0;
 //   h1, h2    : sum S', sum S'^2 over the N window pixels (missing pixels count as S = 0)
 //   s3        : sum S' * K'
 //   sKm, sKm2 : sums of the mask kernels (K and K^2) over the missing pixels
+//   inv_np    : table of 1 / npres
+// `redo` is set when the window is too ill-conditioned for the float32 sums.
 template <bool MASK>
-__device__ __forceinline__ float score_from_sums(const PearsonParams &P, double p, double h1, double h2,
-                                              int nmiss, double s3, double sKm, double sKm2,
-                                              int &nobs, double &amp2) {
-    const double dN = (double)P.N;
-    const double invN = 1.0 / dN;
+__device__ __forceinline__ float score_from_sums(const PearsonParams &P, const double *inv_np,
+                                                 double p, double h1, double h2, int nmiss,
+                                                 double s3, double sKm, double sKm2, int &nobs,
+                                                 bool &redo) {
+    const double invN = P.invN;
     const double m1 = h1 * invN;
     double A1 = m1 + p;
-    double A2 = h2 * invN + 2.0 * p * m1 + p * p;
-    double A3 = (s3 + P.q * h1 + p * P.sumKp) * invN + p * P.q;
+    double A2 = fma(h2, invN, fma(2.0 * p, m1, p * p));
+    double A3 = fma(s3 + fma(P.q, h1, p * P.sumKp), invN, p * P.q);
     nobs = P.N;
-    amp2 = 0.0;
-    if (P.raw_xcorr) return (float)thr0(A3 * dN, P.thr);
+    redo = false;
+    if (P.raw_xcorr) return (float)thr0(A3 * (double)P.N, P.thr);
     A1 = thr0(A1, P.thr);
     A2 = thr0(A2, P.thr);
     A3 = thr0(A3, P.thr);
-    double cov, den2, f = 1.0;
+    double cov, den2, f2 = 1.0;
     bool ok = true;
-    if (!MASK) {
-        const double vS = A2 - A1 * A1;
-        cov = A3 - A1 * P.kmean;
-        den2 = vS * P.kstd * P.kstd;
-        ok = vS >= 0.0;
-    } else if (nmiss == 0) {
-        const double vS = A2 - A1 * A1;
-        const double k2mean = P.k2sum * invN;
-        cov = A3 - A1 * P.kmean;
-        den2 = vS * (k2mean - P.kmean * P.kmean);
+    if (!MASK || nmiss == 0) {
+        const double vS = fma(-A1, A1, A2);
+        cov = fma(-A1, P.kmean, A3);
+        den2 = vS * P.vK0;
+        if (!MASK) ok = vS >= 0.0;
     } else {
         const int npres = P.N - nmiss;
-        f = dN / (double)npres;
+        const double inv = inv_np[npres];
+        const double f = (double)P.N * inv;
+        f2 = f * f;
         sKm = thr0(sKm, P.thr);
         sKm2 = thr0(sKm2, P.thr);
-        const double mK = (P.ksum - sKm) / (double)npres;
-        const double m2K = (P.k2sum - sKm2) / (double)npres;
+        const double mK = (P.ksum - sKm) * inv;
+        const double m2K = (P.k2sum - sKm2) * inv;
         const double mS = A1 * f;
-        const double vS = A2 * f - mS * mS;
-        cov = (A3 - A1 * mK) * f;
-        den2 = vS * (m2K - mK * mK);
+        const double vS = fma(A2, f, -mS * mS);
+        cov = fma(-A1, mK, A3) * f;
+        den2 = vS * fma(-mK, mK, m2K);
         ok = (npres > 0) && (npres >= P.min_present) && !P.kmean_zero;
         if (P.nobs_full && npres != 0) nobs = npres;
     }
     // det:1066,1088-1091: denom = sqrt(den2); |denom| < 1e-10 or NaN -> 0
     float r = 0.f;
     if (ok && den2 >= 1e-20 && den2 < 1e300) {
-        amp2 = (h2 * P.sumKp2 * invN * invN) * f * f / den2;
+        redo = (h2 * P.sumKp2 * invN * invN) * f2 > kAmpLimit2 * den2;
         r = (float)cov * rsqrtf((float)den2);
         if (!(fabsf(r) <= 3.0e38f)) r = 0.f;
         r = fminf(1.f, fmaxf(-1.f, r));
     } else if (ok && A2 != 0.0 && den2 < 1e-20) {
         // a non-zero window whose variance vanished: exactly flat, or flat up to the
         // float32 rounding of the column sums -- let the float64 pass decide
-        amp2 = 1e300;
+        redo = true;
     }
     return r;
 }
@@ -296,6 +296,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 if (!inside) v = 0.f;
                 bool miss = false;
                 if (MASK) {
+                    if (d >= P.sdlo && d <= P.sdhi) v = 0.f;  // counted analytically
                     miss = !(v == v);
                     const unsigned word = __ballot_sync(0xffffffffu, miss);
                     if (lane == 0) bits[iy * NW + (cb >> 5)] = word;
@@ -351,21 +352,29 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         return;
     }
 
-    // double tables (mask branch): prefix sums of the mask kernels along rows, column sums
-    const double *PK = Dt;                        // [KH][KW + 1]
-    const double *PK2 = Dt + KH * (KW + 1);       // [KH][KW + 1]
-    const double *Kcol = Dt + 2 * KH * (KW + 1);  // [KW]
-    const double *K2col = Kcol + KW;              // [KW]
+    // double tables: 1/npres, then (mask branch) prefix sums of the mask kernels along rows,
+    // column sums, and the sums over the declared-missing strip per output diagonal
+    const double *inv_np = Dt;                          // [N + 1]
+    const double *PK = Dt + (P.N + 1);                  // [KH][KW + 1]
+    const double *PK2 = PK + KH * (KW + 1);             // [KH][KW + 1]
+    const double *Kcol = PK2 + KH * (KW + 1);           // [KW]
+    const double *K2col = Kcol + KW;                    // [KW]
+    const double *StK = K2col + KW;                     // [st_n]
+    const double *StK2 = StK + P.st_n;                  // [st_n]
+    const double *StC = StK2 + P.st_n;                  // [st_n]
 
     // ---- main loop + epilogue -----------------------------------------------------------
-    for (int item = tid; item < nitems; item += nthr) {
-        const int g = item / P.NBc, m = item - g * P.NBc;
+    // every lane runs every loop (work is predicated): the epilogue contains warp-wide steps
+    for (int base = 0; base < nitems; base += nthr) {
+        const int item = base + tid;
+        const int g = item < nitems ? item / P.NBc : 0;
+        const int m = item < nitems ? item - g * P.NBc : 0;
         const int Xp0 = xb + RU * g * P.skew + RT * m;  // X' of output column t = 0
         const int cxa = RU * g * P.skew + RT * m;       // aligned tile column of x[0]
         const int Yg = Y0 + RU * g;
-        // skip blocks without any valid output pixel
-        {
-            bool any = false;
+        // blocks without any valid output pixel are skipped
+        bool any = false;
+        if (item < nitems) {
             for (int u = 0; u < RU; ++u) {
                 const int Y = Yg + u;
                 if (Y >= P.oy1) continue;
@@ -373,78 +382,75 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 const int Xa = Xp0 + P.dlo;
                 if (Xa + RT - 1 >= Xlo && Xa <= Xhi) any = true;
             }
-            if (!any) continue;
         }
-
-        unsigned long long acc[RU][RT / 2];
+        float *myacc = accS + tid;
+        if (any) {
+            unsigned long long acc[RU][RT / 2];
 #pragma unroll
-        for (int u = 0; u < RU; ++u)
+            for (int u = 0; u < RU; ++u)
 #pragma unroll
-            for (int t = 0; t < RT / 2; ++t) acc[u][t] = 0ull;
+                for (int t = 0; t < RT / 2; ++t) acc[u][t] = 0ull;
 
-        const int nrow = KH + RU - 1;
+            const int nrow = KH + RU - 1;
 #pragma unroll 1
-        for (int iy = 0; iy < nrow; ++iy) {
-            const ulonglong2 *rp =
-                reinterpret_cast<const ulonglong2 *>(tile + (RU * g + iy) * IC + cxa);
-            // xe[q] = (x[2q], x[2q+1]), xo[q] = (x[2q+1], x[2q+2])
-            unsigned long long xe[2 * NQ], xo[2 * NQ];
+            for (int iy = 0; iy < nrow; ++iy) {
+                const ulonglong2 *rp =
+                    reinterpret_cast<const ulonglong2 *>(tile + (RU * g + iy) * IC + cxa);
+                // xe[q] = (x[2q], x[2q+1]), xo[q] = (x[2q+1], x[2q+2])
+                unsigned long long xe[2 * NQ], xo[2 * NQ];
 #pragma unroll
-            for (int qd = 0; qd < NQ; ++qd) {
-                const ulonglong2 v = rp[qd];
-                xe[2 * qd] = v.x;
-                xe[2 * qd + 1] = v.y;
-            }
-#pragma unroll
-            for (int qd = 0; qd < 2 * NQ - 1; ++qd) {
-                float a0, a1, b0, b1;
-                unpack2(xe[qd], a0, a1);
-                unpack2(xe[qd + 1], b0, b1);
-                xo[qd] = pack2(a1, b0);
-            }
-            xo[2 * NQ - 1] = 0ull;
-#pragma unroll
-            for (int u = 0; u < RU; ++u) {
-                const int i = iy - u;
-                if (i < 0 || i >= KH) continue;  // uniform across the block
-                const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(Kdup + i * KWP);
-                unsigned long long kd[KWP];
-#pragma unroll
-                for (int qd = 0; qd < KWP / 2; ++qd) {
-                    const ulonglong2 v = kp[qd];
-                    kd[2 * qd] = v.x;
-                    kd[2 * qd + 1] = v.y;
+                for (int qd = 0; qd < NQ; ++qd) {
+                    const ulonglong2 v = rp[qd];
+                    xe[2 * qd] = v.x;
+                    xe[2 * qd + 1] = v.y;
                 }
 #pragma unroll
-                for (int j = 0; j < KW; ++j) {
+                for (int qd = 0; qd < 2 * NQ - 1; ++qd) {
+                    float a0, a1, b0, b1;
+                    unpack2(xe[qd], a0, a1);
+                    unpack2(xe[qd + 1], b0, b1);
+                    xo[qd] = pack2(a1, b0);
+                }
+                xo[2 * NQ - 1] = 0ull;
 #pragma unroll
-                    for (int tp = 0; tp < RT / 2; ++tp) {
-                        const int e = off + 2 * tp + j;  // compile-time
-                        fma2(acc[u][tp], (e & 1) ? xo[e >> 1] : xe[e >> 1], kd[j]);
+                for (int u = 0; u < RU; ++u) {
+                    const int i = iy - u;
+                    if (i < 0 || i >= KH) continue;  // uniform across the block
+                    const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(Kdup + i * KWP);
+                    unsigned long long kd[KWP];
+#pragma unroll
+                    for (int qd = 0; qd < KWP / 2; ++qd) {
+                        const ulonglong2 v = kp[qd];
+                        kd[2 * qd] = v.x;
+                        kd[2 * qd + 1] = v.y;
+                    }
+#pragma unroll
+                    for (int j = 0; j < KW; ++j) {
+#pragma unroll
+                        for (int tp = 0; tp < RT / 2; ++tp) {
+                            const int e = off + 2 * tp + j;  // compile-time
+                            fma2(acc[u][tp], (e & 1) ? xo[e >> 1] : xe[e >> 1], kd[j]);
+                        }
                     }
                 }
             }
+            // park the accumulators in shared memory: the epilogue runs as compact loops
+#pragma unroll
+            for (int u = 0; u < RU; ++u)
+#pragma unroll
+                for (int tp = 0; tp < RT / 2; ++tp) {
+                    float lo, hi;
+                    unpack2(acc[u][tp], lo, hi);
+                    myacc[(u * RT + 2 * tp) * nthr] = lo;
+                    myacc[(u * RT + 2 * tp + 1) * nthr] = hi;
+                }
         }
-
-        // park the accumulators in shared memory: the epilogue runs as compact loops
-        float *myacc = accS + tid;
-#pragma unroll
-        for (int u = 0; u < RU; ++u)
-#pragma unroll
-            for (int tp = 0; tp < RT / 2; ++tp) {
-                float lo, hi;
-                unpack2(acc[u][tp], lo, hi);
-                myacc[(u * RT + 2 * tp) * nthr] = lo;
-                myacc[(u * RT + 2 * tp + 1) * nthr] = hi;
-            }
 
         // footprint mask summary: columns missing on every footprint row, rows with other
         // missing pixels
         const int fc0 = cxa + off;  // tile column of footprint column 0
-        unsigned long long colfull = 0ull;
-        unsigned long long rowsel = 0ull;
-        bool anymiss = false;
-        if (MASK) {
+        unsigned long long colfull = 0ull, rowsel = 0ull;
+        if (MASK && any) {
             constexpr unsigned long long FWMASK = (XW >= 64) ? ~0ull : ((1ull << XW) - 1ull);
             unsigned long long band = FWMASK, bor = 0ull;
             const int fr = KH + RU - 1;
@@ -453,8 +459,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 band &= b;
                 bor |= b;
             }
-            anymiss = bor != 0ull;
-            if (anymiss) {
+            if (bor != 0ull) {
                 colfull = band;
                 if (bor & ~band)
                     for (int r = 0; r < fr; ++r) {
@@ -465,40 +470,51 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             }
         }
 
+        // V planes of this block: column c of the footprint is entry (c >> 2) of plane (c & 3)
         const int qbase = cxa >> 2;
 #pragma unroll 1
         for (int u = 0; u < RU; ++u) {
             const int Y = Yg + u;
-            if (Y >= P.oy1) break;
-            const float2 *Vr = V + (RU * g + u) * 4 * VQ;
-            const unsigned char *Vmr = Vm + (RU * g + u) * 4 * VQ;
+            const bool rowok = any && Y < P.oy1;
+            const float2 *Vr = V + (RU * g + u) * 4 * VQ + qbase;
+            const unsigned char *Vmr = Vm + (RU * g + u) * 4 * VQ + qbase;
             double h1 = 0.0, h2 = 0.0;
             int hm = 0;
-#pragma unroll 1
-            for (int e = off; e < off + KW; ++e) {
-                const int s = (e & 3) * VQ + qbase + (e >> 2);
-                const float2 v = Vr[s];
-                h1 += (double)v.x;
-                h2 += (double)v.y;
-                if (MASK) hm += Vmr[s];
+            if (rowok) {
+#pragma unroll
+                for (int e = off; e < off + KW; ++e) {
+                    const float2 v = Vr[(e & 3) * VQ + (e >> 2)];
+                    h1 += (double)v.x;
+                    h2 += (double)v.y;
+                    if (MASK) hm += Vmr[(e & 3) * VQ + (e >> 2)];
+                }
             }
 #pragma unroll 1
             for (int t = 0; t < RT; ++t) {
-                if (t > 0) {
+                if (t > 0 && rowok) {
                     const int e0 = off + t - 1, e1 = off + t - 1 + KW;
-                    const int s0 = (e0 & 3) * VQ + qbase + (e0 >> 2);
-                    const int s1 = (e1 & 3) * VQ + qbase + (e1 >> 2);
-                    const float2 a = Vr[s0], b = Vr[s1];
+                    const float2 a = Vr[(e0 & 3) * VQ + (e0 >> 2)], b = Vr[(e1 & 3) * VQ + (e1 >> 2)];
                     h1 += (double)b.x - (double)a.x;
                     h2 += (double)b.y - (double)a.y;
-                    if (MASK) hm += (int)Vmr[s1] - (int)Vmr[s0];
+                    if (MASK)
+                        hm += (int)Vmr[(e1 & 3) * VQ + (e1 >> 2)] - (int)Vmr[(e0 & 3) * VQ + (e0 >> 2)];
                 }
                 const int X = Xp0 + t + P.dlo;
                 const int d = X - Y;
-                if (X < P.ox0 || X >= P.ox1 || d < P.odlo || d > P.odhi) continue;
-                const int nmiss = MASK ? hm : 0;
+                const bool wok = rowok && X >= P.ox0 && X < P.ox1 && d >= P.odlo && d <= P.odhi;
+                int nmiss = 0;
                 double sKm = 0.0, sKm2 = 0.0;
-                if (MASK && nmiss > 0) {
+                if (MASK && wok) {
+                    nmiss = hm;
+                    // the declared-missing diagonal strip: a function of the window's diagonal
+                    const unsigned sd = (unsigned)(d - P.st_base);
+                    if (sd < (unsigned)P.st_n) {
+                        nmiss += (int)StC[sd];
+                        sKm = StK[sd];
+                        sKm2 = StK2[sd];
+                    }
+                }
+                if (MASK && wok && hm > 0) {
                     // columns missing over the whole footprint: whole kernel columns
                     const unsigned cbw = (unsigned)(colfull >> t) & KWMASK;
                     for (unsigned c = cbw; c; c &= c - 1) {
@@ -524,32 +540,44 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                         }
                     }
                 }
-                double s3 = (double)myacc[(u * RT + t) * nthr];
                 int nobs = P.N;
-                double amp2 = 0.0;
-                float r = score_from_sums<MASK>(P, p, h1, h2, nmiss, s3, sKm, sKm2, nobs, amp2);
-                if (amp2 > kAmpLimit2) {
-                    // ill-conditioned window (flat signal or mostly missing): redo the window
-                    // sums in float64 from the tile (the V entries were rounded to float32)
-                    s3 = 0.0;
-                    double g1 = 0.0, g2 = 0.0;
-                    const float *wp = tile + (RU * g + u) * IC + fc0 + t;
-                    for (int i = 0; i < KH; ++i) {
-                        const float *wr = wp + i * IC;
-                        const float2 *kr = Kdup + i * KWP;
-                        for (int j = 0; j < KW; ++j) {
-                            const double sv = (double)wr[j];
-                            g1 += sv;
-                            g2 = fma(sv, sv, g2);
-                            s3 = fma(sv, (double)kr[j].x, s3);
-                        }
+                bool redo = false;
+                float r = 0.f;
+                if (wok)
+                    r = score_from_sums<MASK>(P, inv_np, p, h1, h2, nmiss,
+                                              (double)myacc[(u * RT + t) * nthr], sKm, sKm2, nobs,
+                                              redo);
+                // ill-conditioned windows (flat signal or mostly missing): the warp redoes the
+                // window sums in float64 from the tile, 32 pixels at a time
+                const int woff = (RU * g + u) * IC + fc0 + t;
+                for (unsigned todo = __ballot_sync(0xffffffffu, redo); todo; todo &= todo - 1) {
+                    const int src = __ffs(todo) - 1;
+                    const float *wp = tile + __shfl_sync(0xffffffffu, woff, src);
+                    double g1 = 0.0, g2 = 0.0, s3 = 0.0;
+                    for (int idx = lane; idx < KH * KW; idx += 32) {
+                        const int i = idx / KW, j = idx - i * KW;
+                        const double sv = (double)wp[i * IC + j];
+                        g1 += sv;
+                        g2 = fma(sv, sv, g2);
+                        s3 = fma(sv, (double)Kdup[i * KWP + j].x, s3);
                     }
-                    r = score_from_sums<MASK>(P, p, g1, g2, nmiss, s3, sKm, sKm2, nobs, amp2);
+                    for (int o = 16; o > 0; o >>= 1) {
+                        g1 += __shfl_xor_sync(0xffffffffu, g1, o);
+                        g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+                        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+                    }
+                    if (lane == src) {
+                        bool again;
+                        r = score_from_sums<MASK>(P, inv_np, p, g1, g2, nmiss, s3, sKm, sKm2, nobs,
+                                                  again);
+                    }
                 }
-                const long long oi =
-                    (long long)(Y - P.osy) * P.out_pitch + ((X - P.osx) - P.out_dlo);
-                P.out[oi] = r;
-                if (P.nobs) P.nobs[oi] = (unsigned short)nobs;
+                if (wok) {
+                    const long long oi =
+                        (long long)(Y - P.osy) * P.out_pitch + ((X - P.osx) - P.out_dlo);
+                    P.out[oi] = r;
+                    if (P.nobs) P.nobs[oi] = (unsigned short)nobs;
+                }
             }
         }
     }
@@ -667,7 +695,18 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
     qd /= nk;
     const float qf = (float)qd;
     P.n_ftab = 2 * K->kh * P.KWP;
-    P.n_dtab = opts->has_mask ? (2 * K->kh * (K->kw + 1) + 2 * K->kw) : 0;
+    // declared-missing strip: tables over the output diagonals whose windows touch it
+    P.sdlo = 0;
+    P.sdhi = -1;
+    P.st_base = 0;
+    P.st_n = 0;
+    if (opts->has_mask && opts->strip_dhi >= opts->strip_dlo) {
+        P.sdlo = opts->strip_dlo;
+        P.sdhi = opts->strip_dhi;
+        P.st_base = P.sdlo - (kh + kw);
+        P.st_n = (P.sdhi + (kh + kw)) - P.st_base + 1;
+    }
+    P.n_dtab = (P.N + 1) + (opts->has_mask ? (2 * K->kh * (K->kw + 1) + 2 * K->kw + 3 * P.st_n) : 0);
     if (opts->has_mask) CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
     const size_t fbytes = (size_t)round_up(P.n_ftab, 4) * sizeof(float);
     const size_t kbytes = fbytes + (size_t)P.n_dtab * sizeof(double);
@@ -685,9 +724,25 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
             sumKp += (double)v;
             sumKp2 += (double)v * (double)v;
         }
+    hd[0] = 0.0;
+    for (int i = 1; i <= P.N; ++i) hd[i] = 1.0 / (double)i;
     if (opts->has_mask) {
-        double *pk = hd, *pk2 = hd + K->kh * (K->kw + 1);
-        double *kc = hd + 2 * K->kh * (K->kw + 1), *k2c = kc + K->kw;
+        double *pk = hd + (P.N + 1), *pk2 = pk + K->kh * (K->kw + 1);
+        double *kc = pk2 + K->kh * (K->kw + 1), *k2c = kc + K->kw;
+        double *stk = k2c + K->kw, *stk2 = stk + P.st_n, *stc = stk2 + P.st_n;
+        // window centred on diagonal d: tap (i, j) sits on diagonal d + (j - kw) - (i - kh)
+        for (int sd = 0; sd < P.st_n; ++sd) {
+            const int d = P.st_base + sd;
+            for (int i = 0; i < K->kh; ++i)
+                for (int j = 0; j < K->kw; ++j) {
+                    const int dt = d + (j - kw) - (i - kh);
+                    if (dt >= P.sdlo && dt <= P.sdhi) {
+                        stk[sd] += K->k_mask[i * K->kw + j];
+                        stk2[sd] += K->k2_mask[i * K->kw + j];
+                        stc[sd] += 1.0;
+                    }
+                }
+        }
         for (int i = 0; i < K->kh; ++i) {
             double a = 0.0, b = 0.0;
             pk[i * (K->kw + 1)] = 0.0;
@@ -826,6 +881,9 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
     P.kmean = K->k_mean;
     P.kstd = K->k_std;
     P.thr = opts->xcorr_threshold;
+    P.invN = 1.0 / (double)P.N;
+    P.vK0 = opts->has_mask ? (K->k2_sum / (double)P.N - K->k_mean * K->k_mean)
+                           : K->k_std * K->k_std;
     P.min_present = (int)((1.0 - opts->missing_tol) * (double)P.N);
     P.kmean_zero = (K->k_mean == 0.0);
     P.has_mask = opts->has_mask;

@@ -109,6 +109,11 @@ typedef struct cs_pearson_opts {
     int32_t tile_rows;       /* 0 = auto */
     int32_t out_row_shift;   /* score of window (Y, X) is written to pixel           */
     int32_t out_col_shift;   /* (Y - out_row_shift, X - out_col_shift) of the output */
+    /* Diagonals strip_dlo <= X - Y <= strip_dhi of the image that the caller declares
+     * entirely missing (the sub-diagonals frame_missing_mask adds for sym_upper,
+     * pre:483-497); handled analytically instead of pixel by pixel.  Empty when
+     * strip_dhi < strip_dlo. */
+    int32_t strip_dlo, strip_dhi;
 } cs_pearson_opts;
 
 int cs_pearson_f32(const cs_layout *Limg, const float *d_img,
