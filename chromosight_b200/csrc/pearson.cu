@@ -12,19 +12,20 @@
 //            aliases -> 0), NaN sentinels -> bit array (warp ballot) + value 0, shift by
 //            the pivot, vertical sliding sums over KH rows in float64 (sum S', sum S'^2,
 //            missing count) -> V;
-//   main     each thread owns an 8x4 block of windows: per input row one conflict-free
-//            LDS.128 sweep of its 20-pixel segment feeds up to 8 x 4 x KW FMAs issued as
+//   main     each thread owns a 4x4 block of windows: per input row one conflict-free
+//            LDS.128 sweep of its 20-pixel segment feeds up to 4 x 4 x KW FMAs issued as
 //            packed fma.rn.f32x2 (two windows per instruction, kernel taps pre-duplicated
 //            in shared memory) -- no mask work in this loop;
 //   epilogue per window: horizontal KW-sums of V, the masked kernel sums from the bit
-//            array (full columns / row runs through prefix tables of K and K^2, float64,
-//            exact), the reference's formulas in float64, one float32 score.
+//            array (missing pixels of a footprint grouped into rectangles, summed through
+//            2-D prefix tables of K and K^2 in float64, exact), the reference's formulas in
+//            float64, one float32 score.
 // No tensor cores: this is a CUDA-core stencil (BASELINE.json north_star).
 #include "common.cuh"
 
 namespace cs {
 
-constexpr int RU = 8;  // window rows per thread
+constexpr int RU = 4;  // window rows per thread
 constexpr int RT = 4;  // window columns per thread
 
 struct PearsonParams {
@@ -49,7 +50,7 @@ struct PearsonParams {
     int min_present, kmean_zero, has_mask, raw_xcorr, nobs_full;
     int sdlo, sdhi, st_base, st_n;  // declared-missing diagonal strip and its tables
     // shared memory carve-up (bytes)
-    int off_V, off_Vm, off_bits, off_K, off_D, off_acc, off_red, off_bar;
+    int off_V, off_Vm, off_bits, off_K, off_D, off_acc, off_grp, off_red, off_bar;
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -117,11 +118,9 @@ constexpr double kAmpLimit2 = 9.0;
 //   h1, h2    : sum S', sum S'^2 over the N window pixels (missing pixels count as S = 0)
 //   s3        : sum S' * K'
 //   sKm, sKm2 : sums of the mask kernels (K and K^2) over the missing pixels
-//   inv_np    : table of 1 / npres
 // `redo` is set when the window is too ill-conditioned for the float32 sums.
 template <bool MASK>
-__device__ __forceinline__ float score_from_sums(const PearsonParams &P, const double *inv_np,
-                                                 double p, double h1, double h2, int nmiss,
+__device__ __forceinline__ float score_from_sums(const PearsonParams &P, double p, double h1, double h2, int nmiss,
                                                  double s3, double sKm, double sKm2, int &nobs,
                                                  bool &redo) {
     const double invN = P.invN;
@@ -144,7 +143,9 @@ __device__ __forceinline__ float score_from_sums(const PearsonParams &P, const d
         if (!MASK) ok = vS >= 0.0;
     } else {
         const int npres = P.N - nmiss;
-        const double inv = inv_np[npres];
+        // 1 / npres: float32 reciprocal + one Newton step (exact to ~1e-15)
+        double inv = (double)__frcp_rn((float)npres);
+        inv = inv * fma(-(double)npres, inv, 2.0);
         const double f = (double)P.N * inv;
         f2 = f * f;
         sKm = thr0(sKm, P.thr);
@@ -181,9 +182,27 @@ __device__ __forceinline__ unsigned long long row_bits(const uint32_t *brow, int
     return ((unsigned long long)hi << 32) | lo;
 }
 
+// Missing pixels of a window given as kernel rows [i0, i1) x the set bits of wb: add the
+// sums of the two mask kernels over them.  IK / IK2 are 2-D prefix tables,
+// IK[i][j] = sum of K[i' < i][j' < j], row pitch KW1.
+__device__ __forceinline__ void add_rects(unsigned wb, int i0, int i1, const double *IK,
+                                          const double *IK2, int KW1, double &sKm, double &sKm2) {
+    const double *t0 = IK + i0 * KW1, *t1 = IK + i1 * KW1;
+    const double *u0 = IK2 + i0 * KW1, *u1 = IK2 + i1 * KW1;
+    while (wb) {
+        const int a = __ffs(wb) - 1;
+        const int b = a + __ffs(~(wb >> a)) - 1;  // first zero above a ends the run (< 32 bits)
+        sKm += (t1[b] - t1[a]) - (t0[b] - t0[a]);
+        sKm2 += (u1[b] - u1[a]) - (u0[b] - u0[a]);
+        wb = (b >= 32) ? 0u : (wb >> b) << b;
+    }
+}
+
+constexpr int kMaxGroups = 4;  // rectangles of missing pixels per footprint kept in shared memory
+
 // ---------------------------------------------------------------- the kernel
 template <int KW, bool MASK>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     constexpr int kw = (KW - 1) / 2;
     constexpr int kwa = (kw + 3) / 4 * 4;
@@ -201,6 +220,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     const float2 *Kdup = reinterpret_cast<const float2 *>(smem + P.off_K);
     const double *Dt = reinterpret_cast<const double *>(smem + P.off_D);
     float *accS = reinterpret_cast<float *>(smem + P.off_acc);
+    unsigned long long *grpS = reinterpret_cast<unsigned long long *>(smem + P.off_grp);
     float *red = reinterpret_cast<float *>(smem + P.off_red);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + P.off_bar);
 
@@ -352,12 +372,12 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         return;
     }
 
-    // double tables: 1/npres, then (mask branch) prefix sums of the mask kernels along rows,
-    // column sums, and the sums over the declared-missing strip per output diagonal
-    const double *inv_np = Dt;                          // [N + 1]
-    const double *PK = Dt + (P.N + 1);                  // [KH][KW + 1]
-    const double *PK2 = PK + KH * (KW + 1);             // [KH][KW + 1]
-    const double *Kcol = PK2 + KH * (KW + 1);           // [KW]
+    // double tables (mask branch): 2-D prefix sums of the mask kernels, their column sums,
+    // and the sums over the declared-missing strip per output diagonal
+    constexpr int KW1 = KW + 1;
+    const double *IK = Dt;                              // [KH + 1][KW + 1]
+    const double *IK2 = IK + (KH + 1) * KW1;            // [KH + 1][KW + 1]
+    const double *Kcol = IK2 + (KH + 1) * KW1;          // [KW]
     const double *K2col = Kcol + KW;                    // [KW]
     const double *StK = K2col + KW;                     // [st_n]
     const double *StK2 = StK + P.st_n;                  // [st_n]
@@ -446,10 +466,13 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 }
         }
 
-        // footprint mask summary: columns missing on every footprint row, rows with other
-        // missing pixels
+        // footprint mask summary.  colfull: columns missing on every footprint row.  The other
+        // missing pixels: consecutive rows with the same pattern form one rectangle group
+        // (a missing row, the visible part of a missing column at the edge of the mask band,
+        // a frame margin); footprints with more groups than fit fall back to row-by-row.
         const int fc0 = cxa + off;  // tile column of footprint column 0
         unsigned long long colfull = 0ull, rowsel = 0ull;
+        int ng = 0;
         if (MASK && any) {
             constexpr unsigned long long FWMASK = (XW >= 64) ? ~0ull : ((1ull << XW) - 1ull);
             unsigned long long band = FWMASK, bor = 0ull;
@@ -461,12 +484,25 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             }
             if (bor != 0ull) {
                 colfull = band;
-                if (bor & ~band)
-                    for (int r = 0; r < fr; ++r) {
-                        const unsigned long long b =
-                            row_bits(bits + (RU * g + r) * NW, fc0) & FWMASK;
-                        if (b & ~band) rowsel |= 1ull << r;
+                if (bor & ~band) {
+                    unsigned long long prev = 0ull;
+                    int start = 0;
+                    for (int r = 0; r <= fr; ++r) {
+                        unsigned long long b = 0ull;
+                        if (r < fr) b = row_bits(bits + (RU * g + r) * NW, fc0) & FWMASK & ~band;
+                        if (b) rowsel |= 1ull << r;
+                        if (b != prev) {
+                            if (prev) {
+                                if (ng < kMaxGroups)  // pattern (< 40 bits) | first row | end row
+                                    grpS[ng * nthr + tid] = prev | ((unsigned long long)start << 40) |
+                                                            ((unsigned long long)r << 48);
+                                ++ng;
+                            }
+                            start = r;
+                            prev = b;
+                        }
                     }
+                }
             }
         }
 
@@ -522,21 +558,25 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                         sKm += Kcol[j];
                         sKm2 += K2col[j];
                     }
-                    // remaining missing pixels, row by row, as runs [a, b) of kernel taps
-                    const unsigned KHMASK = (KH >= 32) ? 0xffffffffu : ((1u << KH) - 1u);
-                    for (unsigned rs = (unsigned)(rowsel >> u) & KHMASK; rs; rs &= rs - 1) {
-                        const int i = __ffs(rs) - 1;
-                        unsigned wb = (unsigned)(row_bits(bits + (RU * g + u + i) * NW, fc0) >> t);
-                        wb &= KWMASK & ~cbw;
-                        const double *pk = PK + i * (KW + 1), *pk2 = PK2 + i * (KW + 1);
-                        while (wb) {
-                            const int a = __ffs(wb) - 1;
-                            const unsigned rest = ~(wb >> a);  // first zero above a ends the run
-                            const int len = __ffs(rest) - 1;   // rest != 0: wb has < 32 bits
-                            const int b = a + len;
-                            sKm += pk[b] - pk[a];
-                            sKm2 += pk2[b] - pk2[a];
-                            wb = (b >= 32) ? 0u : (wb >> b) << b;
+                    if (ng <= kMaxGroups) {
+                        // remaining missing pixels as rectangles: rows [i0, i1) x runs of taps
+                        for (int k = 0; k < ng; ++k) {
+                            const unsigned long long gp = grpS[k * nthr + tid];
+                            const int i0 = max((int)((gp >> 40) & 255) - u, 0);
+                            const int i1 = min((int)(gp >> 48) - u, KH);
+                            if (i0 < i1)
+                                add_rects((unsigned)(gp >> t) & KWMASK, i0, i1, IK, IK2, KW1, sKm,
+                                          sKm2);
+                        }
+                    } else {
+                        // row by row
+                        const unsigned KHMASK = (KH >= 32) ? 0xffffffffu : ((1u << KH) - 1u);
+                        for (unsigned rs = (unsigned)(rowsel >> u) & KHMASK; rs; rs &= rs - 1) {
+                            const int i = __ffs(rs) - 1;
+                            const unsigned wb =
+                                (unsigned)(row_bits(bits + (RU * g + u + i) * NW, fc0) >> t) &
+                                KWMASK & ~cbw;
+                            add_rects(wb, i, i + 1, IK, IK2, KW1, sKm, sKm2);
                         }
                     }
                 }
@@ -544,7 +584,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 bool redo = false;
                 float r = 0.f;
                 if (wok)
-                    r = score_from_sums<MASK>(P, inv_np, p, h1, h2, nmiss,
+                    r = score_from_sums<MASK>(P, p, h1, h2, nmiss,
                                               (double)myacc[(u * RT + t) * nthr], sKm, sKm2, nobs,
                                               redo);
                 // ill-conditioned windows (flat signal or mostly missing): the warp redoes the
@@ -568,7 +608,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     }
                     if (lane == src) {
                         bool again;
-                        r = score_from_sums<MASK>(P, inv_np, p, g1, g2, nmiss, s3, sKm, sKm2, nobs,
+                        r = score_from_sums<MASK>(P, p, g1, g2, nmiss, s3, sKm, sKm2, nobs,
                                                   again);
                     }
                 }
@@ -706,7 +746,7 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
         P.st_base = P.sdlo - (kh + kw);
         P.st_n = (P.sdhi + (kh + kw)) - P.st_base + 1;
     }
-    P.n_dtab = (P.N + 1) + (opts->has_mask ? (2 * K->kh * (K->kw + 1) + 2 * K->kw + 3 * P.st_n) : 0);
+    P.n_dtab = opts->has_mask ? (2 * (K->kh + 1) * (K->kw + 1) + 2 * K->kw + 3 * P.st_n) : 0;
     if (opts->has_mask) CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
     const size_t fbytes = (size_t)round_up(P.n_ftab, 4) * sizeof(float);
     const size_t kbytes = fbytes + (size_t)P.n_dtab * sizeof(double);
@@ -724,12 +764,23 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
             sumKp += (double)v;
             sumKp2 += (double)v * (double)v;
         }
-    hd[0] = 0.0;
-    for (int i = 1; i <= P.N; ++i) hd[i] = 1.0 / (double)i;
     if (opts->has_mask) {
-        double *pk = hd + (P.N + 1), *pk2 = pk + K->kh * (K->kw + 1);
-        double *kc = pk2 + K->kh * (K->kw + 1), *k2c = kc + K->kw;
+        const int kw1 = K->kw + 1;
+        double *ik = hd, *ik2 = ik + (K->kh + 1) * kw1;
+        double *kc = ik2 + (K->kh + 1) * kw1, *k2c = kc + K->kw;
         double *stk = k2c + K->kw, *stk2 = stk + P.st_n, *stc = stk2 + P.st_n;
+        // 2-D prefix tables: ik[i][j] = sum of k_mask[i' < i][j' < j]
+        for (int i = 0; i < K->kh; ++i) {
+            double a = 0.0, b = 0.0;
+            for (int j = 0; j < K->kw; ++j) {
+                a += K->k_mask[i * K->kw + j];
+                b += K->k2_mask[i * K->kw + j];
+                ik[(i + 1) * kw1 + j + 1] = ik[i * kw1 + j + 1] + a;
+                ik2[(i + 1) * kw1 + j + 1] = ik2[i * kw1 + j + 1] + b;
+                kc[j] += K->k_mask[i * K->kw + j];
+                k2c[j] += K->k2_mask[i * K->kw + j];
+            }
+        }
         // window centred on diagonal d: tap (i, j) sits on diagonal d + (j - kw) - (i - kh)
         for (int sd = 0; sd < P.st_n; ++sd) {
             const int d = P.st_base + sd;
@@ -742,19 +793,6 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
                         stc[sd] += 1.0;
                     }
                 }
-        }
-        for (int i = 0; i < K->kh; ++i) {
-            double a = 0.0, b = 0.0;
-            pk[i * (K->kw + 1)] = 0.0;
-            pk2[i * (K->kw + 1)] = 0.0;
-            for (int j = 0; j < K->kw; ++j) {
-                a += K->k_mask[i * K->kw + j];
-                b += K->k2_mask[i * K->kw + j];
-                pk[i * (K->kw + 1) + j + 1] = a;
-                pk2[i * (K->kw + 1) + j + 1] = b;
-                kc[j] += K->k_mask[i * K->kw + j];
-                k2c[j] += K->k2_mask[i * K->kw + j];
-            }
         }
     }
 
@@ -790,7 +828,7 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
         threads = round_up(G * NBc, 32);
         if (threads > 256) threads = 256;
         if (threads < 64) threads = 64;
-        VQ = (IC / 4 + 1) | 1;
+        VQ = (IC / 4) | 1;
         NW = (IC + 31) / 32 + 3;
         size_t o = (size_t)IC * IR * sizeof(float);
         o = (o + 15) / 16 * 16;
@@ -809,12 +847,15 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
         o = (o + 15) / 16 * 16;
         P.off_acc = (int)o;
         o += (size_t)RU * RT * threads * sizeof(float);
+        o = (o + 15) / 16 * 16;
+        P.off_grp = (int)o;
+        if (opts->has_mask) o += (size_t)kMaxGroups * threads * sizeof(unsigned long long);
         P.off_red = (int)o;
         o += 64 * sizeof(float);
         P.off_bar = (int)o;
         o += 16;
         smem = o;
-        if (smem <= 110 * 1024 || (TR == RU && smem <= 227 * 1024)) break;
+        if (smem <= 113 * 1024 || (TR == RU && smem <= 227 * 1024)) break;
     }
     P.TR = TR;
     P.G = TR / RU;
