@@ -226,7 +226,7 @@ class ClockSampler:
 def run_b200(a, kernel):
     import torch
     import torch.distributed as dist
-    from chromosight_b200 import _lib, synthetic
+    from chromosight_b200 import _lib, sharding, synthetic
     from chromosight_b200.session import Session
     from chromosight_b200.utils import detection as cud, preprocessing as cup
 
@@ -261,11 +261,7 @@ def run_b200(a, kernel):
         state["ncand"] = nc
         if world > 1:
             # the one collective of the path: candidate records of every sub-matrix
-            counts = torch.zeros(world, dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(counts, torch.tensor([nc], dtype=torch.int64, device=dev))
-            mx = int(counts.max().item())
-            allc = torch.empty((world, max(mx, 1), 4), dtype=torch.int32, device=dev)
-            dist.all_gather_into_tensor(allc, cand_buf[:max(mx, 1)].contiguous())
+            _, counts = sharding.gather_candidates(cand_buf, nc)
             state["gathered"] = int(counts.sum().item())
         return st
 

@@ -50,37 +50,79 @@ __global__ void count_rows(ScoreView S, const float *__restrict__ sc, int64_t *c
     if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = 0;
 }
 
-// in-place inclusive scan of a[1..n] (a[0] = 0) by a single block
-__global__ void scan_inplace(int64_t *a, int n) {
-    __shared__ long long wsum[32];
-    __shared__ long long carry_s;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    for (int base = 1; base <= n; base += blockDim.x) {
-        const int i = base + tid;
-        long long v = (i <= n) ? a[i] : 0;
-        for (int o = 1; o < 32; o <<= 1) {
-            long long t = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += t;
-        }
-        if (lane == 31) wsum[wid] = v;
-        __syncthreads();
-        if (wid == 0) {
-            long long w = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0;
-            for (int o = 1; o < 32; o <<= 1) {
-                long long t = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += t;
-            }
-            wsum[lane] = w;
-        }
-        __syncthreads();
-        const long long pre = (wid > 0 ? wsum[wid - 1] : 0) + carry_s;
-        if (i <= n) a[i] = v + pre;
-        __syncthreads();
-        if (tid == blockDim.x - 1) carry_s = v + pre;
-        __syncthreads();
+// In-place inclusive scan of a[1..n] (a[0] = 0), three launches: every block scans a chunk
+// of kScanChunk elements and records its total, one block scans the totals, every block adds
+// its offset.
+constexpr int kScanThreads = 256;
+constexpr int kScanPer = 8;
+constexpr int kScanChunk = kScanThreads * kScanPer;
+
+__device__ __forceinline__ long long block_exclusive(long long v, long long *wsum, long long &total) {
+    // exclusive prefix of v over the block (blockDim.x <= 1024); total = block sum
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    long long inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        long long w = (lane < (int)(blockDim.x >> 5)) ? wsum[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        wsum[lane] = w;
+    }
+    __syncthreads();
+    total = wsum[(blockDim.x >> 5) - 1];
+    const long long pre = (wid > 0 ? wsum[wid - 1] : 0) + inc - v;
+    __syncthreads();
+    return pre;
+}
+
+__global__ void scan_chunks(int64_t *a, int n, int64_t *totals) {
+    __shared__ long long wsum[32];
+    const long long base = 1 + (long long)blockIdx.x * kScanChunk + (long long)threadIdx.x * kScanPer;
+    long long v[kScanPer], s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) {
+        v[k] = (base + k <= n) ? a[base + k] : 0;
+        s += v[k];
+    }
+    long long total;
+    long long run = block_exclusive(s, wsum, total);
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k) {
+        run += v[k];
+        if (base + k <= n) a[base + k] = run;
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = total;
+}
+
+// exclusive scan of the chunk totals by one block
+__global__ void scan_totals(int64_t *totals, int m) {
+    __shared__ long long wsum[32];
+    long long carry = 0;
+    for (int base = 0; base < m; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const long long v = i < m ? totals[i] : 0;
+        long long total;
+        const long long pre = block_exclusive(v, wsum, total);
+        if (i < m) totals[i] = carry + pre;
+        carry += total;
+    }
+}
+
+__global__ void scan_add(int64_t *a, int n, const int64_t *totals) {
+    const long long off = totals[blockIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 0) a[0] = 0;
+    if (off == 0) return;
+    const long long base = 1 + (long long)blockIdx.x * kScanChunk + (long long)threadIdx.x * kScanPer;
+#pragma unroll
+    for (int k = 0; k < kScanPer; ++k)
+        if (base + k <= n) a[base + k] += off;
 }
 
 __global__ void emit_rows(ScoreView S, const float *__restrict__ sc,
@@ -173,6 +215,10 @@ static ScoreView make_view(const cs_layout *L, int dmin, int dmax) {
 
 using namespace cs;
 
+extern "C" int64_t cs_scan_scratch(int32_t rows) {
+    return (int64_t)((rows + cs::kScanChunk - 1) / cs::kScanChunk) + 1;
+}
+
 extern "C" int cs_scores_count(const cs_layout *Lo, const float *d_out, int32_t dmin, int32_t dmax,
                                int64_t *d_indptr, int64_t *nnz_host, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -182,8 +228,18 @@ extern "C" int cs_scores_count(const cs_layout *Lo, const float *d_out, int32_t 
     if (grid > 148 * 16) grid = 148 * 16;
     count_rows<<<grid, 256, 0, st>>>(S, d_out, d_indptr);
     CS_LAUNCHED();
-    scan_inplace<<<1, 1024, 0, st>>>(d_indptr, S.rows);
-    CS_LAUNCHED();
+    {
+        // chunk totals live behind the row pointers (the caller sizes d_indptr to rows + 1 +
+        // cs_scan_scratch(rows) elements)
+        const int nchunk = (S.rows + kScanChunk - 1) / kScanChunk;
+        int64_t *totals = d_indptr + (size_t)S.rows + 1;
+        scan_chunks<<<nchunk, kScanThreads, 0, st>>>(d_indptr, S.rows, totals);
+        CS_LAUNCHED();
+        scan_totals<<<1, 1024, 0, st>>>(totals, nchunk);
+        CS_LAUNCHED();
+        scan_add<<<nchunk, kScanThreads, 0, st>>>(d_indptr, S.rows, totals);
+        CS_LAUNCHED();
+    }
     CS_CUDA(cudaGetLastError());
     CS_CUDA(cudaMemcpyAsync(nnz_host, d_indptr + S.rows, sizeof(int64_t), cudaMemcpyDeviceToHost,
                             st));

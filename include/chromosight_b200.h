@@ -129,6 +129,9 @@ int cs_pearson_f32(const cs_layout *Limg, const float *d_img,
  * Two calls: count (fills d_indptr[0..rows], returns nnz in *nnz_host after
  * synchronising the stream) then emit.
  * ------------------------------------------------------------------------ */
+/* d_indptr must hold rows + 1 + cs_scan_scratch(rows) elements (scan workspace behind
+ * the row pointers). */
+int64_t cs_scan_scratch(int32_t rows);
 int cs_scores_count(const cs_layout *Lout, const float *d_out,
                     int32_t dmin, int32_t dmax, /* keep only dmin <= col-row <= dmax */
                     int64_t *d_indptr, int64_t *nnz_host, void *stream);
