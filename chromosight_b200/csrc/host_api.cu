@@ -7,6 +7,7 @@
 //
 // Device and pinned buffers are cached per device and only grow, so steady-state
 // calls do no allocation.
+#include <stdlib.h>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -75,6 +76,9 @@ static int get_ctx(int device, HostCtx **out) {
 static void memcpy_mt(void *dst, const void *src, size_t n) {
     const size_t kMin = 4u << 20;
     unsigned hw = std::thread::hardware_concurrency();
+    // share the host cores between the ranks of one box
+    if (const char *e = getenv("LOCAL_WORLD_SIZE"))
+        if (atoi(e) > 1) hw = hw / (unsigned)atoi(e) > 0 ? hw / (unsigned)atoi(e) : 1;
     int nt = (int)(n / kMin);
     if (nt > 6) nt = 6;
     if (hw && nt > (int)hw) nt = (int)hw;

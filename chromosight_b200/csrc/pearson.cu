@@ -21,6 +21,7 @@
 //            2-D prefix tables of K and K^2 in float64, exact), the reference's formulas in
 //            float64, one float32 score.
 // No tensor cores: this is a CUDA-core stencil (BASELINE.json north_star).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace cs {
@@ -136,12 +137,14 @@ __device__ __forceinline__ float score_from_sums(const PearsonParams &P, double 
     A3 = thr0(A3, P.thr);
     double cov, den2, f2 = 1.0;
     bool ok = true;
-    if (!MASK || nmiss == 0) {
+    if (!MASK) {
         const double vS = fma(-A1, A1, A2);
         cov = fma(-A1, P.kmean, A3);
         den2 = vS * P.vK0;
-        if (!MASK) ok = vS >= 0.0;
+        ok = vS >= 0.0;
     } else {
+        // one branch-free path: with nmiss == 0 these are the unmasked formulas
+        // (f = 1, mK = kernel mean, m2K = mean of K^2)
         const int npres = P.N - nmiss;
         // 1 / npres: float32 reciprocal + one Newton step (exact to ~1e-15)
         double inv = (double)__frcp_rn((float)npres);
@@ -156,8 +159,8 @@ __device__ __forceinline__ float score_from_sums(const PearsonParams &P, double 
         const double vS = fma(A2, f, -mS * mS);
         cov = fma(-A1, mK, A3) * f;
         den2 = vS * fma(-mK, mK, m2K);
-        ok = (npres > 0) && (npres >= P.min_present) && !P.kmean_zero;
-        if (P.nobs_full && npres != 0) nobs = npres;
+        ok = nmiss == 0 || ((npres > 0) && (npres >= P.min_present) && !P.kmean_zero);
+        if (P.nobs_full && nmiss != 0 && npres != 0) nobs = npres;
     }
     // det:1066,1088-1091: denom = sqrt(den2); |denom| < 1e-10 or NaN -> 0
     float r = 0.f;
@@ -174,10 +177,10 @@ __device__ __forceinline__ float score_from_sums(const PearsonParams &P, double 
     return r;
 }
 
-// bits [c0, c0 + 64) of one row of the missing-pixel bit array
-__device__ __forceinline__ unsigned long long row_bits(const uint32_t *brow, int c0) {
-    const int w = c0 >> 5, sh = c0 & 31;
-    const uint32_t a = brow[w], b = brow[w + 1], c = brow[w + 2];
+// 64 bits of the (linear, one bit per tile pixel) missing-pixel bit array from bit `pos` on
+__device__ __forceinline__ unsigned long long row_bits(const uint32_t *bits, int pos) {
+    const int w = pos >> 5, sh = pos & 31;
+    const uint32_t a = bits[w], b = bits[w + 1], c = bits[w + 2];
     const uint32_t lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);
     return ((unsigned long long)hi << 32) | lo;
 }
@@ -213,15 +216,16 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     constexpr unsigned KWMASK = (KW == 32) ? 0xffffffffu : ((1u << KW) - 1u);
 
     extern __shared__ __align__(1024) unsigned char smem[];
-    float *tile = reinterpret_cast<float *>(smem);
-    float2 *V = reinterpret_cast<float2 *>(smem + P.off_V);
-    unsigned char *Vm = smem + P.off_Vm;
-    uint32_t *bits = reinterpret_cast<uint32_t *>(smem + P.off_bits);
-    const float2 *Kdup = reinterpret_cast<const float2 *>(smem + P.off_K);
-    const double *Dt = reinterpret_cast<const double *>(smem + P.off_D);
-    float *accS = reinterpret_cast<float *>(smem + P.off_acc);
-    unsigned long long *grpS = reinterpret_cast<unsigned long long *>(smem + P.off_grp);
-    float *red = reinterpret_cast<float *>(smem + P.off_red);
+    float *__restrict__ tile = reinterpret_cast<float *>(smem);
+    float2 *__restrict__ V = reinterpret_cast<float2 *>(smem + P.off_V);
+    unsigned char *__restrict__ Vm = smem + P.off_Vm;
+    uint32_t *__restrict__ bits = reinterpret_cast<uint32_t *>(smem + P.off_bits);
+    const float2 *__restrict__ Kdup = reinterpret_cast<const float2 *>(smem + P.off_K);
+    const double *__restrict__ Dt = reinterpret_cast<const double *>(smem + P.off_D);
+    float *__restrict__ accS = reinterpret_cast<float *>(smem + P.off_acc);
+    unsigned long long *__restrict__ grpS =
+        reinterpret_cast<unsigned long long *>(smem + P.off_grp);
+    float *__restrict__ red = reinterpret_cast<float *>(smem + P.off_red);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + P.off_bar);
 
     const int tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
@@ -255,7 +259,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         double *Dd = reinterpret_cast<double *>(smem + P.off_D);
         for (int i = tid; i < P.n_dtab; i += nthr) Dd[i] = P.dtab[i];
         if (MASK)
-            for (int i = tid; i < IR * NW; i += nthr) bits[i] = 0u;
+            for (int i = tid; i < NW; i += nthr) bits[i] = 0u;
     }
     __syncthreads();
     mbar_wait(bar, 0);
@@ -298,52 +302,45 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     }
     const double p = (double)pv;
 
-    // ---- phase A: fix-up + bit array + vertical sliding sums --------------------------
+    // ---- phase A1: fix-up of the tile, four pixels per thread ---------------------------
+    // out-of-band aliases and declared-missing strip -> 0, NaN sentinels -> bit array and 0,
+    // then the shift by the pivot
     int anynz = 0;
     {
-        const int ICr = (IC + 31) & ~31;
-        for (int cb = (tid >> 5) << 5; cb < ICr; cb += nthr) {
-            const int ix = cb + lane;
-            const bool live = ix < IC;
-            const int slot = (ix & 3) * VQ + (ix >> 2);
-            const int X = TXp + ix + P.dlo;
-            double r1 = 0.0, r2 = 0.0;
-            int rm = 0;
-            for (int iy = 0; iy < IR; ++iy) {
-                float v = live ? tile[iy * IC + ix] : 0.f;
-                const int d = X - (TY + iy);
-                const bool inside = P.dense ? true : (d >= P.dlo && d <= P.dhi);
-                if (!inside) v = 0.f;
-                bool miss = false;
-                if (MASK) {
-                    if (d >= P.sdlo && d <= P.sdhi) v = 0.f;  // counted analytically
-                    miss = !(v == v);
-                    const unsigned word = __ballot_sync(0xffffffffu, miss);
-                    if (lane == 0) bits[iy * NW + (cb >> 5)] = word;
-                    rm += miss ? 1 : 0;
-                }
-                if (!(v == v)) v = 0.f;  // missing pixels count as S = 0
-                anynz |= (v != 0.f);
-                const float vs = v - pv;
-                if (live) tile[iy * IC + ix] = vs;
-                const double a = (double)vs;
-                r1 += a;
-                r2 = fma(a, a, r2);
-                const int yo = iy - (KH - 1);
-                if (yo >= 0) {
-                    if (live) {
-                        V[yo * 4 * VQ + slot] = make_float2((float)r1, (float)r2);
-                        if (MASK) Vm[yo * 4 * VQ + slot] = (unsigned char)rm;
-                    }
-                    const float w = live ? tile[yo * IC + ix] : -pv;
+        const int ICq4 = IC >> 2;
+        const int nf4 = IR * ICq4;
+        for (int fb = 0; fb < nf4; fb += nthr) {
+            const int f = fb + tid;
+            const bool live = f < nf4;
+            unsigned nib = 0u;
+            if (live) {
+                const int iy = f / ICq4, c4 = (f - iy * ICq4) << 2;
+                float4 *ptr = reinterpret_cast<float4 *>(tile) + f;
+                const float4 v = *ptr;
+                float vv[4] = {v.x, v.y, v.z, v.w};
+                const int d0 = (TXp + c4 + P.dlo) - (TY + iy);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int d = d0 + e;
+                    float x = vv[e];
+                    if (!P.dense && (d < P.dlo || d > P.dhi)) x = 0.f;
                     if (MASK) {
-                        __syncwarp();
-                        rm -= (bits[yo * NW + (cb >> 5)] >> lane) & 1u;
+                        if (d >= P.sdlo && d <= P.sdhi) x = 0.f;  // counted analytically
+                        if (!(x == x)) nib |= 1u << e;
                     }
-                    const double b = (double)w;
-                    r1 -= b;
-                    r2 = fma(-b, b, r2);
+                    if (!(x == x)) x = 0.f;  // missing pixels count as S = 0
+                    anynz |= (x != 0.f);
+                    vv[e] = x - pv;
                 }
+                *ptr = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            }
+            if (MASK) {
+                // eight consecutive threads hold the 32 bits of one word
+                unsigned w = nib << (4 * (lane & 7));
+                w |= __shfl_xor_sync(0xffffffffu, w, 1);
+                w |= __shfl_xor_sync(0xffffffffu, w, 2);
+                w |= __shfl_xor_sync(0xffffffffu, w, 4);
+                if (live && (lane & 7) == 0) bits[f >> 3] = w;
             }
         }
     }
@@ -371,6 +368,46 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         }
         return;
     }
+
+    // ---- phase A2: vertical sliding sums over KH rows, one thread per column ----------
+    {
+        const unsigned KHM = (KH >= 32) ? 0xffffffffu : ((1u << KH) - 1u);
+        for (int cb = (tid >> 5) << 5; cb < IC; cb += nthr) {
+            const bool live = cb + lane < IC;
+            const int ix = live ? cb + lane : IC - 1;  // idle lanes shadow the last column
+            const float *__restrict__ pin = tile + ix;             // row iy
+            const float *__restrict__ pold = tile + ix;            // row iy - (KH - 1)
+            float2 *__restrict__ pv2 = V + (ix & 3) * VQ + (ix >> 2);
+            unsigned char *__restrict__ pvm = Vm + (ix & 3) * VQ + (ix >> 2);
+            double r1 = 0.0, r2 = 0.0;
+            unsigned colbits = 0u;
+            int pos = cb;
+#pragma unroll 2
+            for (int iy = 0; iy < IR; ++iy, pin += IC, pos += IC) {
+                const double a = (double)*pin;
+                r1 += a;
+                r2 = fma(a, a, r2);
+                if (MASK) {
+                    const unsigned w =
+                        __funnelshift_r(bits[pos >> 5], bits[(pos >> 5) + 1], pos & 31);
+                    colbits = (colbits << 1) | ((w >> lane) & 1u);
+                }
+                if (iy >= KH - 1) {
+                    if (live) {
+                        *pv2 = make_float2((float)r1, (float)r2);
+                        if (MASK) *pvm = (unsigned char)__popc(colbits & KHM);
+                    }
+                    pv2 += 4 * VQ;
+                    pvm += 4 * VQ;
+                    const double b = (double)*pold;
+                    pold += IC;
+                    r1 -= b;
+                    r2 = fma(-b, b, r2);
+                }
+            }
+        }
+    }
+    __syncthreads();
 
     // double tables (mask branch): 2-D prefix sums of the mask kernels, their column sums,
     // and the sums over the declared-missing strip per output diagonal
@@ -478,7 +515,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             unsigned long long band = FWMASK, bor = 0ull;
             const int fr = KH + RU - 1;
             for (int r = 0; r < fr; ++r) {
-                const unsigned long long b = row_bits(bits + (RU * g + r) * NW, fc0) & FWMASK;
+                const unsigned long long b = row_bits(bits, (RU * g + r) * IC + fc0) & FWMASK;
                 band &= b;
                 bor |= b;
             }
@@ -489,7 +526,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     int start = 0;
                     for (int r = 0; r <= fr; ++r) {
                         unsigned long long b = 0ull;
-                        if (r < fr) b = row_bits(bits + (RU * g + r) * NW, fc0) & FWMASK & ~band;
+                        if (r < fr) b = row_bits(bits, (RU * g + r) * IC + fc0) & FWMASK & ~band;
                         if (b) rowsel |= 1ull << r;
                         if (b != prev) {
                             if (prev) {
@@ -574,7 +611,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                         for (unsigned rs = (unsigned)(rowsel >> u) & KHMASK; rs; rs &= rs - 1) {
                             const int i = __ffs(rs) - 1;
                             const unsigned wb =
-                                (unsigned)(row_bits(bits + (RU * g + u + i) * NW, fc0) >> t) &
+                                (unsigned)(row_bits(bits, (RU * g + u + i) * IC + fc0) >> t) &
                                 KWMASK & ~cbw;
                             add_rects(wb, i, i + 1, IK, IK2, KW1, sKm, sKm2);
                         }
@@ -802,6 +839,8 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
     // banded traversal when the output band is narrow relative to the region
     P.skew = (Wo + 16 < ncols_out) ? 1 : 0;
     int TR = opts->tile_rows > 0 ? round_up(opts->tile_rows, RU) : 32;
+    if (const char *e = getenv("CS_TILE_ROWS"))  // tuning knob for experiments
+        if (atoi(e) > 0) TR = round_up(atoi(e), RU);
     if (TR > round_up(nrows_out, RU)) TR = round_up(nrows_out, RU);
     size_t smem = 0;
     int NBc = 0, nchunks = 0, IC = 0, IR = 0, VQ = 0, NW = 0, threads = 0;
@@ -829,7 +868,7 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
         if (threads > 256) threads = 256;
         if (threads < 64) threads = 64;
         VQ = (IC / 4) | 1;
-        NW = (IC + 31) / 32 + 3;
+        NW = (IC * IR + 31) / 32 + 4;  // words of the linear bit array
         size_t o = (size_t)IC * IR * sizeof(float);
         o = (o + 15) / 16 * 16;
         P.off_V = (int)o;
@@ -838,7 +877,7 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
         if (opts->has_mask) o += (size_t)TR * 4 * VQ;
         o = (o + 15) / 16 * 16;
         P.off_bits = (int)o;
-        if (opts->has_mask) o += (size_t)IR * NW * sizeof(uint32_t);
+        if (opts->has_mask) o += (size_t)NW * sizeof(uint32_t);
         o = (o + 15) / 16 * 16;
         P.off_K = (int)o;
         o += fbytes;
