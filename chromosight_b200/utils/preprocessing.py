@@ -160,6 +160,44 @@ def truncate_kernel(kernel, prop_info):
     return left @ right
 
 
+def resize_kernel(kernel, kernel_res=None, signal_res=None, factor=None, min_size=7, quiet=False):
+    """Rescale a square, odd kernel by `factor` (or kernel_res / signal_res) with linear
+    interpolation; the result is kept odd and at least min_size wide (pre:731-808)."""
+    import scipy.ndimage as ndi
+    kernel = np.asarray(kernel, dtype=float)
+    km, kn = kernel.shape
+    if km != kn:
+        raise ValueError("kernel must be square.")
+    if km % 2 == 0:
+        raise ValueError("kernel size must be odd.")
+    if factor is not None:
+        if kernel_res is not None or signal_res is not None:
+            raise ValueError("factor is mutually exclusive with resolution "
+                             "parameters (kernel_res and signal_res).")
+        scale = factor
+    else:
+        if kernel_res is None or signal_res is None:
+            raise ValueError("You must provide either a resize factor or the signal and "
+                             "kernel resolutions.")
+        scale = kernel_res / signal_res
+    scale = max(scale, min_size / km)
+    out = ndi.zoom(kernel, scale, order=1)
+    if out.shape[0] % 2 == 0:
+        # one pixel smaller keeps the centre on a pixel (pre:796-806)
+        out = ndi.zoom(kernel, (out.shape[0] - 1) / km, order=1)
+    return out
+
+
+def crop_kernel(kernel, target_size):
+    """Trim equal margins so that the kernel is no larger than target_size (made odd by
+    rounding up), pre:679-728."""
+    tm, tn = (d + 1 - d % 2 for d in target_size)
+    sm, sn = kernel.shape
+    mr = (sm - tm) // 2 if sm > tm else 0
+    mc = (sn - tn) // 2 if sn > tn else 0
+    return kernel[mr:sm - mr, mc:sn - mc]
+
+
 def ztransform(matrix):
     """Global z-score of the stored values (pre:313-334)."""
     out = matrix.copy()

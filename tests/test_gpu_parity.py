@@ -205,3 +205,72 @@ def test_scale_and_shift_properties_large(presets):
     a = r[: h, : h].toarray() if False else r[200: h - 200, :][:, 200: h - 200]
     b = r[h + 200: n - 200, :][:, h + 200: n - 200]
     assert np.abs((a - b)).max() <= 2e-6
+
+
+@pytest.mark.parametrize("kname,ksize,tol,pearson", [("loops", 17, 0.5, 0.3), ("borders", 9, 0.75, 0.15)])
+def test_full_size_map_against_oracle_crops(kname, ksize, tol, pearson, presets):
+    """BASELINE.json's full-size intra map (200k bins, max_dist 200): the oracle cannot
+    take the whole map, but a window only sees its own pixels, so random crops of the
+    full-size result must equal the oracle run on the cropped signal and mask
+    (interior windows); plus candidate thresholding against the host version.
+    loops 17x17 = the metric configuration; borders resized to 9x9 = config 3."""
+    from chromosight_b200 import synthetic
+    from chromosight_b200.session import Session, records_to_numpy
+    from chromosight_b200.utils import preprocessing as cup
+    from oracle import pearson_oracle as po
+    kernel = getattr(presets, kname)["kernels"][0]
+    if ksize != kernel.shape[0]:
+        kernel = cup.resize_kernel(kernel, factor=ksize / kernel.shape[0])
+    k = kernel.shape[0]
+    assert k == ksize
+    n, D = 200_000, 200
+    raw, detect = synthetic.band_counts(n, D + k, seed=11, missing_frac=0.02, max_dist=D)
+    mat = cup.detrend(raw, detectable_bins=detect, max_dist=D + k, max_val=10)
+    mat = cup.diag_trim(mat.tocsr(), D + k)
+    mat.data[np.isnan(mat.data)] = 0
+    mat.eliminate_zeros()
+    mask = cup.make_missing_mask(mat.shape, detect, detect, max_dist=D, sym_upper=True)
+    kw = dict(max_dist=D, sym_upper=True, full=True, missing_tol=tol, pval=True)
+    s = Session()
+    s.upload(mat, kernel, missing_mask=mask, **kw)
+    st = s.run()
+    r, p = s.download()
+    assert st["n_windows"] >= synthetic.n_windows(n, D)
+    assert r.shape == (n, n) and r.nnz == st["nnz"] and abs(r.data).max() <= 1.0
+    assert r.nnz > 0.9 * synthetic.n_windows(n, D)
+    # candidates on the device == thresholding of the downloaded map (det:417-421)
+    cand, nc = s.candidates(pearson, 0, D)
+    rec = records_to_numpy(cand, nc)
+    rt = cup.diag_trim(r, D).tocoo()
+    sel = (rt.data >= pearson)
+    assert nc == int(sel.sum())
+    key = np.sort(rec["row"].astype(np.int64) * n + rec["col"])
+    assert np.array_equal(key, np.sort(rt.row[sel].astype(np.int64) * n + rt.col[sel]))
+    # oracle on crops
+    rng = np.random.default_rng(5)
+    W = D + 3 * k
+    starts = [0, n - 400 - W] + list(rng.integers(100, n - 400 - W - 100, size=6))
+    for a0 in starts:
+        a0 = int(a0)
+        a1 = a0 + 400 + W
+        sub = mat[a0:a1, a0:a1]
+        msub = mask[a0:a1, a0:a1]
+        r0, p0, nob = po.normxcorr2_dense(sub.toarray(), kernel, missing_mask=msub.toarray(),
+                                          return_nobs=True, **kw)
+        # interior: rows whose windows and mask geometry do not touch the crop's frame
+        # (the first/last rows of the whole map are real edges and are compared too)
+        lo = 0 if a0 == 0 else k
+        hi = (a1 - a0) if a1 == n else (a1 - a0) - W
+        got = r[a0 + lo:a0 + hi, a0:a1].toarray()
+        exp = r0[lo:hi, :].copy()
+        gp = p[a0 + lo:a0 + hi, a0:a1].toarray()
+        if a1 != n:
+            # windows reaching beyond the crop's right edge are not comparable
+            cols = np.arange(a1 - a0)[None, :] - (np.arange(lo, hi)[:, None])
+            far = cols > D + 2 * k
+            got[far] = 0
+            exp[far] = 0
+            gp[far] = 0
+            p0 = p0.copy()
+            p0[lo:hi][far] = 0
+        _compare(got, gp, exp, p0[lo:hi], nob[lo:hi])

@@ -134,3 +134,25 @@ def test_label_foci_known_answer():
     assert np.array_equal(lab.toarray(), exp)
     n2, filt = cud.filter_foci(lab.copy(), min_size=3)
     assert n2 == 2 and set(np.unique(filt.data)) == {1, 4}
+
+
+def test_resize_and_crop_kernel(presets):
+    """Sizes and centre of resize_kernel / crop_kernel as pinned by the reference's
+    tests/test_preprocessing.py:118-180 (odd sizes, min_size, centre preserved)."""
+    from chromosight_b200.utils import preprocessing as cup
+    K = presets.loops["kernels"][0]
+    assert cup.resize_kernel(K, factor=9 / 17).shape == (9, 9)
+    assert cup.resize_kernel(K, factor=0.1).shape == (7, 7)          # min_size
+    assert cup.resize_kernel(K, kernel_res=10000, signal_res=5000).shape[0] % 2 == 1
+    up = cup.resize_kernel(K, factor=2.0)
+    assert up.shape[0] % 2 == 1 and np.isclose(up[up.shape[0] // 2, up.shape[1] // 2], K[8, 8])
+    with pytest.raises(ValueError):
+        cup.resize_kernel(K[:, :15], factor=1)
+    with pytest.raises(ValueError):
+        cup.resize_kernel(K[:16, :16], factor=1)
+    with pytest.raises(ValueError):
+        cup.resize_kernel(K, factor=1, kernel_res=1)
+    assert cup.crop_kernel(K, (7, 7)).shape == (7, 7)
+    assert cup.crop_kernel(K, (8, 8)).shape == (9, 9)
+    assert cup.crop_kernel(K, (21, 5)).shape == (17, 5)
+    assert np.array_equal(cup.crop_kernel(K, (7, 7)), K[5:12, 5:12])
