@@ -88,6 +88,19 @@ class Normxcorr2Args(C.Structure):
     ]
 
 
+class GatherArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int32), ("cols", C.c_int32),
+        ("d_indptr", C.c_void_p), ("d_indices", C.c_void_p), ("d_data", C.c_void_p),
+        ("d_valid_row", C.c_void_p), ("d_valid_col", C.c_void_p),
+        ("win_h", C.c_int32), ("win_w", C.c_int32),
+        ("pad_rows", C.c_int32), ("pad_cols", C.c_int32),
+        ("det_shift_row", C.c_int32), ("det_shift_col", C.c_int32),
+        ("nan_subdiag", C.c_int32),
+        ("zero_tol", C.c_double), ("missing_tol", C.c_double),
+    ]
+
+
 class RunStats(C.Structure):
     _fields_ = [
         ("ms_fill", C.c_double), ("ms_pearson", C.c_double),
@@ -118,6 +131,11 @@ _PROTOS = {
                                   _P, _P, _P]),
     "cs_scores_candidates": (C.c_int, [C.POINTER(Layout), _P, _P, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_float, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
+    "cs_window_gather": (C.c_int, [C.POINTER(GatherArgs), _P, C.c_int64, _P, _P, _P]),
+    "cs_scores_lookup": (C.c_int, [C.POINTER(Layout), _P, _P, C.c_int32, C.c_int32, C.c_int32, _P,
+                                    C.c_int64, _P, _P, _P]),
+    "cs_session_validate": (C.c_int, [C.c_void_p, _P, C.c_int64, _P, _P, C.c_int32, C.c_double,
+                                       C.c_double, C.c_int32, _P, _P, _P, _P]),
     "cs_distance_law": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P]),
     "cs_detrend_apply": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_double, _P]),
     "cs_normxcorr2_host": (C.c_int, [C.POINTER(Normxcorr2Args), C.POINTER(CsrResult)]),

@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["image.cu", "pearson.cu", "scores.cu", "detrend.cu", "host_api.cu"]
+SOURCES = ["image.cu", "pearson.cu", "scores.cu", "detrend.cu", "gather.cu", "host_api.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "chromosight_b200.h")]
 LIB = os.path.join(PKG, "libchromosight_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

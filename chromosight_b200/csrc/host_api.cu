@@ -182,7 +182,7 @@ struct cs_session {
     cudaStream_t stream() const { return use_user_st ? user_st : c->st; }
     // device-resident inputs, images and results of this session
     DevBuf sig_indptr, sig_indices, sig_data, m_indptr, m_indices, img, out, nobs, r_indptr,
-        r_indices, r_data, r_p, err;
+        r_indices, r_data, r_p, err, g_coords, g_win, g_flag, g_score, g_p, g_vrow, g_vcol;
     bool uploaded = false, ran = false, empty = false;
     cs_normxcorr2_args a;
     std::vector<double> k_corr, k_mask, k2_mask;
@@ -212,7 +212,8 @@ extern "C" void cs_session_destroy(cs_session *s) {
         if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     DevBuf *bufs[] = {&s->sig_indptr, &s->sig_indices, &s->sig_data, &s->m_indptr, &s->m_indices,
                       &s->img,        &s->out,         &s->nobs,     &s->r_indptr, &s->r_indices,
-                      &s->r_data,     &s->r_p,         &s->err};
+                      &s->r_data,     &s->r_p,         &s->err,      &s->g_coords, &s->g_win,
+                      &s->g_flag,     &s->g_score,     &s->g_p,      &s->g_vrow,   &s->g_vcol};
     cudaSetDevice(s->c->device);
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -570,5 +571,111 @@ extern "C" int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *re
     res->ms_h2d = ms_h2d;
     res->ms_kernels = stt.ms_total;
     res->h2d_bytes = stt.h2d_bytes;
+    return CS_OK;
+}
+
+// validate_patterns (det:18-155) + score / p-value lookup on the session's matrix.
+extern "C" int cs_session_validate(cs_session *s, const int32_t *host_coords, int64_t n_coords,
+                                   const uint8_t *host_valid_row, const uint8_t *host_valid_col,
+                                   int32_t inter, double zero_tol, double missing_tol,
+                                   int32_t score_dmax, double *host_windows, uint8_t *host_valid,
+                                   double *host_score, double *host_log10p) {
+    CS_REQUIRE(s && s->uploaded && s->ran, "cs_session_validate: upload and run first");
+    CS_REQUIRE(n_coords >= 0 && (n_coords == 0 || (host_coords && host_windows && host_valid)),
+               "cs_session_validate: null argument");
+    if (n_coords == 0) return CS_OK;
+    HostCtx *c = s->c;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = s->stream();
+    const cs_normxcorr2_args &a = s->a;
+    const int km = a.kernel.kh, kn = a.kernel.kw;
+    const int kh = (km - 1) / 2, kw = (kn - 1) / 2;
+    const size_t npx = (size_t)km * kn;
+    int rc;
+    if ((rc = s->g_coords.ensure((size_t)n_coords * 4 * sizeof(int32_t)))) return rc;
+    if ((rc = s->g_win.ensure((size_t)n_coords * npx * sizeof(double)))) return rc;
+    if ((rc = s->g_flag.ensure((size_t)n_coords))) return rc;
+    if ((rc = s->g_score.ensure((size_t)n_coords * sizeof(double)))) return rc;
+    if ((rc = s->g_p.ensure((size_t)n_coords * sizeof(double)))) return rc;
+    if ((rc = s->g_vrow.ensure((size_t)a.rows))) return rc;
+    if ((rc = s->g_vcol.ensure((size_t)a.cols))) return rc;
+    // padded coordinates (det:291-298; zero_pad_sparse(mat, kh, kw) pads kw rows and kh columns,
+    // the coordinates are shifted by (kh, kw) -- identical for square kernels) and the
+    // coordinates at which the padded correlation map is read (det:134)
+    std::vector<int32_t> hc((size_t)n_coords * 4);
+    const int sr = a.full ? kh : 0, sc = a.full ? kw : 0;
+    const int pad_r = a.full ? kw : 0, pad_c = a.full ? kh : 0;
+    for (int64_t i = 0; i < n_coords; ++i) {
+        const int32_t c1 = host_coords[2 * i], c2 = host_coords[2 * i + 1];
+        hc[2 * i] = c1 + sr;
+        hc[2 * i + 1] = c2 + sc;
+        hc[(size_t)2 * n_coords + 2 * i] = c1 + sr - pad_r;
+        hc[(size_t)2 * n_coords + 2 * i + 1] = c2 + sc - pad_c;
+    }
+    CS_CUDA(cudaMemcpyAsync(s->g_coords.p, hc.data(), hc.size() * sizeof(int32_t),
+                            cudaMemcpyHostToDevice, st));
+    if (host_valid_row)
+        CS_CUDA(cudaMemcpyAsync(s->g_vrow.p, host_valid_row, (size_t)a.rows, cudaMemcpyHostToDevice, st));
+    if (host_valid_col)
+        CS_CUDA(cudaMemcpyAsync(s->g_vcol.p, host_valid_col, (size_t)a.cols, cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaStreamSynchronize(st));  // hc is about to go out of scope
+    cs_gather_args g;
+    memset(&g, 0, sizeof(g));
+    g.rows = a.rows;
+    g.cols = a.cols;
+    g.d_indptr = (const int64_t *)s->sig_indptr.p;
+    g.d_indices = (const int32_t *)s->sig_indices.p;
+    g.d_data = (const double *)s->sig_data.p;
+    g.d_valid_row = host_valid_row ? (const uint8_t *)s->g_vrow.p : nullptr;
+    g.d_valid_col = host_valid_col ? (const uint8_t *)s->g_vcol.p : nullptr;
+    g.win_h = km;
+    g.win_w = kn;
+    g.pad_rows = pad_r;
+    g.pad_cols = pad_c;
+    g.det_shift_row = sr;
+    g.det_shift_col = sc;
+    g.nan_subdiag = inter ? 0 : (km > kn ? km : kn);
+    g.zero_tol = zero_tol;
+    g.missing_tol = missing_tol;
+    const int32_t *d_pad = (const int32_t *)s->g_coords.p;
+    const int32_t *d_conv = d_pad + (size_t)2 * n_coords;
+    rc = cs_window_gather(&g, d_pad, n_coords, (double *)s->g_win.p, (uint8_t *)s->g_flag.p, st);
+    if (rc) return rc;
+    CS_CUDA(cudaMemcpyAsync(host_windows, s->g_win.p, (size_t)n_coords * npx * sizeof(double),
+                            cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaMemcpyAsync(host_valid, s->g_flag.p, (size_t)n_coords, cudaMemcpyDeviceToHost, st));
+    if (host_score || host_log10p) {
+        if (s->empty) {
+            CS_CUDA(cudaStreamSynchronize(st));
+            for (int64_t i = 0; i < n_coords; ++i) {
+                if (host_score) host_score[i] = 0.0;
+                if (host_log10p) host_log10p[i] = 0.0;
+            }
+            return CS_OK;
+        }
+        const uint16_t *nb = s->want_nobs ? (const uint16_t *)s->nobs.p : nullptr;
+        // scores of the trimmed map (det:270) at the padded-map coordinates
+        rc = cs_scores_lookup(&s->Lo, (const float *)s->out.p, nb, km * kn, inter ? -(1 << 30) : 0,
+                              inter ? (1 << 30) : score_dmax, d_conv, n_coords,
+                              (double *)s->g_score.p, nullptr, st);
+        if (rc) return rc;
+        if (host_score)
+            CS_CUDA(cudaMemcpyAsync(host_score, s->g_score.p, (size_t)n_coords * sizeof(double),
+                                    cudaMemcpyDeviceToHost, st));
+        if (host_log10p) {
+            // p-values of the untrimmed map at the final coordinates (det:337-339): upload them
+            // over the padded ones (already consumed)
+            CS_CUDA(cudaStreamSynchronize(st));
+            CS_CUDA(cudaMemcpyAsync(s->g_coords.p, host_coords, (size_t)n_coords * 2 * sizeof(int32_t),
+                                    cudaMemcpyHostToDevice, st));
+            rc = cs_scores_lookup(&s->Lo, (const float *)s->out.p, nb, km * kn, -(1 << 30), 1 << 30,
+                                  d_pad, n_coords, (double *)s->g_score.p, (double *)s->g_p.p, st);
+            if (rc) return rc;
+            CS_CUDA(cudaMemcpyAsync(host_log10p, s->g_p.p, (size_t)n_coords * sizeof(double),
+                                    cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CS_CUDA(cudaStreamSynchronize(st));
     return CS_OK;
 }

@@ -59,6 +59,7 @@ class Session:
         _lib.check(self._lib.cs_session_upload(self._h, C.byref(a)))
         del keep
         self.shape = csr.shape
+        self.kernel_shape = kernel.shape
         self.pval = bool(pval)
         return self
 
@@ -94,6 +95,32 @@ class Session:
                                                    int(min(dmax, 2 ** 30)), _cuda.ptr(out), cap,
                                                    _cuda.ptr(cnt), C.byref(n)))
         return out, int(min(n.value, cap))
+
+
+    def validate(self, coords, valid_rows, valid_cols, inter, zero_tol, missing_tol, score_dmax):
+        """validate_patterns (det:18-155) on the uploaded matrix and the last scores.
+
+        coords : int array [P, 2] of unpadded (row, col); valid_rows / valid_cols : indices of
+        the detectable bins.  Returns (windows [P, kh, kw] float64 with NaN windows for invalid
+        patterns, valid bool [P], score float64 [P], log10 p float64 [P])."""
+        coords = np.ascontiguousarray(coords, dtype=np.int32).reshape(-1, 2)
+        P = coords.shape[0]
+        km, kn = self.kernel_shape
+        windows = np.empty((P, km, kn), dtype=np.float64)
+        valid = np.zeros(P, dtype=np.uint8)
+        score = np.zeros(P, dtype=np.float64)
+        logp = np.zeros(P, dtype=np.float64)
+        vr = np.zeros(self.shape[0], dtype=np.uint8)
+        vr[np.asarray(valid_rows, dtype=np.int64)] = 1
+        vc = np.zeros(self.shape[1], dtype=np.uint8)
+        vc[np.asarray(valid_cols, dtype=np.int64)] = 1
+        self._bind_stream()
+        if P:
+            _lib.check(self._lib.cs_session_validate(
+                self._h, coords.ctypes.data, P, vr.ctypes.data, vc.ctypes.data, int(bool(inter)),
+                float(zero_tol), float(missing_tol), int(min(score_dmax, 2 ** 30)),
+                windows.ctypes.data, valid.ctypes.data, score.ctypes.data, logp.ctypes.data))
+        return windows, valid.astype(bool), score, logp
 
 
 def records_to_numpy(tensor, count):

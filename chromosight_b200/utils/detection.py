@@ -278,6 +278,132 @@ def normxcorr2(
     return corr, pvals
 
 
+# --------------------------------------------------------------------------- callers of the hot path
+def validate_patterns(coords, matrix, conv_mat, detectable_bins, kernel_matrix, drop=True,
+                      zero_tol=0.3, missing_tol=0.75):
+    """Windows around pattern coordinates, their validation and score (det:18-155).
+
+    One CUDA warp gathers each window from the CSR matrix (csrc/gather.cu) instead of
+    the reference's Python loop.  Returns (DataFrame[bin1, bin2, score], windows)."""
+    import pandas as pd
+    from .. import _cuda
+    t = _cuda.require_cuda()
+    lib = _lib.load()
+    coords = np.asarray(coords).reshape(-1, 2)
+    P = coords.shape[0]
+    csr = sp.csr_matrix(matrix, dtype=np.float64)
+    if not csr.has_sorted_indices:
+        csr = csr.copy()
+        csr.sort_indices()
+    km, kn = kernel_matrix.shape
+    windows = np.full((P, km, kn), np.nan)
+    valid = np.zeros(P, dtype=bool)
+    if P:
+        vr = np.zeros(csr.shape[0], dtype=np.uint8)
+        vr[np.asarray(detectable_bins[0], dtype=np.int64)] = 1
+        vc = np.zeros(csr.shape[1], dtype=np.uint8)
+        vc[np.asarray(detectable_bins[1], dtype=np.int64)] = 1
+        d = dict(indptr=_cuda.to_device(csr.indptr, np.int64), indices=_cuda.to_device(csr.indices, np.int32),
+                 data=_cuda.to_device(csr.data, np.float64), vr=_cuda.to_device(vr), vc=_cuda.to_device(vc),
+                 coords=_cuda.to_device(coords, np.int32))
+        d_win = _cuda.empty(P * km * kn, t.float64)
+        d_ok = _cuda.empty(P, t.uint8)
+        g = _lib.GatherArgs()
+        g.rows, g.cols = csr.shape
+        g.d_indptr, g.d_indices, g.d_data = d["indptr"].data_ptr(), d["indices"].data_ptr(), d["data"].data_ptr()
+        g.d_valid_row, g.d_valid_col = d["vr"].data_ptr(), d["vc"].data_ptr()
+        g.win_h, g.win_w = km, kn
+        g.zero_tol, g.missing_tol = float(zero_tol), float(missing_tol)
+        _lib.check(lib.cs_window_gather(C.byref(g), _cuda.ptr(d["coords"]), P, _cuda.ptr(d_win),
+                                        _cuda.ptr(d_ok), _cuda.stream_ptr()))
+        windows = d_win.cpu().numpy().reshape(P, km, kn)
+        valid = d_ok.cpu().numpy().astype(bool)
+    score = np.full(P, np.nan)
+    if valid.any():
+        cm = sp.csr_matrix(conv_mat)
+        score[valid] = np.asarray(cm[coords[valid, 0], coords[valid, 1]]).ravel()
+    table = pd.DataFrame({"bin1": coords[:, 0], "bin2": coords[:, 1], "score": score})
+    if drop:
+        return table.loc[valid, :], windows[valid]
+    return table, windows
+
+
+def pattern_detector(contact_map, kernel_config, kernel_matrix, coords=None, dump=None, full=False,
+                     tsvd=None):
+    """Detect (or, with `coords`, quantify) one pattern kernel on one sub-matrix
+    (det:177-345).  `contact_map` is anything with the attributes of
+    contacts_map.ContactMap that the reference reads: matrix, detectable_bins, max_dist,
+    inter (and name when dumping).
+
+    The sub-matrix stays in HBM for the whole call: normxcorr2, the thresholding of
+    pick_foci, the window gather / validation and the score and p-value lookups run on
+    the device; only candidate pixels, windows and the final table come back.
+    Returns (DataFrame[bin1, bin2, score, pvalue], windows) or (None, None)."""
+    import pandas as pd
+    from ..session import Session, records_to_numpy
+    kernel_matrix = np.asarray(kernel_matrix, dtype=np.float64)
+    km, kn = kernel_matrix.shape
+    kh, kw = (km - 1) // 2, (kn - 1) // 2
+    quantify = coords is not None
+    shape = contact_map.matrix.shape
+    if min(shape) <= max(kernel_matrix.shape):           # det:237-238
+        return None, None
+    inter = bool(contact_map.inter)
+    missing_mask = None
+    if full:                                             # det:241-250
+        missing_mask = preproc.make_missing_mask(
+            shape, valid_rows=contact_map.detectable_bins[0], valid_cols=contact_map.detectable_bins[1],
+            max_dist=contact_map.max_dist, sym_upper=not inter)
+    sess = Session()
+    try:
+        sess.upload(contact_map.matrix, kernel_matrix, max_dist=contact_map.max_dist,
+                    sym_upper=not inter, full=full, missing_mask=missing_mask, tsvd=tsvd, pval=True,
+                    missing_tol=kernel_config["max_perc_undetected"] / 100)
+        sess.run()
+        dmax = 2 ** 30 if inter else int(contact_map.max_dist)
+        dmin = -(2 ** 30) if inter else 0
+        if dump:
+            import pathlib
+            conv, _ = sess.download()
+            sp.save_npz(pathlib.Path(dump) / f"{contact_map.name}_03_normxcorr2", conv)
+            if not inter:
+                sp.save_npz(pathlib.Path(dump) / f"{contact_map.name}_04_diag_trim",
+                            preproc.diag_trim(conv.tocsr(), contact_map.max_dist))
+        if not quantify:
+            # det:277-283: pixels above the threshold -> foci -> one local maximum per focus;
+            # only the candidate pixels leave the device
+            thr = float(kernel_config["pearson"])
+            cap = 1 << 20
+            while True:
+                rec, n = sess.candidates(thr, dmin, dmax, cap=cap)
+                if n < cap:
+                    break
+                cap *= 4
+            cand = records_to_numpy(rec, n)
+            cmat = sp.coo_matrix((cand["score"].astype(np.float64), (cand["row"], cand["col"])), shape=shape)
+            coords, foci_mat = pick_foci(cmat, thr)
+            if coords is None:
+                return None, None
+            if dump:
+                sp.save_npz(pathlib.Path(dump) / f"{contact_map.name}_05_foci", foci_mat.tocsr())
+        coords = np.array(coords, dtype=np.int64).reshape(-1, 2)
+        if not inter and kernel_config["max_dist"] == 0:
+            # det:311-315: 1-D patterns sit on the diagonal of the padded map
+            coords[:, 0] = coords[:, 1] + ((kw - kh) if full else 0)
+        windows, valid, score, logp = sess.validate(
+            coords, contact_map.detectable_bins[0], contact_map.detectable_bins[1], inter,
+            kernel_config["max_perc_zero"] / 100, kernel_config["max_perc_undetected"] / 100, dmax)
+    finally:
+        sess.close()
+    score = np.where(valid, score, np.nan)
+    table = pd.DataFrame({"bin1": coords[:, 0], "bin2": coords[:, 1], "score": score,
+                          "pvalue": 10.0 ** logp})
+    if not quantify:                                     # det:328: drop in detect mode only
+        table = table.loc[valid, :].reset_index(drop=True)
+        windows = windows[valid]
+    return table, windows
+
+
 # --------------------------------------------------------------------------- foci (host)
 def label_foci(matrix):
     """4-connected component labelling of the non-zero pixels (det:459-554).

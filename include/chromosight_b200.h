@@ -154,6 +154,36 @@ int cs_scores_candidates(const cs_layout *Lout, const float *d_out, const uint16
                          int64_t *n_host, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Window gather + validation: detection.py:18-155 (validate_patterns) on the
+ * zero-padded, sub-diagonal-NaN matrix that pattern_detector builds
+ * (det:291-310), one warp per coordinate.  `d_coords` holds (row, col) pairs in
+ * PADDED coordinates.  Windows that fall outside the matrix or fail the
+ * zero / missing tolerances are filled with NaN and flagged 0 in d_valid.
+ * cs_scores_lookup: conv_mat[p1, p2] (det:134) and the log10 p-value (det:337-339)
+ * at UNPADDED coordinates of the score image; absent pixels read as 0.
+ * ------------------------------------------------------------------------ */
+typedef struct cs_gather_args {
+    int32_t rows, cols;            /* unpadded matrix */
+    const int64_t *d_indptr;       /* device CSR of the unpadded matrix (sorted indices) */
+    const int32_t *d_indices;
+    const double *d_data;
+    const uint8_t *d_valid_row;    /* device, 1 = detectable bin (NULL = all) */
+    const uint8_t *d_valid_col;
+    int32_t win_h, win_w;          /* kernel shape */
+    int32_t pad_rows, pad_cols;    /* zero padding above / left of the matrix (det:291-294) */
+    int32_t det_shift_row, det_shift_col; /* shift of the detectable ids (det:295-296) */
+    int32_t nan_subdiag;           /* big_k of det:300-310, 0 for inter maps */
+    double zero_tol, missing_tol;
+} cs_gather_args;
+int cs_window_gather(const cs_gather_args *a, const int32_t *d_coords, int64_t n_coords,
+                     double *d_windows /* n_coords * win_h * win_w */, uint8_t *d_valid,
+                     void *stream);
+int cs_scores_lookup(const cs_layout *Lout, const float *d_out, const uint16_t *d_nobs,
+                     int32_t nobs_const, int32_t dmin, int32_t dmax, const int32_t *d_coords,
+                     int64_t n_coords, double *d_score, double *d_log10p /* may be NULL */,
+                     void *stream);
+
+/* ------------------------------------------------------------------------
  * Distance-law detrending: preprocessing.py:129-197 (distance_law, smooth=False,
  * fun=nanmean) and preprocessing.py:256-310 (detrend).
  * cs_distance_law: per upper diagonal d <= max_dist, mean of the strictly
@@ -237,6 +267,14 @@ int cs_session_run(cs_session *s, cs_run_stats *stats);
 int cs_session_candidates(cs_session *s, float threshold, int32_t dmin, int32_t dmax,
                           cs_candidate *d_cand, int64_t cap, int64_t *d_count, int64_t *n_host);
 int cs_session_download(cs_session *s, cs_csr_result *res);
+/* validate_patterns on the session's matrix and last scores: host coordinates in
+ * (UNPADDED, n_coords x 2), host results out.  `full`/`inter` select the padding and NaN
+ * sub-diagonals of det:291-310; host_valid_row/col are uint8[rows]/[cols] (1 = detectable). */
+int cs_session_validate(cs_session *s, const int32_t *host_coords, int64_t n_coords,
+                        const uint8_t *host_valid_row, const uint8_t *host_valid_col,
+                        int32_t inter, double zero_tol, double missing_tol, int32_t score_dmax,
+                        double *host_windows, uint8_t *host_valid, double *host_score,
+                        double *host_log10p);
 
 #ifdef __cplusplus
 }

@@ -55,3 +55,34 @@ def load_case(name):
 def presets():
     from chromosight_b200 import kernels
     return kernels
+
+
+def detector_case_names():
+    return sorted(
+        os.path.basename(p)[len("detector_"):-len(".npz")]
+        for p in glob.glob(os.path.join(GOLDEN, "detector_*.npz"))
+    )
+
+
+class DummyMap:
+    """Stand-in for contacts_map.ContactMap with the attributes pattern_detector reads
+    (the reference's tests use the same double, tests/test_detection.py:88-100)."""
+
+    def __init__(self, matrix, max_dist=None, detectable_bins=None, inter=False, name="dummy"):
+        self.matrix = matrix
+        self.max_dist = max_dist
+        self.detectable_bins = detectable_bins
+        self.inter = inter
+        self.name = name
+
+
+def load_detector_case(name):
+    z = np.load(os.path.join(GOLDEN, f"detector_{name}.npz"))
+    meta = json.loads(str(z["meta"]))
+    cmap = DummyMap(load_coo(z, "matrix").tocsr(), meta["max_dist"], (z["detect_rows"], z["detect_cols"]),
+                    meta["inter"])
+    coords = z["coords_in"] if "coords_in" in z.files else None
+    exp = None
+    if not meta["none"]:
+        exp = {k: z[k] for k in ("bin1", "bin2", "pvalue", "score", "windows")}
+    return cmap, meta, z["kernel"], coords, exp

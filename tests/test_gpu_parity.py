@@ -274,3 +274,64 @@ def test_full_size_map_against_oracle_crops(kname, ksize, tol, pearson, presets)
             p0 = p0.copy()
             p0[lo:hi][far] = 0
         _compare(got, gp, exp, p0[lo:hi], nob[lo:hi])
+
+
+from conftest import DummyMap, detector_case_names, load_detector_case  # noqa: E402
+
+
+@pytest.mark.parametrize("name", detector_case_names())
+def test_pattern_detector_golden(name):
+    """The callers of the hot path: pattern_detector with the device-side
+    thresholding, window gather / validation and score lookups, against the reference's
+    own tables.  Foci coordinates and windows must be identical; scores within 1e-5;
+    log10 p-values within 1e-4 relative over the score range where foci live."""
+    from chromosight_b200.utils import detection as cud
+    cmap, meta, kernel, coords, exp = load_detector_case(name)
+    table, windows = cud.pattern_detector(cmap, meta["config"], kernel, coords=coords, full=meta["full"])
+    if exp is None:
+        assert table is None and windows is None
+        return
+    assert list(table.columns) == ["bin1", "bin2", "score", "pvalue"]
+    assert np.array_equal(table.bin1.to_numpy(), exp["bin1"])
+    assert np.array_equal(table.bin2.to_numpy(), exp["bin2"])
+    assert windows.shape == exp["windows"].shape
+    assert np.array_equal(np.isnan(windows), np.isnan(exp["windows"]))
+    assert np.allclose(windows, exp["windows"], rtol=1e-15, atol=0, equal_nan=True)
+    sc = table.score.to_numpy()
+    assert np.array_equal(np.isnan(sc), np.isnan(exp["score"]))
+    assert np.nanmax(np.abs(sc - exp["score"]), initial=0) <= SCORE_TOL
+    lp, lp0 = np.log10(table.pvalue.to_numpy()), np.log10(exp["pvalue"])
+    sel = np.isfinite(lp0) & (lp0 != 0)
+    assert np.array_equal(lp0 == 0, lp == 0)
+    # log10 p is ill-conditioned in r as |r| -> 1 (d log10p / dr ~ n / (1 - r^2)): the 1e-5
+    # score tolerance maps to a few 1e-4 relative there, so compare with 1e-3
+    assert np.allclose(lp[sel], lp0[sel], rtol=1e-3, atol=1e-4)
+
+
+def test_validate_patterns_standalone(presets):
+    """validate_patterns as a function of explicit matrices (det:18-155) against the oracle."""
+    from chromosight_b200.utils import detection as cud
+    from oracle import detector_oracle as do
+    rng = np.random.default_rng(9)
+    n, m = 120, 90
+    a = rng.poisson(3.0, size=(n, m)).astype(float) * (rng.random((n, m)) < 0.8)
+    a[rng.random((n, m)) < 0.01] = np.nan           # stored NaNs (the sub-diagonals of det:300-310)
+    conv = sp.random(n, m, density=0.3, random_state=3, format="csr")
+    vr = np.flatnonzero(rng.random(n) > 0.05)
+    vc = np.flatnonzero(rng.random(m) > 0.05)
+    coords = np.c_[rng.integers(0, n, 200), rng.integers(0, m, 200)]
+    kernel = presets.loops_small["kernels"][0][:, 1:6]          # 7 x 5
+    mr = np.ones(n, bool); mr[vr] = False
+    mc = np.ones(m, bool); mc[vc] = False
+    w0, ok0, s0 = do.validate_patterns_dense(coords, a, conv.toarray(), mr, mc, kernel.shape, 0.4, 0.6)
+    for drop in (True, False):
+        tab, win = cud.validate_patterns(coords, sp.csr_matrix(a), conv, (vr, vc), kernel, drop=drop,
+                                         zero_tol=0.4, missing_tol=0.6)
+        if drop:
+            assert np.array_equal(tab.bin1.to_numpy(), coords[ok0, 0])
+            assert np.allclose(win, w0[ok0], rtol=0, atol=0, equal_nan=True)
+            assert np.allclose(tab.score.to_numpy(), s0[ok0])
+        else:
+            assert len(tab) == 200 and np.allclose(win, w0, rtol=0, atol=0, equal_nan=True)
+            assert np.allclose(tab.score.to_numpy(), s0, equal_nan=True)
+    assert 0 < ok0.sum() < 200

@@ -83,3 +83,25 @@ def test_reference_known_answers():
     valid = np.array([0, 2, 4])
     exp = np.array([[0, 1, 0, 0, 0], [0, 1, 1, 0, 0], [0, 0, 0, 1, 0], [0, 0, 0, 1, 1], [0, 0, 0, 0, 0]], bool)
     assert np.array_equal(po.make_missing_mask_dense((5, 5), valid, valid, max_dist=1, sym_upper=True), exp)
+
+
+from conftest import detector_case_names, load_detector_case  # noqa: E402
+
+
+@pytest.mark.parametrize("name", detector_case_names())
+def test_detector_oracle_matches_reference(name):
+    """pattern_detector / validate_patterns restatement against the reference's own output
+    (coordinates, windows, p-values; scores as the trimmed map read at the coordinates)."""
+    from chromosight_b200.utils.detection import pick_foci      # host code, pinned by foci_cases.npz
+    from oracle import detector_oracle as do
+    cmap, meta, kernel, coords, exp = load_detector_case(name)
+    out = do.pattern_detector_dense(cmap.matrix.toarray(), cmap.detectable_bins, cmap.max_dist, cmap.inter,
+                                    meta["config"], kernel, pick_foci, coords=coords, full=meta["full"])
+    if exp is None:
+        assert out is None
+        return
+    b1, b2, score, pvalue, windows = out
+    assert np.array_equal(b1, exp["bin1"]) and np.array_equal(b2, exp["bin2"])
+    assert np.allclose(windows, exp["windows"], rtol=1e-12, atol=0, equal_nan=True)
+    assert np.allclose(score, exp["score"], rtol=0, atol=1e-9, equal_nan=True)
+    assert np.allclose(np.log10(pvalue), np.log10(exp["pvalue"]), rtol=1e-6, atol=1e-7)
