@@ -31,6 +31,27 @@ extern std::atomic<long long> g_launches;
         }                                                                          \
     } while (0)
 
+// row-ranged building blocks shared by the one-shot and the pipelined host paths
+int fill_begin(const cs_layout *L, float *d_img, int32_t n_rows, int32_t n_cols, int32_t mask_mode,
+               int32_t sym_upper, int32_t max_dist, int32_t frame_mk, int32_t frame_nk,
+               int32_t *d_err, cudaStream_t st);
+int fill_rows(const cs_layout *L, float *d_img, const int64_t *d_sig_indptr,
+              const int32_t *d_sig_indices, const double *d_sig_data, int32_t n_rows, int32_t r0,
+              int32_t r1, int32_t row_off, int32_t col_off, int32_t mask_mode,
+              const int64_t *d_mask_indptr, const int32_t *d_mask_indices, int32_t sym_upper,
+              int32_t max_dist, int32_t frame_mk, int32_t frame_nk, int32_t *d_err,
+              cudaStream_t st);
+// rows [r0, r1) of the score image: per-row counts + chunk-local scan (the slab total lands in
+// d_total), then the offsets (+ base) added, then the CSR entries written
+int scores_count_rows(const cs_layout *Lo, const float *d_out, int32_t dmin, int32_t dmax,
+                      int64_t *d_indptr, int32_t r0, int32_t r1, int64_t *d_total, cudaStream_t st);
+int scores_finish_rows(const cs_layout *Lo, int64_t *d_indptr, int32_t r0, int32_t r1,
+                       int64_t base, cudaStream_t st);
+int scores_emit_rows(const cs_layout *Lo, const float *d_out, const uint16_t *d_nobs,
+                     int32_t nobs_const, int32_t dmin, int32_t dmax, const int64_t *d_indptr,
+                     int32_t r0, int32_t r1, int32_t *d_indices, double *d_data, double *d_log10p,
+                     cudaStream_t st);
+
 #define CS_LAUNCHED() (cs::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }

@@ -40,7 +40,7 @@ constexpr size_t kStageBytes = 32u << 20;
 
 struct HostCtx {
     int device = -1;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr;
     void *stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -62,6 +62,7 @@ static int get_ctx(int device, HostCtx **out) {
     HostCtx *c = new HostCtx();
     c->device = device;
     CS_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    CS_CUDA(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         CS_CUDA(cudaHostAlloc(&c->stage[i], kStageBytes, cudaHostAllocDefault));
         CS_CUDA(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
@@ -139,6 +140,10 @@ static int pin_alloc(HostCtx *c, size_t bytes, void **out) {
     *out = p;
     return CS_OK;
 }
+
+// caller holds no lock on g_ctx_mu (pin_release takes it); used from scope guards
+static void pin_release(void *p);
+static void pin_release_unlocked(void *p) { pin_release(p); }
 
 static void pin_release(void *p) {
     if (!p) return;
@@ -228,7 +233,7 @@ extern "C" int cs_session_set_stream(cs_session *s, void *stream) {
 }
 
 // Plan the call and copy its inputs to the device (through pinned staging).
-extern "C" int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a) {
+static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool skip_payload) {
     CS_REQUIRE(s && a, "cs_session_upload: null argument");
     CS_REQUIRE(a->rows > 0 && a->cols > 0 && a->indptr && a->indices && a->data,
                "cs_session_upload: bad signal");
@@ -337,13 +342,17 @@ extern "C" int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a) {
     // ---- H2D ----------------------------------------------------------------------
     CS_CUDA(cudaEventRecord(s->ev[0], st));
     if ((rc = h2d_staged(c, st, s->sig_indptr.p, a->indptr, n_ip * sizeof(int64_t)))) return rc;
-    if ((rc = h2d_staged(c, st, s->sig_indices.p, a->indices, (size_t)s->nnz_in * sizeof(int32_t))))
-        return rc;
-    if ((rc = h2d_staged(c, st, s->sig_data.p, a->data, (size_t)s->nnz_in * sizeof(double)))) return rc;
+    if (!skip_payload) {
+        if ((rc = h2d_staged(c, st, s->sig_indices.p, a->indices,
+                             (size_t)s->nnz_in * sizeof(int32_t))))
+            return rc;
+        if ((rc = h2d_staged(c, st, s->sig_data.p, a->data, (size_t)s->nnz_in * sizeof(double))))
+            return rc;
+    }
     s->h2d_bytes = n_ip * sizeof(int64_t) + (size_t)s->nnz_in * (sizeof(int32_t) + sizeof(double));
     if (a->has_mask) {
         if ((rc = h2d_staged(c, st, s->m_indptr.p, a->mask_indptr, n_ip * sizeof(int64_t)))) return rc;
-        if (s->nnz_m > 0)
+        if (s->nnz_m > 0 && !skip_payload)
             if ((rc = h2d_staged(c, st, s->m_indices.p, a->mask_indices,
                                  (size_t)s->nnz_m * sizeof(int32_t))))
                 return rc;
@@ -352,6 +361,10 @@ extern "C" int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a) {
     CS_CUDA(cudaEventRecord(s->ev[1], st));
     s->uploaded = true;
     return CS_OK;
+}
+
+extern "C" int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a) {
+    return session_upload_impl(s, a, false);
 }
 
 // fill -> Pearson -> CSR compaction, all on the device, inputs already resident.
@@ -543,6 +556,212 @@ extern "C" int cs_session_download(cs_session *s, cs_csr_result *res) {
     return CS_OK;
 }
 
+// Large calls: the same work as upload + run + download, cut into row slabs so that the
+// upload of slab s+1, the kernels of slab s and the download of slab s-1 overlap (PCIe is
+// full duplex; the CSR result is 5x the input).  Per slab, on the compute stream:
+//   H2D of the CSR rows it adds -> fill of those image rows -> Pearson tiles of its output
+//   rows -> per-row counts + scan; once its non-zero count is known on the host: row
+//   pointers, CSR entries + p-values; then, on the copy stream, its D2H.
+static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_csr_result *res,
+                                int nslab) {
+    int rc = session_upload_impl(s, a, true);
+    if (rc) return rc;
+    if (s->empty) return 1;  // nothing to pipeline: the caller finishes through run + download
+    HostCtx *c = s->c;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = s->stream(), st_d = c->st_copy;
+    const cs_normxcorr2_args &A = s->a;
+    const cs_kernel_desc &K = A.kernel;
+    const int kh = (K.kh - 1) / 2;
+    const size_t n_ip = (size_t)A.rows + 1;
+    memset(res, 0, sizeof(*res));
+    res->rows = A.rows;
+    res->cols = A.cols;
+    res->n_windows = s->n_windows;
+    // worst-case result buffers: every window non-zero
+    const size_t cap = (size_t)s->n_windows;
+    if ((rc = s->r_indices.ensure(cap * sizeof(int32_t)))) return rc;
+    if ((rc = s->r_data.ensure(cap * sizeof(double)))) return rc;
+    if (A.pval)
+        if ((rc = s->r_p.ensure(cap * sizeof(double)))) return rc;
+    void *h_ip = nullptr, *h_ix = nullptr, *h_d = nullptr, *h_p = nullptr, *h_ip2 = nullptr,
+         *h_ix2 = nullptr, *h_tot = nullptr;
+    if ((rc = pin_alloc(c, n_ip * sizeof(int64_t), &h_ip))) return rc;
+    res->indptr = (int64_t *)h_ip;
+    if ((rc = pin_alloc(c, cap * sizeof(int32_t), &h_ix))) return rc;
+    res->indices = (int32_t *)h_ix;
+    if ((rc = pin_alloc(c, cap * sizeof(double), &h_d))) return rc;
+    res->data = (double *)h_d;
+    if (A.pval) {
+        if ((rc = pin_alloc(c, cap * sizeof(double), &h_p))) return rc;
+        res->log10p = (double *)h_p;
+        if ((rc = pin_alloc(c, n_ip * sizeof(int64_t), &h_ip2))) return rc;
+        res->p_indptr = (int64_t *)h_ip2;
+        if ((rc = pin_alloc(c, cap * sizeof(int32_t), &h_ix2))) return rc;
+        res->p_indices = (int32_t *)h_ix2;
+    }
+    if ((rc = pin_alloc(c, (size_t)(nslab + 1) * sizeof(int64_t), &h_tot))) return rc;
+    struct Guard {  // the totals block goes back to the pool whatever happens
+        void *p;
+        ~Guard() { pin_release_unlocked(p); }
+    } guard{h_tot};
+    int64_t *tot = (int64_t *)h_tot;
+    std::vector<cudaEvent_t> ev_tot(nslab), ev_emit(nslab);
+    for (int i = 0; i < nslab; ++i) {
+        CS_CUDA(cudaEventCreateWithFlags(&ev_tot[i], cudaEventDisableTiming));
+        CS_CUDA(cudaEventCreateWithFlags(&ev_emit[i], cudaEventDisableTiming));
+    }
+    struct EvGuard {
+        std::vector<cudaEvent_t> &a, &b;
+        ~EvGuard() {
+            for (auto e : a) cudaEventDestroy(e);
+            for (auto e : b) cudaEventDestroy(e);
+        }
+    } evguard{ev_tot, ev_emit};
+
+    CS_CUDA(cudaEventRecord(s->ev[2], st));
+    rc = fill_begin(&s->Li, (float *)s->img.p, A.rows, A.cols, A.has_mask ? 1 : 0, A.sym_upper,
+                    A.max_dist, A.full ? K.kh : 0, A.full ? K.kw : 0, (int32_t *)s->err.p, st);
+    if (rc) return rc;
+    CS_CUDA(cudaMemsetAsync(s->out.p, 0, (size_t)s->Lo.n_elems * sizeof(float), st));
+    cs_pearson_opts po;
+    memset(&po, 0, sizeof(po));
+    po.has_mask = A.has_mask;
+    po.missing_tol = A.missing_tol;
+    po.xcorr_threshold = A.raw_xcorr ? A.xcorr_threshold : 1e-4;
+    po.raw_xcorr = A.raw_xcorr;
+    po.nobs_full = s->want_nobs ? 1 : 0;
+    po.out_row_shift = s->pr;
+    po.out_col_shift = s->pc;
+    po.strip_dlo = 0;
+    po.strip_dhi = -1;
+    if (A.has_mask && A.full && A.sym_upper) {
+        const int big_k = K.kh > K.kw ? K.kh : K.kw;
+        po.strip_dlo = -big_k;
+        po.strip_dhi = -1;
+    }
+    const uint16_t *nb = s->want_nobs ? (const uint16_t *)s->nobs.p : nullptr;
+    // slab boundaries in image rows (multiples of the tile height)
+    std::vector<int> Yb(nslab + 1);
+    for (int i = 0; i <= nslab; ++i) {
+        long long y = (long long)(s->oy1 - s->oy0) * i / nslab;
+        y = (y + 16) / 32 * 32;
+        Yb[i] = s->oy0 + (int)(y > s->oy1 - s->oy0 ? s->oy1 - s->oy0 : y);
+    }
+    Yb[0] = s->oy0;
+    Yb[nslab] = s->oy1;
+    auto csr_row = [&](int i) { return i == 0 ? 0 : (i == nslab ? A.rows : Yb[i] - s->pr); };
+    int up_end = 0;
+    int64_t base = 0;
+    auto finalize = [&](int k) -> int {
+        CS_CUDA(cudaEventSynchronize(ev_tot[k]));
+        const int64_t nnz_k = tot[k];
+        const int cr0 = csr_row(k), cr1 = csr_row(k + 1);
+        int r = scores_finish_rows(&s->Lo, (int64_t *)s->r_indptr.p, cr0, cr1, base, st);
+        if (r) return r;
+        if (nnz_k > 0) {
+            r = scores_emit_rows(&s->Lo, (const float *)s->out.p, nb, K.kh * K.kw, -(1 << 30),
+                                 1 << 30, (const int64_t *)s->r_indptr.p, cr0, cr1,
+                                 (int32_t *)s->r_indices.p, (double *)s->r_data.p,
+                                 A.pval ? (double *)s->r_p.p : nullptr, st);
+            if (r) return r;
+        }
+        CS_CUDA(cudaEventRecord(ev_emit[k], st));
+        CS_CUDA(cudaStreamWaitEvent(st_d, ev_emit[k], 0));
+        if (nnz_k > 0) {
+            const size_t o = (size_t)base, n = (size_t)nnz_k;
+            CS_CUDA(cudaMemcpyAsync((int32_t *)h_ix + o, (int32_t *)s->r_indices.p + o,
+                                    n * sizeof(int32_t), cudaMemcpyDeviceToHost, st_d));
+            CS_CUDA(cudaMemcpyAsync((double *)h_d + o, (double *)s->r_data.p + o, n * sizeof(double),
+                                    cudaMemcpyDeviceToHost, st_d));
+            if (A.pval) {
+                CS_CUDA(cudaMemcpyAsync((double *)h_p + o, (double *)s->r_p.p + o,
+                                        n * sizeof(double), cudaMemcpyDeviceToHost, st_d));
+                CS_CUDA(cudaMemcpyAsync((int32_t *)h_ix2 + o, (int32_t *)s->r_indices.p + o,
+                                        n * sizeof(int32_t), cudaMemcpyDeviceToHost, st_d));
+            }
+        }
+        base += nnz_k;
+        return CS_OK;
+    };
+    for (int k = 0; k < nslab; ++k) {
+        const int Y0 = Yb[k], Y1 = Yb[k + 1];
+        // signal rows the windows of this slab read: image rows < Y1 + kh
+        int need = Y1 + kh - s->pr;
+        if (need > A.rows || k == nslab - 1) need = A.rows;
+        if (need > up_end) {
+            const int64_t e0 = a->indptr[up_end], e1 = a->indptr[need];
+            if (e1 > e0) {
+                if ((rc = h2d_staged(c, st, (int32_t *)s->sig_indices.p + e0, a->indices + e0,
+                                     (size_t)(e1 - e0) * sizeof(int32_t))))
+                    return rc;
+                if ((rc = h2d_staged(c, st, (double *)s->sig_data.p + e0, a->data + e0,
+                                     (size_t)(e1 - e0) * sizeof(double))))
+                    return rc;
+            }
+            if (A.has_mask) {
+                const int64_t m0 = a->mask_indptr[up_end], m1 = a->mask_indptr[need];
+                if (m1 > m0)
+                    if ((rc = h2d_staged(c, st, (int32_t *)s->m_indices.p + m0,
+                                         a->mask_indices + m0, (size_t)(m1 - m0) * sizeof(int32_t))))
+                        return rc;
+            }
+            rc = fill_rows(&s->Li, (float *)s->img.p, (const int64_t *)s->sig_indptr.p,
+                           (const int32_t *)s->sig_indices.p, (const double *)s->sig_data.p, A.rows,
+                           up_end, need, s->pr, s->pc, A.has_mask ? 1 : 0,
+                           (const int64_t *)s->m_indptr.p, (const int32_t *)s->m_indices.p,
+                           A.sym_upper, A.max_dist, A.full ? K.kh : 0, A.full ? K.kw : 0,
+                           (int32_t *)s->err.p, st);
+            if (rc) return rc;
+            up_end = need;
+        }
+        if (Y1 > Y0) {
+            rc = cs_pearson_f32(&s->Li, (const float *)s->img.p, &K, &po, Y0, Y1, s->ox0, s->ox1,
+                                s->od_lo, s->od_hi, &s->Lo, (float *)s->out.p,
+                                s->want_nobs ? (uint16_t *)s->nobs.p : nullptr, st);
+            if (rc) return rc;
+        }
+        if (k > 0 && (rc = finalize(k - 1))) return rc;
+        // the slab total is written straight into pinned host memory (UVA): a D2H copy on this
+        // stream would queue behind the bulk downloads of the copy stream
+        tot[k] = 0;
+        rc = scores_count_rows(&s->Lo, (const float *)s->out.p, -(1 << 30), 1 << 30,
+                               (int64_t *)s->r_indptr.p, csr_row(k), csr_row(k + 1), tot + k, st);
+        if (rc) return rc;
+        CS_CUDA(cudaEventRecord(ev_tot[k], st));
+    }
+    if ((rc = finalize(nslab - 1))) return rc;
+    int32_t *herr = (int32_t *)(tot + nslab);  // last slot of the pinned totals block
+    CS_CUDA(cudaMemcpyAsync(herr, s->err.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaMemcpyAsync(h_ip, s->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (A.pval)
+        CS_CUDA(cudaMemcpyAsync(h_ip2, s->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                st));
+    CS_CUDA(cudaEventRecord(s->ev[5], st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    CS_CUDA(cudaStreamSynchronize(st_d));
+    if (herr[0] > 0 && A.has_mask) {
+        set_error("There are %d non-zero elements reported as missing.", herr[0]);
+        return CS_ERR_MASKED_SIGNAL;
+    }
+    if (herr[1] > 0 && !A.trim_to_max_dist) {
+        set_error("internal: %d signal pixels fell outside the stored band", herr[1]);
+        return CS_ERR_INVALID;
+    }
+    s->nnz_out = base;
+    s->ran = true;
+    res->nnz = base;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev[2], s->ev[5]);
+    res->ms_kernels = ms;  // upload, kernels and most of the download overlap inside this span
+    res->h2d_bytes = (int64_t)s->h2d_bytes;
+    res->d2h_bytes = (int64_t)(n_ip * sizeof(int64_t) * (A.pval ? 2 : 1) +
+                               (size_t)base * (sizeof(int32_t) * (A.pval ? 2 : 1) +
+                                               sizeof(double) * (A.pval ? 2 : 1)));
+    return CS_OK;
+}
+
 // One-shot: upload + run + download on a per-device cached session.
 extern "C" int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *res) {
     CS_REQUIRE(a && res, "cs_normxcorr2_host: null argument");
@@ -559,7 +778,23 @@ extern "C" int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *re
             cache.push_back(s);
         }
     }
-    int rc = cs_session_upload(s, a);
+    // big calls go through the slab pipeline
+    bool uploaded = false;
+    {
+        long long rows_out = a->full ? a->rows : a->rows - (a->kernel.kh - 1);
+        const int64_t nnz_in = a->indptr ? a->indptr[a->rows] : 0;
+        int nslab = 8;
+        if (const char *e = getenv("CS_PIPELINE_SLABS")) nslab = atoi(e);
+        if (nslab > 1 && nnz_in >= (4 << 20) && rows_out >= 64 * nslab) {
+            int rc = normxcorr2_pipelined(s, a, res, nslab);
+            if (rc != 1) {
+                if (rc) cs_result_free(res);
+                return rc;
+            }
+            uploaded = true;
+        }
+    }
+    int rc = uploaded ? CS_OK : cs_session_upload(s, a);
     if (rc) return rc;
     float ms_h2d = 0.f;
     cs_run_stats stt;

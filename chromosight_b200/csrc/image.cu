@@ -38,11 +38,11 @@ __device__ __forceinline__ long long at(const FillParams &F, int Y, int X) {
 // one warp per CSR row
 __global__ void scatter_signal(FillParams F, const int64_t *__restrict__ indptr,
                                const int32_t *__restrict__ indices,
-                               const double *__restrict__ data, int n_rows, float *img,
+                               const double *__restrict__ data, int r0, int r1, float *img,
                                int *err) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += gridDim.x * wpb) {
+    for (int r = r0 + blockIdx.x * wpb + (threadIdx.x >> 5); r < r1; r += gridDim.x * wpb) {
         const int64_t b = indptr[r], e = indptr[r + 1];
         const int Y = r + F.row_off;
         for (int64_t k = b + lane; k < e; k += 32) {
@@ -61,11 +61,11 @@ __global__ void scatter_signal(FillParams F, const int64_t *__restrict__ indptr,
 
 // user mask pixels -> NaN; counts signal pixels that are non-zero under the mask
 __global__ void scatter_mask(FillParams F, const int64_t *__restrict__ indptr,
-                             const int32_t *__restrict__ indices, int n_rows, int trim_lo,
+                             const int32_t *__restrict__ indices, int r0, int r1, int trim_lo,
                              int trim_hi, int do_trim, float *img, int *err) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += gridDim.x * wpb) {
+    for (int r = r0 + blockIdx.x * wpb + (threadIdx.x >> 5); r < r1; r += gridDim.x * wpb) {
         const int64_t b = indptr[r], e = indptr[r + 1];
         const int Y = r + F.row_off;
         for (int64_t k = b + lane; k < e; k += 32) {
@@ -94,11 +94,11 @@ __global__ void nan_rect(FillParams F, int y0, int y1, int x0, int x1, float *im
 }
 
 // pre:483-497: big_k diagonals below the main diagonal of the framed image
-__global__ void nan_subdiag(FillParams F, int big_k, float *img, int *err) {
-    const long long n = (long long)F.rows * big_k;
+__global__ void nan_subdiag(FillParams F, int big_k, int Y0, int Y1, float *img, int *err) {
+    const long long n = (long long)(Y1 - Y0) * big_k;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
-        const int Y = (int)(i / big_k), X = Y - 1 - (int)(i % big_k);
+        const int Y = Y0 + (int)(i / big_k), X = Y - 1 - (int)(i % big_k);
         if (!stored(F, Y, X)) continue;
         const long long k = at(F, Y, X);
         const float v = img[k];
@@ -147,6 +147,109 @@ extern "C" int cs_layout_dense(cs_layout *L, int32_t rows, int32_t cols) {
     return CS_OK;
 }
 
+namespace cs {
+
+static FillParams make_fill(const cs_layout *L, int row_off, int col_off) {
+    FillParams F;
+    F.rows = L->rows;
+    F.cols = L->cols;
+    F.dlo = L->dlo;
+    F.dhi = L->dhi;
+    F.pitch = L->pitch;
+    F.dense = L->dense;
+    F.row_off = row_off;
+    F.col_off = col_off;
+    return F;
+}
+
+// Zero the image and the error counters, write the margin rectangles of
+// frame_missing_mask (pre:461-480); they never overlap the signal.
+int fill_begin(const cs_layout *L, float *d_img, int32_t n_rows, int32_t n_cols, int32_t mask_mode,
+               int32_t sym_upper, int32_t max_dist, int32_t frame_mk, int32_t frame_nk,
+               int32_t *d_err, cudaStream_t st) {
+    FillParams F = make_fill(L, 0, 0);
+    CS_CUDA(cudaMemsetAsync(d_img, 0, (size_t)L->n_elems * sizeof(float), st));
+    CS_CUDA(cudaMemsetAsync(d_err, 0, 2 * sizeof(int32_t), st));
+    if (mask_mode == 1 && frame_mk > 0) {
+        const int threads = 256;
+        const bool banded = sym_upper && max_dist >= 0;
+        const int H = L->rows, W = L->cols, mk = frame_mk, nk = frame_nk;
+        const int ns = n_cols;
+        struct R {
+            int y0, y1, x0, x1;
+        } rc[4];
+        int nr = 0;
+        if (banded) {
+            const int max_m = max_dist + mk, max_n = max_dist + nk;
+            const int tn = max_n < ns ? max_n : ns;
+            rc[nr++] = {0, mk - 1, nk - 1, nk - 1 + tn};                                 // pre:461-463
+            rc[nr++] = {H - (max_m + 1) > 0 ? H - (max_m + 1) : 0, H, W - (nk - 1), W};  // pre:475
+            rc[nr++] = {0, mk - 1, 0, nk - 1};                                           // pre:477
+        } else {
+            rc[nr++] = {0, mk - 1, 0, W};
+            rc[nr++] = {H - (mk - 1), H, 0, W};
+            rc[nr++] = {0, H, 0, nk - 1};
+            rc[nr++] = {0, H, W - (nk - 1), W};
+        }
+        for (int i = 0; i < nr; ++i) {
+            const long long n = (long long)(rc[i].y1 - rc[i].y0) * (rc[i].x1 - rc[i].x0);
+            if (n <= 0) continue;
+            int g = (int)((n + threads - 1) / threads);
+            if (g > 148 * 8) g = 148 * 8;
+            nan_rect<<<g, threads, 0, st>>>(F, rc[i].y0, rc[i].y1, rc[i].x0, rc[i].x1, d_img);
+            CS_LAUNCHED();
+        }
+    }
+    CS_CUDA(cudaGetLastError());
+    (void)n_rows;
+    return CS_OK;
+}
+
+// Signal rows [r0, r1): scatter the signal, then the user mask, then the sub-diagonal mask
+// of the image rows they occupy (the first / last call also covers the top / bottom frame).
+int fill_rows(const cs_layout *L, float *d_img, const int64_t *d_sig_indptr,
+              const int32_t *d_sig_indices, const double *d_sig_data, int32_t n_rows,
+              int32_t r0, int32_t r1, int32_t row_off, int32_t col_off, int32_t mask_mode,
+              const int64_t *d_mask_indptr, const int32_t *d_mask_indices, int32_t sym_upper,
+              int32_t max_dist, int32_t frame_mk, int32_t frame_nk, int32_t *d_err,
+              cudaStream_t st) {
+    if (r1 <= r0) return CS_OK;
+    FillParams F = make_fill(L, row_off, col_off);
+    const int threads = 256;
+    const int wpb = threads / 32;
+    int grid = (r1 - r0 + wpb - 1) / wpb;
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (d_sig_indptr) {
+        scatter_signal<<<grid, threads, 0, st>>>(F, d_sig_indptr, d_sig_indices, d_sig_data, r0, r1,
+                                                 d_img, d_err);
+        CS_LAUNCHED();
+    }
+    if (mask_mode == 1) {
+        const bool framed = frame_mk > 0;
+        const bool banded = sym_upper && max_dist >= 0;
+        const int big_k = frame_mk > frame_nk ? frame_mk : frame_nk;
+        scatter_mask<<<grid, threads, 0, st>>>(F, d_mask_indptr, d_mask_indices, r0, r1, 0,
+                                               max_dist + big_k, (framed && banded) ? 1 : 0, d_img,
+                                               d_err);
+        CS_LAUNCHED();
+        if (framed && sym_upper) {
+            const int Y0 = r0 == 0 ? 0 : r0 + row_off;
+            const int Y1 = r1 == n_rows ? L->rows : r1 + row_off;
+            const long long n = (long long)(Y1 - Y0) * big_k;
+            int g = (int)((n + threads - 1) / threads);
+            if (g > 148 * 16) g = 148 * 16;
+            if (g > 0) {
+                nan_subdiag<<<g, threads, 0, st>>>(F, big_k, Y0, Y1, d_img, d_err);
+                CS_LAUNCHED();
+            }
+        }
+    }
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+}  // namespace cs
+
 extern "C" int cs_image_fill_f32(const cs_layout *L, float *d_img, const int64_t *d_sig_indptr,
                                  const int32_t *d_sig_indices, const double *d_sig_data,
                                  int32_t n_rows, int32_t n_cols, int32_t row_off, int32_t col_off,
@@ -158,73 +261,11 @@ extern "C" int cs_image_fill_f32(const cs_layout *L, float *d_img, const int64_t
     CS_REQUIRE(L && d_img && d_err, "cs_image_fill_f32: null argument");
     CS_REQUIRE(n_rows + row_off <= L->rows && n_cols + col_off <= L->cols,
                "signal does not fit in the image");
-    FillParams F;
-    F.rows = L->rows;
-    F.cols = L->cols;
-    F.dlo = L->dlo;
-    F.dhi = L->dhi;
-    F.pitch = L->pitch;
-    F.dense = L->dense;
-    F.row_off = row_off;
-    F.col_off = col_off;
-    CS_CUDA(cudaMemsetAsync(d_img, 0, (size_t)L->n_elems * sizeof(float), st));
-    CS_CUDA(cudaMemsetAsync(d_err, 0, 2 * sizeof(int32_t), st));
-    const int threads = 256;
-    const int wpb = threads / 32;
-    if (d_sig_indptr && n_rows > 0) {
-        int grid = (n_rows + wpb - 1) / wpb;
-        if (grid > 148 * 16) grid = 148 * 16;
-        scatter_signal<<<grid, threads, 0, st>>>(F, d_sig_indptr, d_sig_indices, d_sig_data,
-                                                 n_rows, d_img, d_err);
-        CS_LAUNCHED();
-    }
-    if (mask_mode == 1) {
-        CS_REQUIRE(d_mask_indptr && d_mask_indices, "mask arrays missing");
-        const bool framed = frame_mk > 0;
-        const bool banded = sym_upper && max_dist >= 0;
-        const int big_k = frame_mk > frame_nk ? frame_mk : frame_nk;
-        int grid = (n_rows + wpb - 1) / wpb;
-        if (grid > 148 * 16) grid = 148 * 16;
-        scatter_mask<<<grid, threads, 0, st>>>(F, d_mask_indptr, d_mask_indices, n_rows, 0,
-                                               max_dist + big_k, (framed && banded) ? 1 : 0, d_img,
-                                               d_err);
-        CS_LAUNCHED();
-        if (framed) {
-            const int H = L->rows, W = L->cols, mk = frame_mk, nk = frame_nk;
-            const int ns = n_cols;
-            struct R {
-                int y0, y1, x0, x1;
-            } rc[4];
-            int nr = 0;
-            if (banded) {
-                const int max_m = max_dist + mk, max_n = max_dist + nk;
-                const int tn = max_n < ns ? max_n : ns;
-                rc[nr++] = {0, mk - 1, nk - 1, nk - 1 + tn};                           // pre:461-463
-                rc[nr++] = {H - (max_m + 1) > 0 ? H - (max_m + 1) : 0, H, W - (nk - 1), W};  // pre:475
-                rc[nr++] = {0, mk - 1, 0, nk - 1};                                     // pre:477
-            } else {
-                rc[nr++] = {0, mk - 1, 0, W};
-                rc[nr++] = {H - (mk - 1), H, 0, W};
-                rc[nr++] = {0, H, 0, nk - 1};
-                rc[nr++] = {0, H, W - (nk - 1), W};
-            }
-            for (int i = 0; i < nr; ++i) {
-                const long long n = (long long)(rc[i].y1 - rc[i].y0) * (rc[i].x1 - rc[i].x0);
-                if (n <= 0) continue;
-                int g = (int)((n + threads - 1) / threads);
-                if (g > 148 * 8) g = 148 * 8;
-                nan_rect<<<g, threads, 0, st>>>(F, rc[i].y0, rc[i].y1, rc[i].x0, rc[i].x1, d_img);
-                CS_LAUNCHED();
-            }
-            if (sym_upper) {
-                const long long n = (long long)H * big_k;
-                int g = (int)((n + threads - 1) / threads);
-                if (g > 148 * 16) g = 148 * 16;
-                nan_subdiag<<<g, threads, 0, st>>>(F, big_k, d_img, d_err);
-                CS_LAUNCHED();
-            }
-        }
-    }
-    CS_CUDA(cudaGetLastError());
-    return CS_OK;
+    if (mask_mode == 1) CS_REQUIRE(d_mask_indptr && d_mask_indices, "mask arrays missing");
+    int rc = fill_begin(L, d_img, n_rows, n_cols, mask_mode, sym_upper, max_dist, frame_mk, frame_nk,
+                        d_err, st);
+    if (rc) return rc;
+    return fill_rows(L, d_img, d_sig_indptr, d_sig_indices, d_sig_data, n_rows, 0, n_rows, row_off,
+                     col_off, mask_mode, d_mask_indptr, d_mask_indices, sym_upper, max_dist,
+                     frame_mk, frame_nk, d_err, st);
 }

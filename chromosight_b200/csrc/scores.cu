@@ -36,10 +36,11 @@ __device__ __forceinline__ double log10_pval(double r, double n_obs) {
     return log10(erfc(a));
 }
 
-__global__ void count_rows(ScoreView S, const float *__restrict__ sc, int64_t *counts) {
+__global__ void count_rows(ScoreView S, const float *__restrict__ sc, int64_t *counts, int r0,
+                           int r1) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    for (int y = blockIdx.x * wpb + (threadIdx.x >> 5); y < S.rows; y += gridDim.x * wpb) {
+    for (int y = r0 + blockIdx.x * wpb + (threadIdx.x >> 5); y < r1; y += gridDim.x * wpb) {
         int x0, x1;
         row_range(S, y, x0, x1);
         int c = 0;
@@ -47,7 +48,7 @@ __global__ void count_rows(ScoreView S, const float *__restrict__ sc, int64_t *c
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (lane == 0) counts[y + 1] = c;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = 0;
+    if (r0 == 0 && blockIdx.x == 0 && threadIdx.x == 0) counts[0] = 0;
 }
 
 // In-place inclusive scan of a[1..n] (a[0] = 0), three launches: every block scans a chunk
@@ -102,7 +103,7 @@ __global__ void scan_chunks(int64_t *a, int n, int64_t *totals) {
 }
 
 // exclusive scan of the chunk totals by one block
-__global__ void scan_totals(int64_t *totals, int m) {
+__global__ void scan_totals(int64_t *totals, int m, int64_t *grand) {
     __shared__ long long wsum[32];
     long long carry = 0;
     for (int base = 0; base < m; base += blockDim.x) {
@@ -113,11 +114,14 @@ __global__ void scan_totals(int64_t *totals, int m) {
         if (i < m) totals[i] = carry + pre;
         carry += total;
     }
+    if (threadIdx.x == 0 && grand) {
+        *grand = carry;  // may be pinned host memory
+        __threadfence_system();
+    }
 }
 
-__global__ void scan_add(int64_t *a, int n, const int64_t *totals) {
-    const long long off = totals[blockIdx.x];
-    if (blockIdx.x == 0 && threadIdx.x == 0) a[0] = 0;
+__global__ void scan_add(int64_t *a, int n, const int64_t *totals, long long base_off) {
+    const long long off = totals[blockIdx.x] + base_off;
     if (off == 0) return;
     const long long base = 1 + (long long)blockIdx.x * kScanChunk + (long long)threadIdx.x * kScanPer;
 #pragma unroll
@@ -128,10 +132,10 @@ __global__ void scan_add(int64_t *a, int n, const int64_t *totals) {
 __global__ void emit_rows(ScoreView S, const float *__restrict__ sc,
                           const unsigned short *__restrict__ nobs, int nobs_const,
                           const int64_t *__restrict__ indptr, int32_t *indices, double *data,
-                          double *log10p) {
+                          double *log10p, int r0, int r1) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    for (int y = blockIdx.x * wpb + (threadIdx.x >> 5); y < S.rows; y += gridDim.x * wpb) {
+    for (int y = r0 + blockIdx.x * wpb + (threadIdx.x >> 5); y < r1; y += gridDim.x * wpb) {
         int x0, x1;
         row_range(S, y, x0, x1);
         int64_t pos = indptr[y];
@@ -211,37 +215,73 @@ static ScoreView make_view(const cs_layout *L, int dmin, int dmax) {
     return S;
 }
 
+static int64_t *scan_scratch_of(const cs_layout *Lo, int64_t *d_indptr) {
+    // chunk totals live behind the row pointers (d_indptr holds rows + 1 + cs_scan_scratch(rows))
+    return d_indptr + (size_t)Lo->rows + 1;
+}
+
+int scores_count_rows(const cs_layout *Lo, const float *d_out, int32_t dmin, int32_t dmax,
+                      int64_t *d_indptr, int32_t r0, int32_t r1, int64_t *d_total, cudaStream_t st) {
+    if (r1 <= r0) return CS_OK;
+    ScoreView S = make_view(Lo, dmin, dmax);
+    const int n = r1 - r0;
+    int grid = (n + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    count_rows<<<grid, 256, 0, st>>>(S, d_out, d_indptr, r0, r1);
+    CS_LAUNCHED();
+    const int nchunk = (n + kScanChunk - 1) / kScanChunk;
+    int64_t *totals = scan_scratch_of(Lo, d_indptr);
+    scan_chunks<<<nchunk, kScanThreads, 0, st>>>(d_indptr + r0, n, totals);
+    CS_LAUNCHED();
+    scan_totals<<<1, 1024, 0, st>>>(totals, nchunk, d_total);
+    CS_LAUNCHED();
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+int scores_finish_rows(const cs_layout *Lo, int64_t *d_indptr, int32_t r0, int32_t r1, int64_t base,
+                       cudaStream_t st) {
+    if (r1 <= r0) return CS_OK;
+    const int n = r1 - r0;
+    const int nchunk = (n + kScanChunk - 1) / kScanChunk;
+    scan_add<<<nchunk, kScanThreads, 0, st>>>(d_indptr + r0, n, scan_scratch_of(Lo, d_indptr),
+                                              (long long)base);
+    CS_LAUNCHED();
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+int scores_emit_rows(const cs_layout *Lo, const float *d_out, const uint16_t *d_nobs,
+                     int32_t nobs_const, int32_t dmin, int32_t dmax, const int64_t *d_indptr,
+                     int32_t r0, int32_t r1, int32_t *d_indices, double *d_data, double *d_log10p,
+                     cudaStream_t st) {
+    if (r1 <= r0) return CS_OK;
+    ScoreView S = make_view(Lo, dmin, dmax);
+    int grid = (r1 - r0 + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    emit_rows<<<grid, 256, 0, st>>>(S, d_out, d_nobs, nobs_const, d_indptr, d_indices, d_data,
+                                    d_log10p, r0, r1);
+    CS_LAUNCHED();
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
 }  // namespace cs
 
 using namespace cs;
 
 extern "C" int64_t cs_scan_scratch(int32_t rows) {
-    return (int64_t)((rows + cs::kScanChunk - 1) / cs::kScanChunk) + 1;
+    return (int64_t)((rows + cs::kScanChunk - 1) / cs::kScanChunk) + 2;
 }
 
 extern "C" int cs_scores_count(const cs_layout *Lo, const float *d_out, int32_t dmin, int32_t dmax,
                                int64_t *d_indptr, int64_t *nnz_host, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CS_REQUIRE(Lo && d_out && d_indptr && nnz_host, "cs_scores_count: null argument");
-    ScoreView S = make_view(Lo, dmin, dmax);
-    int grid = (S.rows + 7) / 8;
-    if (grid > 148 * 16) grid = 148 * 16;
-    count_rows<<<grid, 256, 0, st>>>(S, d_out, d_indptr);
-    CS_LAUNCHED();
-    {
-        // chunk totals live behind the row pointers (the caller sizes d_indptr to rows + 1 +
-        // cs_scan_scratch(rows) elements)
-        const int nchunk = (S.rows + kScanChunk - 1) / kScanChunk;
-        int64_t *totals = d_indptr + (size_t)S.rows + 1;
-        scan_chunks<<<nchunk, kScanThreads, 0, st>>>(d_indptr, S.rows, totals);
-        CS_LAUNCHED();
-        scan_totals<<<1, 1024, 0, st>>>(totals, nchunk);
-        CS_LAUNCHED();
-        scan_add<<<nchunk, kScanThreads, 0, st>>>(d_indptr, S.rows, totals);
-        CS_LAUNCHED();
-    }
-    CS_CUDA(cudaGetLastError());
-    CS_CUDA(cudaMemcpyAsync(nnz_host, d_indptr + S.rows, sizeof(int64_t), cudaMemcpyDeviceToHost,
+    int rc = scores_count_rows(Lo, d_out, dmin, dmax, d_indptr, 0, Lo->rows, nullptr, st);
+    if (rc) return rc;
+    if ((rc = scores_finish_rows(Lo, d_indptr, 0, Lo->rows, 0, st))) return rc;
+    CS_CUDA(cudaMemcpyAsync(nnz_host, d_indptr + Lo->rows, sizeof(int64_t), cudaMemcpyDeviceToHost,
                             st));
     CS_CUDA(cudaStreamSynchronize(st));
     return CS_OK;
@@ -251,16 +291,9 @@ extern "C" int cs_scores_emit(const cs_layout *Lo, const float *d_out, const uin
                               int32_t nobs_const, int32_t dmin, int32_t dmax,
                               const int64_t *d_indptr, int32_t *d_indices, double *d_data,
                               double *d_log10p, void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
     CS_REQUIRE(Lo && d_out && d_indptr && d_indices && d_data, "cs_scores_emit: null argument");
-    ScoreView S = make_view(Lo, dmin, dmax);
-    int grid = (S.rows + 7) / 8;
-    if (grid > 148 * 16) grid = 148 * 16;
-    emit_rows<<<grid, 256, 0, st>>>(S, d_out, d_nobs, nobs_const, d_indptr, d_indices, d_data,
-                                    d_log10p);
-    CS_LAUNCHED();
-    CS_CUDA(cudaGetLastError());
-    return CS_OK;
+    return scores_emit_rows(Lo, d_out, d_nobs, nobs_const, dmin, dmax, d_indptr, 0, Lo->rows,
+                            d_indices, d_data, d_log10p, (cudaStream_t)stream);
 }
 
 extern "C" int cs_scores_candidates(const cs_layout *Lo, const float *d_out, const uint16_t *d_nobs,

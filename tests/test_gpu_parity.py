@@ -246,6 +246,14 @@ def test_full_size_map_against_oracle_crops(kname, ksize, tol, pearson, presets)
     assert nc == int(sel.sum())
     key = np.sort(rec["row"].astype(np.int64) * n + rec["col"])
     assert np.array_equal(key, np.sort(rt.row[sel].astype(np.int64) * n + rt.col[sel]))
+    # the one-shot host call (slab-pipelined for a map of this size: uploads, kernels and
+    # downloads overlap) returns exactly what the resident session does
+    from chromosight_b200.utils import detection as cud
+    r_h, p_h = cud.normxcorr2(mat, kernel, missing_mask=mask, **kw)
+    for a_, b_ in ((r_h, r), (p_h, p)):
+        assert np.array_equal(a_.indptr, b_.indptr) and np.array_equal(a_.indices, b_.indices)
+        assert np.array_equal(a_.data, b_.data)
+    del r_h, p_h
     # oracle on crops
     rng = np.random.default_rng(5)
     W = D + 3 * k
