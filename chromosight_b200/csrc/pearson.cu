@@ -98,6 +98,11 @@ __device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long
                                      unsigned long long b) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
     unsigned long long r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -113,17 +118,21 @@ __device__ __forceinline__ double thr0(double v, double t) { return fabs(v) < t 
 // float32 sums carry ~1e-6 relative error on well-conditioned windows, and the score
 // error grows like amp = f * rms(S') * rms(K') / (sigma_S * sigma_K).
 constexpr double kAmpLimit2 = 9.0;
+// Same for the column sums, which are computed in float64 and rounded once to float32
+// (relative error 6e-8 each): var(S) loses at most 1.8e-7 * amp^2.
+constexpr double kAmpLimitV = 25.0;
 
 // The reference's formulas (det:1002-1020 no mask, det:1021-1092 masked) from the
 // window sums of the shifted signal S' = S - p and the shifted kernel K' = K_corr - q.
 //   h1, h2    : sum S', sum S'^2 over the N window pixels (missing pixels count as S = 0)
+//   h2_loc    : sum (S' - block pivot)^2, the quantity the float32 product sum was formed on
 //   s3        : sum S' * K'
 //   sKm, sKm2 : sums of the mask kernels (K and K^2) over the missing pixels
 // `redo` is set when the window is too ill-conditioned for the float32 sums.
 template <bool MASK>
-__device__ __forceinline__ float score_from_sums(const PearsonParams &P, double p, double h1, double h2, int nmiss,
-                                                 double s3, double sKm, double sKm2, int &nobs,
-                                                 bool &redo) {
+__device__ __forceinline__ float score_from_sums(const PearsonParams &P, double p, double h1,
+                                                 double h2, double h2_loc, int nmiss, double s3,
+                                                 double sKm, double sKm2, int &nobs, bool &redo) {
     const double invN = P.invN;
     const double m1 = h1 * invN;
     double A1 = m1 + p;
@@ -165,7 +174,10 @@ __device__ __forceinline__ float score_from_sums(const PearsonParams &P, double 
     // det:1066,1088-1091: denom = sqrt(den2); |denom| < 1e-10 or NaN -> 0
     float r = 0.f;
     if (ok && den2 >= 1e-20 && den2 < 1e300) {
-        redo = (h2 * P.sumKp2 * invN * invN) * f2 > kAmpLimit2 * den2;
+        // float32 product sums: conditioned by the spread around the block pivot (h2_loc);
+        // float32-rounded column sums: by the spread around the tile pivot (h2)
+        const double c1 = P.sumKp2 * invN * invN * f2;
+        redo = (h2_loc * c1 > kAmpLimit2 * den2) || (h2 * c1 > kAmpLimitV * den2);
         r = (float)cov * rsqrtf((float)den2);
         if (!(fabsf(r) <= 3.0e38f)) r = 0.f;
         r = fminf(1.f, fmaxf(-1.f, r));
@@ -441,7 +453,18 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             }
         }
         float *myacc = accS + tid;
+        // block pivot: mean of S' over (most of) the footprint, from the column sums of the
+        // block's second row.  The products are formed on S' - pl; exact algebra puts it back.
+        float pl = 0.f;
         if (any) {
+            const float2 *Vr = V + (RU * g + 1) * 4 * VQ + (cxa >> 2);
+            float sacc = 0.f;
+#pragma unroll
+            for (int e = off; e < off + XW; ++e) sacc += Vr[(e & 3) * VQ + (e >> 2)].x;
+            pl = sacc * (1.0f / (float)XW) / (float)KH;
+        }
+        if (any) {
+            const unsigned long long npl2 = pack2(-pl, -pl);
             unsigned long long acc[RU][RT / 2];
 #pragma unroll
             for (int u = 0; u < RU; ++u)
@@ -458,8 +481,8 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
 #pragma unroll
                 for (int qd = 0; qd < NQ; ++qd) {
                     const ulonglong2 v = rp[qd];
-                    xe[2 * qd] = v.x;
-                    xe[2 * qd + 1] = v.y;
+                    xe[2 * qd] = add2(v.x, npl2);
+                    xe[2 * qd + 1] = add2(v.y, npl2);
                 }
 #pragma unroll
                 for (int qd = 0; qd < 2 * NQ - 1; ++qd) {
@@ -620,10 +643,13 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 int nobs = P.N;
                 bool redo = false;
                 float r = 0.f;
-                if (wok)
-                    r = score_from_sums<MASK>(P, p, h1, h2, nmiss,
-                                              (double)myacc[(u * RT + t) * nthr], sKm, sKm2, nobs,
-                                              redo);
+                if (wok) {
+                    // sum S' K' = sum (S' - pl) K' + pl * sum K'
+                    const double dpl = (double)pl;
+                    const double s3 = fma(dpl, P.sumKp, (double)myacc[(u * RT + t) * nthr]);
+                    const double h2_loc = fma((double)P.N * dpl, dpl, fma(-2.0 * dpl, h1, h2));
+                    r = score_from_sums<MASK>(P, p, h1, h2, h2_loc, nmiss, s3, sKm, sKm2, nobs, redo);
+                }
                 // ill-conditioned windows (flat signal or mostly missing): the warp redoes the
                 // window sums in float64 from the tile, 32 pixels at a time
                 const int woff = (RU * g + u) * IC + fc0 + t;
@@ -645,7 +671,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     }
                     if (lane == src) {
                         bool again;
-                        r = score_from_sums<MASK>(P, p, g1, g2, nmiss, s3, sKm, sKm2, nobs,
+                        r = score_from_sums<MASK>(P, p, g1, g2, g2, nmiss, s3, sKm, sKm2, nobs,
                                                   again);
                     }
                 }
