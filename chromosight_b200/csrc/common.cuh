@@ -64,4 +64,18 @@ __host__ __device__ __forceinline__ long long img_index(int pitch, int dlo, int 
 
 __device__ __forceinline__ float quiet_nan_f() { return __int_as_float(0x7fc00000); }
 
+// stats.py:74-81: log10 of the two-sided p-value of a Pearson coefficient through Fisher's z,
+// log10(2 Phi(-|z|)) = log10(erfc(|z| / sqrt 2)), z = atanh(r) sqrt(n - 3).
+// Evaluated as log10(erfcx(a)) - a^2 log10(e) (a = |z| / sqrt 2), which never underflows, in
+// float32: the relative error (~3e-7) is far below what the 1e-5 tolerance on r itself does
+// to log10 p.  scipy's ndtr underflows to exactly 0 once a^2 > log(DBL_MAX): -inf there.
+__device__ __forceinline__ double log10_pval(float r, float n_obs) {
+    const float z = fabsf(atanhf(r)) * sqrtf(n_obs - 3.f);
+    if (z != z) return (double)z;
+    const float a = z * 0.70710678118654752440f;
+    const float a2 = a * a;
+    if (a2 > 7.09782712893383996843e2f) return -INFINITY;
+    return (double)(log10f(erfcxf(a)) - a2 * 0.43429448190325182765f);
+}
+
 }  // namespace cs

@@ -101,14 +101,6 @@ struct LookupView {
     int rows, cols, dlo, dhi, pitch, dense, dmin, dmax;
 };
 
-__device__ __forceinline__ double lookup_log10_pval(double r, double n_obs) {
-    const double z = fabs(atanh(r) * sqrt(n_obs - 3.0));
-    if (z != z) return z;
-    const double a = z * 0.70710678118654752440;
-    if (a * a > 7.09782712893383996843e2) return -INFINITY;
-    return log10(erfc(a));
-}
-
 // scores (and log10 p-values) of the score image at UNPADDED coordinates; pixels outside
 // the image, the stored band or dmin..dmax read as 0 (absent from the sparse map)
 __global__ void lookup_scores(LookupView S, const float *__restrict__ sc,
@@ -124,8 +116,9 @@ __global__ void lookup_scores(LookupView S, const float *__restrict__ sc,
         if (in && !S.dense) in = d >= S.dlo && d <= S.dhi;
         if (in) {
             const long long i = (long long)y * S.pitch + (x - (S.dense ? 0 : S.dlo));
-            v = (double)sc[i];
-            if (v != 0.0) lp = lookup_log10_pval(v, nobs ? (double)nobs[i] : (double)nobs_const);
+            const float vf = sc[i];
+            v = (double)vf;
+            if (vf != 0.f) lp = log10_pval(vf, nobs ? (float)nobs[i] : (float)nobs_const);
         }
         score[p] = v;
         if (log10p) log10p[p] = lp;

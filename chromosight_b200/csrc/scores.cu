@@ -26,16 +26,6 @@ __device__ __forceinline__ long long sidx(const ScoreView &S, int y, int x) {
     return (long long)y * S.pitch + (x - (S.dense ? 0 : S.dlo));
 }
 
-// stats.py:74-81.  2*Phi(-|z|) = erfc(|z|/sqrt 2); scipy's ndtr underflows to exactly
-// 0 once (|z|/sqrt 2)^2 > log(DBL_MAX).
-__device__ __forceinline__ double log10_pval(double r, double n_obs) {
-    const double z = fabs(atanh(r) * sqrt(n_obs - 3.0));
-    if (z != z) return z;
-    const double a = z * 0.70710678118654752440;
-    if (a * a > 7.09782712893383996843e2) return -INFINITY;
-    return log10(erfc(a));
-}
-
 __global__ void count_rows(ScoreView S, const float *__restrict__ sc, int64_t *counts, int r0,
                            int r1) {
     const int lane = threadIdx.x & 31;
@@ -153,8 +143,8 @@ __global__ void emit_rows(ScoreView S, const float *__restrict__ sc,
                 indices[o] = x;
                 data[o] = (double)v;
                 if (log10p) {
-                    const double n = nobs ? (double)nobs[i] : (double)nobs_const;
-                    log10p[o] = log10_pval((double)v, n);
+                    const float n = nobs ? (float)nobs[i] : (float)nobs_const;
+                    log10p[o] = log10_pval(v, n);
                 }
             }
             pos += __popc(m);
@@ -193,8 +183,8 @@ __global__ void emit_candidates(ScoreView S, const float *__restrict__ sc,
                     c.row = y;
                     c.col = x;
                     c.score = v;
-                    const double n = nobs ? (double)nobs[i] : (double)nobs_const;
-                    c.log10p = (float)log10_pval((double)v, n);
+                    const float n = nobs ? (float)nobs[i] : (float)nobs_const;
+                    c.log10p = (float)log10_pval(v, n);
                     out[o] = c;
                 }
             }

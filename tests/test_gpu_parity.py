@@ -32,8 +32,8 @@ def _score_tol(cond):
 
 def _compare(r, p, corr_ref, pval_ref, n_obs=None, cond=None, strict=False):
     """Scores within 1e-5 of the reference everywhere; p-values (a) equal to the
-    reference's formula evaluated at the returned score (1e-9), which pins the
-    device p-value code, and (b) within 1e-4 relative of the reference's own
+    reference's formula evaluated at the returned score (2e-6: float32 evaluation), which
+    pins the device p-value code, and (b) within 1e-4 relative of the reference's own
     values over the score range where foci live (log10 p is ill-conditioned in r
     as |r| -> 1, so (b) is restricted to 0.1 <= |r| <= 0.9)."""
     from oracle import pearson_oracle as po
@@ -53,7 +53,8 @@ def _compare(r, p, corr_ref, pval_ref, n_obs=None, cond=None, strict=False):
             fin = np.isfinite(exp)
             assert np.array_equal(np.isneginf(got), np.isneginf(exp))
             assert np.array_equal(np.isnan(got), np.isnan(exp))
-            assert np.allclose(got[fin], exp[fin], rtol=1e-9, atol=1e-12)
+            # the device evaluates the formula in float32 (log10 erfcx(a) - a^2 log10 e)
+            assert np.allclose(got[fin], exp[fin], rtol=2e-6, atol=2e-6)
         sel = nz & (np.abs(corr_ref) >= 0.1) & (np.abs(corr_ref) <= 0.9) & np.isfinite(pval_ref)
         assert np.allclose(p[sel], pval_ref[sel], rtol=1e-4, atol=1e-4)
         assert np.all(p[~nz] == 0)
