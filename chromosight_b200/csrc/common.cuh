@@ -43,10 +43,13 @@ int fill_rows(const cs_layout *L, float *d_img, const int64_t *d_sig_indptr,
               cudaStream_t st);
 // rows [r0, r1) of the score image: per-row counts + chunk-local scan (the slab total lands in
 // d_total), then the offsets (+ base) added, then the CSR entries written
+// (scratch_off: the range's part of the scan scratch, scan_slot(r0, k) for the k-th range)
 int scores_count_rows(const cs_layout *Lo, const float *d_out, int32_t dmin, int32_t dmax,
-                      int64_t *d_indptr, int32_t r0, int32_t r1, int64_t *d_total, cudaStream_t st);
+                      int64_t *d_indptr, int32_t r0, int32_t r1, int64_t *d_total, cudaStream_t st,
+                      int32_t scratch_off = 0);
 int scores_finish_rows(const cs_layout *Lo, int64_t *d_indptr, int32_t r0, int32_t r1,
-                       int64_t base, cudaStream_t st);
+                       int64_t base, cudaStream_t st, int32_t scratch_off = 0);
+int32_t scan_slot(int32_t r0, int32_t k);
 int scores_emit_rows(const cs_layout *Lo, const float *d_out, const uint16_t *d_nobs,
                      int32_t nobs_const, int32_t dmin, int32_t dmax, const int64_t *d_indptr,
                      int32_t r0, int32_t r1, int32_t *d_indices, double *d_data, double *d_log10p,

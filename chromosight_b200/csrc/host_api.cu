@@ -8,6 +8,7 @@
 // Device and pinned buffers are cached per device and only grow, so steady-state
 // calls do no allocation.
 #include <stdlib.h>
+#include <chrono>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -37,10 +38,16 @@ struct PinBlock {
 };
 
 constexpr size_t kStageBytes = 32u << 20;
+static const size_t kStageChunk = [] {  // one DMA per chunk; two buffers alternate
+    const char *e = getenv("CS_STAGE_CHUNK_MB");
+    size_t mb = (e && atoi(e) > 0) ? (size_t)atoi(e) : 32;
+    if (mb > 32) mb = 32;
+    return mb << 20;
+}();
 
 struct HostCtx {
     int device = -1;
-    cudaStream_t st = nullptr, st_copy = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr, st_emit = nullptr;
     void *stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -63,6 +70,12 @@ static int get_ctx(int device, HostCtx **out) {
     c->device = device;
     CS_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CS_CUDA(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+    {
+        // result compaction of finished slabs overtakes the Pearson tiles of later ones
+        int lo_pri = 0, hi_pri = 0;
+        CS_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        CS_CUDA(cudaStreamCreateWithPriority(&c->st_emit, cudaStreamNonBlocking, hi_pri));
+    }
     for (int i = 0; i < 2; ++i) {
         CS_CUDA(cudaHostAlloc(&c->stage[i], kStageBytes, cudaHostAllocDefault));
         CS_CUDA(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
@@ -73,16 +86,17 @@ static int get_ctx(int device, HostCtx **out) {
     return CS_OK;
 }
 
-// memcpy split over a few host threads: one core moves ~10 GB/s, PCIe 5 takes > 50 GB/s
+// memcpy split over a few host threads.  Measured on the B200 boxes (scripts/pipe_ab.sh): the
+// staging copy competes with the download DMA for host memory bandwidth, and two or three
+// threads are as good as more.  CS_COPY_THREADS overrides the count.
 static void memcpy_mt(void *dst, const void *src, size_t n) {
     const size_t kMin = 4u << 20;
-    unsigned hw = std::thread::hardware_concurrency();
-    // share the host cores between the ranks of one box
-    if (const char *e = getenv("LOCAL_WORLD_SIZE"))
-        if (atoi(e) > 1) hw = hw / (unsigned)atoi(e) > 0 ? hw / (unsigned)atoi(e) : 1;
+    static const int maxt = [] {
+        const char *e = getenv("CS_COPY_THREADS");
+        return (e && atoi(e) > 0) ? atoi(e) : 3;
+    }();
     int nt = (int)(n / kMin);
-    if (nt > 6) nt = 6;
-    if (hw && nt > (int)hw) nt = (int)hw;
+    if (nt > maxt) nt = maxt;
     if (nt <= 1) {
         memcpy(dst, src, n);
         return;
@@ -99,13 +113,32 @@ static void memcpy_mt(void *dst, const void *src, size_t n) {
     for (auto &t : th) t.join();
 }
 
+// true when `p` lies in page-locked host memory CUDA knows about (cudaHostAlloc /
+// cudaHostRegister, e.g. a torch pinned tensor): such buffers are DMA'd directly
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 // pageable host -> device through the two pinned staging buffers (CPU memcpy of chunk
 // i+1 overlaps the DMA of chunk i)
-static int h2d_staged(HostCtx *c, cudaStream_t st, void *dst, const void *src, size_t bytes) {
+template <typename Poll>
+static int h2d_staged(HostCtx *c, cudaStream_t st, void *dst, const void *src, size_t bytes,
+                      Poll poll) {
     size_t done = 0;
     int k = 0;
+    if (bytes >= (1u << 16) && is_pinned(src) && is_pinned((const char *)src + bytes - 1)) {
+        if (int prc = poll()) return prc;
+        CS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return CS_OK;
+    }
     while (done < bytes) {
-        const size_t n = bytes - done < kStageBytes ? bytes - done : kStageBytes;
+        const size_t n = bytes - done < kStageChunk ? bytes - done : kStageChunk;
+        if (int prc = poll()) return prc;
         CS_CUDA(cudaEventSynchronize(c->stage_ev[k]));
         memcpy_mt(c->stage[k], (const char *)src + done, n);
         CS_CUDA(cudaMemcpyAsync((char *)dst + done, c->stage[k], n, cudaMemcpyHostToDevice, st));
@@ -114,6 +147,9 @@ static int h2d_staged(HostCtx *c, cudaStream_t st, void *dst, const void *src, s
         k ^= 1;
     }
     return CS_OK;
+}
+static int h2d_staged(HostCtx *c, cudaStream_t st, void *dst, const void *src, size_t bytes) {
+    return h2d_staged(c, st, dst, src, bytes, [] { return 0; });
 }
 
 static int pin_alloc(HostCtx *c, size_t bytes, void **out) {
@@ -275,12 +311,44 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
         s->oy0 = kh, s->oy1 = a->rows - kh, s->ox0 = kw, s->ox1 = a->cols - kw;
     }
     s->nnz_in = a->indptr[a->rows];
+    int sig_dmin = a->sig_dmin, sig_dmax = a->sig_dmax;
+    if (a->sig_dmin == INT32_MIN) {
+        // diagonal extent from the first and last stored column of every row (two cache
+        // misses per row: split over a few threads)
+        const int nt = a->rows >= (1 << 16) ? 8 : 1;
+        std::vector<int> lo_t(nt, INT32_MAX), hi_t(nt, INT32_MIN);
+        auto scan = [&](int t) {
+            const int r0 = (int)((long long)a->rows * t / nt), r1 = (int)((long long)a->rows * (t + 1) / nt);
+            int lo = INT32_MAX, hi = INT32_MIN;
+            for (int r = r0; r < r1; ++r) {
+                const int64_t e0 = a->indptr[r], e1 = a->indptr[r + 1];
+                if (e1 <= e0) continue;
+                const int l = a->indices[e0] - r, h = a->indices[e1 - 1] - r;
+                if (l < lo) lo = l;
+                if (h > hi) hi = h;
+            }
+            lo_t[t] = lo;
+            hi_t[t] = hi;
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(scan, t);
+        scan(0);
+        for (auto &t : th) t.join();
+        int dmin = INT32_MAX, dmax = INT32_MIN;
+        for (int t = 0; t < nt; ++t) {
+            if (lo_t[t] < dmin) dmin = lo_t[t];
+            if (hi_t[t] > dmax) dmax = hi_t[t];
+        }
+        if (dmin > dmax) dmin = 0, dmax = -1;
+        s->a.sig_dmin = sig_dmin = dmin;
+        s->a.sig_dmax = sig_dmax = dmax;
+    }
     s->empty = (s->oy1 <= s->oy0) || (s->ox1 <= s->ox0) || s->nnz_in == 0 ||
-               a->sig_dmax < a->sig_dmin;
+               sig_dmax < sig_dmin;
     // diagonal ranges in image coordinates
     const int sh = pc - pr;
-    long long od_lo = (long long)a->sig_dmin + sh - (kh + kw);
-    long long od_hi = (long long)a->sig_dmax + sh + (kh + kw);
+    long long od_lo = (long long)sig_dmin + sh - (kh + kw);
+    long long od_hi = (long long)sig_dmax + sh + (kh + kw);
     if (a->sym_upper && od_lo < sh) od_lo = sh;  // det:1098-1099 (triu of the cropped map)
     if (a->trim_to_max_dist && a->max_dist >= 0 && od_hi > (long long)a->max_dist + sh)
         od_hi = (long long)a->max_dist + sh;
@@ -570,7 +638,7 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
     HostCtx *c = s->c;
     std::lock_guard<std::mutex> lk(c->mu);
     CS_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = s->stream(), st_d = c->st_copy;
+    cudaStream_t st = s->stream(), st_d = c->st_copy, st_e = c->st_emit;
     const cs_normxcorr2_args &A = s->a;
     const cs_kernel_desc &K = A.kernel;
     const int kh = (K.kh - 1) / 2;
@@ -620,6 +688,24 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
         }
     } evguard{ev_tot, ev_emit};
 
+    // CS_TRACE=1: per-slab timeline on stderr (host clock and device events, ms from the start)
+    const bool trace = getenv("CS_TRACE") != nullptr;
+    auto now = [] {
+        return std::chrono::duration<double, std::milli>(
+                   std::chrono::steady_clock::now().time_since_epoch())
+            .count();
+    };
+    const double t_begin = now();
+    std::vector<double> th0(nslab, 0), th1(nslab, 0), tf0(nslab, 0), tf1(nslab, 0);
+    std::vector<cudaEvent_t> tev(trace ? 4 * nslab : 0);
+    for (auto &e : tev) CS_CUDA(cudaEventCreate(&e));
+    struct TevGuard {
+        std::vector<cudaEvent_t> &v;
+        ~TevGuard() {
+            for (auto e : v) cudaEventDestroy(e);
+        }
+    } tevguard{tev};
+
     CS_CUDA(cudaEventRecord(s->ev[2], st));
     rc = fill_begin(&s->Li, (float *)s->img.p, A.rows, A.cols, A.has_mask ? 1 : 0, A.sym_upper,
                     A.max_dist, A.full ? K.kh : 0, A.full ? K.kw : 0, (int32_t *)s->err.p, st);
@@ -642,12 +728,23 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
         po.strip_dhi = -1;
     }
     const uint16_t *nb = s->want_nobs ? (const uint16_t *)s->nobs.p : nullptr;
-    // slab boundaries in image rows (multiples of the tile height)
+    // slab boundaries in image rows (multiples of the tile height); the first slabs are small
+    // so that the download -- the longest leg -- starts early
     std::vector<int> Yb(nslab + 1);
-    for (int i = 0; i <= nslab; ++i) {
-        long long y = (long long)(s->oy1 - s->oy0) * i / nslab;
-        y = (y + 16) / 32 * 32;
-        Yb[i] = s->oy0 + (int)(y > s->oy1 - s->oy0 ? s->oy1 - s->oy0 : y);
+    {
+        std::vector<double> w(nslab, 1.0);
+        if (nslab >= 6) w[0] = 0.15, w[1] = 0.3, w[2] = 0.6;
+        double tot_w = 0.0, acc_w = 0.0;
+        for (double v : w) tot_w += v;
+        const int R = s->oy1 - s->oy0;
+        Yb[0] = s->oy0;
+        for (int i = 1; i <= nslab; ++i) {
+            acc_w += w[i - 1];
+            long long y = (long long)((double)R * acc_w / tot_w);
+            y = (y + 16) / 32 * 32;
+            Yb[i] = s->oy0 + (int)(y > R ? R : y);
+            if (Yb[i] < Yb[i - 1]) Yb[i] = Yb[i - 1];
+        }
     }
     Yb[0] = s->oy0;
     Yb[nslab] = s->oy1;
@@ -655,20 +752,27 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
     int up_end = 0;
     int64_t base = 0;
     auto finalize = [&](int k) -> int {
+        if (trace) tf0[k] = now() - t_begin;
         CS_CUDA(cudaEventSynchronize(ev_tot[k]));
+        if (trace) tf1[k] = now() - t_begin;
         const int64_t nnz_k = tot[k];
         const int cr0 = csr_row(k), cr1 = csr_row(k + 1);
-        int r = scores_finish_rows(&s->Lo, (int64_t *)s->r_indptr.p, cr0, cr1, base, st);
+        // on the high-priority stream: ordered after the slab's counts, not after the tiles of
+        // the slabs enqueued since
+        CS_CUDA(cudaStreamWaitEvent(st_e, ev_tot[k], 0));
+        int r = scores_finish_rows(&s->Lo, (int64_t *)s->r_indptr.p, cr0, cr1, base, st_e,
+                                   scan_slot(cr0, k));
         if (r) return r;
         if (nnz_k > 0) {
             r = scores_emit_rows(&s->Lo, (const float *)s->out.p, nb, K.kh * K.kw, -(1 << 30),
                                  1 << 30, (const int64_t *)s->r_indptr.p, cr0, cr1,
                                  (int32_t *)s->r_indices.p, (double *)s->r_data.p,
-                                 A.pval ? (double *)s->r_p.p : nullptr, st);
+                                 A.pval ? (double *)s->r_p.p : nullptr, st_e);
             if (r) return r;
         }
-        CS_CUDA(cudaEventRecord(ev_emit[k], st));
+        CS_CUDA(cudaEventRecord(ev_emit[k], st_e));
         CS_CUDA(cudaStreamWaitEvent(st_d, ev_emit[k], 0));
+        if (trace) CS_CUDA(cudaEventRecord(tev[4 * k + 2], st_d));
         if (nnz_k > 0) {
             const size_t o = (size_t)base, n = (size_t)nnz_k;
             CS_CUDA(cudaMemcpyAsync((int32_t *)h_ix + o, (int32_t *)s->r_indices.p + o,
@@ -682,11 +786,26 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
                                         n * sizeof(int32_t), cudaMemcpyDeviceToHost, st_d));
             }
         }
+        if (trace) CS_CUDA(cudaEventRecord(tev[4 * k + 3], st_d));
         base += nnz_k;
+        return CS_OK;
+    };
+    // slabs whose totals are known are finalized (row pointers, CSR entries, download) as soon
+    // as possible: between the staging chunks of later slabs and after every enqueue
+    int n_counted = 0, n_final = 0;
+    auto poll = [&]() -> int {
+        while (n_final < n_counted && cudaEventQuery(ev_tot[n_final]) == cudaSuccess) {
+            if (int r = finalize(n_final)) return r;
+            ++n_final;
+        }
         return CS_OK;
     };
     for (int k = 0; k < nslab; ++k) {
         const int Y0 = Yb[k], Y1 = Yb[k + 1];
+        if (trace) {
+            th0[k] = now() - t_begin;
+            CS_CUDA(cudaEventRecord(tev[4 * k], st));
+        }
         // signal rows the windows of this slab read: image rows < Y1 + kh
         int need = Y1 + kh - s->pr;
         if (need > A.rows || k == nslab - 1) need = A.rows;
@@ -694,17 +813,18 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
             const int64_t e0 = a->indptr[up_end], e1 = a->indptr[need];
             if (e1 > e0) {
                 if ((rc = h2d_staged(c, st, (int32_t *)s->sig_indices.p + e0, a->indices + e0,
-                                     (size_t)(e1 - e0) * sizeof(int32_t))))
+                                     (size_t)(e1 - e0) * sizeof(int32_t), poll)))
                     return rc;
                 if ((rc = h2d_staged(c, st, (double *)s->sig_data.p + e0, a->data + e0,
-                                     (size_t)(e1 - e0) * sizeof(double))))
+                                     (size_t)(e1 - e0) * sizeof(double), poll)))
                     return rc;
             }
             if (A.has_mask) {
                 const int64_t m0 = a->mask_indptr[up_end], m1 = a->mask_indptr[need];
                 if (m1 > m0)
                     if ((rc = h2d_staged(c, st, (int32_t *)s->m_indices.p + m0,
-                                         a->mask_indices + m0, (size_t)(m1 - m0) * sizeof(int32_t))))
+                                         a->mask_indices + m0, (size_t)(m1 - m0) * sizeof(int32_t),
+                                         poll)))
                         return rc;
             }
             rc = fill_rows(&s->Li, (float *)s->img.p, (const int64_t *)s->sig_indptr.p,
@@ -722,25 +842,50 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
                                 s->want_nobs ? (uint16_t *)s->nobs.p : nullptr, st);
             if (rc) return rc;
         }
-        if (k > 0 && (rc = finalize(k - 1))) return rc;
         // the slab total is written straight into pinned host memory (UVA): a D2H copy on this
         // stream would queue behind the bulk downloads of the copy stream
         tot[k] = 0;
         rc = scores_count_rows(&s->Lo, (const float *)s->out.p, -(1 << 30), 1 << 30,
-                               (int64_t *)s->r_indptr.p, csr_row(k), csr_row(k + 1), tot + k, st);
+                               (int64_t *)s->r_indptr.p, csr_row(k), csr_row(k + 1), tot + k, st,
+                               scan_slot(csr_row(k), k));
         if (rc) return rc;
         CS_CUDA(cudaEventRecord(ev_tot[k], st));
+        n_counted = k + 1;
+        if (trace) {
+            CS_CUDA(cudaEventRecord(tev[4 * k + 1], st));
+            th1[k] = now() - t_begin;
+        }
+        if ((rc = poll())) return rc;
     }
-    if ((rc = finalize(nslab - 1))) return rc;
+    for (; n_final < nslab; ++n_final)
+        if ((rc = finalize(n_final))) return rc;
     int32_t *herr = (int32_t *)(tot + nslab);  // last slot of the pinned totals block
     CS_CUDA(cudaMemcpyAsync(herr, s->err.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CS_CUDA(cudaMemcpyAsync(h_ip, s->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    // row pointers: final once every slab has been finalized (the copy stream follows them all)
+    CS_CUDA(cudaMemcpyAsync(h_ip, s->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                            st_d));
     if (A.pval)
         CS_CUDA(cudaMemcpyAsync(h_ip2, s->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost,
-                                st));
+                                st_d));
+    // the span ends when the last download has landed
+    CS_CUDA(cudaEventRecord(ev_emit[0], st_d));
+    CS_CUDA(cudaStreamWaitEvent(st, ev_emit[0], 0));
     CS_CUDA(cudaEventRecord(s->ev[5], st));
     CS_CUDA(cudaStreamSynchronize(st));
     CS_CUDA(cudaStreamSynchronize(st_d));
+    if (trace) {
+        fprintf(stderr, "slab  host:enq0  enq1  fin_wait0 fin_wait1 | dev:compute0 compute1 d2h0 d2h1 (ms)\n");
+        for (int k = 0; k < nslab; ++k) {
+            float c0 = 0, c1 = 0, d0 = 0, d1 = 0;
+            cudaEventElapsedTime(&c0, s->ev[2], tev[4 * k]);
+            cudaEventElapsedTime(&c1, s->ev[2], tev[4 * k + 1]);
+            cudaEventElapsedTime(&d0, s->ev[2], tev[4 * k + 2]);
+            cudaEventElapsedTime(&d1, s->ev[2], tev[4 * k + 3]);
+            fprintf(stderr, "%4d  %8.2f %8.2f %8.2f %8.2f | %8.2f %8.2f %8.2f %8.2f  nnz %lld\n", k,
+                    th0[k], th1[k], tf0[k], tf1[k], c0, c1, d0, d1, (long long)tot[k]);
+        }
+        fprintf(stderr, "host total %.2f ms\n", now() - t_begin);
+    }
     if (herr[0] > 0 && A.has_mask) {
         set_error("There are %d non-zero elements reported as missing.", herr[0]);
         return CS_ERR_MASKED_SIGNAL;
@@ -783,7 +928,7 @@ extern "C" int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *re
     {
         long long rows_out = a->full ? a->rows : a->rows - (a->kernel.kh - 1);
         const int64_t nnz_in = a->indptr ? a->indptr[a->rows] : 0;
-        int nslab = 8;
+        int nslab = 12;
         if (const char *e = getenv("CS_PIPELINE_SLABS")) nslab = atoi(e);
         if (nslab > 1 && nnz_in >= (4 << 20) && rows_out >= 64 * nslab) {
             int rc = normxcorr2_pipelined(s, a, res, nslab);

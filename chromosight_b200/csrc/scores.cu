@@ -211,7 +211,8 @@ static int64_t *scan_scratch_of(const cs_layout *Lo, int64_t *d_indptr) {
 }
 
 int scores_count_rows(const cs_layout *Lo, const float *d_out, int32_t dmin, int32_t dmax,
-                      int64_t *d_indptr, int32_t r0, int32_t r1, int64_t *d_total, cudaStream_t st) {
+                      int64_t *d_indptr, int32_t r0, int32_t r1, int64_t *d_total, cudaStream_t st,
+                      int32_t scratch_off) {
     if (r1 <= r0) return CS_OK;
     ScoreView S = make_view(Lo, dmin, dmax);
     const int n = r1 - r0;
@@ -220,7 +221,7 @@ int scores_count_rows(const cs_layout *Lo, const float *d_out, int32_t dmin, int
     count_rows<<<grid, 256, 0, st>>>(S, d_out, d_indptr, r0, r1);
     CS_LAUNCHED();
     const int nchunk = (n + kScanChunk - 1) / kScanChunk;
-    int64_t *totals = scan_scratch_of(Lo, d_indptr);
+    int64_t *totals = scan_scratch_of(Lo, d_indptr) + scratch_off;
     scan_chunks<<<nchunk, kScanThreads, 0, st>>>(d_indptr + r0, n, totals);
     CS_LAUNCHED();
     scan_totals<<<1, 1024, 0, st>>>(totals, nchunk, d_total);
@@ -230,11 +231,12 @@ int scores_count_rows(const cs_layout *Lo, const float *d_out, int32_t dmin, int
 }
 
 int scores_finish_rows(const cs_layout *Lo, int64_t *d_indptr, int32_t r0, int32_t r1, int64_t base,
-                       cudaStream_t st) {
+                       cudaStream_t st, int32_t scratch_off) {
     if (r1 <= r0) return CS_OK;
     const int n = r1 - r0;
     const int nchunk = (n + kScanChunk - 1) / kScanChunk;
-    scan_add<<<nchunk, kScanThreads, 0, st>>>(d_indptr + r0, n, scan_scratch_of(Lo, d_indptr),
+    scan_add<<<nchunk, kScanThreads, 0, st>>>(d_indptr + r0, n,
+                                              scan_scratch_of(Lo, d_indptr) + scratch_off,
                                               (long long)base);
     CS_LAUNCHED();
     CS_CUDA(cudaGetLastError());
@@ -260,9 +262,12 @@ int scores_emit_rows(const cs_layout *Lo, const float *d_out, const uint16_t *d_
 
 using namespace cs;
 
+// Row ranges scanned independently (the slabs of the host pipeline) own disjoint parts of
+// the scratch: a range starting at row r0, the k-th of a call, uses cs_scan_slot(r0, k).
 extern "C" int64_t cs_scan_scratch(int32_t rows) {
-    return (int64_t)((rows + cs::kScanChunk - 1) / cs::kScanChunk) + 2;
+    return (int64_t)((rows + cs::kScanChunk - 1) / cs::kScanChunk) + 2 + 256;
 }
+int32_t cs::scan_slot(int32_t r0, int32_t k) { return r0 / cs::kScanChunk + k; }
 
 extern "C" int cs_scores_count(const cs_layout *Lo, const float *d_out, int32_t dmin, int32_t dmax,
                                int64_t *d_indptr, int64_t *nnz_host, void *stream) {

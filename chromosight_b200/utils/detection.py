@@ -32,21 +32,6 @@ def _as_f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-def _diag_extent(csr):
-    """Smallest and largest stored diagonal (col - row) of a CSR matrix."""
-    if csr.nnz == 0:
-        return 0, -1
-    counts = np.diff(csr.indptr)
-    rows = np.flatnonzero(counts)
-    if csr.has_sorted_indices:
-        first = csr.indices[csr.indptr[rows]]
-        last = csr.indices[csr.indptr[rows + 1] - 1]
-        return int((first - rows).min()), int((last - rows).max())
-    r = np.repeat(np.arange(csr.shape[0]), counts)
-    d = csr.indices - r
-    return int(d.min()), int(d.max())
-
-
 def _canonical_csr(mat, dtype):
     csr = mat.tocsr() if sp.issparse(mat) else sp.csr_matrix(mat)
     if csr.dtype != dtype:
@@ -102,7 +87,8 @@ def _build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, t
     a.full = int(bool(full))
     a.pval = int(bool(pval))
     a.trim_to_max_dist = int(bool(trim_to_max_dist))
-    a.sig_dmin, a.sig_dmax = _diag_extent(csr)
+    # canonical CSR (sorted rows): the library measures the diagonal extent itself
+    a.sig_dmin, a.sig_dmax = -(2 ** 31), -1
     a.kernel = _kernel_desc(kernel, tsvd, keep)
     a.missing_tol = float(missing_tol)
     a.device = _device_index() if device is None else int(device)

@@ -234,7 +234,8 @@ typedef struct cs_normxcorr2_args {
     int32_t full;
     int32_t pval;
     int32_t trim_to_max_dist; /* extension: drop scores beyond max_dist (det:270) */
-    int32_t sig_dmin, sig_dmax; /* diagonal extent of the stored signal (col-row) */
+    int32_t sig_dmin, sig_dmax; /* diagonal extent of the stored signal (col-row); sig_dmin ==
+                                 * INT32_MIN: measured by the library (indices sorted per row) */
     cs_kernel_desc kernel;
     double missing_tol;
     int32_t device;

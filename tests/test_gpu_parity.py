@@ -255,6 +255,13 @@ def test_full_size_map_against_oracle_crops(kname, ksize, tol, pearson, presets)
         assert np.array_equal(a_.indptr, b_.indptr) and np.array_equal(a_.indices, b_.indices)
         assert np.array_equal(a_.data, b_.data)
     del r_h, p_h
+    # the same call with page-locked input arrays (direct DMA instead of staging)
+    from chromosight_b200 import _cuda
+    r_h, p_h = cud.normxcorr2(_cuda.pin_sparse(mat), kernel, missing_mask=_cuda.pin_sparse(mask), **kw)
+    for a_, b_ in ((r_h, r), (p_h, p)):
+        assert np.array_equal(a_.indptr, b_.indptr) and np.array_equal(a_.indices, b_.indices)
+        assert np.array_equal(a_.data, b_.data)
+    del r_h, p_h
     # oracle on crops
     rng = np.random.default_rng(5)
     W = D + 3 * k
