@@ -124,6 +124,9 @@ _PROTOS = {
     "cs_pearson_f32": (C.c_int, [C.POINTER(Layout), _P, C.POINTER(KernelDesc), C.POINTER(PearsonOpts),
                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.POINTER(Layout), _P, _P, _P]),
+    "cs_pearson_tile_rows": (C.c_int, [C.POINTER(Layout), C.POINTER(KernelDesc), C.POINTER(PearsonOpts),
+                                        C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.POINTER(C.c_int32)]),
     "cs_scan_scratch": (C.c_int64, [C.c_int32]),
     "cs_scores_count": (C.c_int, [C.POINTER(Layout), _P, C.c_int32, C.c_int32, _P,
                                    C.POINTER(C.c_int64), _P]),

@@ -728,6 +728,11 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
         po.strip_dhi = -1;
     }
     const uint16_t *nb = s->want_nobs ? (const uint16_t *)s->nobs.p : nullptr;
+    int32_t TRp = 32;
+    if ((rc = cs_pearson_tile_rows(&s->Li, &K, &po, s->oy0, s->oy1, s->ox0, s->ox1, s->od_lo,
+                                   s->od_hi, &TRp)))
+        return rc;
+    po.tile_rows = TRp;
     // slab boundaries in image rows (multiples of the tile height); the first slabs are small
     // so that the download -- the longest leg -- starts early
     std::vector<int> Yb(nslab + 1);
@@ -741,7 +746,7 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
         for (int i = 1; i <= nslab; ++i) {
             acc_w += w[i - 1];
             long long y = (long long)((double)R * acc_w / tot_w);
-            y = (y + 16) / 32 * 32;
+            y = (y + TRp / 2) / TRp * TRp;
             Yb[i] = s->oy0 + (int)(y > R ? R : y);
             if (Yb[i] < Yb[i - 1]) Yb[i] = Yb[i - 1];
         }

@@ -26,8 +26,12 @@
 
 namespace cs {
 
-constexpr int RU = 4;  // window rows per thread
-constexpr int RT = 4;  // window columns per thread
+constexpr int RU = 2;  // window rows per thread
+constexpr int RT = 8;  // window columns per thread
+// column shift of row group g in a banded (skewed) traversal: the band moves right by one
+// column per row; blocks stay 16-byte aligned in the tile
+__host__ __device__ __forceinline__ int skew_shift(int g) { return (RU * g) & ~3; }
+constexpr int kSkewSlack = (RU % 4) ? 3 : 0;  // columns lost to that rounding
 
 struct PearsonParams {
     // image
@@ -38,7 +42,7 @@ struct PearsonParams {
     int TR, G, NBc, nchunks, skew;
     int IC, IR, VQ, NW;
     // kernel geometry
-    int KH, KW, KWP, N;
+    int KH, KW, KWP2, N;
     // output image
     float *out;
     unsigned short *nobs;
@@ -224,7 +228,9 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     constexpr int off = kwa - kw;
     constexpr int XW = RT + KW - 1;           // pixels of one footprint row
     constexpr int NQ = (off + XW + 3) / 4;    // float4 loads per footprint row
-    constexpr int KWP = (KW + 1) / 2 * 2;     // taps padded to an even count
+    constexpr int KWP2 = (KW + 1 + 3) / 4 * 4;  // floats of one padded tap row
+    constexpr int NP = (KW + 1) / 2;            // tap pairs per kernel row
+    static_assert(((off + RT - 1) >> 1) + NP <= 2 * NQ, "tap pairs run past the loaded segment");
     constexpr unsigned KWMASK = (KW == 32) ? 0xffffffffu : ((1u << KW) - 1u);
 
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -232,7 +238,10 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     float2 *__restrict__ V = reinterpret_cast<float2 *>(smem + P.off_V);
     unsigned char *__restrict__ Vm = smem + P.off_Vm;
     uint32_t *__restrict__ bits = reinterpret_cast<uint32_t *>(smem + P.off_bits);
-    const float2 *__restrict__ Kdup = reinterpret_cast<const float2 *>(smem + P.off_K);
+    // taps K' = K_corr - q, two rows of KWP2 floats per kernel row: the row padded with
+    // zeros (pairs (k0,k1),(k2,k3),... for windows at an even tile column) and the same row
+    // shifted right by one (pairs (0,k0),(k1,k2),... for windows at an odd tile column)
+    const float *__restrict__ Ktab = reinterpret_cast<const float *>(smem + P.off_K);
     const double *__restrict__ Dt = reinterpret_cast<const double *>(smem + P.off_D);
     float *__restrict__ accS = reinterpret_cast<float *>(smem + P.off_acc);
     unsigned long long *__restrict__ grpS =
@@ -252,7 +261,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         const int v = P.skew ? (Y0 + P.odlo - P.dlo) : (P.ox0 - P.dlo);
         xb = (v >= 0 ? v / 4 : -((-v + 3) / 4)) * 4;
     }
-    xb += 4 * ch * P.NBc;
+    xb += RT * ch * P.NBc;
     const int TXp = xb - kwa;  // X' of tile column 0
     const int TY = Y0 - kh;    // image row of tile row 0
     const int IC = P.IC, IR = P.IR, NW = P.NW, VQ = P.VQ;
@@ -363,7 +372,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         // all-zero signal: every score of the tile is 0 (variance 0 -> det:1088-1091)
         for (int item = tid; item < nitems; item += nthr) {
             const int g = item / P.NBc, m = item - g * P.NBc;
-            const int Xp0 = xb + RU * g * P.skew + RT * m;
+            const int Xp0 = xb + skew_shift(g) * P.skew + RT * m;
             for (int u = 0; u < RU; ++u) {
                 const int Y = Y0 + RU * g + u;
                 if (Y >= P.oy1) continue;
@@ -438,8 +447,8 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         const int item = base + tid;
         const int g = item < nitems ? item / P.NBc : 0;
         const int m = item < nitems ? item - g * P.NBc : 0;
-        const int Xp0 = xb + RU * g * P.skew + RT * m;  // X' of output column t = 0
-        const int cxa = RU * g * P.skew + RT * m;       // aligned tile column of x[0]
+        const int Xp0 = xb + skew_shift(g) * P.skew + RT * m;  // X' of output column t = 0
+        const int cxa = skew_shift(g) * P.skew + RT * m;       // aligned tile column of x[0]
         const int Yg = Y0 + RU * g;
         // blocks without any valid output pixel are skipped
         bool any = false;
@@ -465,19 +474,20 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         }
         if (any) {
             const unsigned long long npl2 = pack2(-pl, -pl);
-            unsigned long long acc[RU][RT / 2];
+            // one packed accumulator per window: .lo and .hi collect alternate taps
+            unsigned long long acc[RU][RT];
 #pragma unroll
             for (int u = 0; u < RU; ++u)
 #pragma unroll
-                for (int t = 0; t < RT / 2; ++t) acc[u][t] = 0ull;
+                for (int t = 0; t < RT; ++t) acc[u][t] = 0ull;
 
             const int nrow = KH + RU - 1;
 #pragma unroll 1
             for (int iy = 0; iy < nrow; ++iy) {
                 const ulonglong2 *rp =
                     reinterpret_cast<const ulonglong2 *>(tile + (RU * g + iy) * IC + cxa);
-                // xe[q] = (x[2q], x[2q+1]), xo[q] = (x[2q+1], x[2q+2])
-                unsigned long long xe[2 * NQ], xo[2 * NQ];
+                // xe[q] = (x[2q], x[2q+1]) - block pivot
+                unsigned long long xe[2 * NQ];
 #pragma unroll
                 for (int qd = 0; qd < NQ; ++qd) {
                     const ulonglong2 v = rp[qd];
@@ -485,32 +495,26 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     xe[2 * qd + 1] = add2(v.y, npl2);
                 }
 #pragma unroll
-                for (int qd = 0; qd < 2 * NQ - 1; ++qd) {
-                    float a0, a1, b0, b1;
-                    unpack2(xe[qd], a0, a1);
-                    unpack2(xe[qd + 1], b0, b1);
-                    xo[qd] = pack2(a1, b0);
-                }
-                xo[2 * NQ - 1] = 0ull;
-#pragma unroll
                 for (int u = 0; u < RU; ++u) {
                     const int i = iy - u;
                     if (i < 0 || i >= KH) continue;  // uniform across the block
-                    const ulonglong2 *kp = reinterpret_cast<const ulonglong2 *>(Kdup + i * KWP);
-                    unsigned long long kd[KWP];
+                    const ulonglong2 *kp =
+                        reinterpret_cast<const ulonglong2 *>(Ktab + i * 2 * KWP2);
+                    unsigned long long ke[KWP2 / 2], ko[KWP2 / 2];
 #pragma unroll
-                    for (int qd = 0; qd < KWP / 2; ++qd) {
-                        const ulonglong2 v = kp[qd];
-                        kd[2 * qd] = v.x;
-                        kd[2 * qd + 1] = v.y;
+                    for (int qd = 0; qd < KWP2 / 4; ++qd) {
+                        const ulonglong2 a = kp[qd], b = kp[KWP2 / 4 + qd];
+                        ke[2 * qd] = a.x;
+                        ke[2 * qd + 1] = a.y;
+                        ko[2 * qd] = b.x;
+                        ko[2 * qd + 1] = b.y;
                     }
 #pragma unroll
-                    for (int j = 0; j < KW; ++j) {
+                    for (int t = 0; t < RT; ++t) {
+                        const int c = off + t;  // compile-time after unrolling
 #pragma unroll
-                        for (int tp = 0; tp < RT / 2; ++tp) {
-                            const int e = off + 2 * tp + j;  // compile-time
-                            fma2(acc[u][tp], (e & 1) ? xo[e >> 1] : xe[e >> 1], kd[j]);
-                        }
+                        for (int mm = 0; mm < NP; ++mm)
+                            fma2(acc[u][t], xe[(c >> 1) + mm], (c & 1) ? ko[mm] : ke[mm]);
                     }
                 }
             }
@@ -518,11 +522,10 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
 #pragma unroll
             for (int u = 0; u < RU; ++u)
 #pragma unroll
-                for (int tp = 0; tp < RT / 2; ++tp) {
+                for (int t = 0; t < RT; ++t) {
                     float lo, hi;
-                    unpack2(acc[u][tp], lo, hi);
-                    myacc[(u * RT + 2 * tp) * nthr] = lo;
-                    myacc[(u * RT + 2 * tp + 1) * nthr] = hi;
+                    unpack2(acc[u][t], lo, hi);
+                    myacc[(u * RT + t) * nthr] = lo + hi;
                 }
         }
 
@@ -662,7 +665,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                         const double sv = (double)wp[i * IC + j];
                         g1 += sv;
                         g2 = fma(sv, sv, g2);
-                        s3 = fma(sv, (double)Kdup[i * KWP + j].x, s3);
+                        s3 = fma(sv, (double)Ktab[i * 2 * KWP2 + j], s3);
                     }
                     for (int o = 16; o > 0; o >>= 1) {
                         g1 += __shfl_xor_sync(0xffffffffu, g1, o);
@@ -745,12 +748,14 @@ static thread_local KtabRing g_ring;
 
 using namespace cs;
 
-extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_kernel_desc *K,
-                              const cs_pearson_opts *opts, int32_t oy0, int32_t oy1, int32_t ox0,
-                              int32_t ox1, int32_t odlo, int32_t odhi, const cs_layout *Lo,
-                              float *d_out, uint16_t *d_nobs, void *stream) {
+// plan_only: stop after the tiling has been chosen and report the tile height
+static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel_desc *K,
+                        const cs_pearson_opts *opts, int32_t oy0, int32_t oy1, int32_t ox0,
+                        int32_t ox1, int32_t odlo, int32_t odhi, const cs_layout *Lo, float *d_out,
+                        uint16_t *d_nobs, void *stream, bool plan_only, int32_t *tile_rows_out) {
     cudaStream_t st = (cudaStream_t)stream;
-    CS_REQUIRE(Li && d_img && K && opts && Lo && d_out, "cs_pearson_f32: null argument");
+    CS_REQUIRE(Li && K && opts && (plan_only || (d_img && Lo && d_out)),
+               "cs_pearson_f32: null argument");
     CS_REQUIRE(K->kh >= 1 && K->kw >= 3 && (K->kh & 1) && (K->kw & 1),
                "kernel shape must be odd (got %dx%d)", K->kh, K->kw);
     CS_REQUIRE(K->kh <= 31 && K->kw <= 31, "kernel %dx%d too large (31x31 at most)", K->kh, K->kw);
@@ -784,20 +789,20 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
     P.odhi = odhi;
     P.KH = K->kh;
     P.KW = K->kw;
-    P.KWP = (K->kw + 1) / 2 * 2;
+    P.KWP2 = round_up(K->kw + 1, 4);
     P.N = K->kh * K->kw;
     const int kwa = round_up(kw, 4);
     const int nrows_out = oy1 - oy0;
 
     // ---- tables -------------------------------------------------------------------
-    // float: K' = K_corr - q, every tap duplicated (k, k) for the packed FMAs, [KH][KWP]
+    // float: K' = K_corr - q as two padded rows per kernel row (see Ktab), [KH][2][KWP2]
     // double (mask): row prefix sums of K_mask and K2_mask [KH][KW+1] each, column sums [KW] each
     const int nk = K->kh * K->kw;
     double qd = 0.0;
     for (int i = 0; i < nk; ++i) qd += K->k_corr[i];
     qd /= nk;
     const float qf = (float)qd;
-    P.n_ftab = 2 * K->kh * P.KWP;
+    P.n_ftab = 2 * K->kh * P.KWP2;
     // declared-missing strip: tables over the output diagonals whose windows touch it
     P.sdlo = 0;
     P.sdhi = -1;
@@ -822,8 +827,8 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
     for (int i = 0; i < K->kh; ++i)
         for (int j = 0; j < K->kw; ++j) {
             const float v = (float)(K->k_corr[i * K->kw + j] - (double)qf);
-            hf[2 * (i * P.KWP + j)] = v;
-            hf[2 * (i * P.KWP + j) + 1] = v;
+            hf[(2 * i) * P.KWP2 + j] = v;          // (k0,k1),(k2,k3),...
+            hf[(2 * i + 1) * P.KWP2 + j + 1] = v;  // (0,k0),(k1,k2),...
             sumKp += (double)v;
             sumKp2 += (double)v * (double)v;
         }
@@ -877,9 +882,9 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
             return CS_ERR_INVALID;
         }
         const int G = TR / RU;
-        const int span = P.skew ? (Wo + RU - 1 + 3) : (ncols_out + 3);
+        const int span = P.skew ? (Wo + RU - 1 + 3 + kSkewSlack) : (ncols_out + 3);
         const int nblk_total = (span + RT - 1) / RT;
-        const int nb_max = (256 - 2 * kwa - RU * (G - 1) * P.skew) / RT;
+        const int nb_max = (256 - 2 * kwa - skew_shift(G - 1) * P.skew) / RT;
         if (nb_max < 1) continue;
         // aim at <= 256 items per tile and a box of at most 256 columns
         int nb_want = 256 / G;
@@ -887,7 +892,7 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
         if (nb_want < 1) nb_want = 1;
         nchunks = (nblk_total + nb_want - 1) / nb_want;
         NBc = (nblk_total + nchunks - 1) / nchunks;
-        IC = RT * NBc + RU * (G - 1) * P.skew + 2 * kwa;
+        IC = RT * NBc + skew_shift(G - 1) * P.skew + 2 * kwa;
         IR = TR + K->kh - 1;
         if (IR > 256 || IC > 256) continue;
         threads = round_up(G * NBc, 32);
@@ -921,6 +926,11 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
         o += 16;
         smem = o;
         if (smem <= 113 * 1024 || (TR == RU && smem <= 227 * 1024)) break;
+    }
+    if (plan_only) {
+        free(hk);
+        if (tile_rows_out) *tile_rows_out = TR;
+        return CS_OK;
     }
     P.TR = TR;
     P.G = TR / RU;
@@ -1019,4 +1029,21 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
     if (opts->has_mask)
         return launch_mask<true>(K->kw, tmap, P, (int)grid_ll, threads, smem, st);
     return launch_mask<false>(K->kw, tmap, P, (int)grid_ll, threads, smem, st);
+}
+
+extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_kernel_desc *K,
+                              const cs_pearson_opts *opts, int32_t oy0, int32_t oy1, int32_t ox0,
+                              int32_t ox1, int32_t odlo, int32_t odhi, const cs_layout *Lo,
+                              float *d_out, uint16_t *d_nobs, void *stream) {
+    return pearson_impl(Li, d_img, K, opts, oy0, oy1, ox0, ox1, odlo, odhi, Lo, d_out, d_nobs,
+                        stream, false, nullptr);
+}
+
+extern "C" int cs_pearson_tile_rows(const cs_layout *Li, const cs_kernel_desc *K,
+                                    const cs_pearson_opts *opts, int32_t oy0, int32_t oy1,
+                                    int32_t ox0, int32_t ox1, int32_t odlo, int32_t odhi,
+                                    int32_t *tile_rows) {
+    CS_REQUIRE(tile_rows, "cs_pearson_tile_rows: null argument");
+    return pearson_impl(Li, nullptr, K, opts, oy0, oy1, ox0, ox1, odlo, odhi, nullptr, nullptr,
+                        nullptr, nullptr, true, tile_rows);
 }

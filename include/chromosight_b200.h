@@ -122,6 +122,14 @@ int cs_pearson_f32(const cs_layout *Limg, const float *d_img,
                    int32_t odlo, int32_t odhi,
                    const cs_layout *Lout, float *d_out, uint16_t *d_nobs,
                    void *stream);
+/* Height (output rows) of the tiles cs_pearson_f32 would use for this call.  A caller that
+ * splits one region into row ranges (the slab pipeline of cs_normxcorr2_host) cuts at
+ * multiples of it and passes it back as opts->tile_rows, so that every tile -- and with it
+ * every float32 rounding -- is the same as in a single launch. */
+int cs_pearson_tile_rows(const cs_layout *Limg, const cs_kernel_desc *K,
+                         const cs_pearson_opts *opts,
+                         int32_t oy0, int32_t oy1, int32_t ox0, int32_t ox1,
+                         int32_t odlo, int32_t odhi, int32_t *tile_rows);
 
 /* ------------------------------------------------------------------------
  * Score map -> CSR (what normxcorr2 returns, det:1098-1131): non-zero scores
