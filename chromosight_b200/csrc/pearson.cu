@@ -40,7 +40,7 @@ struct PearsonParams {
     int oy0, oy1, ox0, ox1, odlo, odhi;
     // tiling
     int TR, G, NBc, nchunks, skew;
-    int IC, IR, VQ, NW;
+    int IC, IR, NW;
     // kernel geometry
     int KH, KW, KWP2, N;
     // output image
@@ -55,7 +55,7 @@ struct PearsonParams {
     int min_present, kmean_zero, has_mask, raw_xcorr, nobs_full;
     int sdlo, sdhi, st_base, st_n;  // declared-missing diagonal strip and its tables
     // shared memory carve-up (bytes)
-    int off_V, off_Vm, off_bits, off_K, off_D, off_acc, off_grp, off_red, off_bar;
+    int off_bits, off_K, off_D, off_stat, off_grp, off_bar;
 };
 
 // ---------------------------------------------------------------- PTX helpers
@@ -105,6 +105,11 @@ __device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
     unsigned long long r;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
@@ -235,18 +240,15 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
 
     extern __shared__ __align__(1024) unsigned char smem[];
     float *__restrict__ tile = reinterpret_cast<float *>(smem);
-    float2 *__restrict__ V = reinterpret_cast<float2 *>(smem + P.off_V);
-    unsigned char *__restrict__ Vm = smem + P.off_Vm;
     uint32_t *__restrict__ bits = reinterpret_cast<uint32_t *>(smem + P.off_bits);
     // taps K' = K_corr - q, two rows of KWP2 floats per kernel row: the row padded with
     // zeros (pairs (k0,k1),(k2,k3),... for windows at an even tile column) and the same row
     // shifted right by one (pairs (0,k0),(k1,k2),... for windows at an odd tile column)
     const float *__restrict__ Ktab = reinterpret_cast<const float *>(smem + P.off_K);
     const double *__restrict__ Dt = reinterpret_cast<const double *>(smem + P.off_D);
-    float *__restrict__ accS = reinterpret_cast<float *>(smem + P.off_acc);
+    float *__restrict__ statS = reinterpret_cast<float *>(smem + P.off_stat);
     unsigned long long *__restrict__ grpS =
         reinterpret_cast<unsigned long long *>(smem + P.off_grp);
-    float *__restrict__ red = reinterpret_cast<float *>(smem + P.off_red);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + P.off_bar);
 
     const int tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
@@ -264,7 +266,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     xb += RT * ch * P.NBc;
     const int TXp = xb - kwa;  // X' of tile column 0
     const int TY = Y0 - kh;    // image row of tile row 0
-    const int IC = P.IC, IR = P.IR, NW = P.NW, VQ = P.VQ;
+    const int IC = P.IC, IR = P.IR, NW = P.NW;
 
     if (tid == 0) {
         mbar_init(bar, 1);
@@ -285,92 +287,52 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     __syncthreads();
     mbar_wait(bar, 0);
 
-    // ---- pivot: mean of the in-band, non-missing pixels of every 4th tile row ----
-    float pv;
-    {
-        float lsum = 0.f, lcnt = 0.f;
-        const int ICq4 = IC >> 2;
-        const int nrow_s = (IR + 3) >> 2;
-        for (int i = tid; i < nrow_s * ICq4; i += nthr) {
-            const int iy = (i / ICq4) << 2, c4 = (i - (i / ICq4) * ICq4) << 2;
-            const float4 v = *reinterpret_cast<const float4 *>(tile + iy * IC + c4);
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-            const int d0 = (TXp + c4 + P.dlo) - (TY + iy);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const bool inside = P.dense ? true : (d0 + e >= P.dlo && d0 + e <= P.dhi);
-                if (inside && vv[e] == vv[e]) {
-                    lsum += vv[e];
-                    lcnt += 1.f;
-                }
-            }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
-            lcnt += __shfl_xor_sync(0xffffffffu, lcnt, o);
-        }
-        if (lane == 0) {
-            red[tid >> 5] = lsum;
-            red[8 + (tid >> 5)] = lcnt;
-        }
-        __syncthreads();
-        float ts = 0.f, tc = 0.f;
-        for (int w = 0; w < (nthr >> 5); ++w) {
-            ts += red[w];
-            tc += red[8 + w];
-        }
-        pv = tc > 0.f ? ts / tc : 0.f;
-    }
-    const double p = (double)pv;
-
-    // ---- phase A1: fix-up of the tile, four pixels per thread ---------------------------
-    // out-of-band aliases and declared-missing strip -> 0, NaN sentinels -> bit array and 0,
-    // then the shift by the pivot
+    // ---- phase A: fix-up of the tile, four pixels per thread ---------------------- [sec:A1]
+    // out-of-band aliases and declared-missing strip -> 0, NaN sentinels -> bit array and 0
+    // (missing pixels count as S = 0, det:1050-1060)
     int anynz = 0;
     {
         const int ICq4 = IC >> 2;
-        const int nf4 = IR * ICq4;
-        for (int fb = 0; fb < nf4; fb += nthr) {
-            const int f = fb + tid;
-            const bool live = f < nf4;
-            unsigned nib = 0u;
-            if (live) {
-                const int iy = f / ICq4, c4 = (f - iy * ICq4) << 2;
-                float4 *ptr = reinterpret_cast<float4 *>(tile) + f;
-                const float4 v = *ptr;
-                float vv[4] = {v.x, v.y, v.z, v.w};
-                const int d0 = (TXp + c4 + P.dlo) - (TY + iy);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int d = d0 + e;
-                    float x = vv[e];
-                    if (!P.dense && (d < P.dlo || d > P.dhi)) x = 0.f;
-                    if (MASK) {
-                        if (d >= P.sdlo && d <= P.sdhi) x = 0.f;  // counted analytically
-                        if (!(x == x)) nib |= 1u << e;
-                    }
-                    if (!(x == x)) x = 0.f;  // missing pixels count as S = 0
-                    anynz |= (x != 0.f);
-                    vv[e] = x - pv;
-                }
-                *ptr = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        for (int iy = tid >> 5; iy < IR; iy += nthr >> 5) {
+            // in-band tile columns of this row: [clo, chi)
+            const int dbase = (TXp + P.dlo) - (TY + iy);  // diagonal of tile column 0
+            int clo = 0, chi = IC, slo = 0, shi = 0;
+            if (!P.dense) {
+                clo = max(P.dlo - dbase, 0);
+                chi = min(P.dhi - dbase + 1, IC);
             }
             if (MASK) {
-                // eight consecutive threads hold the 32 bits of one word
-                unsigned w = nib << (4 * (lane & 7));
-                w |= __shfl_xor_sync(0xffffffffu, w, 1);
-                w |= __shfl_xor_sync(0xffffffffu, w, 2);
-                w |= __shfl_xor_sync(0xffffffffu, w, 4);
-                if (live && (lane & 7) == 0) bits[f >> 3] = w;
+                slo = P.sdlo - dbase;
+                shi = P.sdhi - dbase + 1;  // declared-missing strip: counted analytically
+            }
+            for (int c4 = lane; c4 < ICq4; c4 += 32) {
+                float4 *ptr = reinterpret_cast<float4 *>(tile + iy * IC) + c4;
+                const float4 v = *ptr;
+                float vv[4] = {v.x, v.y, v.z, v.w};
+                unsigned nib = 0u;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = 4 * c4 + e;
+                    float x = vv[e];
+                    if (c < clo || c >= chi) x = 0.f;
+                    if (MASK && c >= slo && c < shi) x = 0.f;
+                    if (!(x == x)) {
+                        if (MASK) nib |= 1u << e;
+                        x = 0.f;  // missing pixels count as S = 0
+                    }
+                    anynz |= (x != 0.f);
+                    vv[e] = x;
+                }
+                *ptr = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                if (MASK && nib) atomicOr(&bits[(iy * IC + 4 * c4) >> 5], nib << ((iy * IC + 4 * c4) & 31));
             }
         }
     }
     const int tnz = __syncthreads_or(anynz);
 
-    const int nitems = P.G * P.NBc;
     if (!tnz) {
         // all-zero signal: every score of the tile is 0 (variance 0 -> det:1088-1091)
-        for (int item = tid; item < nitems; item += nthr) {
+        for (int item = tid; item < P.G * P.NBc; item += nthr) {
             const int g = item / P.NBc, m = item - g * P.NBc;
             const int Xp0 = xb + skew_shift(g) * P.skew + RT * m;
             for (int u = 0; u < RU; ++u) {
@@ -390,46 +352,6 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         return;
     }
 
-    // ---- phase A2: vertical sliding sums over KH rows, one thread per column ----------
-    {
-        const unsigned KHM = (KH >= 32) ? 0xffffffffu : ((1u << KH) - 1u);
-        for (int cb = (tid >> 5) << 5; cb < IC; cb += nthr) {
-            const bool live = cb + lane < IC;
-            const int ix = live ? cb + lane : IC - 1;  // idle lanes shadow the last column
-            const float *__restrict__ pin = tile + ix;             // row iy
-            const float *__restrict__ pold = tile + ix;            // row iy - (KH - 1)
-            float2 *__restrict__ pv2 = V + (ix & 3) * VQ + (ix >> 2);
-            unsigned char *__restrict__ pvm = Vm + (ix & 3) * VQ + (ix >> 2);
-            double r1 = 0.0, r2 = 0.0;
-            unsigned colbits = 0u;
-            int pos = cb;
-#pragma unroll 2
-            for (int iy = 0; iy < IR; ++iy, pin += IC, pos += IC) {
-                const double a = (double)*pin;
-                r1 += a;
-                r2 = fma(a, a, r2);
-                if (MASK) {
-                    const unsigned w =
-                        __funnelshift_r(bits[pos >> 5], bits[(pos >> 5) + 1], pos & 31);
-                    colbits = (colbits << 1) | ((w >> lane) & 1u);
-                }
-                if (iy >= KH - 1) {
-                    if (live) {
-                        *pv2 = make_float2((float)r1, (float)r2);
-                        if (MASK) *pvm = (unsigned char)__popc(colbits & KHM);
-                    }
-                    pv2 += 4 * VQ;
-                    pvm += 4 * VQ;
-                    const double b = (double)*pold;
-                    pold += IC;
-                    r1 -= b;
-                    r2 = fma(-b, b, r2);
-                }
-            }
-        }
-    }
-    __syncthreads();
-
     // double tables (mask branch): 2-D prefix sums of the mask kernels, their column sums,
     // and the sums over the declared-missing strip per output diagonal
     constexpr int KW1 = KW + 1;
@@ -441,18 +363,30 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     const double *StK2 = StK + P.st_n;                  // [st_n]
     const double *StC = StK2 + P.st_n;                  // [st_n]
 
-    // ---- main loop + epilogue -----------------------------------------------------------
+    // ---- blocks of RU x RT windows, one per thread -------------------------------------
+    // Lanes 0-3 / 4-7 of every quarter-warp take blocks of row groups g / g + 2: in a banded
+    // traversal their tile columns differ by 4 (mod 8), which makes the 16-byte loads of a
+    // quarter-warp hit disjoint banks.
+    const int NQd = (P.NBc + 3) >> 2;
+    const int nitems = 8 * NQd * 2 * ((P.G + 3) >> 2);
     // every lane runs every loop (work is predicated): the epilogue contains warp-wide steps
     for (int base = 0; base < nitems; base += nthr) {
-        const int item = base + tid;
-        const int g = item < nitems ? item / P.NBc : 0;
-        const int m = item < nitems ? item - g * P.NBc : 0;
+        int g, m;
+        bool live;
+        {
+            const int idx = base + tid;
+            const int rest = idx >> 3, M = rest % NQd, pr = rest / NQd;
+            g = (pr >> 1) * 4 + (pr & 1) + 2 * ((idx >> 2) & 1);
+            m = 4 * M + (idx & 3);
+            live = idx < nitems && g < P.G && m < P.NBc;
+            if (!live) g = m = 0;
+        }
         const int Xp0 = xb + skew_shift(g) * P.skew + RT * m;  // X' of output column t = 0
         const int cxa = skew_shift(g) * P.skew + RT * m;       // aligned tile column of x[0]
         const int Yg = Y0 + RU * g;
         // blocks without any valid output pixel are skipped
         bool any = false;
-        if (item < nitems) {
+        if (live) {
             for (int u = 0; u < RU; ++u) {
                 const int Y = Yg + u;
                 if (Y >= P.oy1) continue;
@@ -461,18 +395,28 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 if (Xa + RT - 1 >= Xlo && Xa <= Xhi) any = true;
             }
         }
-        float *myacc = accS + tid;
-        // block pivot: mean of S' over (most of) the footprint, from the column sums of the
-        // block's second row.  The products are formed on S' - pl; exact algebra puts it back.
+        // per-window results of the two passes, parked in shared memory: the epilogue runs as
+        // compact loops.  [k], [NWB + k], [2 NWB + k] with k = u * RT + t.
+        constexpr int NWB = RU * RT;
+        float *mystat = statS + tid;
         float pl = 0.f;
-        if (any) {
-            const float2 *Vr = V + (RU * g + 1) * 4 * VQ + (cxa >> 2);
+        if (any) {                                                           // [sec:pivot]
+            // block pivot: mean of the middle footprint row.  Sums and products are formed on
+            // S - pl (any pivot is algebraically exact; a close one keeps float32 accurate).
+            const float4 *rp4 = reinterpret_cast<const float4 *>(
+                tile + (RU * g + (KH + RU - 1) / 2) * IC + cxa);
             float sacc = 0.f;
 #pragma unroll
-            for (int e = off; e < off + XW; ++e) sacc += Vr[(e & 3) * VQ + (e >> 2)].x;
-            pl = sacc * (1.0f / (float)XW) / (float)KH;
+            for (int qd = 0; qd < NQ; ++qd) {
+                const float4 v = rp4[qd];
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (4 * qd + e >= off && 4 * qd + e < off + XW) sacc += vv[e];
+            }
+            pl = sacc * (1.0f / (float)XW);
         }
-        if (any) {
+        if (any) {                                                           // [sec:main]
             const unsigned long long npl2 = pack2(-pl, -pl);
             // one packed accumulator per window: .lo and .hi collect alternate taps
             unsigned long long acc[RU][RT];
@@ -518,15 +462,81 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     }
                 }
             }
-            // park the accumulators in shared memory: the epilogue runs as compact loops
 #pragma unroll
             for (int u = 0; u < RU; ++u)
 #pragma unroll
                 for (int t = 0; t < RT; ++t) {
                     float lo, hi;
                     unpack2(acc[u][t], lo, hi);
-                    myacc[(u * RT + t) * nthr] = lo + hi;
+                    mystat[(u * RT + t) * nthr] = lo + hi;
                 }
+        }
+        if (any) {                                                           // [sec:sums]
+            // window sums of (S - pl) and (S - pl)^2: column sums over KH rows in packed
+            // registers, then KW-wide sliding sums along the row
+            const unsigned long long npl2 = pack2(-pl, -pl);
+            unsigned long long cs[2 * NQ], cq[2 * NQ];
+#pragma unroll
+            for (int q = 0; q < 2 * NQ; ++q) cs[q] = cq[q] = 0ull;
+#pragma unroll 1
+            for (int iy = 0; iy < KH; ++iy) {
+                const ulonglong2 *rp =
+                    reinterpret_cast<const ulonglong2 *>(tile + (RU * g + iy) * IC + cxa);
+#pragma unroll
+                for (int qd = 0; qd < NQ; ++qd) {
+                    const ulonglong2 v = rp[qd];
+                    const unsigned long long a = add2(v.x, npl2), b = add2(v.y, npl2);
+                    cs[2 * qd] = add2(cs[2 * qd], a);
+                    cs[2 * qd + 1] = add2(cs[2 * qd + 1], b);
+                    fma2(cq[2 * qd], a, a);
+                    fma2(cq[2 * qd + 1], b, b);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                if (u > 0) {
+                    // rows [u, u + KH): row u + KH - 1 enters, row u - 1 leaves
+                    const ulonglong2 *rin = reinterpret_cast<const ulonglong2 *>(
+                        tile + (RU * g + u + KH - 1) * IC + cxa);
+                    const ulonglong2 *rout =
+                        reinterpret_cast<const ulonglong2 *>(tile + (RU * g + u - 1) * IC + cxa);
+                    const unsigned long long pl2 = pack2(pl, pl);
+#pragma unroll
+                    for (int qd = 0; qd < NQ; ++qd) {
+                        const ulonglong2 vi = rin[qd], vo = rout[qd];
+                        const unsigned long long a = add2(vi.x, npl2), b = add2(vi.y, npl2);
+                        const unsigned long long c = add2(vo.x, npl2), d = add2(vo.y, npl2);
+                        const unsigned long long nc = sub2(pl2, vo.x), nd = sub2(pl2, vo.y);
+                        cs[2 * qd] = add2(add2(cs[2 * qd], a), nc);
+                        cs[2 * qd + 1] = add2(add2(cs[2 * qd + 1], b), nd);
+                        fma2(cq[2 * qd], a, a);
+                        fma2(cq[2 * qd + 1], b, b);
+                        fma2(cq[2 * qd], nc, c);  // - (x - pl)^2
+                        fma2(cq[2 * qd + 1], nd, d);
+                    }
+                }
+                float col[4 * NQ], cqq[4 * NQ];
+#pragma unroll
+                for (int q = 0; q < 2 * NQ; ++q) {
+                    unpack2(cs[q], col[2 * q], col[2 * q + 1]);
+                    unpack2(cq[q], cqq[2 * q], cqq[2 * q + 1]);
+                }
+                float g1 = 0.f, g2 = 0.f;
+#pragma unroll
+                for (int e = off; e < off + KW; ++e) {
+                    g1 += col[e];
+                    g2 += cqq[e];
+                }
+#pragma unroll
+                for (int t = 0; t < RT; ++t) {
+                    if (t > 0) {
+                        g1 += col[off + t + KW - 1] - col[off + t - 1];
+                        g2 += cqq[off + t + KW - 1] - cqq[off + t - 1];
+                    }
+                    mystat[(NWB + u * RT + t) * nthr] = g1;
+                    mystat[(2 * NWB + u * RT + t) * nthr] = g2;
+                }
+            }
         }
 
         // footprint mask summary.  colfull: columns missing on every footprint row.  The other
@@ -534,11 +544,11 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         // (a missing row, the visible part of a missing column at the edge of the mask band,
         // a frame margin); footprints with more groups than fit fall back to row-by-row.
         const int fc0 = cxa + off;  // tile column of footprint column 0
-        unsigned long long colfull = 0ull, rowsel = 0ull;
+        unsigned long long colfull = 0ull, rowsel = 0ull, bor = 0ull;                // [sec:masksum]
         int ng = 0;
         if (MASK && any) {
             constexpr unsigned long long FWMASK = (XW >= 64) ? ~0ull : ((1ull << XW) - 1ull);
-            unsigned long long band = FWMASK, bor = 0ull;
+            unsigned long long band = FWMASK;
             const int fr = KH + RU - 1;
             for (int r = 0; r < fr; ++r) {
                 const unsigned long long b = row_bits(bits, (RU * g + r) * IC + fc0) & FWMASK;
@@ -569,53 +579,30 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             }
         }
 
-        // V planes of this block: column c of the footprint is entry (c >> 2) of plane (c & 3)
-        const int qbase = cxa >> 2;
 #pragma unroll 1
         for (int u = 0; u < RU; ++u) {
             const int Y = Yg + u;
             const bool rowok = any && Y < P.oy1;
-            const float2 *Vr = V + (RU * g + u) * 4 * VQ + qbase;
-            const unsigned char *Vmr = Vm + (RU * g + u) * 4 * VQ + qbase;
-            double h1 = 0.0, h2 = 0.0;
-            int hm = 0;
-            if (rowok) {
-#pragma unroll
-                for (int e = off; e < off + KW; ++e) {
-                    const float2 v = Vr[(e & 3) * VQ + (e >> 2)];
-                    h1 += (double)v.x;
-                    h2 += (double)v.y;
-                    if (MASK) hm += Vmr[(e & 3) * VQ + (e >> 2)];
-                }
-            }
 #pragma unroll 1
             for (int t = 0; t < RT; ++t) {
-                if (t > 0 && rowok) {
-                    const int e0 = off + t - 1, e1 = off + t - 1 + KW;
-                    const float2 a = Vr[(e0 & 3) * VQ + (e0 >> 2)], b = Vr[(e1 & 3) * VQ + (e1 >> 2)];
-                    h1 += (double)b.x - (double)a.x;
-                    h2 += (double)b.y - (double)a.y;
-                    if (MASK)
-                        hm += (int)Vmr[(e1 & 3) * VQ + (e1 >> 2)] - (int)Vmr[(e0 & 3) * VQ + (e0 >> 2)];
-                }
                 const int X = Xp0 + t + P.dlo;
                 const int d = X - Y;
                 const bool wok = rowok && X >= P.ox0 && X < P.ox1 && d >= P.odlo && d <= P.odhi;
                 int nmiss = 0;
                 double sKm = 0.0, sKm2 = 0.0;
-                if (MASK && wok) {
-                    nmiss = hm;
+                if (MASK && wok) {                                           // [sec:strip]
                     // the declared-missing diagonal strip: a function of the window's diagonal
                     const unsigned sd = (unsigned)(d - P.st_base);
                     if (sd < (unsigned)P.st_n) {
-                        nmiss += (int)StC[sd];
+                        nmiss = (int)StC[sd];
                         sKm = StK[sd];
                         sKm2 = StK2[sd];
                     }
                 }
-                if (MASK && wok && hm > 0) {
+                if (MASK && wok && ((unsigned)(bor >> t) & KWMASK)) {        // [sec:rects]
                     // columns missing over the whole footprint: whole kernel columns
                     const unsigned cbw = (unsigned)(colfull >> t) & KWMASK;
+                    nmiss += KH * __popc(cbw);
                     for (unsigned c = cbw; c; c &= c - 1) {
                         const int j = __ffs(c) - 1;
                         sKm += Kcol[j];
@@ -627,9 +614,11 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                             const unsigned long long gp = grpS[k * nthr + tid];
                             const int i0 = max((int)((gp >> 40) & 255) - u, 0);
                             const int i1 = min((int)(gp >> 48) - u, KH);
-                            if (i0 < i1)
-                                add_rects((unsigned)(gp >> t) & KWMASK, i0, i1, IK, IK2, KW1, sKm,
-                                          sKm2);
+                            const unsigned wb = (unsigned)(gp >> t) & KWMASK;
+                            if (i0 < i1 && wb) {
+                                nmiss += (i1 - i0) * __popc(wb);
+                                add_rects(wb, i0, i1, IK, IK2, KW1, sKm, sKm2);
+                            }
                         }
                     } else {
                         // row by row
@@ -639,46 +628,48 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                             const unsigned wb =
                                 (unsigned)(row_bits(bits, (RU * g + u + i) * IC + fc0) >> t) &
                                 KWMASK & ~cbw;
+                            nmiss += __popc(wb);
                             add_rects(wb, i, i + 1, IK, IK2, KW1, sKm, sKm2);
                         }
                     }
                 }
-                int nobs = P.N;
+                int nobs = P.N;                                              // [sec:score]
                 bool redo = false;
                 float r = 0.f;
                 if (wok) {
-                    // sum S' K' = sum (S' - pl) K' + pl * sum K'
-                    const double dpl = (double)pl;
-                    const double s3 = fma(dpl, P.sumKp, (double)myacc[(u * RT + t) * nthr]);
-                    const double h2_loc = fma((double)P.N * dpl, dpl, fma(-2.0 * dpl, h1, h2));
-                    r = score_from_sums<MASK>(P, p, h1, h2, h2_loc, nmiss, s3, sKm, sKm2, nobs, redo);
+                    const int k = u * RT + t;
+                    const double s3 = (double)mystat[k * nthr];
+                    const double g1 = (double)mystat[(NWB + k) * nthr];
+                    const double g2 = (double)mystat[(2 * NWB + k) * nthr];
+                    r = score_from_sums<MASK>(P, (double)pl, g1, g2, g2, nmiss, s3, sKm, sKm2, nobs,
+                                              redo);
                 }
                 // ill-conditioned windows (flat signal or mostly missing): the warp redoes the
-                // window sums in float64 from the tile, 32 pixels at a time
+                // window sums in float64 from the tile, 32 pixels at a time      [sec:redo]
                 const int woff = (RU * g + u) * IC + fc0 + t;
                 for (unsigned todo = __ballot_sync(0xffffffffu, redo); todo; todo &= todo - 1) {
                     const int src = __ffs(todo) - 1;
                     const float *wp = tile + __shfl_sync(0xffffffffu, woff, src);
-                    double g1 = 0.0, g2 = 0.0, s3 = 0.0;
+                    double h1 = 0.0, h2 = 0.0, s3 = 0.0;
                     for (int idx = lane; idx < KH * KW; idx += 32) {
                         const int i = idx / KW, j = idx - i * KW;
                         const double sv = (double)wp[i * IC + j];
-                        g1 += sv;
-                        g2 = fma(sv, sv, g2);
+                        h1 += sv;
+                        h2 = fma(sv, sv, h2);
                         s3 = fma(sv, (double)Ktab[i * 2 * KWP2 + j], s3);
                     }
                     for (int o = 16; o > 0; o >>= 1) {
-                        g1 += __shfl_xor_sync(0xffffffffu, g1, o);
-                        g2 += __shfl_xor_sync(0xffffffffu, g2, o);
+                        h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+                        h2 += __shfl_xor_sync(0xffffffffu, h2, o);
                         s3 += __shfl_xor_sync(0xffffffffu, s3, o);
                     }
                     if (lane == src) {
                         bool again;
-                        r = score_from_sums<MASK>(P, p, g1, g2, g2, nmiss, s3, sKm, sKm2, nobs,
+                        r = score_from_sums<MASK>(P, 0.0, h1, h2, h2, nmiss, s3, sKm, sKm2, nobs,
                                                   again);
                     }
                 }
-                if (wok) {
+                if (wok) {                                                   // [sec:store]
                     const long long oi =
                         (long long)(Y - P.osy) * P.out_pitch + ((X - P.osx) - P.out_dlo);
                     P.out[oi] = r;
@@ -874,7 +865,7 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
         if (atoi(e) > 0) TR = round_up(atoi(e), RU);
     if (TR > round_up(nrows_out, RU)) TR = round_up(nrows_out, RU);
     size_t smem = 0;
-    int NBc = 0, nchunks = 0, IC = 0, IR = 0, VQ = 0, NW = 0, threads = 0;
+    int NBc = 0, nchunks = 0, IC = 0, IR = 0, NW = 0, threads = 0;
     for (;; TR -= RU) {
         if (TR < RU) {
             free(hk);
@@ -895,17 +886,11 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
         IC = RT * NBc + skew_shift(G - 1) * P.skew + 2 * kwa;
         IR = TR + K->kh - 1;
         if (IR > 256 || IC > 256) continue;
-        threads = round_up(G * NBc, 32);
+        threads = round_up(8 * ((NBc + 3) / 4) * 2 * ((G + 3) / 4), 32);  // padded item count
         if (threads > 256) threads = 256;
         if (threads < 64) threads = 64;
-        VQ = (IC / 4) | 1;
         NW = (IC * IR + 31) / 32 + 4;  // words of the linear bit array
         size_t o = (size_t)IC * IR * sizeof(float);
-        o = (o + 15) / 16 * 16;
-        P.off_V = (int)o;
-        o += (size_t)TR * 4 * VQ * sizeof(float2);
-        P.off_Vm = (int)o;
-        if (opts->has_mask) o += (size_t)TR * 4 * VQ;
         o = (o + 15) / 16 * 16;
         P.off_bits = (int)o;
         if (opts->has_mask) o += (size_t)NW * sizeof(uint32_t);
@@ -915,13 +900,11 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
         P.off_D = (int)o;
         o += (size_t)P.n_dtab * sizeof(double);
         o = (o + 15) / 16 * 16;
-        P.off_acc = (int)o;
-        o += (size_t)RU * RT * threads * sizeof(float);
+        P.off_stat = (int)o;
+        o += (size_t)3 * RU * RT * threads * sizeof(float);
         o = (o + 15) / 16 * 16;
         P.off_grp = (int)o;
         if (opts->has_mask) o += (size_t)kMaxGroups * threads * sizeof(unsigned long long);
-        P.off_red = (int)o;
-        o += 64 * sizeof(float);
         P.off_bar = (int)o;
         o += 16;
         smem = o;
@@ -938,7 +921,6 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
     P.nchunks = nchunks;
     P.IC = IC;
     P.IR = IR;
-    P.VQ = VQ;
     P.NW = NW;
     const int nrb = (nrows_out + TR - 1) / TR;
     const long long grid_ll = (long long)nrb * nchunks;
