@@ -58,7 +58,7 @@ struct PearsonParams {
     int off_bits, off_K, off_D, off_stat, off_grp, off_bar;
 };
 
-// ---------------------------------------------------------------- PTX helpers
+// ---------------------------------------------------------------- PTX helpers  // [sec:packedops]
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -121,7 +121,7 @@ __device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
 
-__device__ __forceinline__ double thr0(double v, double t) { return fabs(v) < t ? 0.0 : v; }
+__device__ __forceinline__ double thr0(double v, double t) { return fabs(v) < t ? 0.0 : v; }  // [sec:scorefn]
 
 // Squared error amplification above which a window is recomputed in float64: the
 // float32 sums carry ~1e-6 relative error on well-conditioned windows, and the score
@@ -198,7 +198,7 @@ __device__ __forceinline__ float score_from_sums(const PearsonParams &P, double 
     return r;
 }
 
-// 64 bits of the (linear, one bit per tile pixel) missing-pixel bit array from bit `pos` on
+// 64 bits of the (linear, one bit per tile pixel) missing-pixel bit array from bit `pos` on  // [sec:maskfn]
 __device__ __forceinline__ unsigned long long row_bits(const uint32_t *bits, int pos) {
     const int w = pos >> 5, sh = pos & 31;
     const uint32_t a = bits[w], b = bits[w + 1], c = bits[w + 2];
@@ -222,7 +222,7 @@ __device__ __forceinline__ void add_rects(unsigned wb, int i0, int i1, const dou
     }
 }
 
-constexpr int kMaxGroups = 4;  // rectangles of missing pixels per footprint kept in shared memory
+constexpr int kMaxGroups = 4;  // rectangles of missing pixels per footprint kept in shared memory  // [sec:kernelsetup]
 
 // ---------------------------------------------------------------- the kernel
 template <int KW, bool MASK>
@@ -308,23 +308,26 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             for (int c4 = lane; c4 < ICq4; c4 += 32) {
                 float4 *ptr = reinterpret_cast<float4 *>(tile + iy * IC) + c4;
                 const float4 v = *ptr;
-                float vv[4] = {v.x, v.y, v.z, v.w};
-                unsigned nib = 0u;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = 4 * c4 + e;
-                    float x = vv[e];
-                    if (c < clo || c >= chi) x = 0.f;
-                    if (MASK && c >= slo && c < shi) x = 0.f;
-                    if (!(x == x)) {
-                        if (MASK) nib |= 1u << e;
-                        x = 0.f;  // missing pixels count as S = 0
-                    }
-                    anynz |= (x != 0.f);
-                    vv[e] = x;
+                const int c0 = 4 * c4;
+                // 4-bit sets over the pixels of this float4: in the band and off the strip
+                // (`keep`), NaN sentinels among those (`nb`)
+                const unsigned inb = (0xfu << min(max(clo - c0, 0), 4)) & (0xfu >> min(max(c0 + 4 - chi, 0), 4));
+                unsigned keep = inb & 0xfu;
+                if (MASK) {
+                    const unsigned str = (0xfu << min(max(slo - c0, 0), 4)) &
+                                         (0xfu >> min(max(c0 + 4 - shi, 0), 4)) & 0xfu;
+                    keep &= ~str;
                 }
-                *ptr = make_float4(vv[0], vv[1], vv[2], vv[3]);
-                if (MASK && nib) atomicOr(&bits[(iy * IC + 4 * c4) >> 5], nib << ((iy * IC + 4 * c4) & 31));
+                const unsigned nan4 = (unsigned)(v.x != v.x) | ((unsigned)(v.y != v.y) << 1) |
+                                      ((unsigned)(v.z != v.z) << 2) | ((unsigned)(v.w != v.w) << 3);
+                const unsigned nb = nan4 & keep;
+                const unsigned live = keep & ~nan4;  // pixels that keep their value
+                const float4 w = make_float4((live & 1u) ? v.x : 0.f, (live & 2u) ? v.y : 0.f,
+                                             (live & 4u) ? v.z : 0.f, (live & 8u) ? v.w : 0.f);
+                anynz |= (__float_as_uint(w.x) | __float_as_uint(w.y) | __float_as_uint(w.z) |
+                          __float_as_uint(w.w)) != 0u;
+                if (live != 0xfu) *ptr = w;
+                if (MASK && nb) atomicOr(&bits[(iy * IC + c0) >> 5], nb << ((iy * IC + c0) & 31));
             }
         }
     }
