@@ -305,23 +305,32 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 slo = P.sdlo - dbase;
                 shi = P.sdhi - dbase + 1;  // declared-missing strip: counted analytically
             }
-            for (int c4 = lane; c4 < ICq4; c4 += 32) {
+            // keep-bits of the row, 32 columns per lane (lanes 0..7): in the band, off the strip
+            unsigned rowword;
+            {
+                const int base = 32 * lane;
+                const int a = min(max(clo - base, 0), 32), b = min(max(chi - base, 0), 32);
+                rowword = (unsigned)(((1ull << b) - 1ull) & ~((1ull << a) - 1ull));
+                if (MASK) {
+                    const int sa = min(max(slo - base, 0), 32), sb = min(max(shi - base, 0), 32);
+                    if (sb > sa) rowword &= ~(unsigned)(((1ull << sb) - 1ull) & ~((1ull << sa) - 1ull));
+                }
+            }
+            for (int cb = 0; cb < ICq4; cb += 32) {
+                const int c4 = cb + lane;
+                const int c0 = 4 * c4;
+                const unsigned kwd = __shfl_sync(0xffffffffu, rowword, (c0 >> 5) & 31);
+                if (c4 >= ICq4) continue;
                 float4 *ptr = reinterpret_cast<float4 *>(tile + iy * IC) + c4;
                 const float4 v = *ptr;
-                const int c0 = 4 * c4;
-                // 4-bit sets over the pixels of this float4: in the band and off the strip
-                // (`keep`), NaN sentinels among those (`nb`)
-                const unsigned inb = (0xfu << min(max(clo - c0, 0), 4)) & (0xfu >> min(max(c0 + 4 - chi, 0), 4));
-                unsigned keep = inb & 0xfu;
-                if (MASK) {
-                    const unsigned str = (0xfu << min(max(slo - c0, 0), 4)) &
-                                         (0xfu >> min(max(c0 + 4 - shi, 0), 4)) & 0xfu;
-                    keep &= ~str;
-                }
-                const unsigned nan4 = (unsigned)(v.x != v.x) | ((unsigned)(v.y != v.y) << 1) |
-                                      ((unsigned)(v.z != v.z) << 2) | ((unsigned)(v.w != v.w) << 3);
-                const unsigned nb = nan4 & keep;
-                const unsigned live = keep & ~nan4;  // pixels that keep their value
+                const unsigned keep = (kwd >> (c0 & 31)) & 0xfu;
+                // NaN sentinels among the kept pixels -> bit array; dropped and missing pixels -> 0
+                unsigned live = keep;
+                if (v.x != v.x) live &= ~1u;
+                if (v.y != v.y) live &= ~2u;
+                if (v.z != v.z) live &= ~4u;
+                if (v.w != v.w) live &= ~8u;
+                const unsigned nb = keep & ~live;
                 const float4 w = make_float4((live & 1u) ? v.x : 0.f, (live & 2u) ? v.y : 0.f,
                                              (live & 4u) ? v.z : 0.f, (live & 8u) ? v.w : 0.f);
                 anynz |= (__float_as_uint(w.x) | __float_as_uint(w.y) | __float_as_uint(w.z) |
