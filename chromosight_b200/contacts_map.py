@@ -1,0 +1,155 @@
+"""Genome / sub-matrix model around the hot path, mirroring chromosight.utils.contacts_map
+(contacts_map.py:79-450 HicGenome, 453-638 ContactMap) without the `cooler` package: the
+file is read by chromosight_b200.cool.CoolFile and the per-sub-matrix preprocessing
+(distance-law detrend, band trimming) runs through chromosight_b200.utils.preprocessing,
+i.e. on the GPU.
+
+Only what `detect` / `quantify` need is here: ICE balancing
+(`cooler.balance_cooler`), sub-sampling and the dump decorators are out of scope; a file
+must carry a `weight` column, or be used raw (`norm="raw"`).
+"""
+import numpy as np
+import pandas as pd
+
+from . import cool as _cool
+from .utils import preprocessing as preproc
+
+
+class ContactMap:
+    """One intra- or inter-chromosomal sub-matrix (contacts_map.py:453-638).  The attributes
+    the hot path reads are `matrix`, `detectable_bins`, `max_dist`, `inter`, `name`."""
+
+    def __init__(self, clr, extent, inter=False, detectable_bins=None, max_dist=None,
+                 largest_kernel=0, use_norm=True, smooth=False, name=None):
+        self.clr = clr
+        self.extent = extent
+        self.inter = inter
+        self.max_dist = max_dist
+        self.largest_kernel = largest_kernel
+        self.use_norm = use_norm
+        self.smooth = smooth
+        self.name = name
+        self.matrix = None
+        self.detectable_bins = detectable_bins
+        if detectable_bins is None:
+            raise ValueError("detectable_bins are required (get_detectable_bins is not mirrored)")
+
+    @property
+    def keep_distance(self):
+        """Diagonals kept in an intra map: scan distance plus a kernel margin (cm:629-638)."""
+        n = self.matrix.shape[0]
+        return (n if self.max_dist is None else min(self.max_dist, n)) + self.largest_kernel
+
+    def create_mat(self):
+        """Load, balance, detrend and trim the sub-matrix (cm:527-548)."""
+        (s1, e1), (s2, e2) = self.extent
+        self.matrix = self.clr.matrix(sparse=True, balance=self.use_norm)[s1:e1, s2:e2]
+        if self.inter:
+            # cm:598-601
+            self.matrix.data[np.isnan(self.matrix.data)] = 0.0
+            self.matrix.data = self.matrix.data / np.nanmedian(self.matrix.data)
+        else:
+            # cm:607-624: distance-law detrend (GPU) then band trim
+            self.matrix = preproc.detrend(
+                self.matrix, max_dist=self.keep_distance, smooth=self.smooth,
+                detectable_bins=self.detectable_bins[0], max_val=10 if self.use_norm else None)
+            self.matrix = preproc.diag_trim(self.matrix.tocsr(), self.keep_distance)
+        if self.use_norm:
+            self.matrix.data[np.isnan(self.matrix.data)] = 0
+        else:
+            # raw matrices have no NaN: blank the undetectable bins explicitly (cm:541-547)
+            m = self.matrix.tolil()
+            m[preproc.valid_to_missing(self.detectable_bins[0], m.shape[0]), :] = 0
+            m[:, preproc.valid_to_missing(self.detectable_bins[1], m.shape[1])] = 0
+            self.matrix = m.tocoo()
+        self.matrix.eliminate_zeros()
+
+    def destroy_mat(self):
+        self.matrix = None
+
+
+class HicGenome:
+    """Whole-genome contact map split into sub-matrices (contacts_map.py:79-450)."""
+
+    def __init__(self, path, inter=False, kernel_config=None, smooth=False):
+        self.clr = path if isinstance(path, _cool.CoolFile) else _cool.CoolFile(path)
+        self.bins = self.clr.bins()[:]
+        self.inter = inter
+        self.kernel_config = kernel_config
+        self.smooth = smooth
+        self.sub_mats = None
+        self.detectable_bins = None
+        self.use_norm = True
+        self.max_dist = None
+        self.largest_kernel = 3
+        if kernel_config is not None:
+            self.compute_max_dist()
+
+    def compute_max_dist(self):
+        """cm:166-180"""
+        try:
+            self.max_dist = max(self.kernel_config["max_dist"] // self.clr.binsize, 1)
+            self.largest_kernel = max(k.shape[0] for k in self.kernel_config["kernels"])
+        except (ValueError, TypeError):
+            self.max_dist = None
+            self.largest_kernel = 3
+
+    def normalize(self, norm="auto", n_mads=5, threads=1):
+        """cm:182-233, minus the balancing itself: existing weights are reused."""
+        if norm not in ("auto", "raw", "force"):
+            raise ValueError("norm must be one of: auto, raw, force")
+        if "weight" not in self.bins.columns or norm == "force":
+            raise NotImplementedError(
+                "ICE balancing (cooler.balance_cooler) is outside this package: balance the "
+                "file with cooler first, or use norm='raw' on a file with weights")
+        self.use_norm = norm != "raw"
+        self.detectable_bins = np.flatnonzero(np.isfinite(self.bins.weight.values))
+
+    def make_sub_matrices(self):
+        """Table [chr1, chr2, contact_map] of the intra (and, with inter=True, the upper
+        inter) sub-matrices (cm:235-322)."""
+        d = self.detectable_bins
+        rows = []
+        for i1, chr1 in enumerate(self.clr.chromnames):
+            for i2, chr2 in enumerate(self.clr.chromnames):
+                if not (i1 == i2 or (i1 < i2 and self.inter)):
+                    continue
+                s1, e1 = self.clr.extent(chr1)
+                s2, e2 = self.clr.extent(chr2)
+                det = (d[(d >= s1) & (d < e1)] - s1, d[(d >= s2) & (d < e2)] - s2)
+                kw = dict(extent=[(s1, e1), (s2, e2)], detectable_bins=det, use_norm=self.use_norm,
+                          smooth=self.smooth, name=f"{chr1}-{chr2}")
+                if i1 == i2:
+                    cm = ContactMap(self.clr, inter=False, max_dist=self.max_dist,
+                                    largest_kernel=self.largest_kernel, **kw)
+                else:
+                    cm = ContactMap(self.clr, inter=True, **kw)
+                rows.append({"chr1": chr1, "chr2": chr2, "contact_map": cm})
+        self.sub_mats = pd.DataFrame(rows, columns=["chr1", "chr2", "contact_map"])
+        return self.sub_mats
+
+    def get_full_mat_pattern(self, chr1, chr2, patterns):
+        """Sub-matrix bins -> whole-genome bins (cm:336-364)."""
+        full = patterns.copy()
+        full["bin1"] = full.bin1 + self.clr.extent(chr1)[0]
+        full["bin2"] = full.bin2 + self.clr.extent(chr2)[0]
+        return full
+
+    def get_sub_mat_pattern(self, chr1, chr2, patterns):
+        """Whole-genome bins -> sub-matrix bins (cm:366-394)."""
+        sub = patterns.copy()
+        sub["bin1"] = sub.bin1 - self.clr.extent(chr1)[0]
+        sub["bin2"] = sub.bin2 - self.clr.extent(chr2)[0]
+        return sub
+
+    def bins_to_coords(self, bin_idx):
+        """cm:396-414"""
+        return self.bins.iloc[np.asarray(bin_idx), :][["chrom", "start", "end"]]
+
+    def coords_to_bins(self, coords):
+        """Genomic positions (DataFrame[chrom, pos]) -> whole-genome bin ids, in the order of
+        the input (cm:416-450)."""
+        pos = (coords.pos // self.clr.binsize) * self.clr.binsize
+        key = pd.MultiIndex.from_arrays([self.bins.chrom.astype(str), self.bins.start])
+        look = pd.Series(np.arange(len(self.bins)), index=key)
+        return look.reindex(pd.MultiIndex.from_arrays([coords.chrom.astype(str), pos])).values

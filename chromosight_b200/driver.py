@@ -1,0 +1,108 @@
+"""Sharded `detect` over the sub-matrices of a genome: the loop of cmd_detect
+(cli/chromosight.py:702-860) with one rank per GPU in place of the multiprocessing pool
+(cli:738-755), SURVEY 8e / 8f-4.
+
+Every rank runs `pattern_detector` (GPU) on its share of the sub-matrices; the per-sub-matrix
+tables -- a few KB -- are exchanged with one `all_gather_object` per kernel iteration, after
+which every rank holds the same global table and does the reference's global host steps
+(neighbour removal, minimum distance, FDR; cli:807-848) redundantly.
+"""
+import numpy as np
+import pandas as pd
+
+from . import sharding
+from .utils import detection as cud
+from .utils.stats import fdr_correction
+
+
+def unit_costs(hic_genome):
+    """Windows per sub-matrix: (D + 1) * n for an intra map, ms * ns for an inter map."""
+    costs = []
+    for _, row in hic_genome.sub_mats.iterrows():
+        (s1, e1), (s2, e2) = row.contact_map.extent
+        if row.contact_map.inter:
+            costs.append(float(e1 - s1) * float(e2 - s2))
+        else:
+            D = hic_genome.max_dist if hic_genome.max_dist is not None else (e1 - s1)
+            costs.append(float(min(D, e1 - s1) + 1) * float(e1 - s1))
+    return costs
+
+
+def _world():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), dist
+    except Exception:
+        pass
+    return 0, 1, None
+
+
+def detect_sub_matrices(hic_genome, cfg, kernel_matrix, full=True, tsvd=None):
+    """One pass of `_detect_sub_mat` (cli:601-622) over all sub-matrices, sharded over the
+    ranks.  Returns the list of result dicts {coords, windows, chr1, chr2} in sub-matrix
+    order, identical on every rank."""
+    rank, world, dist = _world()
+    mine = sharding.partition_units(unit_costs(hic_genome), world)[rank]
+    local = {}
+    for u in mine:
+        row = hic_genome.sub_mats.iloc[u]
+        cm = row.contact_map
+        cm.create_mat()
+        coords, windows = cud.pattern_detector(cm, cfg, kernel_matrix, full=full, tsvd=tsvd)
+        cm.destroy_mat()
+        local[u] = {"coords": coords, "windows": windows, "chr1": row.chr1, "chr2": row.chr2}
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, local)
+        local = {}
+        for p in parts:
+            local.update(p)
+    return [local[u] for u in sorted(local)]
+
+
+def detect(hic_genome, cfg, full=True, tsvd=None):
+    """Pattern detection on every sub-matrix with every kernel of `cfg`, then the global
+    filters (cli:720-860).  Returns (table, windows) or (None, None) when nothing is found;
+    the table has the columns the reference writes (chrom1 ... qvalue)."""
+    if hic_genome.sub_mats is None:
+        hic_genome.make_sub_matrices()
+    all_coords, all_windows = [], []
+    for kernel_id, kernel_matrix in enumerate(cfg["kernels"]):
+        kernel_matrix = np.asarray(kernel_matrix, dtype=np.float64)
+        for it in range(cfg["max_iterations"]):
+            results = detect_sub_matrices(hic_genome, cfg, kernel_matrix, full=full, tsvd=tsvd)
+            coords = [hic_genome.get_full_mat_pattern(d["chr1"], d["chr2"], d["coords"])
+                      for d in results if d["coords"] is not None]
+            wins = [d["windows"] for d in results if d["windows"] is not None]
+            if not wins:
+                break  # nothing found with this kernel: next kernel (cli:786-788)
+            wins = np.concatenate(wins, axis=0)
+            tab = pd.concat(coords, axis=0).reset_index(drop=True)
+            tab["kernel_id"] = kernel_id
+            tab["iteration"] = it
+            all_coords.append(tab)
+            all_windows.append(wins)
+            kernel_matrix = cud.pileup_patterns(wins)  # cli:791
+    if not all_coords:
+        return None, None
+    tab = pd.concat(all_coords, axis=0).reset_index(drop=True)
+    wins = np.concatenate(all_windows, axis=0)
+    binsize = hic_genome.clr.binsize
+    sep = max(int(cfg["min_separation"] // binsize), 1)
+    keep = cud.remove_neighbours(tab, win_size=sep)
+    tab, wins = tab.loc[keep, :].reset_index(drop=True), wins[keep]
+    c1 = hic_genome.bins_to_coords(tab.bin1).reset_index(drop=True)
+    c1.columns = [f"{c}1" for c in c1.columns]
+    c2 = hic_genome.bins_to_coords(tab.bin2).reset_index(drop=True)
+    c2.columns = [f"{c}2" for c in c2.columns]
+    tab = pd.concat([tab, c1, c2], axis=1)
+    near = (tab.chrom1.astype(str) == tab.chrom2.astype(str)) & \
+           (np.abs(tab.start2 - tab.start1) < cfg["min_dist"])
+    tab, wins = tab.loc[~near, :], wins[~near.values]
+    nanp = tab.pvalue.isnull()
+    tab, wins = tab.loc[~nanp, :].reset_index(drop=True), wins[~nanp.values]
+    tab["qvalue"] = fdr_correction(tab["pvalue"])
+    cols = ["chrom1", "start1", "end1", "chrom2", "start2", "end2", "bin1", "bin2", "kernel_id",
+            "iteration", "score", "pvalue", "qvalue"]
+    return tab.loc[:, cols], wins

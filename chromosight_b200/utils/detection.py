@@ -456,3 +456,43 @@ def pick_foci(mat_conv, pearson, min_size=2):
         best = members[np.argmax(scores[members])]  # first maximum, as np.argmax
         coords[k] = labelled.row[best], labelled.col[best]
     return coords, labelled
+
+
+def pileup_patterns(pattern_windows):
+    """Arithmetic mean of a stack of windows, ignoring NaN (det:158-174)."""
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        return np.nanmean(np.asarray(pattern_windows, dtype=np.float64), axis=0)
+
+
+def remove_neighbours(patterns, win_size=8):
+    """Patterns closer than win_size pixels (on both axes) to a better-scoring one are
+    dropped (det:348-384): boolean mask over the rows of `patterns` (DataFrame with bin1,
+    bin2, score), greedy by decreasing score.  Same result as the reference's O(P^2) Python
+    loop; candidates are looked up through a grid of win_size x win_size buckets."""
+    n = len(patterns)
+    keep = np.ones(n, dtype=bool)
+    if n == 0:
+        return keep
+    b1 = np.asarray(patterns.bin1, dtype=np.int64)
+    b2 = np.asarray(patterns.bin2, dtype=np.int64)
+    score = np.asarray(patterns.score, dtype=np.float64)
+    # descending score, NaN last, ties in input order (what sort_values gives)
+    order = np.argsort(-np.nan_to_num(score, nan=-np.inf), kind="stable")
+    w = max(int(win_size), 1)
+    cell = {}
+    for i in range(n):
+        cell.setdefault((b1[i] // w, b2[i] // w), []).append(i)
+    dead = np.zeros(n, dtype=bool)
+    for i in order:
+        if dead[i]:
+            continue
+        c1, c2 = b1[i] // w, b2[i] // w
+        for a in (c1 - 1, c1, c1 + 1):
+            for b in (c2 - 1, c2, c2 + 1):
+                for j in cell.get((a, b), ()):
+                    if j != i and abs(b1[j] - b1[i]) < w and abs(b2[j] - b2[i]) < w:
+                        dead[j] = True
+    keep[dead] = False
+    return keep

@@ -1,0 +1,137 @@
+"""Real-data plumbing (BASELINE.json configs[0]: detect loops on data_test/example.cool).
+
+CPU part: the minimal .cool (HDF5) reader against the tables stored in the fixture, and the
+genome / sub-matrix model's bookkeeping.  GPU part: ContactMap.create_mat + pattern_detector
+on every chromosome against what the unmodified reference produced from the same file
+(tests/golden/make_golden_cool.py), and the sharded detect driver on top."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import GOLDEN
+
+REF_COOL = "/root/reference/data_test/example.cool"
+
+
+@pytest.fixture(scope="module")
+def fx():
+    return np.load(os.path.join(GOLDEN, "cool_example_loops.npz"), allow_pickle=False)
+
+
+def cool_from_fixture(fx):
+    from chromosight_b200.cool import CoolFile
+    return CoolFile.from_tables(fx["chrom_names"], fx["chrom_sizes"], fx["bin_chrom"], fx["bin_start"],
+                                fx["bin_end"], fx["bin_weight"], fx["pix_bin1"], fx["pix_bin2"],
+                                fx["pix_count"], binsize=int(fx["binsize"]))
+
+
+def loops_config(fx):
+    cfg = json.loads(str(fx["config"]))
+    cfg["kernels"] = [np.array(fx["kernel"])]
+    return cfg
+
+
+@pytest.mark.skipif(not os.path.exists(REF_COOL), reason="reference test data not present")
+def test_cool_reader_reads_the_reference_file(fx):
+    from chromosight_b200.cool import CoolFile, load_cool
+    c = CoolFile(REF_COOL)
+    # what cooler recorded about its own tables
+    assert c.info["nbins"] == c.shape[0] == 720 and c.info["nchroms"] == 3
+    pix = c.pixels()[:]
+    assert c.info["nnz"] == len(pix) and c.info["sum"] == pix["count"].sum()
+    assert c.binsize == 1000 and c.chromnames == ["chr1", "chr2", "chr3"]
+    assert [c.extent(n) for n in c.chromnames] == [(0, 127), (127, 549), (549, 720)]
+    bins = c.bins()[:]
+    for a, b in ((bins.start.values, fx["bin_start"]), (bins.end.values, fx["bin_end"]),
+                 (pix.bin1_id.values, fx["pix_bin1"]), (pix.bin2_id.values, fx["pix_bin2"]),
+                 (pix["count"].values, fx["pix_count"])):
+        assert np.array_equal(a, b)
+    assert np.array_equal(bins.weight.values, fx["bin_weight"], equal_nan=True)
+    mat, chroms, bins2, bs = load_cool(REF_COOL)   # io.py:20-78
+    assert mat.shape == (720, 720) and bs == 1000 and (mat.row <= mat.col).all()
+    assert list(chroms.start_bin) == [0, 127, 549] and list(chroms.end_bin) == [127, 549, 720]
+    with pytest.raises(ValueError):
+        CoolFile(__file__)
+
+
+def test_genome_model_bookkeeping(fx):
+    import pandas as pd
+    from chromosight_b200.contacts_map import HicGenome
+    clr = cool_from_fixture(fx)
+    m = clr.matrix(balance=True)[0:127, 0:127]
+    assert abs(sp.csr_matrix(np.nan_to_num(m.toarray())) - sp.csr_matrix(np.nan_to_num(m.toarray())).T).max() < 1e-15
+    raw = clr.matrix(balance=False)[127:549, 549:720]
+    assert raw.shape == (422, 171)
+    hg = HicGenome(clr, inter=False, kernel_config=loops_config(fx))
+    assert hg.max_dist == int(fx["max_dist"]) and hg.largest_kernel == 17
+    hg.normalize()
+    assert len(hg.detectable_bins) == int(np.isfinite(fx["bin_weight"]).sum())
+    assert len(hg.make_sub_matrices()) == 3                      # test_contacts_map.py:50-65
+    hg2 = HicGenome(clr, inter=True, kernel_config=loops_config(fx))
+    hg2.normalize()
+    assert len(hg2.make_sub_matrices()) == 6
+    # test_contacts_map.py:130-136: chr1:0 and chr2:4000 are bins 0 and 131
+    idx = hg.coords_to_bins(pd.DataFrame({"chrom": ["chr1", "chr2"], "pos": [0, 4000]}))
+    assert list(idx) == [0, 131]
+    assert list(hg.bins_to_coords([131]).start) == [4000]
+    t = pd.DataFrame({"bin1": [3], "bin2": [5]})
+    assert hg.get_sub_mat_pattern("chr2", "chr2", hg.get_full_mat_pattern("chr2", "chr2", t)).equals(t)
+    with pytest.raises(NotImplementedError):
+        hg.normalize(norm="force")
+
+
+@pytest.mark.gpu
+def test_example_cool_detect_loops_matches_reference(fx):
+    from chromosight_b200.contacts_map import HicGenome
+    from chromosight_b200.utils import detection as cud
+    cfg = loops_config(fx)
+    kernel = cfg["kernels"][0]
+    hg = HicGenome(cool_from_fixture(fx), inter=False, kernel_config=cfg)
+    hg.normalize()
+    hg.make_sub_matrices()
+    total = 0
+    for _, row in hg.sub_mats.iterrows():
+        chrom, cm = row.chr1, row.contact_map
+        cm.create_mat()
+        exp = sp.coo_matrix((fx[f"{chrom}_matrix_val"], (fx[f"{chrom}_matrix_row"], fx[f"{chrom}_matrix_col"])),
+                            shape=tuple(fx[f"{chrom}_matrix_shape"])).tocsr()
+        got = cm.matrix.tocsr()
+        assert got.shape == exp.shape and got.nnz == exp.nnz
+        assert abs(got - exp).max() <= 1e-12 * abs(exp).max()
+        table, windows = cud.pattern_detector(cm, cfg, kernel, full=True)
+        n = int(fx[f"{chrom}_n"])
+        total += n
+        assert len(table) == n
+        assert np.array_equal(table.bin1.values, fx[f"{chrom}_bin1"])
+        assert np.array_equal(table.bin2.values, fx[f"{chrom}_bin2"])
+        assert np.abs(table.score.values - fx[f"{chrom}_score"]).max() <= 1e-5
+        lp, lp0 = np.log10(table.pvalue.values), np.log10(fx[f"{chrom}_pvalue"])
+        assert np.allclose(lp, lp0, rtol=2e-4, atol=1e-4)
+        assert np.allclose(windows, fx[f"{chrom}_windows"], rtol=1e-12, atol=0, equal_nan=True)
+        cm.destroy_mat()
+    assert total == 135
+
+
+@pytest.mark.gpu
+def test_detect_driver_on_example_cool(fx):
+    from chromosight_b200 import driver
+    from chromosight_b200.contacts_map import HicGenome
+    cfg = loops_config(fx)
+    hg = HicGenome(cool_from_fixture(fx), inter=False, kernel_config=cfg)
+    hg.normalize()
+    table, windows = driver.detect(hg, cfg, full=True)
+    assert list(table.columns) == ["chrom1", "start1", "end1", "chrom2", "start2", "end2", "bin1", "bin2",
+                                   "kernel_id", "iteration", "score", "pvalue", "qvalue"]
+    assert len(table) == len(windows) and 0 < len(table) <= 135
+    # global filters of cli:807-848: separated patterns, minimum distance, q-values
+    sep = max(cfg["min_separation"] // 1000, 1)
+    b = table[["bin1", "bin2"]].values
+    d = np.abs(b[:, None, :] - b[None, :, :])
+    close = (d[..., 0] < sep) & (d[..., 1] < sep)
+    assert close.sum() == len(table)
+    assert (np.abs(table.start2 - table.start1) >= cfg["min_dist"]).all()
+    assert ((table.qvalue >= table.pvalue - 1e-15) & (table.qvalue <= 1)).all()
+    assert (table.chrom1.astype(str) == table.chrom2.astype(str)).all()
