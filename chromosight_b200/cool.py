@@ -332,6 +332,7 @@ class CoolFile:
             bs = int(w[0]) if len(w) == 1 else None
         self.binsize = None if bs is None else int(bs)
         n = len(self._bins)
+        self._sorted = None
         self.shape = (n, n)
         self.info = root_attrs
 
@@ -361,17 +362,35 @@ class CoolFile:
         e1 = n if e1 is None else e1
         e2 = n if e2 is None else e2
         b1, b2 = self._pix.bin1_id.values, self._pix.bin2_id.values
-        val = self._pix["count"].values.astype(np.float64)
+        cnt = self._pix["count"].values
+        w = None
         if balance:
             if "weight" not in self._bins.columns:
                 raise ValueError("no 'weight' column: balance the file first")
             w = self._bins.weight.values
-            val = val * w[b1] * w[b2]
-        up = (b1 >= s1) & (b1 < e1) & (b2 >= s2) & (b2 < e2)
-        lo = (b2 >= s1) & (b2 < e1) & (b1 >= s2) & (b1 < e2) & (b1 != b2)
-        rows = np.concatenate([b1[up] - s1, b2[lo] - s1])
-        cols = np.concatenate([b2[up] - s2, b1[lo] - s2])
-        vals = np.concatenate([val[up], val[lo]])
+        # pixels are sorted by bin1 (cooler's indexes/bin1_offset): slice, then filter bin2
+        if self._sorted is None:
+            self._sorted = bool((np.diff(b1) >= 0).all())
+
+        def block(ra, rb, ca, cb):
+            """stored pixels with bin1 in [ra, rb) and bin2 in [ca, cb)"""
+            if self._sorted:
+                lo, hi = np.searchsorted(b1, [ra, rb])
+                sel = np.flatnonzero((b2[lo:hi] >= ca) & (b2[lo:hi] < cb)) + lo
+            else:
+                sel = np.flatnonzero((b1 >= ra) & (b1 < rb) & (b2 >= ca) & (b2 < cb))
+            r, c = b1[sel], b2[sel]
+            v = cnt[sel].astype(np.float64)
+            if w is not None:
+                v = v * w[r] * w[c]
+            return r, c, v
+
+        ur, uc, uv = block(s1, e1, s2, e2)                 # stored as is
+        lr, lc, lv = block(s2, e2, s1, e1)                 # mirrored: (bin2, bin1)
+        off = lr != lc
+        rows = np.concatenate([ur - s1, lc[off] - s1])
+        cols = np.concatenate([uc - s2, lr[off] - s2])
+        vals = np.concatenate([uv, lv[off]])
         return sp.coo_matrix((vals, (rows, cols)), shape=(e1 - s1, e2 - s2))
 
 

@@ -106,3 +106,94 @@ def detect(hic_genome, cfg, full=True, tsvd=None):
     cols = ["chrom1", "start1", "end1", "chrom2", "start2", "end2", "bin1", "bin2", "kernel_id",
             "iteration", "score", "pvalue", "qvalue"]
     return tab.loc[:, cols], wins
+
+
+def _chrom_positions(positions, hic_genome, chr1, chr2):
+    """Positions falling on one sub-matrix, in sub-matrix bins (cli:262-293): (index into
+    `positions`, int array [P, 2])."""
+    sel = np.flatnonzero((positions.chrom1.values == chr1) & (positions.chrom2.values == chr2))
+    if len(sel) == 0:
+        return sel, np.zeros((0, 2), dtype=np.int64)
+    sub = positions.iloc[sel]
+    b1 = hic_genome.coords_to_bins(pd.DataFrame({"chrom": sub.chrom1.values, "pos": sub.pos1.values}))
+    b2 = hic_genome.coords_to_bins(pd.DataFrame({"chrom": sub.chrom2.values, "pos": sub.pos2.values}))
+    ok = ~(np.isnan(b1) | np.isnan(b2))   # positions outside the map are ignored
+    s1, s2 = hic_genome.clr.extent(chr1)[0], hic_genome.clr.extent(chr2)[0]
+    coords = np.stack([b1[ok] - s1, b2[ok] - s2], axis=1).astype(np.int64)
+    return sel[ok], coords
+
+
+def quantify(hic_genome, cfg, bed2d, tsvd=None, return_windows=True):
+    """Correlation score of every position of `bed2d` (DataFrame chrom1, start1, end1, chrom2,
+    start2, end2) with the kernels of `cfg`: the loop of cmd_quantify (cli:295-496), sharded by
+    sub-matrix.  `cfg` is modified like the reference does (max_dist = furthest pair,
+    min_dist = 0).  Returns (table sorted by bins with score / pvalue / qvalue, windows of the
+    best kernel per position or None)."""
+    rank, world, dist = _world()
+    bed2d = bed2d.reset_index(drop=True).copy()
+    furthest = int(np.max(bed2d.start2 - bed2d.start1))
+    cfg["max_dist"] = min(furthest, hic_genome.clr.shape[0] * hic_genome.clr.binsize)
+    cfg["min_dist"] = 0
+    hic_genome.kernel_config = cfg
+    hic_genome.compute_max_dist()
+    hic_genome.make_sub_matrices()
+    n = len(bed2d)
+    positions = bed2d.copy()
+    positions["pos1"] = (positions.start1 + positions.end1) // 2
+    positions["pos2"] = (positions.start2 + positions.end2) // 2
+    km, kn = np.asarray(cfg["kernels"][0]).shape
+    mine = set(sharding.partition_units(unit_costs(hic_genome), world)[rank])
+    best_score = np.full(n, np.nan)
+    best_p = np.full(n, np.nan)
+    best_win = np.full((n, km, kn), np.nan) if return_windows else None
+    for kernel_matrix in cfg["kernels"]:
+        kernel_matrix = np.asarray(kernel_matrix, dtype=np.float64)
+        score = np.full(n, np.nan)
+        pval = np.full(n, np.nan)
+        wins = {}
+        for u, (_, row) in enumerate(hic_genome.sub_mats.iterrows()):
+            if u not in mine:
+                continue
+            idx, coords = _chrom_positions(positions, hic_genome, row.chr1, row.chr2)
+            if len(idx) == 0:
+                continue            # no position on this sub-matrix: not scanned (cli:239-241)
+            cm = row.contact_map
+            cm.create_mat()
+            table, windows = cud.pattern_detector(cm, cfg, kernel_matrix, coords=coords, full=True,
+                                                  tsvd=tsvd)
+            cm.destroy_mat()
+            if table is None:
+                continue
+            score[idx] = table.score.values
+            pval[idx] = table.pvalue.values
+            if return_windows:
+                wins[u] = (idx, windows)
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, (np.flatnonzero(~np.isnan(score) | ~np.isnan(pval)),
+                                           score, pval, wins if return_windows else {}))
+            for sel, sc, pv, w in parts:
+                score[sel], pval[sel] = sc[sel], pv[sel]
+                wins.update(w)
+        # the best kernel of each position (cli:442-450: highest score; NaN never wins)
+        better = (~np.isnan(score)) & (np.isnan(best_score) | (score >= best_score))
+        first = np.isnan(best_score) & np.isnan(score) & np.isnan(best_p)
+        best_p = np.where(better | first, pval, best_p)
+        best_score = np.where(better, score, best_score)
+        if return_windows:
+            for idx, w in wins.values():
+                take = better[idx] | first[idx]
+                best_win[idx[take]] = w[take]
+    out = bed2d.loc[:, ["chrom1", "start1", "end1", "chrom2", "start2", "end2"]].copy()
+    out["bin1"] = hic_genome.coords_to_bins(out[["chrom1", "start1"]].rename(
+        columns={"chrom1": "chrom", "start1": "pos"}))
+    out["bin2"] = hic_genome.coords_to_bins(out[["chrom2", "start2"]].rename(
+        columns={"chrom2": "chrom", "start2": "pos"}))
+    out["score"] = best_score
+    out["pvalue"] = best_p
+    out["qvalue"] = fdr_correction(out["pvalue"])
+    bad = np.isnan(out.score.values)
+    out.loc[bad, ["pvalue", "qvalue"]] = np.nan
+    order = np.lexsort((out.bin2.values, out.bin1.values))     # cli:476-480
+    out = out.iloc[order].reset_index(drop=True)
+    return out, (best_win[order] if return_windows else None)

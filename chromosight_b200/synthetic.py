@@ -10,7 +10,8 @@ import numpy as np
 import scipy.sparse as sp
 
 
-def band_counts(n, n_diags, seed=0, missing_frac=0.02, loops_per_bin=0.01, max_dist=None):
+def band_counts(n, n_diags, seed=0, missing_frac=0.02, loops_per_bin=0.01, max_dist=None,
+                density_floor=0.05):
     """Raw (not detrended) upper-band contact map.
 
     Parameters
@@ -27,6 +28,9 @@ def band_counts(n, n_diags, seed=0, missing_frac=0.02, loops_per_bin=0.01, max_d
         Planted 3x3 blobs per bin.
     max_dist : int or None
         Loops are planted at distances U[12, max_dist - 10] (defaults to n_diags).
+    density_floor : float
+        Smallest fraction of populated pixels of a diagonal (1.0: fully populated band, in
+        which planted loops survive the max_perc_zero validation of pattern_detector).
 
     Returns
     -------
@@ -37,7 +41,7 @@ def band_counts(n, n_diags, seed=0, missing_frac=0.02, loops_per_bin=0.01, max_d
     W = n_diags + 1
     d = np.arange(W)
     lam = 200.0 / (1.0 + d) ** 0.8 + 2.0
-    density = np.maximum(0.05, 1.0 / (1.0 + d / 50.0))
+    density = np.maximum(density_floor, 1.0 / (1.0 + d / 50.0))
     band = rng.poisson(lam[None, :], size=(n, W)).astype(np.float64)
     band *= rng.random((n, W)) < density[None, :]
     if max_dist is None:
@@ -82,3 +86,45 @@ def n_windows(n, max_dist):
     """Pearson windows of an intra map scanned up to max_dist."""
     D = min(max_dist, n - 1)
     return (D + 1) * n - D * (D + 1) // 2
+
+
+def genome_cool(chrom_bins, binsize=10_000, n_diags=217, seed=0, missing_frac=0.02, inter_density=0.0,
+                density_floor=0.05):
+    """A whole synthetic genome as a chromosight_b200.cool.CoolFile:
+    one `band_counts` map per chromosome (seed + chromosome index), all-ones balancing
+    weights with NaN on the undetectable bins, optionally `inter_density` random
+    inter-chromosomal pixels (Gamma(2, 0.5) * 4, rounded up)."""
+    from .cool import CoolFile
+    rng = np.random.default_rng(seed + 7919)
+    starts = np.concatenate([[0], np.cumsum(chrom_bins)]).astype(np.int64)
+    N = int(starts[-1])
+    names = [f"chr{i + 1}" for i in range(len(chrom_bins))]
+    b1, b2, cnt = [], [], []
+    weight = np.ones(N)
+    for i, n in enumerate(chrom_bins):
+        mat, detect = band_counts(int(n), n_diags, seed=seed + i, missing_frac=missing_frac,
+                                  max_dist=max(n_diags - 17, 30), density_floor=density_floor)
+        coo = mat.tocoo()
+        b1.append(coo.row + starts[i])
+        b2.append(coo.col + starts[i])
+        cnt.append(coo.data)
+        miss = np.ones(int(n), dtype=bool)
+        miss[detect] = False
+        weight[starts[i]:starts[i + 1]][miss] = np.nan
+    if inter_density > 0:
+        for i in range(len(chrom_bins)):
+            for j in range(i + 1, len(chrom_bins)):
+                ms, ns = int(chrom_bins[i]), int(chrom_bins[j])
+                k = int(ms * ns * inter_density)
+                r = rng.integers(0, ms, size=k) + starts[i]
+                c = rng.integers(0, ns, size=k) + starts[j]
+                key = np.unique(r * N + c)
+                b1.append(key // N)
+                b2.append(key % N)
+                cnt.append(np.ceil(rng.gamma(2.0, 0.5, size=len(key)) * 4))
+    b1, b2, cnt = np.concatenate(b1), np.concatenate(b2), np.concatenate(cnt)
+    order = np.lexsort((b2, b1))
+    chrom_id = np.repeat(np.arange(len(chrom_bins)), chrom_bins)
+    start = np.concatenate([np.arange(n) * binsize for n in chrom_bins])
+    return CoolFile.from_tables(names, np.asarray(chrom_bins) * binsize, chrom_id, start, start + binsize,
+                                weight, b1[order], b2[order], cnt[order], binsize=binsize)

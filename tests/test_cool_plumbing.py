@@ -135,3 +135,53 @@ def test_detect_driver_on_example_cool(fx):
     assert (np.abs(table.start2 - table.start1) >= cfg["min_dist"]).all()
     assert ((table.qvalue >= table.pvalue - 1e-15) & (table.qvalue <= 1)).all()
     assert (table.chrom1.astype(str) == table.chrom2.astype(str)).all()
+
+
+@pytest.mark.gpu
+def test_quantify_driver_matches_per_chromosome_calls(fx, presets):
+    """cmd_quantify plumbing (cli:295-496): positions -> sub-matrix bins -> pattern_detector ->
+    back to the input table, best kernel per position, sorted by whole-genome bins."""
+    import pandas as pd
+    from chromosight_b200 import driver
+    from chromosight_b200.contacts_map import HicGenome
+    from chromosight_b200.utils import detection as cud
+    rng = np.random.default_rng(3)
+    clr = cool_from_fixture(fx)
+    rows = []
+    for chrom in clr.chromnames:
+        s, e = clr.extent(chrom)
+        n = e - s
+        b1 = rng.integers(0, n - 40, size=60)
+        b2 = b1 + rng.integers(2, 40, size=60)
+        for a, b in zip(b1, b2):
+            rows.append((chrom, a * 1000, a * 1000 + 1000, chrom, b * 1000, b * 1000 + 1000))
+    rows.append(("chr1", 10 ** 9, 10 ** 9 + 1000, "chr1", 10 ** 9 + 5000, 10 ** 9 + 6000))  # off the map
+    bed = pd.DataFrame(rows, columns=["chrom1", "start1", "end1", "chrom2", "start2", "end2"])
+    bed = bed.sample(frac=1.0, random_state=1).reset_index(drop=True)
+    cfg = dict(presets.borders)
+    cfg["kernels"] = [np.array(k) for k in cfg["kernels"]]
+    hg = HicGenome(clr, inter=False, kernel_config=cfg)
+    hg.normalize()
+    table, windows = driver.quantify(hg, cfg, bed)
+    assert len(table) == len(bed) == len(windows)
+    assert list(table.columns) == ["chrom1", "start1", "end1", "chrom2", "start2", "end2", "bin1", "bin2",
+                                   "score", "pvalue", "qvalue"]
+    key = table.bin1.fillna(10 ** 12).values * 10 ** 6 + table.bin2.fillna(0).values
+    assert (np.diff(key) >= 0).all()
+    # the same positions straight through pattern_detector, per chromosome and kernel
+    checked = 0
+    for _, row in hg.sub_mats.iterrows():
+        s = clr.extent(row.chr1)[0]
+        sub = table[(table.chrom1 == row.chr1) & table.bin1.notna()]
+        coords = np.stack([sub.bin1.values - s, sub.bin2.values - s], axis=1).astype(np.int64)
+        row.contact_map.create_mat()
+        best = np.full(len(sub), np.nan)
+        for k in cfg["kernels"]:
+            t, _ = cud.pattern_detector(row.contact_map, cfg, k, coords=coords, full=True)
+            best = np.fmax(best, t.score.values)
+        row.contact_map.destroy_mat()
+        assert np.allclose(sub.score.values, best, rtol=0, atol=1e-6, equal_nan=True)
+        checked += len(sub)
+    assert checked == len(bed) - 1
+    off = table[table.bin1.isna()]
+    assert len(off) == 1 and np.isnan(off.score.values[0]) and np.isnan(off.pvalue.values[0])
