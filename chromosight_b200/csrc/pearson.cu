@@ -51,6 +51,7 @@ struct PearsonParams {
     const float *ftab;
     const double *dtab;
     int n_ftab, n_dtab;
+    int dbg;  // CS_DEBUG_SKIP bit mask (timing experiments only): see the kernel
     double q, sumKp, sumKp2, ksum, k2sum, kmean, kstd, thr, invN, vK0;
     int min_present, kmean_zero, has_mask, raw_xcorr, nobs_full;
     int sdlo, sdhi, st_base, st_n;  // declared-missing diagonal strip and its tables
@@ -101,6 +102,10 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 __device__ __forceinline__ void fma2(unsigned long long &acc, unsigned long long a,
                                      unsigned long long b) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+// acc.{lo,hi} += a.{lo,hi}
+__device__ __forceinline__ void acc2(unsigned long long &acc, unsigned long long a) {
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(a));
 }
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
     unsigned long long r;
@@ -278,9 +283,9 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     // tables -> shared memory while the tile is in flight
     {
         float *Kf = reinterpret_cast<float *>(smem + P.off_K);
-        for (int i = tid; i < P.n_ftab; i += nthr) Kf[i] = P.ftab[i];
+        for (int i = (P.dbg & 128) ? P.n_ftab : tid; i < P.n_ftab; i += nthr) Kf[i] = P.ftab[i];
         double *Dd = reinterpret_cast<double *>(smem + P.off_D);
-        for (int i = tid; i < P.n_dtab; i += nthr) Dd[i] = P.dtab[i];
+        for (int i = (P.dbg & 128) ? P.n_dtab : tid; i < P.n_dtab; i += nthr) Dd[i] = P.dtab[i];
         if (MASK)
             for (int i = tid; i < NW; i += nthr) bits[i] = 0u;
     }
@@ -293,7 +298,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     int anynz = 0;
     {
         const int ICq4 = IC >> 2;
-        for (int iy = tid >> 5; iy < IR; iy += nthr >> 5) {
+        for (int iy = (P.dbg & 16) ? IR : (tid >> 5); iy < IR; iy += nthr >> 5) {
             // in-band tile columns of this row: [clo, chi)
             const int dbase = (TXp + P.dlo) - (TY + iy);  // diagonal of tile column 0
             int clo = 0, chi = IC, slo = 0, shi = 0;
@@ -382,12 +387,15 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     const int NQd = (P.NBc + 3) >> 2;
     const int nitems = 8 * NQd * 2 * ((P.G + 3) >> 2);
     // every lane runs every loop (work is predicated): the epilogue contains warp-wide steps
-    for (int base = 0; base < nitems; base += nthr) {
+    for (int base = (P.dbg & 256) ? nitems : 0; base < nitems; base += nthr) {
         int g, m;
         bool live;
         {
             const int idx = base + tid;
-            const int rest = idx >> 3, M = rest % NQd, pr = rest / NQd;
+            // a warp = 4 column blocks x 8 row groups: a missing row or column then touches
+            // most lanes of the warps it crosses (less divergence in the mask code)
+            const int npair = 2 * ((P.G + 3) >> 2);
+            const int rest = idx >> 3, pr = rest % npair, M = rest / npair;
             g = (pr >> 1) * 4 + (pr & 1) + 2 * ((idx >> 2) & 1);
             m = 4 * M + (idx & 3);
             live = idx < nitems && g < P.G && m < P.NBc;
@@ -428,7 +436,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             }
             pl = sacc * (1.0f / (float)XW);
         }
-        if (any) {                                                           // [sec:main]
+        if (any && !(P.dbg & 8)) {                                           // [sec:main]
             const unsigned long long npl2 = pack2(-pl, -pl);
             // one packed accumulator per window: .lo and .hi collect alternate taps
             unsigned long long acc[RU][RT];
@@ -483,7 +491,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     mystat[(u * RT + t) * nthr] = lo + hi;
                 }
         }
-        if (any) {                                                           // [sec:sums]
+        if (any && !(P.dbg & 4)) {                                           // [sec:sums]
             // window sums of (S - pl) and (S - pl)^2: column sums over KH rows in packed
             // registers, then KW-wide sliding sums along the row
             const unsigned long long npl2 = pack2(-pl, -pl);
@@ -498,8 +506,8 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 for (int qd = 0; qd < NQ; ++qd) {
                     const ulonglong2 v = rp[qd];
                     const unsigned long long a = add2(v.x, npl2), b = add2(v.y, npl2);
-                    cs[2 * qd] = add2(cs[2 * qd], a);
-                    cs[2 * qd + 1] = add2(cs[2 * qd + 1], b);
+                    acc2(cs[2 * qd], a);
+                    acc2(cs[2 * qd + 1], b);
                     fma2(cq[2 * qd], a, a);
                     fma2(cq[2 * qd + 1], b, b);
                 }
@@ -558,7 +566,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         const int fc0 = cxa + off;  // tile column of footprint column 0
         unsigned long long colfull = 0ull, rowsel = 0ull, bor = 0ull;                // [sec:masksum]
         int ng = 0;
-        if (MASK && any) {
+        if (MASK && any && !(P.dbg & 1)) {
             constexpr unsigned long long FWMASK = (XW >= 64) ? ~0ull : ((1ull << XW) - 1ull);
             unsigned long long band = FWMASK;
             const int fr = KH + RU - 1;
@@ -591,15 +599,27 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             }
         }
 
+        // valid windows of the block, bit k = u * RT + t
+        unsigned okb = 0u;
+        if (any) {
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                const int Y = Yg + u;
+                // columns of the row: [max(ox0, Y + odlo), min(ox1 - 1, Y + odhi)] as t range
+                const int tlo = max(max(P.ox0, Y + P.odlo) - (Xp0 + P.dlo), 0);
+                const int thi = min(min(P.ox1 - 1, Y + P.odhi) - (Xp0 + P.dlo), RT - 1);
+                if (Y < P.oy1 && thi >= tlo)
+                    okb |= (((2u << thi) - 1u) & ~((1u << tlo) - 1u)) << (u * RT);
+            }
+        }
 #pragma unroll 1
         for (int u = 0; u < RU; ++u) {
             const int Y = Yg + u;
-            const bool rowok = any && Y < P.oy1;
 #pragma unroll 1
             for (int t = 0; t < RT; ++t) {
                 const int X = Xp0 + t + P.dlo;
                 const int d = X - Y;
-                const bool wok = rowok && X >= P.ox0 && X < P.ox1 && d >= P.odlo && d <= P.odhi;
+                const bool wok = (okb >> (u * RT + t)) & 1u;
                 int nmiss = 0;
                 double sKm = 0.0, sKm2 = 0.0;
                 if (MASK && wok) {                                           // [sec:strip]
@@ -653,8 +673,12 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     const double s3 = (double)mystat[k * nthr];
                     const double g1 = (double)mystat[(NWB + k) * nthr];
                     const double g2 = (double)mystat[(2 * NWB + k) * nthr];
-                    r = score_from_sums<MASK>(P, (double)pl, g1, g2, g2, nmiss, s3, sKm, sKm2, nobs,
-                                              redo);
+                    if (P.dbg & 2)
+                        r = (float)(s3 + g1 + g2);
+                    else
+                        r = score_from_sums<MASK>(P, (double)pl, g1, g2, g2, nmiss, s3, sKm, sKm2,
+                                                  nobs, redo);
+                    if (P.dbg & 32) redo = false;
                 }
                 // ill-conditioned windows (flat signal or mostly missing): the warp redoes the
                 // window sums in float64 from the tile, 32 pixels at a time      [sec:redo]
@@ -681,11 +705,49 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                                                   again);
                     }
                 }
-                if (wok) {                                                   // [sec:store]
-                    const long long oi =
-                        (long long)(Y - P.osy) * P.out_pitch + ((X - P.osx) - P.out_dlo);
-                    P.out[oi] = r;
-                    if (P.nobs) P.nobs[oi] = (unsigned short)nobs;
+                if (wok) {
+                    // score and observation count replace s3 and g1 in the window's slots
+                    mystat[(u * RT + t) * nthr] = r;
+                    mystat[(NWB + u * RT + t) * nthr] = __int_as_float(nobs);
+                }
+            }
+        }
+        // ---- scores (and observation counts) to the output band, 16 bytes at a time where
+        // the row of eight windows is complete and aligned                     [sec:store]
+        if (!(P.dbg & 64)) {
+#pragma unroll
+            for (int u = 0; u < RU; ++u) {
+                const unsigned ob = (okb >> (u * RT)) & ((1u << RT) - 1u);
+                if (!ob) continue;
+                const int Y = Yg + u;
+                const long long oi0 =
+                    (long long)(Y - P.osy) * P.out_pitch + ((Xp0 + P.dlo - P.osx) - P.out_dlo);
+                float rr[RT];
+                int nn[RT];
+#pragma unroll
+                for (int t = 0; t < RT; ++t) {
+                    rr[t] = mystat[(u * RT + t) * nthr];
+                    nn[t] = __float_as_int(mystat[(NWB + u * RT + t) * nthr]);
+                }
+                if (ob == ((1u << RT) - 1u) && (oi0 & 3) == 0) {
+#pragma unroll
+                    for (int t = 0; t < RT; t += 4)
+                        *reinterpret_cast<float4 *>(P.out + oi0 + t) =
+                            make_float4(rr[t], rr[t + 1], rr[t + 2], rr[t + 3]);
+                    if (P.nobs) {
+#pragma unroll
+                        for (int t = 0; t < RT; t += 4)
+                            *reinterpret_cast<uint2 *>(P.nobs + oi0 + t) = make_uint2(
+                                (unsigned)nn[t] | ((unsigned)nn[t + 1] << 16),
+                                (unsigned)nn[t + 2] | ((unsigned)nn[t + 3] << 16));
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < RT; ++t)
+                        if ((ob >> t) & 1u) {
+                            P.out[oi0 + t] = rr[t];
+                            if (P.nobs) P.nobs[oi0 + t] = (unsigned short)nn[t];
+                        }
                 }
             }
         }
@@ -997,6 +1059,7 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
     P.min_present = (int)((1.0 - opts->missing_tol) * (double)P.N);
     P.kmean_zero = (K->k_mean == 0.0);
     P.has_mask = opts->has_mask;
+    P.dbg = getenv("CS_DEBUG_SKIP") ? atoi(getenv("CS_DEBUG_SKIP")) : 0;
     P.raw_xcorr = opts->raw_xcorr;
     P.nobs_full = opts->nobs_full;
 
