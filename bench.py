@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--n", type=int, default=200_000, help="bins of the synthetic chromosome")
     ap.add_argument("--max-dist", type=int, default=200, help="scan distance in bins (2 Mb @ 10 kb)")
     ap.add_argument("--kernel", default="loops")
+    ap.add_argument("--win-size", type=int, default=0,
+                    help="resize the kernel to this (odd) width like `--win-size` of the CLI (cli:690-695)")
+    ap.add_argument("--kernel-index", type=int, default=0)
     ap.add_argument("--pearson", type=float, default=0.3)
     ap.add_argument("--cpu-rows", type=int, default=12_000, help="rows of the CPU-baseline slab")
     ap.add_argument("--ref-rows", type=int, default=2_000, help="rows per worker per step (--impl reference)")
@@ -389,7 +392,10 @@ def traffic_from_profile():
 def main():
     a = parse_args()
     from chromosight_b200 import kernels
-    kernel = np.asarray(getattr(kernels, a.kernel)["kernels"][0], dtype=np.float64)
+    kernel = np.asarray(getattr(kernels, a.kernel)["kernels"][a.kernel_index], dtype=np.float64)
+    if a.win_size:
+        from chromosight_b200.utils import preprocessing as hostpre
+        kernel = hostpre.resize_kernel(kernel, factor=a.win_size / kernel.shape[0])
     if a.impl == "reference":
         run_reference(a, kernel)
     else:
