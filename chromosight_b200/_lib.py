@@ -55,6 +55,9 @@ class Candidate(C.Structure):
 
 
 CANDIDATE_DTYPE = np.dtype([("row", "<i4"), ("col", "<i4"), ("score", "<f4"), ("log10p", "<f4")])
+# cs_focus records (24 B)
+FOCUS_DTYPE = np.dtype([("first_row", "<i4"), ("first_col", "<i4"), ("row", "<i4"), ("col", "<i4"),
+                        ("score", "<f4"), ("size", "<i4")])
 
 
 class CsrResult(C.Structure):
@@ -148,6 +151,11 @@ _PROTOS = {
     "cs_session_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cs_session_upload": (C.c_int, [C.c_void_p, C.POINTER(Normxcorr2Args)]),
     "cs_session_run": (C.c_int, [C.c_void_p, C.POINTER(RunStats)]),
+    "cs_foci_work_bytes": (C.c_int64, [C.POINTER(Layout)]),
+    "cs_scores_foci": (C.c_int, [C.POINTER(Layout), _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, _P, _P,
+                                  C.c_int64, _P, C.POINTER(C.c_int64), _P]),
+    "cs_session_foci": (C.c_int, [C.c_void_p, C.c_double, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64,
+                                   C.POINTER(C.c_int64)]),
     "cs_session_candidates": (C.c_int, [C.c_void_p, C.c_float, C.c_int32, C.c_int32, _P, C.c_int64,
                                          _P, C.POINTER(C.c_int64)]),
     "cs_session_download": (C.c_int, [C.c_void_p, C.POINTER(CsrResult)]),

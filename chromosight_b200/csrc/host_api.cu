@@ -8,6 +8,7 @@
 // Device and pinned buffers are cached per device and only grow, so steady-state
 // calls do no allocation.
 #include <stdlib.h>
+#include <algorithm>
 #include <chrono>
 #include <mutex>
 #include <thread>
@@ -223,7 +224,8 @@ struct cs_session {
     cudaStream_t stream() const { return use_user_st ? user_st : c->st; }
     // device-resident inputs, images and results of this session
     DevBuf sig_indptr, sig_indices, sig_data, m_indptr, m_indices, img, out, nobs, r_indptr,
-        r_indices, r_data, r_p, err, g_coords, g_win, g_flag, g_score, g_p, g_vrow, g_vcol;
+        r_indices, r_data, r_p, err, g_coords, g_win, g_flag, g_score, g_p, g_vrow, g_vcol, f_work,
+        f_rec;
     bool uploaded = false, ran = false, empty = false;
     cs_normxcorr2_args a;
     std::vector<double> k_corr, k_mask, k2_mask;
@@ -254,7 +256,8 @@ extern "C" void cs_session_destroy(cs_session *s) {
     DevBuf *bufs[] = {&s->sig_indptr, &s->sig_indices, &s->sig_data, &s->m_indptr, &s->m_indices,
                       &s->img,        &s->out,         &s->nobs,     &s->r_indptr, &s->r_indices,
                       &s->r_data,     &s->r_p,         &s->err,      &s->g_coords, &s->g_win,
-                      &s->g_flag,     &s->g_score,     &s->g_p,      &s->g_vrow,   &s->g_vcol};
+                      &s->g_flag,     &s->g_score,     &s->g_p,      &s->g_vrow,   &s->g_vcol,
+                      &s->f_work,     &s->f_rec};
     cudaSetDevice(s->c->device);
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -555,6 +558,40 @@ extern "C" int cs_session_candidates(cs_session *s, float threshold, int32_t dmi
                                 s->want_nobs ? (const uint16_t *)s->nobs.p : nullptr,
                                 s->a.kernel.kh * s->a.kernel.kw, dmin, dmax, threshold, d_cand, cap,
                                 d_count, n_host, s->stream());
+}
+
+// pick_foci (det:387-456) on the scores of the last run; records sorted by first pixel.
+extern "C" int cs_session_foci(cs_session *s, double threshold, int32_t dmin, int32_t dmax,
+                               int32_t min_size, cs_focus *host_foci, int64_t cap,
+                               int64_t *n_host) {
+    CS_REQUIRE(s && s->ran && n_host && (cap == 0 || host_foci), "cs_session_foci: bad arguments");
+    HostCtx *c = s->c;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CS_CUDA(cudaSetDevice(c->device));
+    *n_host = 0;
+    if (s->empty) return CS_OK;
+    cudaStream_t st = s->stream();
+    int rc;
+    if ((rc = s->f_work.ensure((size_t)cs_foci_work_bytes(&s->Lo)))) return rc;
+    int64_t dcap = cap > 0 ? cap : 1;
+    if ((rc = s->f_rec.ensure((size_t)dcap * sizeof(cs_focus) + 64))) return rc;
+    int64_t *d_count = (int64_t *)((char *)s->f_rec.p + (size_t)dcap * sizeof(cs_focus));
+    d_count = (int64_t *)(((uintptr_t)d_count + 7) & ~(uintptr_t)7);
+    int64_t n = 0;
+    rc = cs_scores_foci(&s->Lo, (const float *)s->out.p, dmin, dmax, threshold, min_size,
+                        s->f_work.p, (cs_focus *)s->f_rec.p, dcap, d_count, &n, st);
+    if (rc) return rc;
+    *n_host = n;
+    const int64_t m = n < cap ? n : cap;
+    if (m > 0) {
+        CS_CUDA(cudaMemcpyAsync(host_foci, s->f_rec.p, (size_t)m * sizeof(cs_focus),
+                                cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaStreamSynchronize(st));
+        std::sort(host_foci, host_foci + m, [](const cs_focus &a, const cs_focus &b) {
+            return a.first_row != b.first_row ? a.first_row < b.first_row : a.first_col < b.first_col;
+        });
+    }
+    return CS_OK;
 }
 
 // D2H of the CSR result of the last run into pooled pinned buffers.

@@ -192,6 +192,148 @@ __global__ void emit_candidates(ScoreView S, const float *__restrict__ sc,
     }
 }
 
+// ---------------------------------------------------------------------------
+// pick_foci on the device (detection.py:387-456, label_foci 459-554, filter_foci 557-592):
+// pixels with score >= threshold form 4-connected foci; foci of at least min_size pixels
+// yield one record: the focus' first pixel in row-major order (which numbers the foci) and
+// its best pixel (highest score, first in row-major order among equals).
+// Labels live in a uint32 image with the score image's layout; the label of a focus is the
+// linear index of its first pixel (union by smaller index), so no renumbering pass is needed.
+// ---------------------------------------------------------------------------
+constexpr unsigned kNoLabel = 0xffffffffu;
+
+__device__ __forceinline__ bool is_candidate(float v, double thr) {
+    return v != 0.f && (double)v >= thr;  // the reference compares float64 values
+}
+
+__device__ __forceinline__ unsigned uf_find(const unsigned *lab, unsigned i) {
+    unsigned p = ((const volatile unsigned *)lab)[i];
+    while (p != i) {
+        i = p;
+        p = ((const volatile unsigned *)lab)[i];
+    }
+    return i;
+}
+
+__device__ __forceinline__ void uf_union(unsigned *lab, unsigned a, unsigned b) {
+    for (;;) {
+        a = uf_find(lab, a);
+        b = uf_find(lab, b);
+        if (a == b) return;
+        if (a > b) {
+            const unsigned t = a;
+            a = b;
+            b = t;
+        }
+        // hang the larger root under the smaller one
+        const unsigned old = atomicMin(&lab[b], a);
+        if (old == b) return;
+        b = old;
+    }
+}
+
+// pass 1: label = own index for candidates, none elsewhere; statistics cleared
+__global__ void foci_init(ScoreView S, const float *__restrict__ sc, double thr, unsigned *lab,
+                          unsigned *cnt, unsigned long long *best) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int y = blockIdx.x * wpb + (threadIdx.x >> 5); y < S.rows; y += gridDim.x * wpb) {
+        int x0, x1;
+        row_range(S, y, x0, x1);
+        for (int x = x0 + lane; x < x1; x += 32) {
+            const long long i = sidx(S, y, x);
+            const bool c = is_candidate(sc[i], thr);
+            lab[i] = c ? (unsigned)i : kNoLabel;
+            if (c) {
+                cnt[i] = 0u;
+                best[i] = 0ull;
+            }
+        }
+    }
+}
+
+// pass 2: unions with the left and the upper neighbour (4-connectivity, det:508-540)
+__global__ void foci_merge(ScoreView S, unsigned *lab) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int y = blockIdx.x * wpb + (threadIdx.x >> 5); y < S.rows; y += gridDim.x * wpb) {
+        int x0, x1, u0 = 0, u1 = 0;
+        row_range(S, y, x0, x1);
+        if (y > 0) row_range(S, y - 1, u0, u1);
+        for (int x = x0 + lane; x < x1; x += 32) {
+            const long long i = sidx(S, y, x);
+            if (lab[i] == kNoLabel) continue;
+            if (x > x0 && lab[i - 1] != kNoLabel) uf_union(lab, (unsigned)i, (unsigned)(i - 1));
+            if (y > 0 && x >= u0 && x < u1) {
+                const long long j = sidx(S, y - 1, x);
+                if (lab[j] != kNoLabel) uf_union(lab, (unsigned)i, (unsigned)j);
+            }
+        }
+    }
+}
+
+// monotone map float -> uint32 (larger float, larger key)
+__device__ __forceinline__ unsigned float_key(float v) {
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// pass 3: every candidate adds itself to its root: size, and the best (score, first index)
+__global__ void foci_reduce(ScoreView S, const float *__restrict__ sc, unsigned *lab,
+                            unsigned *cnt, unsigned long long *best) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int y = blockIdx.x * wpb + (threadIdx.x >> 5); y < S.rows; y += gridDim.x * wpb) {
+        int x0, x1;
+        row_range(S, y, x0, x1);
+        for (int x = x0 + lane; x < x1; x += 32) {
+            const long long i = sidx(S, y, x);
+            if (lab[i] == kNoLabel) continue;
+            const unsigned r = uf_find(lab, (unsigned)i);
+            lab[i] = r;  // flatten
+            atomicAdd(&cnt[r], 1u);
+            // larger score wins; among equal scores the smaller index
+            const unsigned long long key =
+                ((unsigned long long)float_key(sc[i]) << 32) | (unsigned long long)(~(unsigned)i);
+            atomicMax(&best[r], key);
+        }
+    }
+}
+
+// pass 4: one record per root with enough pixels
+__global__ void foci_emit(ScoreView S, const float *__restrict__ sc, const unsigned *lab,
+                          const unsigned *cnt, const unsigned long long *best, int min_size,
+                          cs_focus *out, long long cap, unsigned long long *count) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int xoff = S.dense ? 0 : S.dlo;
+    for (int y = blockIdx.x * wpb + (threadIdx.x >> 5); y < S.rows; y += gridDim.x * wpb) {
+        int x0, x1;
+        row_range(S, y, x0, x1);
+        for (int x = x0 + lane; x < x1; x += 32) {
+            const long long i = sidx(S, y, x);
+            if (lab[i] != (unsigned)i || (int)cnt[i] < min_size) continue;
+            const unsigned long long o = atomicAdd(count, 1ull);
+            if ((long long)o >= cap) continue;
+            const unsigned bi = ~(unsigned)(best[i] & 0xffffffffull);
+            cs_focus f;
+            f.first_row = y;
+            f.first_col = x;
+            if (S.dense) {
+                f.row = (int)(bi / (unsigned)S.pitch);
+                f.col = (int)(bi - (unsigned)f.row * (unsigned)S.pitch);
+            } else {
+                // band: index = row * (pitch + 1) + (col - row - dlo)
+                f.row = (int)(bi / (unsigned)(S.pitch + 1));
+                f.col = f.row + (int)(bi - (unsigned)f.row * (unsigned)(S.pitch + 1)) + xoff;
+            }
+            f.score = sc[bi];
+            f.size = (int)cnt[i];
+            out[o] = f;
+        }
+    }
+}
+
 static ScoreView make_view(const cs_layout *L, int dmin, int dmax) {
     ScoreView S;
     S.rows = L->rows;
@@ -303,6 +445,43 @@ extern "C" int cs_scores_candidates(const cs_layout *Lo, const float *d_out, con
     if (grid > 148 * 16) grid = 148 * 16;
     emit_candidates<<<grid, 256, 0, st>>>(S, d_out, d_nobs, nobs_const, threshold, d_cand,
                                           (long long)cap, (unsigned long long *)d_count);
+    CS_LAUNCHED();
+    CS_CUDA(cudaGetLastError());
+    CS_CUDA(cudaMemcpyAsync(n_host, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    return CS_OK;
+}
+
+extern "C" int64_t cs_foci_work_bytes(const cs_layout *L) {
+    if (!L) return 0;
+    // label (4 B) + size (4 B) + best (8 B) per image element
+    return (int64_t)L->n_elems * 16 + 256;
+}
+
+extern "C" int cs_scores_foci(const cs_layout *L, const float *d_scores, int32_t dmin, int32_t dmax,
+                              double threshold, int32_t min_size, void *d_work, cs_focus *d_foci,
+                              int64_t cap, int64_t *d_count, int64_t *n_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CS_REQUIRE(L && d_scores && d_work && d_foci && d_count && n_host,
+               "cs_scores_foci: null argument");
+    CS_REQUIRE(L->n_elems < (1ll << 32) - 1, "score image too large for 32-bit focus labels");
+    if (!L->dense) CS_REQUIRE(L->pitch >= L->dhi - L->dlo, "band layout pitch too small");
+    ScoreView S = make_view(L, dmin, dmax);
+    unsigned char *w = (unsigned char *)d_work;
+    unsigned long long *best = (unsigned long long *)w;              // 8-byte aligned first
+    unsigned *lab = (unsigned *)(w + (size_t)L->n_elems * 8);
+    unsigned *cnt = lab + L->n_elems;
+    CS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    int grid = (S.rows + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    foci_init<<<grid, 256, 0, st>>>(S, d_scores, threshold, lab, cnt, best);
+    CS_LAUNCHED();
+    foci_merge<<<grid, 256, 0, st>>>(S, lab);
+    CS_LAUNCHED();
+    foci_reduce<<<grid, 256, 0, st>>>(S, d_scores, lab, cnt, best);
+    CS_LAUNCHED();
+    foci_emit<<<grid, 256, 0, st>>>(S, d_scores, lab, cnt, best, min_size, d_foci, cap,
+                                    (unsigned long long *)d_count);
     CS_LAUNCHED();
     CS_CUDA(cudaGetLastError());
     CS_CUDA(cudaMemcpyAsync(n_host, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, st));

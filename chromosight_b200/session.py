@@ -97,6 +97,22 @@ class Session:
         return out, int(min(n.value, cap))
 
 
+    def foci(self, threshold, dmin=0, dmax=2 ** 30, min_size=2, cap=1 << 16):
+        """pick_foci (det:387-456) on the device: 4-connected foci of the pixels with score >=
+        threshold on diagonals dmin..dmax, at least min_size pixels each.  Returns a structured
+        array (_lib.FOCUS_DTYPE) in the reference's focus order (by first pixel, row-major); (row,
+        col) of a record is the focus' local maximum."""
+        self._bind_stream()
+        while True:
+            rec = np.zeros(cap, dtype=_lib.FOCUS_DTYPE)
+            n = C.c_int64(0)
+            _lib.check(self._lib.cs_session_foci(self._h, C.c_double(threshold), int(max(dmin, -(2 ** 30))),
+                                                 int(min(dmax, 2 ** 30)), int(min_size),
+                                                 rec.ctypes.data, cap, C.byref(n)))
+            if n.value <= cap:
+                return rec[: n.value]
+            cap = int(n.value)
+
     def validate(self, coords, valid_rows, valid_cols, inter, zero_tol, missing_tol, score_dmax):
         """validate_patterns (det:18-155) on the uploaded matrix and the last scores.
 

@@ -356,22 +356,30 @@ def pattern_detector(contact_map, kernel_config, kernel_matrix, coords=None, dum
                 sp.save_npz(pathlib.Path(dump) / f"{contact_map.name}_04_diag_trim",
                             preproc.diag_trim(conv.tocsr(), contact_map.max_dist))
         if not quantify:
-            # det:277-283: pixels above the threshold -> foci -> one local maximum per focus;
-            # only the candidate pixels leave the device
+            # det:277-283: pixels above the threshold -> 4-connected foci -> one local maximum
+            # per focus, on the device (csrc/scores.cu); only the foci leave it
             thr = float(kernel_config["pearson"])
-            cap = 1 << 20
-            while True:
-                rec, n = sess.candidates(thr, dmin, dmax, cap=cap)
-                if n < cap:
-                    break
-                cap *= 4
-            cand = records_to_numpy(rec, n)
-            cmat = sp.coo_matrix((cand["score"].astype(np.float64), (cand["row"], cand["col"])), shape=shape)
-            coords, foci_mat = pick_foci(cmat, thr)
-            if coords is None:
-                return None, None
             if dump:
+                # the dump wants the labelled matrix: candidates to the host, host labelling
+                import pathlib
+                cap = 1 << 20
+                while True:
+                    rec, n = sess.candidates(thr, dmin, dmax, cap=cap)
+                    if n < cap:
+                        break
+                    cap *= 4
+                cand = records_to_numpy(rec, n)
+                cmat = sp.coo_matrix((cand["score"].astype(np.float64), (cand["row"], cand["col"])),
+                                     shape=shape)
+                coords, foci_mat = pick_foci(cmat, thr)
+                if coords is None:
+                    return None, None
                 sp.save_npz(pathlib.Path(dump) / f"{contact_map.name}_05_foci", foci_mat.tocsr())
+            else:
+                foci = sess.foci(thr, dmin, dmax, min_size=2)
+                if len(foci) == 0:
+                    return None, None
+                coords = np.stack([foci["row"], foci["col"]], axis=1)
         coords = np.array(coords, dtype=np.int64).reshape(-1, 2)
         if not inter and kernel_config["max_dist"] == 0:
             # det:311-315: 1-D patterns sit on the diagonal of the padded map

@@ -161,6 +161,23 @@ int cs_scores_candidates(const cs_layout *Lout, const float *d_out, const uint16
                          cs_candidate *d_cand, int64_t cap, int64_t *d_count,
                          int64_t *n_host, void *stream);
 
+/* pick_foci on the device (det:387-456 with label_foci det:459-554 and filter_foci
+ * det:557-592): pixels with score >= threshold on diagonals dmin..dmax form 4-connected foci;
+ * every focus of at least min_size pixels yields one record.  Foci are numbered by their first
+ * pixel in row-major order (records come unordered: sort by (first_row, first_col)); (row, col)
+ * is the focus' highest score, the first in row-major order among equals, as np.argmax picks it.
+ * d_work: cs_foci_work_bytes(L) bytes of device scratch. */
+typedef struct cs_focus {
+    int32_t first_row, first_col;
+    int32_t row, col;
+    float score;
+    int32_t size;
+} cs_focus;
+int64_t cs_foci_work_bytes(const cs_layout *Lout);
+int cs_scores_foci(const cs_layout *Lout, const float *d_out, int32_t dmin, int32_t dmax,
+                   double threshold, int32_t min_size, void *d_work, cs_focus *d_foci,
+                   int64_t cap, int64_t *d_count, int64_t *n_host, void *stream);
+
 /* ------------------------------------------------------------------------
  * Window gather + validation: detection.py:18-155 (validate_patterns) on the
  * zero-padded, sub-diagonal-NaN matrix that pattern_detector builds
@@ -276,6 +293,10 @@ int cs_session_run(cs_session *s, cs_run_stats *stats);
 int cs_session_candidates(cs_session *s, float threshold, int32_t dmin, int32_t dmax,
                           cs_candidate *d_cand, int64_t cap, int64_t *d_count, int64_t *n_host);
 int cs_session_download(cs_session *s, cs_csr_result *res);
+/* cs_scores_foci on the scores of the last run: at most `cap` records into host_foci, sorted by
+ * first pixel (the reference's focus order); *n_host = number of foci found. */
+int cs_session_foci(cs_session *s, double threshold, int32_t dmin, int32_t dmax, int32_t min_size,
+                    cs_focus *host_foci, int64_t cap, int64_t *n_host);
 /* validate_patterns on the session's matrix and last scores: host coordinates in
  * (UNPADDED, n_coords x 2), host results out.  `full`/`inter` select the padding and NaN
  * sub-diagonals of det:291-310; host_valid_row/col are uint8[rows]/[cols] (1 = detectable). */

@@ -351,3 +351,44 @@ def test_validate_patterns_standalone(presets):
             assert len(tab) == 200 and np.allclose(win, w0, rtol=0, atol=0, equal_nan=True)
             assert np.allclose(tab.score.to_numpy(), s0, equal_nan=True)
     assert 0 < ok0.sum() < 200
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("thr", [0.3, 0.15, 0.05])
+def test_device_foci_match_host_pick_foci(thr, presets):
+    """pick_foci (det:387-456) on the device (4-connected labelling by union-find, size filter,
+    per-focus argmax) against the host mirror, which is pinned to the reference
+    (test_foci_match_reference): same foci, same order, same local maxima."""
+    import scipy.sparse as sp
+    from chromosight_b200 import synthetic
+    from chromosight_b200.session import Session, records_to_numpy
+    from chromosight_b200.utils import detection as cud, preprocessing as cup
+    kernel = np.asarray(presets.loops["kernels"][0], dtype=np.float64)
+    n, D, k = 6000, 120, kernel.shape[0]
+    raw, detect = synthetic.band_counts(n, D + k, seed=11, missing_frac=0.02, max_dist=D)
+    mat = cup.detrend(raw, detectable_bins=detect, max_dist=D + k, max_val=10)
+    mat = cup.diag_trim(mat.tocsr(), D + k)
+    mat.data[np.isnan(mat.data)] = 0
+    mat.eliminate_zeros()
+    mask = cup.make_missing_mask(mat.shape, detect, detect, max_dist=D, sym_upper=True)
+    sess = Session()
+    try:
+        sess.upload(mat, kernel, max_dist=D, sym_upper=True, full=True, missing_mask=mask,
+                    missing_tol=0.5, pval=True)
+        sess.run()
+        foci = sess.foci(thr, 0, D, min_size=2, cap=64)        # small cap: exercises the regrow
+        rec, nc = sess.candidates(thr, 0, D)
+        cand = records_to_numpy(rec, nc)
+    finally:
+        sess.close()
+    cmat = sp.coo_matrix((cand["score"].astype(np.float64), (cand["row"], cand["col"])), shape=mat.shape)
+    coords, labelled = cud.pick_foci(cmat, thr)
+    assert coords is not None and len(coords) > 20
+    assert len(foci) == len(coords)
+    assert np.array_equal(np.stack([foci["row"], foci["col"]], axis=1), coords)
+    # sizes and first pixels agree with the labelled matrix of the host
+    lab = labelled.tocsr()
+    ids = np.asarray(lab[foci["first_row"], foci["first_col"]]).ravel()
+    assert np.array_equal(ids, np.sort(ids)) and len(np.unique(ids)) == len(ids)
+    sizes = np.bincount(labelled.data.astype(np.int64))[ids.astype(np.int64)]
+    assert np.array_equal(sizes, foci["size"])
