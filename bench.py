@@ -47,7 +47,7 @@ BYTES_PER_WINDOW = 8  # one fp32 pixel in + one fp32 score out
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=200_000, help="bins of the synthetic chromosome")
@@ -364,7 +364,8 @@ def run_b200(a, kernel):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 storage, f32 FMA + f64 window statistics",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "dtype_detail": "float32 image and sums (centred), float64 score formulas; CSR results float64",
         "data": "synthetic", "config": workload_config(a, kernel),
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "step_breakdown_ms": {"fill": float(np.mean(ms_fill)), "pearson": float(np.mean(ms_pearson)),
