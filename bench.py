@@ -57,7 +57,7 @@ def parse_args():
                     help="resize the kernel to this (odd) width like `--win-size` of the CLI (cli:690-695)")
     ap.add_argument("--kernel-index", type=int, default=0)
     ap.add_argument("--pearson", type=float, default=0.3)
-    ap.add_argument("--cpu-rows", type=int, default=12_000, help="rows of the CPU-baseline slab")
+    ap.add_argument("--cpu-rows", type=int, default=50_000, help="rows of the CPU-baseline slab")
     ap.add_argument("--ref-rows", type=int, default=2_000, help="rows per worker per step (--impl reference)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
