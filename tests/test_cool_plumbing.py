@@ -185,3 +185,33 @@ def test_quantify_driver_matches_per_chromosome_calls(fx, presets):
     assert checked == len(bed) - 1
     off = table[table.bin1.isna()]
     assert len(off) == 1 and np.isnan(off.score.values[0]) and np.isnan(off.pvalue.values[0])
+
+
+def test_driver_host_plumbing(fx):
+    """The parts of the sharded drivers that need no GPU: window-count costs per sub-matrix and
+    the positions -> sub-matrix bins mapping of cmd_quantify (cli:262-293)."""
+    import pandas as pd
+    from chromosight_b200 import driver, sharding
+    from chromosight_b200.contacts_map import HicGenome
+    cfg = loops_config(fx)
+    hg = HicGenome(cool_from_fixture(fx), inter=True, kernel_config=cfg)
+    hg.normalize()
+    hg.make_sub_matrices()
+    costs = driver.unit_costs(hg)
+    D = int(fx["max_dist"])
+    sizes = {"chr1": 127, "chr2": 422, "chr3": 171}
+    exp = []
+    for _, row in hg.sub_mats.iterrows():
+        a, b = sizes[row.chr1], sizes[row.chr2]
+        exp.append(float(a * b) if row.chr1 != row.chr2 else float((min(D, a) + 1) * a))
+    assert costs == exp
+    parts = sharding.partition_units(costs, 2)
+    assert sorted(parts[0] + parts[1]) == list(range(6))
+    pos = pd.DataFrame({"chrom1": ["chr2", "chr1", "chr2", "chr9"], "pos1": [4500, 0, 10 ** 9, 5],
+                        "chrom2": ["chr2", "chr1", "chr2", "chr9"], "pos2": [9999, 126999, 10 ** 9, 9]})
+    idx, coords = driver._chrom_positions(pos, hg, "chr2", "chr2")
+    assert list(idx) == [0] and coords.tolist() == [[4, 9]]       # the off-map position is dropped
+    idx, coords = driver._chrom_positions(pos, hg, "chr1", "chr1")
+    assert list(idx) == [1] and coords.tolist() == [[0, 126]]
+    idx, coords = driver._chrom_positions(pos, hg, "chr3", "chr3")
+    assert len(idx) == 0 and coords.shape == (0, 2)
