@@ -50,7 +50,7 @@ struct PearsonParams {
     // tables (device): float part then double part, copied to shared memory by every CTA
     const float *ftab;
     const double *dtab;
-    int n_ftab, n_dtab;
+    int n_ftab, n_dtab, tab_bytes;
     int dbg;  // CS_DEBUG_SKIP bit mask (timing experiments only): see the kernel
     double q, sumKp, sumKp2, ksum, k2sum, kmean, kstd, thr, invN, vK0;
     int min_present, kmean_zero, has_mask, raw_xcorr, nobs_full;
@@ -96,6 +96,15 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+// 1-D bulk copy global -> shared memory, completion counted on the mbarrier (bytes % 16 == 0)
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes,
+                                             uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
 // two float32 FMAs per instruction (FFMA2): acc.{lo,hi} += a.{lo,hi} * b.{lo,hi}
@@ -277,18 +286,14 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         mbar_init(bar, 1);
         fence_barrier_init();
         fence_proxy_async();
-        mbar_expect_tx(bar, (uint32_t)(IC * IR * sizeof(float)));
+        // the tile (2-D tensor box) and the kernel tables (one linear block: float part, then
+        // float64 part) arrive through the same barrier
+        mbar_expect_tx(bar, (uint32_t)(IC * IR * sizeof(float)) + (uint32_t)P.tab_bytes);
         tma_load_2d(tile, &tmap, bar, TXp, TY);
+        bulk_load_1d(smem + P.off_K, P.ftab, (uint32_t)P.tab_bytes, bar);
     }
-    // tables -> shared memory while the tile is in flight
-    {
-        float *Kf = reinterpret_cast<float *>(smem + P.off_K);
-        for (int i = (P.dbg & 128) ? P.n_ftab : tid; i < P.n_ftab; i += nthr) Kf[i] = P.ftab[i];
-        double *Dd = reinterpret_cast<double *>(smem + P.off_D);
-        for (int i = (P.dbg & 128) ? P.n_dtab : tid; i < P.n_dtab; i += nthr) Dd[i] = P.dtab[i];
-        if (MASK)
-            for (int i = tid; i < NW; i += nthr) bits[i] = 0u;
-    }
+    if (MASK)
+        for (int i = tid; i < NW; i += nthr) bits[i] = 0u;
     __syncthreads();
     mbar_wait(bar, 0);
 
@@ -882,7 +887,8 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
     P.n_dtab = opts->has_mask ? (2 * (K->kh + 1) * (K->kw + 1) + 2 * K->kw + 3 * P.st_n) : 0;
     if (opts->has_mask) CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
     const size_t fbytes = (size_t)round_up(P.n_ftab, 4) * sizeof(float);
-    const size_t kbytes = fbytes + (size_t)P.n_dtab * sizeof(double);
+    const size_t kbytes = (fbytes + (size_t)P.n_dtab * sizeof(double) + 15) / 16 * 16;
+    P.tab_bytes = (int)kbytes;
     unsigned char *hk = (unsigned char *)malloc(kbytes);
     if (!hk) return CS_ERR_NOMEM;
     memset(hk, 0, kbytes);
