@@ -48,7 +48,7 @@ static const size_t kStageChunk = [] {  // one DMA per chunk; two buffers altern
 
 struct HostCtx {
     int device = -1;
-    cudaStream_t st = nullptr, st_copy = nullptr, st_emit = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr, st_emit = nullptr, st_up = nullptr;
     void *stage[2] = {nullptr, nullptr};
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -71,6 +71,7 @@ static int get_ctx(int device, HostCtx **out) {
     c->device = device;
     CS_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
     CS_CUDA(cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking));
+    CS_CUDA(cudaStreamCreateWithFlags(&c->st_up, cudaStreamNonBlocking));
     {
         // result compaction of finished slabs overtakes the Pearson tiles of later ones
         int lo_pri = 0, hi_pri = 0;
@@ -669,13 +670,22 @@ extern "C" int cs_session_download(cs_session *s, cs_csr_result *res) {
 //   pointers, CSR entries + p-values; then, on the copy stream, its D2H.
 static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_csr_result *res,
                                 int nslab) {
+    const auto t_enter = std::chrono::steady_clock::now();
     int rc = session_upload_impl(s, a, true);
     if (rc) return rc;
     if (s->empty) return 1;  // nothing to pipeline: the caller finishes through run + download
+    const double ms_plan = std::chrono::duration<double, std::milli>(
+                               std::chrono::steady_clock::now() - t_enter).count();
     HostCtx *c = s->c;
     std::lock_guard<std::mutex> lk(c->mu);
     CS_CUDA(cudaSetDevice(c->device));
-    cudaStream_t st = s->stream(), st_d = c->st_copy, st_e = c->st_emit;
+    cudaStream_t st = s->stream(), st_d = c->st_copy, st_e = c->st_emit, st_h = c->st_up;
+    {
+        // uploads normally run in line with the kernels; CS_UPLOAD_STREAM=1 lets them run ahead on
+        // their own stream (measured: no difference, the download is the floor either way)
+        const char *e = getenv("CS_UPLOAD_STREAM");
+        if (!e || atoi(e) == 0) st_h = st;
+    }
     const cs_normxcorr2_args &A = s->a;
     const cs_kernel_desc &K = A.kernel;
     const int kh = (K.kh - 1) / 2;
@@ -712,18 +722,20 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
         ~Guard() { pin_release_unlocked(p); }
     } guard{h_tot};
     int64_t *tot = (int64_t *)h_tot;
-    std::vector<cudaEvent_t> ev_tot(nslab), ev_emit(nslab);
+    std::vector<cudaEvent_t> ev_tot(nslab), ev_emit(nslab), ev_up(nslab);
     for (int i = 0; i < nslab; ++i) {
         CS_CUDA(cudaEventCreateWithFlags(&ev_tot[i], cudaEventDisableTiming));
         CS_CUDA(cudaEventCreateWithFlags(&ev_emit[i], cudaEventDisableTiming));
+        CS_CUDA(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
     }
     struct EvGuard {
-        std::vector<cudaEvent_t> &a, &b;
+        std::vector<cudaEvent_t> &a, &b, &c;
         ~EvGuard() {
             for (auto e : a) cudaEventDestroy(e);
             for (auto e : b) cudaEventDestroy(e);
+            for (auto e : c) cudaEventDestroy(e);
         }
-    } evguard{ev_tot, ev_emit};
+    } evguard{ev_tot, ev_emit, ev_up};
 
     // CS_TRACE=1: per-slab timeline on stderr (host clock and device events, ms from the start)
     const bool trace = getenv("CS_TRACE") != nullptr;
@@ -854,21 +866,24 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
         if (need > up_end) {
             const int64_t e0 = a->indptr[up_end], e1 = a->indptr[need];
             if (e1 > e0) {
-                if ((rc = h2d_staged(c, st, (int32_t *)s->sig_indices.p + e0, a->indices + e0,
+                if ((rc = h2d_staged(c, st_h, (int32_t *)s->sig_indices.p + e0, a->indices + e0,
                                      (size_t)(e1 - e0) * sizeof(int32_t), poll)))
                     return rc;
-                if ((rc = h2d_staged(c, st, (double *)s->sig_data.p + e0, a->data + e0,
+                if ((rc = h2d_staged(c, st_h, (double *)s->sig_data.p + e0, a->data + e0,
                                      (size_t)(e1 - e0) * sizeof(double), poll)))
                     return rc;
             }
             if (A.has_mask) {
                 const int64_t m0 = a->mask_indptr[up_end], m1 = a->mask_indptr[need];
                 if (m1 > m0)
-                    if ((rc = h2d_staged(c, st, (int32_t *)s->m_indices.p + m0,
+                    if ((rc = h2d_staged(c, st_h, (int32_t *)s->m_indices.p + m0,
                                          a->mask_indices + m0, (size_t)(m1 - m0) * sizeof(int32_t),
                                          poll)))
                         return rc;
             }
+            // uploads run ahead on their own stream; the slab's kernels wait for its rows only
+            CS_CUDA(cudaEventRecord(ev_up[k], st_h));
+            CS_CUDA(cudaStreamWaitEvent(st, ev_up[k], 0));
             rc = fill_rows(&s->Li, (float *)s->img.p, (const int64_t *)s->sig_indptr.p,
                            (const int32_t *)s->sig_indices.p, (const double *)s->sig_data.p, A.rows,
                            up_end, need, s->pr, s->pc, A.has_mask ? 1 : 0,
@@ -926,7 +941,8 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
             fprintf(stderr, "%4d  %8.2f %8.2f %8.2f %8.2f | %8.2f %8.2f %8.2f %8.2f  nnz %lld\n", k,
                     th0[k], th1[k], tf0[k], tf1[k], c0, c1, d0, d1, (long long)tot[k]);
         }
-        fprintf(stderr, "host total %.2f ms\n", now() - t_begin);
+        fprintf(stderr, "host total %.2f ms (plan + row pointers before it: %.2f ms)\n",
+                now() - t_begin, ms_plan);
     }
     if (herr[0] > 0 && A.has_mask) {
         set_error("There are %d non-zero elements reported as missing.", herr[0]);
