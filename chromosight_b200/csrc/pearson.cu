@@ -22,6 +22,7 @@
 //            float64, one float32 score.
 // No tensor cores: this is a CUDA-core stencil (BASELINE.json north_star).
 #include <stdlib.h>
+#include <vector>
 #include "common.cuh"
 
 namespace cs {
@@ -759,6 +760,76 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     }
 }
 
+// ---------------------------------------------------------------- wide kernels
+// One warp per window, any kernel size: the path for kernels wider than the tiled kernel's
+// 31 columns (the 81 x 81 centromere preset scans one or two diagonals, so the window count is
+// small and the footprint large).  The six window sums of det:1002-1092 are accumulated in
+// float64 straight from the image in HBM / L2 (NaN sentinel = missing pixel, pixels off the
+// stored band = 0), then the same formulas as everywhere else.
+struct WideParams {
+    const float *img;
+    int pitch, dlo, dhi, dense;
+    const double *kc, *km, *k2m;  // K_corr, K_mask, K2_mask [KH * KW]
+};
+
+template <bool MASK>
+__global__ void __launch_bounds__(256)
+pearson_wide(const PearsonParams P, const WideParams W) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int KH = P.KH, KW = P.KW, kh = (KH - 1) / 2, kw = (KW - 1) / 2;
+    for (int Y = P.oy0 + blockIdx.x; Y < P.oy1; Y += gridDim.x) {
+        const int Xlo = max(P.ox0, Y + P.odlo), Xhi = min(P.ox1 - 1, Y + P.odhi);
+        for (int X = Xlo + blockIdx.y * wpb + (threadIdx.x >> 5); X <= Xhi; X += gridDim.y * wpb) {
+            double h1 = 0.0, h2 = 0.0, s3 = 0.0, sKm = 0.0, sKm2 = 0.0;
+            int nmiss = 0;
+            for (int idx = lane; idx < KH * KW; idx += 32) {
+                const int i = idx / KW, j = idx - i * KW;
+                const int Yp = Y - kh + i, Xp = X - kw + j;
+                float v = 0.f;
+                if (W.dense)
+                    v = W.img[(long long)Yp * W.pitch + Xp];
+                else {
+                    const int d = Xp - Yp;
+                    if (d >= W.dlo && d <= W.dhi) v = W.img[(long long)Yp * W.pitch + (Xp - W.dlo)];
+                }
+                if (!(v == v)) {  // missing pixel: counts as S = 0
+                    if (MASK) {
+                        ++nmiss;
+                        sKm += W.km[idx];
+                        sKm2 += W.k2m[idx];
+                    }
+                    continue;
+                }
+                const double sv = (double)v;
+                h1 += sv;
+                h2 = fma(sv, sv, h2);
+                s3 = fma(sv, W.kc[idx], s3);
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+                h2 += __shfl_xor_sync(0xffffffffu, h2, o);
+                s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+                if (MASK) {
+                    sKm += __shfl_xor_sync(0xffffffffu, sKm, o);
+                    sKm2 += __shfl_xor_sync(0xffffffffu, sKm2, o);
+                    nmiss += __shfl_xor_sync(0xffffffffu, nmiss, o);
+                }
+            }
+            if (lane == 0) {
+                int nobs;
+                bool redo;
+                // raw sums: pivot 0 and (P.q = 0) the unshifted kernel
+                const float r = score_from_sums<MASK>(P, 0.0, h1, h2, h2, nmiss, s3, sKm, sKm2, nobs,
+                                                      redo);
+                const long long oi =
+                    (long long)(Y - P.osy) * P.out_pitch + ((X - P.osx) - P.out_dlo);
+                P.out[oi] = r;
+                if (P.nobs) P.nobs[oi] = (unsigned short)nobs;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                     const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -818,6 +889,94 @@ static thread_local KtabRing g_ring;
 
 using namespace cs;
 
+// kernels wider than 31: the one-warp-per-window kernel
+static int pearson_wide_launch(const cs_layout *Li, const float *d_img, const cs_kernel_desc *K,
+                               const cs_pearson_opts *opts, int32_t oy0, int32_t oy1, int32_t ox0,
+                               int32_t ox1, int32_t odlo, int32_t odhi, const cs_layout *Lo,
+                               float *d_out, uint16_t *d_nobs, cudaStream_t st) {
+    PearsonParams P;
+    memset(&P, 0, sizeof(P));
+    const int nk = K->kh * K->kw;
+    P.oy0 = oy0, P.oy1 = oy1, P.ox0 = ox0, P.ox1 = ox1;
+    const int dmin_poss = ox0 - (oy1 - 1), dmax_poss = (ox1 - 1) - oy0;
+    P.odlo = odlo < dmin_poss ? dmin_poss : odlo;
+    P.odhi = odhi > dmax_poss ? dmax_poss : odhi;
+    CS_REQUIRE(P.odhi >= P.odlo, "empty output diagonal range");
+    P.KH = K->kh, P.KW = K->kw, P.N = nk;
+    P.osy = opts->out_row_shift, P.osx = opts->out_col_shift;
+    P.out = d_out, P.nobs = d_nobs;
+    P.out_pitch = Lo->pitch;
+    P.out_dlo = Lo->dense ? 0 : Lo->dlo;
+    {
+        bool ok = oy0 - P.osy >= 0 && ox0 - P.osx >= 0 && Lo->rows >= oy1 - P.osy &&
+                  Lo->cols >= ox1 - P.osx;
+        const int sh = P.osx - P.osy;
+        if (ok && !Lo->dense) ok = Lo->dlo <= P.odlo - sh && Lo->dhi >= P.odhi - sh;
+        if (!ok) {
+            set_error("output image does not cover scores on diagonals [%d,%d]", P.odlo - sh,
+                      P.odhi - sh);
+            return CS_ERR_INVALID;
+        }
+    }
+    if (opts->has_mask) CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
+    double sumK = 0.0;
+    for (int i = 0; i < nk; ++i) sumK += K->k_corr[i];
+    P.q = 0.0;
+    P.sumKp = sumK;
+    P.sumKp2 = 0.0;
+    P.ksum = K->k_sum, P.k2sum = K->k2_sum, P.kmean = K->k_mean, P.kstd = K->k_std;
+    P.thr = opts->xcorr_threshold;
+    P.invN = 1.0 / (double)nk;
+    P.vK0 = opts->has_mask ? (K->k2_sum / (double)nk - K->k_mean * K->k_mean) : K->k_std * K->k_std;
+    P.min_present = (int)((1.0 - opts->missing_tol) * (double)nk);
+    P.kmean_zero = (K->k_mean == 0.0);
+    P.has_mask = opts->has_mask;
+    P.raw_xcorr = opts->raw_xcorr;
+    P.nobs_full = opts->nobs_full;
+    // tables: K_corr, K_mask, K2_mask as float64
+    const size_t tbytes = (size_t)3 * nk * sizeof(double);
+    std::vector<double> h((size_t)3 * nk, 0.0);
+    for (int i = 0; i < nk; ++i) {
+        h[i] = K->k_corr[i];
+        if (opts->has_mask) {
+            h[nk + i] = K->k_mask[i];
+            h[2 * nk + i] = K->k2_mask[i];
+        }
+    }
+    KtabRing &ring = g_ring;
+    const int slot = ring.next;
+    ring.next = (ring.next + 1) % 8;
+    if (ring.cap[slot] < tbytes) {
+        if (ring.buf[slot]) cudaFree(ring.buf[slot]);
+        ring.buf[slot] = nullptr;
+        ring.cap[slot] = 0;
+        CS_CUDA(cudaMalloc(&ring.buf[slot], tbytes));
+        ring.cap[slot] = tbytes;
+    }
+    CS_CUDA(cudaMemcpyAsync(ring.buf[slot], h.data(), tbytes, cudaMemcpyHostToDevice, st));
+    CS_CUDA(cudaStreamSynchronize(st));  // `h` is pageable and local
+    WideParams Wp;
+    Wp.img = d_img;
+    Wp.pitch = Li->pitch;
+    Wp.dense = Li->dense;
+    Wp.dlo = Li->dense ? 0 : Li->dlo;
+    Wp.dhi = Li->dense ? 0 : Li->dhi;
+    Wp.kc = (const double *)ring.buf[slot];
+    Wp.km = Wp.kc + nk;
+    Wp.k2m = Wp.km + nk;
+    const int nrows = oy1 - oy0;
+    const int Wo = P.odhi - P.odlo + 1, ncols = ox1 - ox0;
+    const int per_row = Wo < ncols ? Wo : ncols;
+    dim3 grid((unsigned)(nrows < (1 << 20) ? nrows : (1 << 20)), (unsigned)((per_row + 7) / 8 > 64 ? 64 : (per_row + 7) / 8));
+    if (opts->has_mask)
+        pearson_wide<true><<<grid, 256, 0, st>>>(P, Wp);
+    else
+        pearson_wide<false><<<grid, 256, 0, st>>>(P, Wp);
+    CS_LAUNCHED();
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
 // plan_only: stop after the tiling has been chosen and report the tile height
 static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel_desc *K,
                         const cs_pearson_opts *opts, int32_t oy0, int32_t oy1, int32_t ox0,
@@ -828,11 +987,20 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
                "cs_pearson_f32: null argument");
     CS_REQUIRE(K->kh >= 1 && K->kw >= 3 && (K->kh & 1) && (K->kw & 1),
                "kernel shape must be odd (got %dx%d)", K->kh, K->kw);
-    CS_REQUIRE(K->kh <= 31 && K->kw <= 31, "kernel %dx%d too large (31x31 at most)", K->kh, K->kw);
+    CS_REQUIRE(K->kh <= 255 && K->kw <= 255, "kernel %dx%d too large (255x255 at most)", K->kh,
+               K->kw);
     CS_REQUIRE(oy1 > oy0 && ox1 > ox0, "empty output region");
     const int kh = (K->kh - 1) / 2, kw = (K->kw - 1) / 2;
     CS_REQUIRE(oy0 - kh >= 0 && oy1 + kh <= Li->rows && ox0 - kw >= 0 && ox1 + kw <= Li->cols,
                "output region needs windows outside the image");
+    if (K->kh > 31 || K->kw > 31) {
+        if (plan_only) {
+            if (tile_rows_out) *tile_rows_out = 32;
+            return CS_OK;
+        }
+        return pearson_wide_launch(Li, d_img, K, opts, oy0, oy1, ox0, ox1, odlo, odhi, Lo, d_out,
+                                   d_nobs, st);
+    }
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
