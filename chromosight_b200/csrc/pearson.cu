@@ -5,21 +5,24 @@
 // matrix coordinates), possibly one of several column chunks.  The input tile
 // ((TR+KH-1) rows x IC columns, matrix coordinates) is fetched with ONE TMA box
 // load out of the skewed band (the row stride of the tensor map is `pitch`, see
-// cs_layout).  Then, all in shared memory:
-//   pivot    sampled mean of the tile (any pivot is algebraically exact; a good one
-//            keeps the float32 products small);
-//   phase A  one thread per column walks down the tile: band fix-up (out-of-band
-//            aliases -> 0), NaN sentinels -> bit array (warp ballot) + value 0, shift by
-//            the pivot, vertical sliding sums over KH rows in float64 (sum S', sum S'^2,
-//            missing count) -> V;
-//   main     each thread owns a 4x4 block of windows: per input row one conflict-free
-//            LDS.128 sweep of its 20-pixel segment feeds up to 4 x 4 x KW FMAs issued as
-//            packed fma.rn.f32x2 (two windows per instruction, kernel taps pre-duplicated
-//            in shared memory) -- no mask work in this loop;
-//   epilogue per window: horizontal KW-sums of V, the masked kernel sums from the bit
-//            array (missing pixels of a footprint grouped into rectangles, summed through
-//            2-D prefix tables of K and K^2 in float64, exact), the reference's formulas in
-//            float64, one float32 score.
+// cs_layout); the kernel tables arrive by a bulk copy on the same mbarrier.  Then,
+// all in shared memory:
+//   fix-up   one warp per tile row: out-of-band aliases and the declared strip -> 0, NaN
+//            sentinels -> bit array + value 0 (per-row keep words, branch-free);
+//   per thread, a block of RU x RT = 2 x 8 windows (footprint 18 x 24 pixels for 17 x 17):
+//   pivot    mean of the middle footprint row; all sums are taken on S - pivot (exact
+//            algebra, keeps float32 accurate);
+//   FMA pass per input row one LDS.128 sweep of the 24-pixel segment, then per window 9
+//            packed fma.rn.f32x2 whose two halves collect alternate taps (aligned register
+//            pairs: no shuffles, no duplicated taps) -- no mask work in this loop;
+//   sums     packed column sums of S - pivot and its square over KH rows, then KW-wide
+//            sliding sums along the row;
+//   epilogue per window: masked kernel sums and the missing count from the bit array
+//            (missing pixels of a footprint grouped into rectangles, summed through 2-D
+//            prefix tables of K and K^2 in float64, exact), the reference's formulas in
+//            float64, one float32 score (+ uint16 observation count); ill-conditioned
+//            windows are redone in float64 from the tile by the whole warp.
+// Kernels wider than 31 columns take pearson_wide (one warp per window, float64).
 // No tensor cores: this is a CUDA-core stencil (BASELINE.json north_star).
 #include <stdlib.h>
 #include <vector>
