@@ -55,6 +55,7 @@ struct PearsonParams {
     const float *ftab;
     const double *dtab;
     int n_ftab, n_dtab, tab_bytes;
+    unsigned long long *cnt;  // CS_DEBUG_COUNT: statistics of the mask code (experiments)
     int dbg;  // CS_DEBUG_SKIP bit mask (timing experiments only): see the kernel
     double q, sumKp, sumKp2, ksum, k2sum, kmean, kstd, thr, invN, vK0;
     int min_present, kmean_zero, has_mask, raw_xcorr, nobs_full;
@@ -621,6 +622,21 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     okb |= (((2u << thi) - 1u) & ~((1u << tlo) - 1u)) << (u * RT);
             }
         }
+        if (P.cnt && MASK && any) {
+            constexpr unsigned long long FWM2 = (XW >= 64) ? ~0ull : ((1ull << XW) - 1ull);
+            atomicAdd(&P.cnt[0], 1ull);                       // blocks
+            if (bor) atomicAdd(&P.cnt[1], 1ull);              // blocks with any missing pixel
+            if (ng > 0) atomicAdd(&P.cnt[2], 1ull);           // blocks with groups
+            if (ng > kMaxGroups) atomicAdd(&P.cnt[3], 1ull);  // blocks on the row-by-row path
+            atomicAdd(&P.cnt[4], (unsigned long long)ng);     // groups
+            for (int k = 0; k < min(ng, kMaxGroups); ++k) {
+                const unsigned long long gp = grpS[k * nthr + tid];
+                if ((gp & ((1ull << 40) - 1ull)) == (FWM2 & ~colfull)) atomicAdd(&P.cnt[5], 1ull);  // full rows
+                atomicAdd(&P.cnt[6], (unsigned long long)((int)(gp >> 48) - (int)((gp >> 40) & 255)));  // rows in groups
+            }
+            if (colfull) atomicAdd(&P.cnt[7], 1ull);          // blocks with full columns
+        }
+        if (P.dbg & 512) bor = 0ull;  // timing experiment: summary computed, window sums skipped
 #pragma unroll 1
         for (int u = 0; u < RU; ++u) {
             const int Y = Yg + u;
@@ -642,14 +658,15 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 }
                 if (MASK && wok && ((unsigned)(bor >> t) & KWMASK)) {        // [sec:rects]
                     // columns missing over the whole footprint: whole kernel columns
-                    const unsigned cbw = (unsigned)(colfull >> t) & KWMASK;
+                    const unsigned cbw = (P.dbg & 1024) ? 0u : ((unsigned)(colfull >> t) & KWMASK);
                     nmiss += KH * __popc(cbw);
                     for (unsigned c = cbw; c; c &= c - 1) {
                         const int j = __ffs(c) - 1;
                         sKm += Kcol[j];
                         sKm2 += K2col[j];
                     }
-                    if (ng <= kMaxGroups) {
+                    if (P.dbg & 2048) {
+                    } else if (ng <= kMaxGroups) {
                         // remaining missing pixels as rectangles: rows [i0, i1) x runs of taps
                         for (int k = 0; k < ng; ++k) {
                             const unsigned long long gp = grpS[k * nthr + tid];
@@ -1237,6 +1254,13 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
     P.kmean_zero = (K->k_mean == 0.0);
     P.has_mask = opts->has_mask;
     P.dbg = getenv("CS_DEBUG_SKIP") ? atoi(getenv("CS_DEBUG_SKIP")) : 0;
+    P.cnt = nullptr;
+    static unsigned long long *g_cnt = nullptr;
+    if (getenv("CS_DEBUG_COUNT")) {
+        if (!g_cnt) cudaMalloc(&g_cnt, 16 * sizeof(unsigned long long));
+        cudaMemsetAsync(g_cnt, 0, 16 * sizeof(unsigned long long), st);
+        P.cnt = g_cnt;
+    }
     P.raw_xcorr = opts->raw_xcorr;
     P.nobs_full = opts->nobs_full;
 
@@ -1260,9 +1284,18 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
             return CS_ERR_CUDA;
         }
     }
-    if (opts->has_mask)
-        return launch_mask<true>(K->kw, tmap, P, (int)grid_ll, threads, smem, st);
-    return launch_mask<false>(K->kw, tmap, P, (int)grid_ll, threads, smem, st);
+    int lrc = opts->has_mask ? launch_mask<true>(K->kw, tmap, P, (int)grid_ll, threads, smem, st)
+                             : launch_mask<false>(K->kw, tmap, P, (int)grid_ll, threads, smem, st);
+    if (P.cnt && lrc == CS_OK) {
+        unsigned long long h[16];
+        cudaMemcpyAsync(h, P.cnt, sizeof(h), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        fprintf(stderr,
+                "mask stats: blocks %llu, with missing %llu, with groups %llu, row-by-row %llu, groups "
+                "%llu (full rows %llu, rows in groups %llu), blocks with full columns %llu\n",
+                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+    }
+    return lrc;
 }
 
 extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_kernel_desc *K,
