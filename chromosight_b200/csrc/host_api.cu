@@ -9,6 +9,7 @@
 // calls do no allocation.
 #include <stdlib.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <mutex>
 #include <thread>
@@ -95,7 +96,16 @@ static void memcpy_mt(void *dst, const void *src, size_t n) {
     const size_t kMin = 4u << 20;
     static const int maxt = [] {
         const char *e = getenv("CS_COPY_THREADS");
-        return (e && atoi(e) > 0) ? atoi(e) : 3;
+        if (e && atoi(e) > 0) return atoi(e);
+        int n = 3;
+        // the ranks of one box share its cores
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (const char *w = getenv("LOCAL_WORLD_SIZE"))
+            if (atoi(w) > 1 && hw) {
+                const int share = (int)hw / (2 * atoi(w));
+                n = share < 1 ? 1 : (share < n ? share : n);
+            }
+        return n;
     }();
     int nt = (int)(n / kMin);
     if (nt > maxt) nt = maxt;
@@ -737,6 +747,50 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
         }
     } evguard{ev_tot, ev_emit, ev_up};
 
+    // The p-value matrix owns a second copy of the column indices (the two returned matrices
+    // share no storage).  It is made on the host, by a helper thread that follows the
+    // downloads slab by slab, instead of crossing PCIe twice: the download is the floor of
+    // this call and the indices are a sixth of it.  CS_HOST_INDEX_COPY=0 restores the DMA.
+    bool host_ix2 = A.pval;
+    if (const char *e = getenv("CS_HOST_INDEX_COPY"))
+        if (atoi(e) == 0) host_ix2 = false;
+    struct IxCopier {
+        std::vector<cudaEvent_t> ev;          // slab's index download has landed
+        std::vector<int64_t> off, cnt;
+        std::atomic<int> n_enq{0};
+        std::atomic<bool> stop{false};
+        std::thread th;
+        ~IxCopier() {
+            stop.store(true);
+            if (th.joinable()) th.join();
+            for (auto e : ev) cudaEventDestroy(e);
+        }
+    } ixc;
+    if (host_ix2) {
+        ixc.ev.resize(nslab);
+        ixc.off.assign(nslab, 0);
+        ixc.cnt.assign(nslab, 0);
+        for (int i = 0; i < nslab; ++i)
+            CS_CUDA(cudaEventCreateWithFlags(&ixc.ev[i], cudaEventDisableTiming));
+        const int dev = c->device;
+        int32_t *src = (int32_t *)h_ix, *dst = (int32_t *)h_ix2;
+        IxCopier *ic = &ixc;
+        const int ns = nslab;
+        ixc.th = std::thread([ic, src, dst, dev, ns] {
+            cudaSetDevice(dev);
+            for (int k = 0; k < ns; ++k) {
+                while (ic->n_enq.load(std::memory_order_acquire) <= k) {
+                    if (ic->stop.load()) return;
+                    std::this_thread::sleep_for(std::chrono::microseconds(20));
+                }
+                if (ic->cnt[k] == 0) continue;
+                if (cudaEventSynchronize(ic->ev[k]) != cudaSuccess) return;
+                // a few threads: one core does not keep up with the DMA it follows
+                memcpy_mt(dst + ic->off[k], src + ic->off[k], (size_t)ic->cnt[k] * sizeof(int32_t));
+            }
+        });
+    }
+
     // CS_TRACE=1: per-slab timeline on stderr (host clock and device events, ms from the start)
     const bool trace = getenv("CS_TRACE") != nullptr;
     auto now = [] {
@@ -831,15 +885,22 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
             const size_t o = (size_t)base, n = (size_t)nnz_k;
             CS_CUDA(cudaMemcpyAsync((int32_t *)h_ix + o, (int32_t *)s->r_indices.p + o,
                                     n * sizeof(int32_t), cudaMemcpyDeviceToHost, st_d));
+            if (host_ix2) {
+                CS_CUDA(cudaEventRecord(ixc.ev[k], st_d));
+                ixc.off[k] = (int64_t)o;
+                ixc.cnt[k] = (int64_t)n;
+            }
             CS_CUDA(cudaMemcpyAsync((double *)h_d + o, (double *)s->r_data.p + o, n * sizeof(double),
                                     cudaMemcpyDeviceToHost, st_d));
             if (A.pval) {
                 CS_CUDA(cudaMemcpyAsync((double *)h_p + o, (double *)s->r_p.p + o,
                                         n * sizeof(double), cudaMemcpyDeviceToHost, st_d));
-                CS_CUDA(cudaMemcpyAsync((int32_t *)h_ix2 + o, (int32_t *)s->r_indices.p + o,
-                                        n * sizeof(int32_t), cudaMemcpyDeviceToHost, st_d));
+                if (!host_ix2)
+                    CS_CUDA(cudaMemcpyAsync((int32_t *)h_ix2 + o, (int32_t *)s->r_indices.p + o,
+                                            n * sizeof(int32_t), cudaMemcpyDeviceToHost, st_d));
             }
         }
+        if (host_ix2) ixc.n_enq.store(k + 1, std::memory_order_release);
         if (trace) CS_CUDA(cudaEventRecord(tev[4 * k + 3], st_d));
         base += nnz_k;
         return CS_OK;
@@ -930,6 +991,7 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
     CS_CUDA(cudaEventRecord(s->ev[5], st));
     CS_CUDA(cudaStreamSynchronize(st));
     CS_CUDA(cudaStreamSynchronize(st_d));
+    if (host_ix2 && ixc.th.joinable()) ixc.th.join();  // the last slab's index copy
     if (trace) {
         fprintf(stderr, "slab  host:enq0  enq1  fin_wait0 fin_wait1 | dev:compute0 compute1 d2h0 d2h1 (ms)\n");
         for (int k = 0; k < nslab; ++k) {
@@ -960,7 +1022,7 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
     res->ms_kernels = ms;  // upload, kernels and most of the download overlap inside this span
     res->h2d_bytes = (int64_t)s->h2d_bytes;
     res->d2h_bytes = (int64_t)(n_ip * sizeof(int64_t) * (A.pval ? 2 : 1) +
-                               (size_t)base * (sizeof(int32_t) * (A.pval ? 2 : 1) +
+                               (size_t)base * (sizeof(int32_t) * ((A.pval && !host_ix2) ? 2 : 1) +
                                                sizeof(double) * (A.pval ? 2 : 1)));
     return CS_OK;
 }
