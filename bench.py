@@ -241,6 +241,8 @@ def run_b200(a, kernel):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line (NCCL prints its version banner there otherwise)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     n, D, k = a.n, a.max_dist, kernel.shape[0]
     kw = call_kwargs(D)

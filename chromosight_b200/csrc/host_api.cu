@@ -752,8 +752,12 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
     // downloads slab by slab, instead of crossing PCIe twice: the download is the floor of
     // this call and the indices are a sixth of it.  CS_HOST_INDEX_COPY=0 restores the DMA.
     bool host_ix2 = A.pval;
-    if (const char *e = getenv("CS_HOST_INDEX_COPY"))
-        if (atoi(e) == 0) host_ix2 = false;
+    // several ranks on one box compete for host memory bandwidth: measured at 2 ranks, the host
+    // copy costs more than the DMA it saves (36 ms instead of 26 ms per call), so it is used by
+    // single-rank processes only
+    if (const char *w = getenv("LOCAL_WORLD_SIZE"))
+        if (atoi(w) > 1) host_ix2 = false;
+    if (const char *e = getenv("CS_HOST_INDEX_COPY")) host_ix2 = A.pval && atoi(e) != 0;
     struct IxCopier {
         std::vector<cudaEvent_t> ev;          // slab's index download has landed
         std::vector<int64_t> off, cnt;
