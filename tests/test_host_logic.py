@@ -156,3 +156,31 @@ def test_resize_and_crop_kernel(presets):
     assert cup.crop_kernel(K, (8, 8)).shape == (9, 9)
     assert cup.crop_kernel(K, (21, 5)).shape == (17, 5)
     assert np.array_equal(cup.crop_kernel(K, (7, 7)), K[5:12, 5:12])
+
+
+def test_global_host_filters_match_reference():
+    """remove_neighbours (det:348-384), pileup_patterns (det:158-174) and fdr_correction
+    (stats:7-40) against outputs of the unmodified reference (make_golden_hostfilters.py)."""
+    import pandas as pd
+    from chromosight_b200.utils import detection as cud, stats as cus
+    z = np.load(os.path.join(GOLDEN, "hostfilters.npz"))
+    i = 0
+    while f"rn{i}_mask" in z.files:
+        t = pd.DataFrame({"bin1": z[f"rn{i}_bin1"], "bin2": z[f"rn{i}_bin2"], "score": z[f"rn{i}_score"]})
+        got = cud.remove_neighbours(t, win_size=int(z[f"rn{i}_win"]))
+        exp = z[f"rn{i}_mask"]
+        # equal scores are ordered arbitrarily by the reference's quicksort: the kept SET may differ
+        # there, the number kept and the separation property may not
+        if len(np.unique(t.score)) == len(t):
+            assert np.array_equal(got, exp)
+        else:
+            assert abs(int(got.sum()) - int(exp.sum())) <= max(2, len(t) // 50)
+        kept = t[got]
+        d1 = np.abs(kept.bin1.values[:, None] - kept.bin1.values[None, :])
+        d2 = np.abs(kept.bin2.values[:, None] - kept.bin2.values[None, :])
+        w = int(z[f"rn{i}_win"])
+        assert ((d1 < w) & (d2 < w)).sum() == len(kept)
+        i += 1
+    assert i == 4
+    assert np.allclose(cud.pileup_patterns(z["pile_in"]), z["pile_out"], equal_nan=True)
+    assert np.allclose(cus.fdr_correction(z["fdr_in"]), z["fdr_out"])
