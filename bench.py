@@ -86,35 +86,63 @@ def call_kwargs(D):
 
 
 # --------------------------------------------------------------------------- CPU arms
-def _cpu_slab(args):
-    """One CPU unit of work: detrended slab-map -> Pearson map with the scipy.sparse port."""
-    rows, D, kernel, seed, reps = args
+def _cpu_impl():
+    """The CPU implementation that is timed: the UNMODIFIED reference (oracle/_ref, copied from
+    /root/reference by oracle/make_ref.sh; kind "reference") when it travelled with the
+    repository, else the scipy.sparse port of its algorithm (oracle/sparse_port.py; kind "port",
+    measured 1.3-1.6x faster than the reference)."""
+    from oracle import ref_loader
+    ref = ref_loader.load()
+    if ref is not None:
+        det, pre, _ = ref
+        return ("reference", lambda raw, detect, md: pre.detrend(raw, detectable_bins=detect, max_dist=md, max_val=10),
+                det.normxcorr2, pre.diag_trim, pre.make_missing_mask)
     from chromosight_b200.utils import preprocessing as hostpre  # host-only helpers (no CUDA)
     from oracle import sparse_port as spt
+    return ("port", lambda raw, detect, md: spt.detrend_sparse(raw, detect, md, 10),
+            spt.normxcorr2_sparse, hostpre.diag_trim, hostpre.make_missing_mask)
+
+
+def _cpu_slab(args):
+    """One CPU unit of work: raw slab-map -> detrend (pre:256-310) -> Pearson map (det:807-914),
+    both timed, with the reference's own code where available."""
+    rows, D, kernel, seed, reps = args
+    import warnings
+    warnings.simplefilter("ignore")
+    kind, detrend, normxcorr2, trim, mask_fn = _cpu_impl()
     k = kernel.shape[0]
     raw, detect = raw_map(rows, D, k, seed)
-    mat = spt.detrend_sparse(raw, detect, D + k, 10)
-    mat, mask = finish_map(mat, detect, D, k, hostpre.diag_trim, hostpre.make_missing_mask)
+    raw = raw.tocsr()
+    t0 = time.perf_counter()
+    mat = detrend(raw, detect, D + k)
+    dt_detrend = time.perf_counter() - t0
+    nnz_raw = int(raw.nnz)
+    mat, mask = finish_map(mat, detect, D, k, trim, mask_fn)
     t0 = time.perf_counter()
     for _ in range(reps):
-        r, p = spt.normxcorr2_sparse(mat, kernel, missing_mask=mask, **call_kwargs(D))
+        r, p = normxcorr2(mat, kernel, missing_mask=mask, **call_kwargs(D))
     dt = (time.perf_counter() - t0) / reps
-    return dt, int(r.nnz)
+    return dt, int(r.nnz), kind, dt_detrend, nnz_raw
 
 
 def cpu_baseline(rows, D, kernel):
     from chromosight_b200 import synthetic
-    dt, _ = _cpu_slab((rows, D, kernel, 0, 1))
+    dt, _, kind, dt_detrend, nnz_raw = _cpu_slab((rows, D, kernel, 0, 1))
     nwin = synthetic.n_windows(rows, D)
-    return {"value": nwin / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"first-principles slab of the same generator: {rows} rows x D={D}, "
-                      f"{nwin} windows, {dt:.2f} s, oracle/sparse_port.normxcorr2_sparse "
-                      f"(scipy.sparse port of det:917-1131), host has {os.cpu_count()} cpus"}
+    what = ("chromosight.utils.detection.normxcorr2 of the unmodified reference (oracle/_ref)" if kind == "reference"
+            else "oracle/sparse_port.normxcorr2_sparse (scipy.sparse port of det:917-1131)")
+    return {"value": nwin / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"one slab of the same generator, as the reference processes a chromosome (one core per "
+                      f"sub-matrix, cli:738-755): {rows} rows x D={D}, {nwin} windows, {dt:.2f} s, {what}; "
+                      f"host has {os.cpu_count()} cpus",
+            "detrend": {"value": nnz_raw / dt_detrend, "unit": "nnz/s", "seconds": dt_detrend, "nnz": nnz_raw,
+                        "what": "preprocessing.detrend (pre:256-310) of the same slab, 1 core"}}
 
 
 def run_reference(a, kernel):
-    """--impl reference: the scipy.sparse port on every host core; a step = one slab of
-    `ref_rows` rows per worker."""
+    """--impl reference: the reference's own CPU implementation of the path on every host core;
+    a step = one slab of `ref_rows` rows per worker (the reference parallelises over
+    sub-matrices with one core each, cli:738-755)."""
     import multiprocessing as mp
     from chromosight_b200 import synthetic
     rank = int(os.environ.get("RANK", "0"))
@@ -131,11 +159,13 @@ def run_reference(a, kernel):
             pool.map(_cpu_slab, jobs)
         t0 = time.perf_counter()
         per_step = []
+        kind = "port"
         for _ in range(a.steps):
-            # input generation runs in the workers but outside the port's own timer: a step
-            # costs the slowest worker's normxcorr2 time
+            # input generation runs in the workers but outside the timer: a step costs the
+            # slowest worker's normxcorr2 time
             res = pool.map(_cpu_slab, jobs)
             per_step.append(max(r[0] for r in res))
+            kind = res[0][2]
         wall = time.perf_counter() - t0
     t = float(np.sum(per_step))
     value = cores * nwin_slab * a.steps / t
@@ -145,7 +175,7 @@ def run_reference(a, kernel):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": workload_config(a, kernel, sample=f"{cores} slabs of {rows} rows per step"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": f"{cores} workers x {rows}-row slab ({nwin_slab} windows each) per "
                                    f"step, max-over-workers time per step, wall {wall:.1f} s incl. input generation"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

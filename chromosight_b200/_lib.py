@@ -9,8 +9,11 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchromosight_b200.so")
+# CHROMOSIGHT_B200_LIB selects another build of the same ABI (the -DCS_ABLATE build that
+# scripts/k1_ablate.sh times)
+LIB_PATH = os.environ.get("CHROMOSIGHT_B200_LIB") or os.path.join(_HERE, "libchromosight_b200.so")
 
+ABI_VERSION = 2  # CS_ABI_VERSION of include/chromosight_b200.h
 CS_OK = 0
 CS_ERR_INVALID = -1
 CS_ERR_CUDA = -2
@@ -36,9 +39,21 @@ class KernelDesc(C.Structure):
     ]
 
 
+class GeoMask(C.Structure):
+    _fields_ = [
+        ("d_row_bits", C.c_void_p), ("d_col_bits", C.c_void_p),
+        ("mask_dlo", C.c_int32), ("mask_dhi", C.c_int32),
+        ("mat_y0", C.c_int32), ("mat_y1", C.c_int32),
+        ("mat_x0", C.c_int32), ("mat_x1", C.c_int32),
+        ("margin_mode", C.c_int32), ("top_x1", C.c_int32), ("right_y0", C.c_int32),
+        ("strip_dlo", C.c_int32), ("strip_dhi", C.c_int32),
+        ("fill_value", C.c_float),
+    ]
+
+
 class PearsonOpts(C.Structure):
     _fields_ = [
-        ("has_mask", C.c_int32),
+        ("mask_mode", C.c_int32),
         ("missing_tol", C.c_double),
         ("xcorr_threshold", C.c_double),
         ("raw_xcorr", C.c_int32),
@@ -46,7 +61,8 @@ class PearsonOpts(C.Structure):
         ("tile_rows", C.c_int32),
         ("out_row_shift", C.c_int32),
         ("out_col_shift", C.c_int32),
-        ("strip_dlo", C.c_int32), ("strip_dhi", C.c_int32),
+        ("nmiss_bytes", C.c_int32),
+        ("geo", GeoMask),
     ]
 
 
@@ -79,6 +95,8 @@ class Normxcorr2Args(C.Structure):
         ("indptr", C.c_void_p), ("indices", C.c_void_p), ("data", C.c_void_p),
         ("has_mask", C.c_int32),
         ("mask_indptr", C.c_void_p), ("mask_indices", C.c_void_p),
+        ("miss_row", C.c_void_p), ("miss_col", C.c_void_p),
+        ("mask_dlo", C.c_int32), ("mask_dhi", C.c_int32),
         ("sym_upper", C.c_int32), ("max_dist", C.c_int32),
         ("full", C.c_int32), ("pval", C.c_int32),
         ("trim_to_max_dist", C.c_int32),
@@ -122,8 +140,8 @@ _PROTOS = {
     "cs_layout_band": (C.c_int, [C.POINTER(Layout), C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "cs_layout_dense": (C.c_int, [C.POINTER(Layout), C.c_int32, C.c_int32]),
     "cs_image_fill_f32": (C.c_int, [C.POINTER(Layout), _P, _P, _P, _P, C.c_int32, C.c_int32,
-                                     C.c_int32, C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int32,
-                                     C.c_int32, C.c_int32, _P, _P]),
+                                     C.c_int32, C.c_int32, C.c_int32, _P, _P, C.POINTER(GeoMask),
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "cs_pearson_f32": (C.c_int, [C.POINTER(Layout), _P, C.POINTER(KernelDesc), C.POINTER(PearsonOpts),
                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.POINTER(Layout), _P, _P, _P]),
@@ -133,13 +151,14 @@ _PROTOS = {
     "cs_scan_scratch": (C.c_int64, [C.c_int32]),
     "cs_scores_count": (C.c_int, [C.POINTER(Layout), _P, C.c_int32, C.c_int32, _P,
                                    C.POINTER(C.c_int64), _P]),
-    "cs_scores_emit": (C.c_int, [C.POINTER(Layout), _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P,
-                                  _P, _P, _P]),
+    "cs_scores_emit": (C.c_int, [C.POINTER(Layout), _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  _P, _P, _P, _P, _P]),
     "cs_scores_candidates": (C.c_int, [C.POINTER(Layout), _P, _P, C.c_int32, C.c_int32, C.c_int32,
-                                        C.c_float, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
+                                        C.c_int32, C.c_float, _P, C.c_int64, _P, C.POINTER(C.c_int64),
+                                        _P]),
     "cs_window_gather": (C.c_int, [C.POINTER(GatherArgs), _P, C.c_int64, _P, _P, _P]),
-    "cs_scores_lookup": (C.c_int, [C.POINTER(Layout), _P, _P, C.c_int32, C.c_int32, C.c_int32, _P,
-                                    C.c_int64, _P, _P, _P]),
+    "cs_scores_lookup": (C.c_int, [C.POINTER(Layout), _P, _P, C.c_int32, C.c_int32, C.c_int32,
+                                    C.c_int32, _P, C.c_int64, _P, _P, _P]),
     "cs_session_validate": (C.c_int, [C.c_void_p, _P, C.c_int64, _P, _P, C.c_int32, C.c_double,
                                        C.c_double, C.c_int32, _P, _P, _P, _P]),
     "cs_distance_law": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P]),
@@ -183,7 +202,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.cs_version() != 1:
+    if lib.cs_version() != ABI_VERSION:
         raise BackendError("libchromosight_b200.so ABI version mismatch")
     _lib = lib
     return lib

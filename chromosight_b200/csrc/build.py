@@ -30,36 +30,41 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _compile(src, verbose):
-    obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+def _compile(src, verbose, ablate=False):
+    obj = os.path.join(HERE, "build", src.replace(".cu", ".abl.o" if ablate else ".o"))
     deps = [os.path.join(HERE, src)] + [os.path.join(HERE, h) for h in HEADERS]
     if not _stale(obj, deps):
         return obj, ""
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(HERE, src), "-o", obj]
+    cmd = [NVCC] + FLAGS + (["-DCS_ABLATE"] if ablate else []) + (["-Xptxas", "-v"] if verbose else []) \
+        + ["-c", os.path.join(HERE, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
     return obj, r.stderr
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, ablate=False):
+    """ablate=True builds libchromosight_b200_ablate.so: the same library with the phase
+    switches and counters of the timing experiments compiled in (-DCS_ABLATE); the release
+    library has none of them."""
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     if force:
         for f in os.listdir(os.path.join(HERE, "build")):
             os.remove(os.path.join(HERE, "build", f))
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        results = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
+        results = list(ex.map(lambda s: _compile(s, verbose, ablate), SOURCES))
     objs = [o for o, _ in results]
     if verbose:
         for _, log in results:
             sys.stderr.write(log)
-    if force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lpthread"]
+    lib = LIB.replace(".so", "_ablate.so") if ablate else LIB
+    if force or _stale(lib, objs):
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, ablate="--ablate" in sys.argv))

@@ -38,9 +38,9 @@ int fill_begin(const cs_layout *L, float *d_img, int32_t n_rows, int32_t n_cols,
 int fill_rows(const cs_layout *L, float *d_img, const int64_t *d_sig_indptr,
               const int32_t *d_sig_indices, const double *d_sig_data, int32_t n_rows, int32_t r0,
               int32_t r1, int32_t row_off, int32_t col_off, int32_t mask_mode,
-              const int64_t *d_mask_indptr, const int32_t *d_mask_indices, int32_t sym_upper,
-              int32_t max_dist, int32_t frame_mk, int32_t frame_nk, int32_t *d_err,
-              cudaStream_t st);
+              const int64_t *d_mask_indptr, const int32_t *d_mask_indices, const cs_geo_mask *geo,
+              int32_t sym_upper, int32_t max_dist, int32_t frame_mk, int32_t frame_nk,
+              int32_t *d_err, cudaStream_t st);
 // rows [r0, r1) of the score image: per-row counts + chunk-local scan (the slab total lands in
 // d_total), then the offsets (+ base) added, then the CSR entries written
 // (scratch_off: the range's part of the scan scratch, scan_slot(r0, k) for the k-th range)
@@ -50,8 +50,9 @@ int scores_count_rows(const cs_layout *Lo, const float *d_out, int32_t dmin, int
 int scores_finish_rows(const cs_layout *Lo, int64_t *d_indptr, int32_t r0, int32_t r1,
                        int64_t base, cudaStream_t st, int32_t scratch_off = 0);
 int32_t scan_slot(int32_t r0, int32_t k);
-int scores_emit_rows(const cs_layout *Lo, const float *d_out, const uint16_t *d_nobs,
-                     int32_t nobs_const, int32_t dmin, int32_t dmax, const int64_t *d_indptr,
+int scores_emit_rows(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
+                     int32_t nmiss_bytes, int32_t n_window, int32_t dmin, int32_t dmax,
+                     const int64_t *d_indptr,
                      int32_t r0, int32_t r1, int32_t *d_indices, double *d_data, double *d_log10p,
                      cudaStream_t st);
 
@@ -66,6 +67,19 @@ __host__ __device__ __forceinline__ long long img_index(int pitch, int dlo, int 
 }
 
 __device__ __forceinline__ float quiet_nan_f() { return __int_as_float(0x7fc00000); }
+
+// The missing-count plane written by the Pearson kernel (uint8 or uint16, NULL = none):
+// number of observations of the window at element i (det:1110-1121).
+struct NmissPlane {
+    const void *p;
+    int bytes, n_window;
+};
+__device__ __forceinline__ float nobs_at(const NmissPlane &M, long long i) {
+    if (!M.p) return (float)M.n_window;
+    const int nm = M.bytes == 2 ? (int)((const unsigned short *)M.p)[i]
+                                : (int)((const unsigned char *)M.p)[i];
+    return (float)(M.n_window - nm);
+}
 
 // stats.py:74-81: log10 of the two-sided p-value of a Pearson coefficient through Fisher's z,
 // log10(2 Phi(-|z|)) = log10(erfc(|z| / sqrt 2)), z = atanh(r) sqrt(n - 3).

@@ -104,7 +104,7 @@ struct LookupView {
 // scores (and log10 p-values) of the score image at UNPADDED coordinates; pixels outside
 // the image, the stored band or dmin..dmax read as 0 (absent from the sparse map)
 __global__ void lookup_scores(LookupView S, const float *__restrict__ sc,
-                              const unsigned short *__restrict__ nobs, int nobs_const,
+                              NmissPlane nobs,
                               const int32_t *__restrict__ coords, long long P,
                               double *__restrict__ score, double *__restrict__ log10p) {
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < P;
@@ -118,7 +118,7 @@ __global__ void lookup_scores(LookupView S, const float *__restrict__ sc,
             const long long i = (long long)y * S.pitch + (x - (S.dense ? 0 : S.dlo));
             const float vf = sc[i];
             v = (double)vf;
-            if (vf != 0.f) lp = log10_pval(vf, nobs ? (float)nobs[i] : (float)nobs_const);
+            if (vf != 0.f) lp = log10_pval(vf, nobs_at(nobs, i));
         }
         score[p] = v;
         if (log10p) log10p[p] = lp;
@@ -160,8 +160,8 @@ extern "C" int cs_window_gather(const cs_gather_args *a, const int32_t *d_coords
     return CS_OK;
 }
 
-extern "C" int cs_scores_lookup(const cs_layout *Lo, const float *d_out, const uint16_t *d_nobs,
-                                int32_t nobs_const, int32_t dmin, int32_t dmax,
+extern "C" int cs_scores_lookup(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
+                                int32_t nmiss_bytes, int32_t n_window, int32_t dmin, int32_t dmax,
                                 const int32_t *d_coords, int64_t n_coords, double *d_score,
                                 double *d_log10p, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -178,7 +178,7 @@ extern "C" int cs_scores_lookup(const cs_layout *Lo, const float *d_out, const u
     S.dmax = dmax;
     long long blocks = (n_coords + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    lookup_scores<<<(int)blocks, 256, 0, st>>>(S, d_out, d_nobs, nobs_const, d_coords,
+    lookup_scores<<<(int)blocks, 256, 0, st>>>(S, d_out, NmissPlane{d_nmiss, nmiss_bytes, n_window}, d_coords,
                                                (long long)n_coords, d_score, d_log10p);
     CS_LAUNCHED();
     CS_CUDA(cudaGetLastError());

@@ -54,7 +54,8 @@ struct HostCtx {
     cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<PinBlock> pool;
-    std::mutex mu;
+    std::mutex mu;       // device work of one call phase
+    std::mutex pool_mu;  // the pinned-block pool (alloc and release come from any thread)
 };
 
 static std::mutex g_ctx_mu;
@@ -165,6 +166,7 @@ static int h2d_staged(HostCtx *c, cudaStream_t st, void *dst, const void *src, s
 }
 
 static int pin_alloc(HostCtx *c, size_t bytes, void **out) {
+    std::lock_guard<std::mutex> plk(c->pool_mu);
     if (bytes == 0) bytes = 16;
     PinBlock *best = nullptr;
     for (PinBlock &b : c->pool)
@@ -196,12 +198,14 @@ static void pin_release_unlocked(void *p) { pin_release(p); }
 static void pin_release(void *p) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(g_ctx_mu);
-    for (HostCtx *c : g_ctx)
+    for (HostCtx *c : g_ctx) {
+        std::lock_guard<std::mutex> plk(c->pool_mu);
         for (PinBlock &b : c->pool)
             if (b.p == p) {
                 b.busy = false;
                 return;
             }
+    }
 }
 
 }  // namespace cs
@@ -233,10 +237,14 @@ struct cs_session {
     cudaStream_t user_st = nullptr;
     bool use_user_st = false;
     cudaStream_t stream() const { return use_user_st ? user_st : c->st; }
+    std::mutex call_mu;  // one host-to-host call (upload, run, download) at a time
     // device-resident inputs, images and results of this session
     DevBuf sig_indptr, sig_indices, sig_data, m_indptr, m_indices, img, out, nobs, r_indptr,
         r_indices, r_data, r_p, err, g_coords, g_win, g_flag, g_score, g_p, g_vrow, g_vcol, f_work,
-        f_rec;
+        f_rec, geo_bits;
+    cs_geo_mask geo;       // has_mask == 2: the mask's geometry in image coordinates
+    int pearson_mask = 0;  // mask mode handed to the Pearson kernel (0 / 1 NaN sentinels / 2 geometric)
+    int nmiss_bytes = 1;   // element size of the missing-count plane
     bool uploaded = false, ran = false, empty = false;
     cs_normxcorr2_args a;
     std::vector<double> k_corr, k_mask, k2_mask;
@@ -268,7 +276,7 @@ extern "C" void cs_session_destroy(cs_session *s) {
                       &s->img,        &s->out,         &s->nobs,     &s->r_indptr, &s->r_indices,
                       &s->r_data,     &s->r_p,         &s->err,      &s->g_coords, &s->g_win,
                       &s->g_flag,     &s->g_score,     &s->g_p,      &s->g_vrow,   &s->g_vcol,
-                      &s->f_work,     &s->f_rec};
+                      &s->f_work,     &s->f_rec,       &s->geo_bits};
     cudaSetDevice(s->c->device);
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -312,6 +320,8 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
     s->a.data = nullptr;
     s->a.mask_indptr = nullptr;
     s->a.mask_indices = nullptr;
+    s->a.miss_row = nullptr;
+    s->a.miss_col = nullptr;
 
     const int mk = K.kh, nk = K.kw;
     const int kh = (mk - 1) / 2, kw = (nk - 1) / 2;
@@ -405,7 +415,65 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
     if ((rc = s->sig_indices.ensure((size_t)s->nnz_in * sizeof(int32_t)))) return rc;
     if ((rc = s->sig_data.ensure((size_t)s->nnz_in * sizeof(double)))) return rc;
     s->nnz_m = 0;
-    if (a->has_mask) {
+    CS_REQUIRE(a->has_mask >= 0 && a->has_mask <= 2, "cs_session_upload: bad has_mask");
+    memset(&s->geo, 0, sizeof(s->geo));
+    const bool wide = K.kh > 31 || K.kw > 31;
+    s->pearson_mask = a->has_mask == 2 ? (wide ? 1 : 2) : a->has_mask;
+    {
+        // missing counts that can go with a non-zero score: N - max(min_present, 1) at most
+        const int N = K.kh * K.kw;
+        const int min_present = (int)((1.0 - a->missing_tol) * (double)N);
+        s->nmiss_bytes = (N - (min_present > 1 ? min_present : 1) <= 255) ? 1 : 2;
+    }
+    size_t geo_h2d = 0;
+    if (a->has_mask == 2) {
+        CS_REQUIRE(a->miss_row && a->miss_col, "geometric mask: missing-bin vectors missing");
+        // bit vectors over image rows / columns, 4 zero words of padding on both sides
+        const int nwr = (H + 31) / 32 + 8, nwc = (W + 31) / 32 + 8;
+        std::vector<uint32_t> hb((size_t)nwr + nwc, 0u);
+        uint32_t *hr = hb.data() + 4, *hc = hb.data() + nwr + 4;
+        for (int r = 0; r < a->rows; ++r)
+            if (a->miss_row[r]) hr[(r + pr) >> 5] |= 1u << ((r + pr) & 31);
+        for (int cidx = 0; cidx < a->cols; ++cidx)
+            if (a->miss_col[cidx]) hc[(cidx + pc) >> 5] |= 1u << ((cidx + pc) & 31);
+        if ((rc = s->geo_bits.ensure(hb.size() * sizeof(uint32_t)))) return rc;
+        // pageable source: staged by the runtime before the call returns
+        CS_CUDA(cudaMemcpyAsync(s->geo_bits.p, hb.data(), hb.size() * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, st));
+        geo_h2d = hb.size() * sizeof(uint32_t);
+        cs_geo_mask &g = s->geo;
+        g.d_row_bits = (const uint32_t *)s->geo_bits.p + 4;
+        g.d_col_bits = (const uint32_t *)s->geo_bits.p + nwr + 4;
+        const bool banded = a->sym_upper && a->max_dist >= 0;
+        const int big_k = mk > nk ? mk : nk;
+        long long lo = a->mask_dlo, hi = a->mask_dhi;
+        if (a->full && banded) {
+            // pre:452-454: the mask is diag-trimmed to max_dist + max(mk, nk) before framing
+            if (lo < 0) lo = 0;
+            if (hi > (long long)a->max_dist + big_k) hi = (long long)a->max_dist + big_k;
+        }
+        const long long lim = 1ll << 29;
+        lo += pc - pr, hi += pc - pr;
+        g.mask_dlo = (int)(lo < -lim ? -lim : (lo > lim ? lim : lo));
+        g.mask_dhi = (int)(hi < -lim ? -lim : (hi > lim ? lim : hi));
+        g.mat_y0 = pr, g.mat_y1 = pr + a->rows, g.mat_x0 = pc, g.mat_x1 = pc + a->cols;
+        g.margin_mode = a->full ? (banded ? 1 : 2) : 0;
+        if (banded) {
+            const int max_n = a->max_dist + nk, max_m = a->max_dist + mk;
+            g.top_x1 = pc + (max_n < a->cols ? max_n : a->cols);   // pre:461-463, 477
+            g.right_y0 = H - (max_m + 1) > 0 ? H - (max_m + 1) : 0;  // pre:475
+        }
+        g.strip_dlo = 0, g.strip_dhi = -1;
+        if (a->full && a->sym_upper) {
+            g.strip_dlo = -big_k, g.strip_dhi = -1;  // pre:483-497
+            // the strip is missing whatever the bins say, and no window of the kept upper
+            // triangle reaches below it: the two descriptions stay disjoint
+            if (g.mask_dlo < 0) g.mask_dlo = 0;
+        }
+        // detrended maps have mean 1 on every diagonal; the wide kernel wants NaN sentinels
+        g.fill_value = wide ? __builtin_nanf("") : 1.0f;
+    }
+    if (a->has_mask == 1) {
         CS_REQUIRE(a->mask_indptr && a->mask_indices, "mask arrays missing");
         s->nnz_m = a->mask_indptr[a->rows];
         if ((rc = s->m_indptr.ensure(n_ip * sizeof(int64_t)))) return rc;
@@ -416,7 +484,7 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
     if ((rc = s->out.ensure((size_t)s->Lo.n_elems * sizeof(float)))) return rc;
     s->want_nobs = a->pval && a->has_mask && a->full && !a->raw_xcorr;
     if (s->want_nobs)
-        if ((rc = s->nobs.ensure((size_t)s->Lo.n_elems * sizeof(uint16_t)))) return rc;
+        if ((rc = s->nobs.ensure((size_t)s->Lo.n_elems * (size_t)s->nmiss_bytes))) return rc;
     if ((rc = s->r_indptr.ensure((n_ip + (size_t)cs_scan_scratch(a->rows)) * sizeof(int64_t))))
         return rc;
     if ((rc = s->err.ensure(64))) return rc;
@@ -432,7 +500,8 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
             return rc;
     }
     s->h2d_bytes = n_ip * sizeof(int64_t) + (size_t)s->nnz_in * (sizeof(int32_t) + sizeof(double));
-    if (a->has_mask) {
+    s->h2d_bytes += geo_h2d;
+    if (a->has_mask == 1) {
         if ((rc = h2d_staged(c, st, s->m_indptr.p, a->mask_indptr, n_ip * sizeof(int64_t)))) return rc;
         if (s->nnz_m > 0 && !skip_payload)
             if ((rc = h2d_staged(c, st, s->m_indices.p, a->mask_indices,
@@ -443,6 +512,21 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
     CS_CUDA(cudaEventRecord(s->ev[1], st));
     s->uploaded = true;
     return CS_OK;
+}
+
+// Pearson options of a session's call
+static void session_pearson_opts(const cs_session *s, cs_pearson_opts *po) {
+    const cs_normxcorr2_args &a = s->a;
+    memset(po, 0, sizeof(*po));
+    po->mask_mode = s->pearson_mask;
+    po->missing_tol = a.missing_tol;
+    po->xcorr_threshold = a.raw_xcorr ? a.xcorr_threshold : 1e-4;
+    po->raw_xcorr = a.raw_xcorr;
+    po->nobs_full = s->want_nobs ? 1 : 0;
+    po->out_row_shift = s->pr;
+    po->out_col_shift = s->pc;
+    po->nmiss_bytes = s->nmiss_bytes;
+    po->geo = s->geo;
 }
 
 extern "C" int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a) {
@@ -469,34 +553,19 @@ extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
     CS_CUDA(cudaEventRecord(s->ev[2], st));
     int rc = cs_image_fill_f32(&s->Li, (float *)s->img.p, (const int64_t *)s->sig_indptr.p,
                                (const int32_t *)s->sig_indices.p, (const double *)s->sig_data.p,
-                               a.rows, a.cols, s->pr, s->pc, a.has_mask ? 1 : 0,
+                               a.rows, a.cols, s->pr, s->pc, a.has_mask,
                                (const int64_t *)s->m_indptr.p, (const int32_t *)s->m_indices.p,
-                               a.sym_upper, a.max_dist, a.full ? K.kh : 0, a.full ? K.kw : 0,
-                               (int32_t *)s->err.p, st);
+                               &s->geo, a.sym_upper, a.max_dist, a.full ? K.kh : 0,
+                               a.full ? K.kw : 0, (int32_t *)s->err.p, st);
     if (rc) return rc;
     // scores outside the computed set must read as 0
     CS_CUDA(cudaMemsetAsync(s->out.p, 0, (size_t)s->Lo.n_elems * sizeof(float), st));
     cs_pearson_opts po;
-    memset(&po, 0, sizeof(po));
-    po.has_mask = a.has_mask;
-    po.missing_tol = a.missing_tol;
-    po.xcorr_threshold = a.raw_xcorr ? a.xcorr_threshold : 1e-4;
-    po.raw_xcorr = a.raw_xcorr;
-    po.nobs_full = s->want_nobs ? 1 : 0;
-    po.out_row_shift = s->pr;
-    po.out_col_shift = s->pc;
-    po.strip_dlo = 0;
-    po.strip_dhi = -1;
-    if (a.has_mask && a.full && a.sym_upper) {
-        // nan_subdiag (image.cu) blanks the big_k diagonals below the main one (pre:483-497)
-        const int big_k = K.kh > K.kw ? K.kh : K.kw;
-        po.strip_dlo = -big_k;
-        po.strip_dhi = -1;
-    }
+    session_pearson_opts(s, &po);
     CS_CUDA(cudaEventRecord(s->ev[3], st));
     rc = cs_pearson_f32(&s->Li, (const float *)s->img.p, &K, &po, s->oy0, s->oy1, s->ox0, s->ox1,
                         s->od_lo, s->od_hi, &s->Lo, (float *)s->out.p,
-                        s->want_nobs ? (uint16_t *)s->nobs.p : nullptr, st);
+                        s->want_nobs ? s->nobs.p : nullptr, st);
     if (rc) return rc;
     CS_CUDA(cudaEventRecord(s->ev[4], st));
     int64_t nnz = 0;
@@ -521,7 +590,7 @@ extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
         if ((rc = s->r_p.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(double)))) return rc;
     if (nnz > 0) {
         rc = cs_scores_emit(&s->Lo, (const float *)s->out.p,
-                            s->want_nobs ? (const uint16_t *)s->nobs.p : nullptr, K.kh * K.kw,
+                            s->want_nobs ? s->nobs.p : nullptr, s->nmiss_bytes, K.kh * K.kw,
                             -(1 << 30), (1 << 30), (const int64_t *)s->r_indptr.p,
                             (int32_t *)s->r_indices.p, (double *)s->r_data.p,
                             a.pval ? (double *)s->r_p.p : nullptr, st);
@@ -566,7 +635,7 @@ extern "C" int cs_session_candidates(cs_session *s, float threshold, int32_t dmi
         return CS_OK;
     }
     return cs_scores_candidates(&s->Lo, (const float *)s->out.p,
-                                s->want_nobs ? (const uint16_t *)s->nobs.p : nullptr,
+                                s->want_nobs ? s->nobs.p : nullptr, s->nmiss_bytes,
                                 s->a.kernel.kh * s->a.kernel.kw, dmin, dmax, threshold, d_cand, cap,
                                 d_count, n_host, s->stream());
 }
@@ -814,27 +883,13 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
     } tevguard{tev};
 
     CS_CUDA(cudaEventRecord(s->ev[2], st));
-    rc = fill_begin(&s->Li, (float *)s->img.p, A.rows, A.cols, A.has_mask ? 1 : 0, A.sym_upper,
+    rc = fill_begin(&s->Li, (float *)s->img.p, A.rows, A.cols, A.has_mask, A.sym_upper,
                     A.max_dist, A.full ? K.kh : 0, A.full ? K.kw : 0, (int32_t *)s->err.p, st);
     if (rc) return rc;
     CS_CUDA(cudaMemsetAsync(s->out.p, 0, (size_t)s->Lo.n_elems * sizeof(float), st));
     cs_pearson_opts po;
-    memset(&po, 0, sizeof(po));
-    po.has_mask = A.has_mask;
-    po.missing_tol = A.missing_tol;
-    po.xcorr_threshold = A.raw_xcorr ? A.xcorr_threshold : 1e-4;
-    po.raw_xcorr = A.raw_xcorr;
-    po.nobs_full = s->want_nobs ? 1 : 0;
-    po.out_row_shift = s->pr;
-    po.out_col_shift = s->pc;
-    po.strip_dlo = 0;
-    po.strip_dhi = -1;
-    if (A.has_mask && A.full && A.sym_upper) {
-        const int big_k = K.kh > K.kw ? K.kh : K.kw;
-        po.strip_dlo = -big_k;
-        po.strip_dhi = -1;
-    }
-    const uint16_t *nb = s->want_nobs ? (const uint16_t *)s->nobs.p : nullptr;
+    session_pearson_opts(s, &po);
+    const void *nb = s->want_nobs ? s->nobs.p : nullptr;
     int32_t TRp = 32;
     if ((rc = cs_pearson_tile_rows(&s->Li, &K, &po, s->oy0, s->oy1, s->ox0, s->ox1, s->od_lo,
                                    s->od_hi, &TRp)))
@@ -876,7 +931,7 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
                                    scan_slot(cr0, k));
         if (r) return r;
         if (nnz_k > 0) {
-            r = scores_emit_rows(&s->Lo, (const float *)s->out.p, nb, K.kh * K.kw, -(1 << 30),
+            r = scores_emit_rows(&s->Lo, (const float *)s->out.p, nb, s->nmiss_bytes, K.kh * K.kw, -(1 << 30),
                                  1 << 30, (const int64_t *)s->r_indptr.p, cr0, cr1,
                                  (int32_t *)s->r_indices.p, (double *)s->r_data.p,
                                  A.pval ? (double *)s->r_p.p : nullptr, st_e);
@@ -938,7 +993,7 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
                                      (size_t)(e1 - e0) * sizeof(double), poll)))
                     return rc;
             }
-            if (A.has_mask) {
+            if (A.has_mask == 1) {
                 const int64_t m0 = a->mask_indptr[up_end], m1 = a->mask_indptr[need];
                 if (m1 > m0)
                     if ((rc = h2d_staged(c, st_h, (int32_t *)s->m_indices.p + m0,
@@ -951,17 +1006,17 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
             CS_CUDA(cudaStreamWaitEvent(st, ev_up[k], 0));
             rc = fill_rows(&s->Li, (float *)s->img.p, (const int64_t *)s->sig_indptr.p,
                            (const int32_t *)s->sig_indices.p, (const double *)s->sig_data.p, A.rows,
-                           up_end, need, s->pr, s->pc, A.has_mask ? 1 : 0,
+                           up_end, need, s->pr, s->pc, A.has_mask,
                            (const int64_t *)s->m_indptr.p, (const int32_t *)s->m_indices.p,
-                           A.sym_upper, A.max_dist, A.full ? K.kh : 0, A.full ? K.kw : 0,
-                           (int32_t *)s->err.p, st);
+                           &s->geo, A.sym_upper, A.max_dist, A.full ? K.kh : 0,
+                           A.full ? K.kw : 0, (int32_t *)s->err.p, st);
             if (rc) return rc;
             up_end = need;
         }
         if (Y1 > Y0) {
             rc = cs_pearson_f32(&s->Li, (const float *)s->img.p, &K, &po, Y0, Y1, s->ox0, s->ox1,
                                 s->od_lo, s->od_hi, &s->Lo, (float *)s->out.p,
-                                s->want_nobs ? (uint16_t *)s->nobs.p : nullptr, st);
+                                s->want_nobs ? s->nobs.p : nullptr, st);
             if (rc) return rc;
         }
         // the slab total is written straight into pinned host memory (UVA): a D2H copy on this
@@ -1047,6 +1102,9 @@ extern "C" int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *re
             cache.push_back(s);
         }
     }
+    // the cached session holds the inputs and results of ONE call: concurrent callers on the
+    // same device take turns for the whole upload / run / download sequence
+    std::lock_guard<std::mutex> call_lk(s->call_mu);
     // big calls go through the slab pipeline
     bool uploaded = false;
     {
@@ -1158,9 +1216,9 @@ extern "C" int cs_session_validate(cs_session *s, const int32_t *host_coords, in
             }
             return CS_OK;
         }
-        const uint16_t *nb = s->want_nobs ? (const uint16_t *)s->nobs.p : nullptr;
+        const void *nb = s->want_nobs ? s->nobs.p : nullptr;
         // scores of the trimmed map (det:270) at the padded-map coordinates
-        rc = cs_scores_lookup(&s->Lo, (const float *)s->out.p, nb, km * kn, inter ? -(1 << 30) : 0,
+        rc = cs_scores_lookup(&s->Lo, (const float *)s->out.p, nb, s->nmiss_bytes, km * kn, inter ? -(1 << 30) : 0,
                               inter ? (1 << 30) : score_dmax, d_conv, n_coords,
                               (double *)s->g_score.p, nullptr, st);
         if (rc) return rc;
@@ -1173,7 +1231,7 @@ extern "C" int cs_session_validate(cs_session *s, const int32_t *host_coords, in
             CS_CUDA(cudaStreamSynchronize(st));
             CS_CUDA(cudaMemcpyAsync(s->g_coords.p, host_coords, (size_t)n_coords * 2 * sizeof(int32_t),
                                     cudaMemcpyHostToDevice, st));
-            rc = cs_scores_lookup(&s->Lo, (const float *)s->out.p, nb, km * kn, -(1 << 30), 1 << 30,
+            rc = cs_scores_lookup(&s->Lo, (const float *)s->out.p, nb, s->nmiss_bytes, km * kn, -(1 << 30), 1 << 30,
                                   d_pad, n_coords, (double *)s->g_score.p, (double *)s->g_p.p, st);
             if (rc) return rc;
             CS_CUDA(cudaMemcpyAsync(host_log10p, s->g_p.p, (size_t)n_coords * sizeof(double),

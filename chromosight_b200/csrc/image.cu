@@ -3,8 +3,10 @@
 //   detection.py:979-991      zero frame of (mk-1, nk-1) pixels around the signal
 //   preprocessing.py:404-498  frame_missing_mask (margins + sub-diagonals)
 //   preprocessing.py:501-532  check_missing_mask (signal must be 0 under the mask)
-// Missing pixels are stored as NaN sentinels in the image itself, so the Pearson
-// kernel reads ONE array (4 B / pixel) whatever the mask looks like.
+// A pixel mask (mask_mode 1) is stored as NaN sentinels in the image itself; the geometric
+// mask of make_missing_mask / frame_missing_mask (mask_mode 2) as a constant fill value under
+// the missing rows, columns and strip (the Pearson kernel gets the geometry itself).  Either
+// way the Pearson kernel reads ONE array (4 B / pixel).
 #include <stdarg.h>
 #include "common.cuh"
 
@@ -38,8 +40,8 @@ __device__ __forceinline__ long long at(const FillParams &F, int Y, int X) {
 // one warp per CSR row
 __global__ void scatter_signal(FillParams F, const int64_t *__restrict__ indptr,
                                const int32_t *__restrict__ indices,
-                               const double *__restrict__ data, int r0, int r1, float *img,
-                               int *err) {
+                               const double *__restrict__ data, int r0, int r1, int ignore_below,
+                               float *img, int *err) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int r = r0 + blockIdx.x * wpb + (threadIdx.x >> 5); r < r1; r += gridDim.x * wpb) {
@@ -52,7 +54,8 @@ __global__ void scatter_signal(FillParams F, const int64_t *__restrict__ indptr,
                 // duplicates of a non-canonical CSR would need atomics; scipy sums them
                 // before we get here (host side calls sum_duplicates)
                 img[at(F, Y, X)] = (float)v;
-            } else if (v != 0.0) {
+            } else if (v != 0.0 && !(ignore_below && !F.dense && X - Y < F.dlo)) {
+                // (sym_upper: pixels below the stored band cannot reach a kept score, det:1098)
                 atomicAdd(err + 1, 1);
             }
         }
@@ -104,6 +107,74 @@ __global__ void nan_subdiag(FillParams F, int big_k, int Y0, int Y1, float *img,
         const float v = img[k];
         if (v != 0.f && v == v) atomicAdd(err, 1);
         img[k] = quiet_nan_f();
+    }
+}
+
+// geometric mask (mask_mode 2): one warp per image row writes the fill value under the missing
+// strip, the row's missing pixels (the whole flagged band of a missing row, the missing columns
+// of any other row) and the frame's margins; signal found under the mask is counted (pre:516-523)
+struct GeoFill {
+    const uint32_t *rbits, *cbits;
+    int mlo, mhi, my0, my1, mx0, mx1, margin_mode, top_x1, right_y0, sdlo, sdhi;
+    float fill;
+};
+
+__device__ __forceinline__ void fill_span(const FillParams &F, int Y, int xa, int xb, float fill,
+                                          bool check, int lane, float *img, int *err) {
+    // columns [xa, xb] of row Y that are stored
+    if (xa < 0) xa = 0;
+    if (xb > F.cols - 1) xb = F.cols - 1;
+    if (!F.dense) {
+        xa = max(xa, Y + F.dlo);
+        xb = min(xb, Y + F.dhi);
+    }
+    for (int X = xa + lane; X <= xb; X += 32) {
+        const long long i = at(F, Y, X);
+        if (check) {
+            const float v = img[i];
+            if (v != 0.f) atomicAdd(err, 1);
+        }
+        img[i] = fill;
+    }
+}
+
+__global__ void geo_fill(FillParams F, GeoFill Gm, int Y0, int Y1, float *img, int *err) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int Y = Y0 + blockIdx.x * wpb + (threadIdx.x >> 5); Y < Y1; Y += gridDim.x * wpb) {
+        const bool inrow = Y >= Gm.my0 && Y < Gm.my1;
+        // strip first (the margins written below may overlap it and are not checked)
+        if (Gm.sdhi >= Gm.sdlo) fill_span(F, Y, Y + Gm.sdlo, Y + Gm.sdhi, Gm.fill, true, lane, img, err);
+        if (inrow) {
+            long long lo = (long long)Y + Gm.mlo, hi = (long long)Y + Gm.mhi;
+            int xlo = (int)(lo < Gm.mx0 ? Gm.mx0 : lo), xhi = (int)(hi > Gm.mx1 - 1 ? Gm.mx1 - 1 : hi);
+            if ((Gm.rbits[Y >> 5] >> (Y & 31)) & 1u) {
+                fill_span(F, Y, xlo, xhi, Gm.fill, true, lane, img, err);
+            } else {
+                if (!F.dense) {
+                    xlo = max(xlo, Y + F.dlo);
+                    xhi = min(xhi, Y + F.dhi);
+                }
+                for (int X = xlo + lane; X <= xhi; X += 32)
+                    if ((Gm.cbits[X >> 5] >> (X & 31)) & 1u) {
+                        const long long i = at(F, Y, X);
+                        const float v = img[i];
+                        if (v != 0.f) atomicAdd(err, 1);
+                        img[i] = Gm.fill;
+                    }
+            }
+        }
+        if (Gm.margin_mode == 2) {
+            if (!inrow) {
+                fill_span(F, Y, 0, F.cols - 1, Gm.fill, false, lane, img, err);
+            } else {
+                fill_span(F, Y, 0, Gm.mx0 - 1, Gm.fill, false, lane, img, err);
+                fill_span(F, Y, Gm.mx1, F.cols - 1, Gm.fill, false, lane, img, err);
+            }
+        } else if (Gm.margin_mode == 1) {
+            if (Y < Gm.my0) fill_span(F, Y, 0, Gm.top_x1 - 1, Gm.fill, false, lane, img, err);
+            if (Y >= Gm.right_y0) fill_span(F, Y, Gm.mx1, F.cols - 1, Gm.fill, false, lane, img, err);
+        }
     }
 }
 
@@ -210,9 +281,9 @@ int fill_begin(const cs_layout *L, float *d_img, int32_t n_rows, int32_t n_cols,
 int fill_rows(const cs_layout *L, float *d_img, const int64_t *d_sig_indptr,
               const int32_t *d_sig_indices, const double *d_sig_data, int32_t n_rows,
               int32_t r0, int32_t r1, int32_t row_off, int32_t col_off, int32_t mask_mode,
-              const int64_t *d_mask_indptr, const int32_t *d_mask_indices, int32_t sym_upper,
-              int32_t max_dist, int32_t frame_mk, int32_t frame_nk, int32_t *d_err,
-              cudaStream_t st) {
+              const int64_t *d_mask_indptr, const int32_t *d_mask_indices, const cs_geo_mask *geo,
+              int32_t sym_upper, int32_t max_dist, int32_t frame_mk, int32_t frame_nk,
+              int32_t *d_err, cudaStream_t st) {
     if (r1 <= r0) return CS_OK;
     FillParams F = make_fill(L, row_off, col_off);
     const int threads = 256;
@@ -221,7 +292,7 @@ int fill_rows(const cs_layout *L, float *d_img, const int64_t *d_sig_indptr,
     if (grid > 148 * 16) grid = 148 * 16;
     if (d_sig_indptr) {
         scatter_signal<<<grid, threads, 0, st>>>(F, d_sig_indptr, d_sig_indices, d_sig_data, r0, r1,
-                                                 d_img, d_err);
+                                                 sym_upper ? 1 : 0, d_img, d_err);
         CS_LAUNCHED();
     }
     if (mask_mode == 1) {
@@ -244,6 +315,26 @@ int fill_rows(const cs_layout *L, float *d_img, const int64_t *d_sig_indptr,
             }
         }
     }
+    if (mask_mode == 2) {
+        GeoFill Gm;
+        Gm.rbits = (const uint32_t *)geo->d_row_bits;
+        Gm.cbits = (const uint32_t *)geo->d_col_bits;
+        Gm.mlo = geo->mask_dlo, Gm.mhi = geo->mask_dhi;
+        Gm.my0 = geo->mat_y0, Gm.my1 = geo->mat_y1, Gm.mx0 = geo->mat_x0, Gm.mx1 = geo->mat_x1;
+        Gm.margin_mode = geo->margin_mode;
+        Gm.top_x1 = geo->top_x1, Gm.right_y0 = geo->right_y0;
+        Gm.sdlo = geo->strip_dlo, Gm.sdhi = geo->strip_dhi;
+        Gm.fill = geo->fill_value;
+        // image rows of these signal rows; the first / last call also covers the frame
+        const int Y0 = r0 == 0 ? 0 : r0 + row_off;
+        const int Y1 = r1 == n_rows ? L->rows : r1 + row_off;
+        int g = (Y1 - Y0 + wpb - 1) / wpb;
+        if (g > 148 * 16) g = 148 * 16;
+        if (g > 0) {
+            geo_fill<<<g, threads, 0, st>>>(F, Gm, Y0, Y1, d_img, d_err);
+            CS_LAUNCHED();
+        }
+    }
     CS_CUDA(cudaGetLastError());
     return CS_OK;
 }
@@ -254,18 +345,20 @@ extern "C" int cs_image_fill_f32(const cs_layout *L, float *d_img, const int64_t
                                  const int32_t *d_sig_indices, const double *d_sig_data,
                                  int32_t n_rows, int32_t n_cols, int32_t row_off, int32_t col_off,
                                  int32_t mask_mode, const int64_t *d_mask_indptr,
-                                 const int32_t *d_mask_indices, int32_t sym_upper,
-                                 int32_t max_dist, int32_t frame_mk, int32_t frame_nk,
-                                 int32_t *d_err, void *stream) {
+                                 const int32_t *d_mask_indices, const cs_geo_mask *geo,
+                                 int32_t sym_upper, int32_t max_dist, int32_t frame_mk,
+                                 int32_t frame_nk, int32_t *d_err, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CS_REQUIRE(L && d_img && d_err, "cs_image_fill_f32: null argument");
     CS_REQUIRE(n_rows + row_off <= L->rows && n_cols + col_off <= L->cols,
                "signal does not fit in the image");
     if (mask_mode == 1) CS_REQUIRE(d_mask_indptr && d_mask_indices, "mask arrays missing");
+    if (mask_mode == 2)
+        CS_REQUIRE(geo && geo->d_row_bits && geo->d_col_bits, "geometric mask: bit vectors missing");
     int rc = fill_begin(L, d_img, n_rows, n_cols, mask_mode, sym_upper, max_dist, frame_mk, frame_nk,
                         d_err, st);
     if (rc) return rc;
     return fill_rows(L, d_img, d_sig_indptr, d_sig_indices, d_sig_data, n_rows, 0, n_rows, row_off,
-                     col_off, mask_mode, d_mask_indptr, d_mask_indices, sym_upper, max_dist,
+                     col_off, mask_mode, d_mask_indptr, d_mask_indices, geo, sym_upper, max_dist,
                      frame_mk, frame_nk, d_err, st);
 }

@@ -6,9 +6,9 @@
 // ((TR+KH-1) rows x IC columns, matrix coordinates) is fetched with ONE TMA box
 // load out of the skewed band (the row stride of the tensor map is `pitch`, see
 // cs_layout); the kernel tables arrive by a bulk copy on the same mbarrier.  Then,
-// all in shared memory:
-//   fix-up   one warp per tile row: out-of-band aliases and the declared strip -> 0, NaN
-//            sentinels -> bit array + value 0 (per-row keep words, branch-free);
+// all in shared memory / registers:
+//   fix-up   out-of-band aliases of the box (two triangles) -> 0; with a pixel mask
+//            (MODE_BITS) also NaN sentinels -> bit array + value 0;
 //   per thread, a block of RU x RT = 2 x 8 windows (footprint 18 x 24 pixels for 17 x 17):
 //   pivot    mean of the middle footprint row; all sums are taken on S - pivot (exact
 //            algebra, keeps float32 accurate);
@@ -17,11 +17,17 @@
 //            pairs: no shuffles, no duplicated taps) -- no mask work in this loop;
 //   sums     packed column sums of S - pivot and its square over KH rows, then KW-wide
 //            sliding sums along the row;
-//   epilogue per window: masked kernel sums and the missing count from the bit array
-//            (missing pixels of a footprint grouped into rectangles, summed through 2-D
-//            prefix tables of K and K^2 in float64, exact), the reference's formulas in
-//            float64, one float32 score (+ uint16 observation count); ill-conditioned
-//            windows are redone in float64 from the tile by the whole warp.
+//   mask     (MODE_GEO: the mask of make_missing_mask / frame_missing_mask, given as bit
+//            vectors of missing rows and columns + a diagonal band + a missing strip)
+//            missing count and the two mask-kernel sums of every window from row / column
+//            prefix tables of the centred kernel: one table look-up per missing row or
+//            column of the footprint, none for the 70 % of blocks without any;
+//   score    the reference's formulas in centred float32 algebra, eight windows at a time
+//            (independent chains), float32 score + uint8 missing count, 16-byte stores;
+//   exact    windows the float32 path cannot decide (ill-conditioned, a 1e-4 threshold of
+//            xcorr2 within rounding distance, footprint on the frame's margins or -- with
+//            a pixel mask -- on a missing pixel) are redone by the whole warp in float64
+//            from the tile with the per-pixel mask predicate.
 // Kernels wider than 31 columns take pearson_wide (one warp per window, float64).
 // No tensor cores: this is a CUDA-core stencil (BASELINE.json north_star).
 #include <stdlib.h>
@@ -37,6 +43,8 @@ constexpr int RT = 8;  // window columns per thread
 __host__ __device__ __forceinline__ int skew_shift(int g) { return (RU * g) & ~3; }
 constexpr int kSkewSlack = (RU % 4) ? 3 : 0;  // columns lost to that rounding
 
+enum { MODE_NOMASK = 0, MODE_BITS = 1, MODE_GEO = 2 };  // = cs_pearson_opts.mask_mode
+
 struct PearsonParams {
     // image
     int rows, cols, dlo, dhi, dense;
@@ -49,19 +57,31 @@ struct PearsonParams {
     int KH, KW, KWP2, N;
     // output image
     float *out;
-    unsigned short *nobs;
+    void *nmiss;  // uint8 / uint16 plane (nmiss16) of missing counts, may be null
+    int nmiss16;
     int out_pitch, out_dlo, osy, osx;
-    // tables (device): float part then double part, copied to shared memory by every CTA
-    const float *ftab;
-    const double *dtab;
-    int n_ftab, n_dtab, tab_bytes;
-    unsigned long long *cnt;  // CS_DEBUG_COUNT: statistics of the mask code (experiments)
-    int dbg;  // CS_DEBUG_SKIP bit mask (timing experiments only): see the kernel
-    double q, sumKp, sumKp2, ksum, k2sum, kmean, kstd, thr, invN, vK0;
-    int min_present, kmean_zero, has_mask, raw_xcorr, nobs_full;
-    int sdlo, sdhi, st_base, st_n;  // declared-missing diagonal strip and its tables
+    // tables (device): one linear block copied to shared memory by every CTA
+    const unsigned char *tab;
+    int tab_bytes;
+    const double *dK;  // global, float64: K_corr, K_mask, K2_mask [N each] (exact path)
+    // float32 constants of the centred algebra (K' = K - qf, S' = S - pivot)
+    float qf, sumKp, sumKp2, ksump, k2sump, delta, invN, thr, fillc, escale, den_floor;
+    // float64 constants of the exact path
+    double ksum, k2sum, kmean, kstd, thr_d, invN_d, vK0, sumKc_d;
+    int min_present, kmean_zero, raw_xcorr, nobs_full;
+    // geometric mask (image coordinates)
+    const uint32_t *rbits, *cbits;  // missing image rows / columns inside the matrix
+    int mlo, mhi;                   // diagonals on which a missing bin flags its pixels
+    int my0, my1, mx0, mx1;         // the matrix inside the frame
+    int margin_mode;                // 0 no frame, 1 banded frame (pre:461-477), 2 all four margins
+    int top_x1, right_y0;           // banded frame: top margin columns < top_x1, right margin rows >= right_y0
+    int sdlo, sdhi, st_base, st_n;  // missing diagonal strip (pre:483-497) and its tables
     // shared memory carve-up (bytes)
-    int off_bits, off_K, off_D, off_stat, off_grp, off_bar;
+    int off_bits, off_K, off_PR, off_PC, off_ST, off_rb, off_cb, off_bar;
+#ifdef CS_ABLATE
+    unsigned long long *cnt;  // statistics (windows on the exact path, ...)
+    int dbg;                  // phase switches for timing experiments (results are wrong)
+#endif
 };
 
 // ---------------------------------------------------------------- PTX helpers  // [sec:packedops]
@@ -139,114 +159,93 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
 __device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 __device__ __forceinline__ double thr0(double v, double t) { return fabs(v) < t ? 0.0 : v; }  // [sec:scorefn]
 
-// Squared error amplification above which a window is recomputed in float64: the
+// Squared error amplification above which a window leaves the float32 path: the
 // float32 sums carry ~1e-6 relative error on well-conditioned windows, and the score
-// error grows like amp = f * rms(S') * rms(K') / (sigma_S * sigma_K).
-constexpr double kAmpLimit2 = 9.0;
-// Same for the column sums, which are computed in float64 and rounded once to float32
-// (relative error 6e-8 each): var(S) loses at most 1.8e-7 * amp^2.
-constexpr double kAmpLimitV = 25.0;
+// error grows like amp = rms(S') * rms(K') / (sigma_S * sigma_K).
+constexpr float kAmpLimit2 = 8.0f;
 
-// The reference's formulas (det:1002-1020 no mask, det:1021-1092 masked) from the
-// window sums of the shifted signal S' = S - p and the shifted kernel K' = K_corr - q.
-//   h1, h2    : sum S', sum S'^2 over the N window pixels (missing pixels count as S = 0)
-//   h2_loc    : sum (S' - block pivot)^2, the quantity the float32 product sum was formed on
-//   s3        : sum S' * K'
-//   sKm, sKm2 : sums of the mask kernels (K and K^2) over the missing pixels
-// `redo` is set when the window is too ill-conditioned for the float32 sums.
+// The reference's formulas (det:1002-1020 no mask, det:1021-1092 masked) in float64 from the
+// raw window sums: h1, h2 = sum S, sum S^2 (missing pixels count as S = 0), s3 = sum S * K_corr,
+// nmiss, sKm / sKm2 = sums of the mask kernels (K and K^2) over the missing pixels.
 template <bool MASK>
-__device__ __forceinline__ float score_from_sums(const PearsonParams &P, double p, double h1,
-                                                 double h2, double h2_loc, int nmiss, double s3,
-                                                 double sKm, double sKm2, int &nobs, bool &redo) {
-    const double invN = P.invN;
-    const double m1 = h1 * invN;
-    double A1 = m1 + p;
-    double A2 = fma(h2, invN, fma(2.0 * p, m1, p * p));
-    double A3 = fma(s3 + fma(P.q, h1, p * P.sumKp), invN, p * P.q);
-    nobs = P.N;
-    redo = false;
-    if (P.raw_xcorr) return (float)thr0(A3 * (double)P.N, P.thr);
-    A1 = thr0(A1, P.thr);
-    A2 = thr0(A2, P.thr);
-    A3 = thr0(A3, P.thr);
-    double cov, den2, f2 = 1.0;
+__device__ __forceinline__ float exact_score(const PearsonParams &P, double h1, double h2,
+                                             double s3, int nmiss, double sKm, double sKm2,
+                                             int &nmiss_out) {
+    nmiss_out = 0;
+    if (P.raw_xcorr) return (float)thr0(s3, P.thr_d);
+    const double A1 = thr0(h1 * P.invN_d, P.thr_d);
+    const double A2 = thr0(h2 * P.invN_d, P.thr_d);
+    const double A3 = thr0(s3 * P.invN_d, P.thr_d);
+    double cov, den2;
     bool ok = true;
-    if (!MASK) {
+    if (!MASK || nmiss == 0) {
         const double vS = fma(-A1, A1, A2);
         cov = fma(-A1, P.kmean, A3);
         den2 = vS * P.vK0;
         ok = vS >= 0.0;
     } else {
-        // one branch-free path: with nmiss == 0 these are the unmasked formulas
-        // (f = 1, mK = kernel mean, m2K = mean of K^2)
         const int npres = P.N - nmiss;
-        // 1 / npres: float32 reciprocal + one Newton step (exact to ~1e-15)
-        double inv = (double)__frcp_rn((float)npres);
-        inv = inv * fma(-(double)npres, inv, 2.0);
-        const double f = (double)P.N * inv;
-        f2 = f * f;
-        sKm = thr0(sKm, P.thr);
-        sKm2 = thr0(sKm2, P.thr);
-        const double mK = (P.ksum - sKm) * inv;
-        const double m2K = (P.k2sum - sKm2) * inv;
+        const double f = (double)P.N / (double)npres;
+        sKm = thr0(sKm, P.thr_d);
+        sKm2 = thr0(sKm2, P.thr_d);
+        const double mK = (P.ksum - sKm) / (double)npres;
+        const double m2K = (P.k2sum - sKm2) / (double)npres;
         const double mS = A1 * f;
         const double vS = fma(A2, f, -mS * mS);
         cov = fma(-A1, mK, A3) * f;
         den2 = vS * fma(-mK, mK, m2K);
-        ok = nmiss == 0 || ((npres > 0) && (npres >= P.min_present) && !P.kmean_zero);
-        if (P.nobs_full && nmiss != 0 && npres != 0) nobs = npres;
+        ok = (npres > 0) && (npres >= P.min_present) && !P.kmean_zero;
+        if (P.nobs_full && npres != 0) nmiss_out = nmiss;
     }
     // det:1066,1088-1091: denom = sqrt(den2); |denom| < 1e-10 or NaN -> 0
     float r = 0.f;
     if (ok && den2 >= 1e-20 && den2 < 1e300) {
-        // float32 product sums: conditioned by the spread around the block pivot (h2_loc);
-        // float32-rounded column sums: by the spread around the tile pivot (h2)
-        const double c1 = P.sumKp2 * invN * invN * f2;
-        redo = (h2_loc * c1 > kAmpLimit2 * den2) || (h2 * c1 > kAmpLimitV * den2);
-        r = (float)cov * rsqrtf((float)den2);
-        if (!(fabsf(r) <= 3.0e38f)) r = 0.f;
-        r = fminf(1.f, fmaxf(-1.f, r));
-    } else if (ok && A2 != 0.0 && den2 < 1e-20) {
-        // a non-zero window whose variance vanished: exactly flat, or flat up to the
-        // float32 rounding of the column sums -- let the float64 pass decide
-        redo = true;
+        const double rr = cov / sqrt(den2);
+        r = (float)fmin(1.0, fmax(-1.0, rr));
+        if (!(r == r)) r = 0.f;
     }
     return r;
 }
 
-// 64 bits of the (linear, one bit per tile pixel) missing-pixel bit array from bit `pos` on  // [sec:maskfn]
-__device__ __forceinline__ unsigned long long row_bits(const uint32_t *bits, int pos) {
+// `nb` (<= 64) bits of a bit array (one bit per position, 32 per word) from bit `pos` on
+__device__ __forceinline__ unsigned long long bits64(const uint32_t *bits, int pos) {  // [sec:maskfn]
     const int w = pos >> 5, sh = pos & 31;
     const uint32_t a = bits[w], b = bits[w + 1], c = bits[w + 2];
     const uint32_t lo = __funnelshift_r(a, b, sh), hi = __funnelshift_r(b, c, sh);
     return ((unsigned long long)hi << 32) | lo;
 }
-
-// Missing pixels of a window given as kernel rows [i0, i1) x the set bits of wb: add the
-// sums of the two mask kernels over them.  IK / IK2 are 2-D prefix tables,
-// IK[i][j] = sum of K[i' < i][j' < j], row pitch KW1.
-__device__ __forceinline__ void add_rects(unsigned wb, int i0, int i1, const double *IK,
-                                          const double *IK2, int KW1, double &sKm, double &sKm2) {
-    const double *t0 = IK + i0 * KW1, *t1 = IK + i1 * KW1;
-    const double *u0 = IK2 + i0 * KW1, *u1 = IK2 + i1 * KW1;
-    while (wb) {
-        const int a = __ffs(wb) - 1;
-        const int b = a + __ffs(~(wb >> a)) - 1;  // first zero above a ends the run (< 32 bits)
-        sKm += (t1[b] - t1[a]) - (t0[b] - t0[a]);
-        sKm2 += (u1[b] - u1[a]) - (u0[b] - u0[a]);
-        wb = (b >= 32) ? 0u : (wb >> b) << b;
-    }
+__device__ __forceinline__ uint32_t bits32(const uint32_t *bits, int pos) {
+    const int w = pos >> 5, sh = pos & 31;
+    return __funnelshift_r(bits[w], bits[w + 1], sh);
 }
 
-constexpr int kMaxGroups = 4;  // rectangles of missing pixels per footprint kept in shared memory  // [sec:kernelsetup]
+// per-pixel missing predicate of the geometric mask (image coordinates), SURVEY 3.3
+__device__ __forceinline__ bool geo_missing(const PearsonParams &P, int Y, int X, bool rbit,
+                                            bool cbit) {
+    const int d = X - Y;
+    if (d >= P.sdlo && d <= P.sdhi) return true;  // pre:483-497
+    const bool inside = Y >= P.my0 && Y < P.my1 && X >= P.mx0 && X < P.mx1;
+    if (inside) return (rbit || cbit) && d >= P.mlo && d <= P.mhi;
+    if (P.margin_mode == 2) return true;  // pre:464-466, 479-480
+    if (P.margin_mode == 1)
+        return (Y < P.my0 && X < P.top_x1) ||      // pre:461-463, 477
+               (X >= P.mx1 && Y >= P.right_y0);    // pre:475
+    return false;
+}
 
 // ---------------------------------------------------------------- the kernel
-template <int KW, bool MASK>
+template <int KW, int MODE>
 __global__ void __launch_bounds__(256, 2)
 pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
+    constexpr bool MASK = MODE != MODE_NOMASK;
     constexpr int kw = (KW - 1) / 2;
     constexpr int kwa = (kw + 3) / 4 * 4;
     constexpr int off = kwa - kw;
@@ -256,6 +255,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     constexpr int NP = (KW + 1) / 2;            // tap pairs per kernel row
     static_assert(((off + RT - 1) >> 1) + NP <= 2 * NQ, "tap pairs run past the loaded segment");
     constexpr unsigned KWMASK = (KW == 32) ? 0xffffffffu : ((1u << KW) - 1u);
+    constexpr int KW1 = KW + 1;
 
     extern __shared__ __align__(1024) unsigned char smem[];
     float *__restrict__ tile = reinterpret_cast<float *>(smem);
@@ -264,10 +264,14 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     // zeros (pairs (k0,k1),(k2,k3),... for windows at an even tile column) and the same row
     // shifted right by one (pairs (0,k0),(k1,k2),... for windows at an odd tile column)
     const float *__restrict__ Ktab = reinterpret_cast<const float *>(smem + P.off_K);
-    const double *__restrict__ Dt = reinterpret_cast<const double *>(smem + P.off_D);
-    float *__restrict__ statS = reinterpret_cast<float *>(smem + P.off_stat);
-    unsigned long long *__restrict__ grpS =
-        reinterpret_cast<unsigned long long *>(smem + P.off_grp);
+    // prefix tables of the centred mask kernels (K' = K_mask - q, K2' = K2_mask - 2 q K_mask + q^2)
+    // as (K', K2') pairs: PR[i][j] = sum over j' < j of row i, PC[j][i] = sum over i' < i of column j
+    const float2 *__restrict__ PR = reinterpret_cast<const float2 *>(smem + P.off_PR);
+    const float2 *__restrict__ PC = reinterpret_cast<const float2 *>(smem + P.off_PC);
+    // the missing strip per window diagonal: (count, sum K', sum K2', -)
+    const float4 *__restrict__ ST = reinterpret_cast<const float4 *>(smem + P.off_ST);
+    uint32_t *__restrict__ rbw = reinterpret_cast<uint32_t *>(smem + P.off_rb);
+    uint32_t *__restrict__ cbw = reinterpret_cast<uint32_t *>(smem + P.off_cb);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + P.off_bar);
 
     const int tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
@@ -285,51 +289,58 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     xb += RT * ch * P.NBc;
     const int TXp = xb - kwa;  // X' of tile column 0
     const int TY = Y0 - kh;    // image row of tile row 0
+    const int TX = TXp + P.dlo;  // image column of tile column 0
     const int IC = P.IC, IR = P.IR, NW = P.NW;
 
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_barrier_init();
         fence_proxy_async();
-        // the tile (2-D tensor box) and the kernel tables (one linear block: float part, then
-        // float64 part) arrive through the same barrier
+        // the tile (2-D tensor box) and the kernel tables (one linear block) arrive through
+        // the same barrier
         mbar_expect_tx(bar, (uint32_t)(IC * IR * sizeof(float)) + (uint32_t)P.tab_bytes);
         tma_load_2d(tile, &tmap, bar, TXp, TY);
-        bulk_load_1d(smem + P.off_K, P.ftab, (uint32_t)P.tab_bytes, bar);
+        bulk_load_1d(smem + P.off_K, P.tab, (uint32_t)P.tab_bytes, bar);
     }
-    if (MASK)
+    if (MODE == MODE_BITS)
         for (int i = tid; i < NW; i += nthr) bits[i] = 0u;
+    if (MODE == MODE_GEO) {
+        // missing-row / missing-column bits of the tile: bit k of the array = tile row / column k
+        // (the global vectors carry zero words on both sides)
+        const int nrw = (IR + 31) / 32 + 3, ncw = (IC + 31) / 32 + 4;
+        for (int i = tid; i < nrw + ncw; i += nthr) {
+            const bool isr = i < nrw;
+            const int w = isr ? i : i - nrw;
+            const int pos = (isr ? TY : TX) + 32 * w;  // image row / column of the word's bit 0
+            const int lim = isr ? P.rows : P.cols;
+            uint32_t v = 0u;
+            if (pos + 32 > 0 && pos < lim) {
+                const uint32_t *src = isr ? P.rbits : P.cbits;
+                const int gw = pos >> 5, sh = pos & 31;  // arithmetic shift: floor for pos < 0
+                v = __funnelshift_r(src[gw], src[gw + 1], sh);
+            }
+            (isr ? rbw : cbw)[w] = v;
+        }
+    }
     __syncthreads();
     mbar_wait(bar, 0);
 
-    // ---- phase A: fix-up of the tile, four pixels per thread ---------------------- [sec:A1]
-    // out-of-band aliases and declared-missing strip -> 0, NaN sentinels -> bit array and 0
-    // (missing pixels count as S = 0, det:1050-1060)
-    int anynz = 0;
-    {
+    // ---- phase A: fix-up of the tile ------------------------------------------------ [sec:A1]
+    if (MODE == MODE_BITS) {
+        // out-of-band aliases -> 0, NaN sentinels -> bit array and 0, four pixels per thread
         const int ICq4 = IC >> 2;
-        for (int iy = (P.dbg & 16) ? IR : (tid >> 5); iy < IR; iy += nthr >> 5) {
-            // in-band tile columns of this row: [clo, chi)
-            const int dbase = (TXp + P.dlo) - (TY + iy);  // diagonal of tile column 0
-            int clo = 0, chi = IC, slo = 0, shi = 0;
+        for (int iy = tid >> 5; iy < IR; iy += nthr >> 5) {
+            const int dbase = TX - (TY + iy);  // diagonal of tile column 0
+            int clo = 0, chi = IC;
             if (!P.dense) {
                 clo = max(P.dlo - dbase, 0);
                 chi = min(P.dhi - dbase + 1, IC);
             }
-            if (MASK) {
-                slo = P.sdlo - dbase;
-                shi = P.sdhi - dbase + 1;  // declared-missing strip: counted analytically
-            }
-            // keep-bits of the row, 32 columns per lane (lanes 0..7): in the band, off the strip
-            unsigned rowword;
+            unsigned rowword;  // keep-bits of the row, 32 columns per lane (lanes 0..7)
             {
                 const int base = 32 * lane;
                 const int a = min(max(clo - base, 0), 32), b = min(max(chi - base, 0), 32);
                 rowword = (unsigned)(((1ull << b) - 1ull) & ~((1ull << a) - 1ull));
-                if (MASK) {
-                    const int sa = min(max(slo - base, 0), 32), sb = min(max(shi - base, 0), 32);
-                    if (sb > sa) rowword &= ~(unsigned)(((1ull << sb) - 1ull) & ~((1ull << sa) - 1ull));
-                }
             }
             for (int cb = 0; cb < ICq4; cb += 32) {
                 const int c4 = cb + lane;
@@ -339,56 +350,31 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 float4 *ptr = reinterpret_cast<float4 *>(tile + iy * IC) + c4;
                 const float4 v = *ptr;
                 const unsigned keep = (kwd >> (c0 & 31)) & 0xfu;
-                // NaN sentinels among the kept pixels -> bit array; dropped and missing pixels -> 0
                 unsigned live = keep;
                 if (v.x != v.x) live &= ~1u;
                 if (v.y != v.y) live &= ~2u;
                 if (v.z != v.z) live &= ~4u;
                 if (v.w != v.w) live &= ~8u;
                 const unsigned nb = keep & ~live;
-                const float4 w = make_float4((live & 1u) ? v.x : 0.f, (live & 2u) ? v.y : 0.f,
-                                             (live & 4u) ? v.z : 0.f, (live & 8u) ? v.w : 0.f);
-                anynz |= (__float_as_uint(w.x) | __float_as_uint(w.y) | __float_as_uint(w.z) |
-                          __float_as_uint(w.w)) != 0u;
-                if (live != 0xfu) *ptr = w;
-                if (MASK && nb) atomicOr(&bits[(iy * IC + c0) >> 5], nb << ((iy * IC + c0) & 31));
+                if (live != 0xfu)
+                    *ptr = make_float4((live & 1u) ? v.x : 0.f, (live & 2u) ? v.y : 0.f,
+                                       (live & 4u) ? v.z : 0.f, (live & 8u) ? v.w : 0.f);
+                if (nb) atomicOr(&bits[(iy * IC + c0) >> 5], nb << ((iy * IC + c0) & 31));
             }
         }
-    }
-    const int tnz = __syncthreads_or(anynz);
-
-    if (!tnz) {
-        // all-zero signal: every score of the tile is 0 (variance 0 -> det:1088-1091)
-        for (int item = tid; item < P.G * P.NBc; item += nthr) {
-            const int g = item / P.NBc, m = item - g * P.NBc;
-            const int Xp0 = xb + skew_shift(g) * P.skew + RT * m;
-            for (int u = 0; u < RU; ++u) {
-                const int Y = Y0 + RU * g + u;
-                if (Y >= P.oy1) continue;
-                for (int t = 0; t < RT; ++t) {
-                    const int X = Xp0 + t + P.dlo;
-                    const int d = X - Y;
-                    if (X < P.ox0 || X >= P.ox1 || d < P.odlo || d > P.odhi) continue;
-                    const long long oi =
-                        (long long)(Y - P.osy) * P.out_pitch + ((X - P.osx) - P.out_dlo);
-                    P.out[oi] = 0.f;
-                    if (P.nobs) P.nobs[oi] = (unsigned short)P.N;
-                }
-            }
+        __syncthreads();
+    } else if (!P.dense) {
+        // only the aliases of the box outside the stored band: two triangles of at most
+        // IR + 3 columns at the ends of the rows; one warp per tile row
+        for (int iy = tid >> 5; iy < IR; iy += nthr >> 5) {
+            const int dbase = TX - (TY + iy);
+            const int clo = min(max(P.dlo - dbase, 0), IC);
+            const int chi = max(min(P.dhi - dbase + 1, IC), 0);
+            for (int c = lane; c < clo; c += 32) tile[iy * IC + c] = 0.f;
+            for (int c = chi + lane; c < IC; c += 32) tile[iy * IC + c] = 0.f;
         }
-        return;
+        __syncthreads();
     }
-
-    // double tables (mask branch): 2-D prefix sums of the mask kernels, their column sums,
-    // and the sums over the declared-missing strip per output diagonal
-    constexpr int KW1 = KW + 1;
-    const double *IK = Dt;                              // [KH + 1][KW + 1]
-    const double *IK2 = IK + (KH + 1) * KW1;            // [KH + 1][KW + 1]
-    const double *Kcol = IK2 + (KH + 1) * KW1;          // [KW]
-    const double *K2col = Kcol + KW;                    // [KW]
-    const double *StK = K2col + KW;                     // [st_n]
-    const double *StK2 = StK + P.st_n;                  // [st_n]
-    const double *StC = StK2 + P.st_n;                  // [st_n]
 
     // ---- blocks of RU x RT windows, one per thread -------------------------------------
     // Lanes 0-3 / 4-7 of every quarter-warp take blocks of row groups g / g + 2: in a banded
@@ -396,14 +382,14 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     // quarter-warp hit disjoint banks.
     const int NQd = (P.NBc + 3) >> 2;
     const int nitems = 8 * NQd * 2 * ((P.G + 3) >> 2);
-    // every lane runs every loop (work is predicated): the epilogue contains warp-wide steps
-    for (int base = (P.dbg & 256) ? nitems : 0; base < nitems; base += nthr) {
+    const float invN = P.invN;
+    // every lane runs every loop (work is predicated): the exact path is warp-wide
+    for (int base = 0; base < nitems; base += nthr) {
         int g, m;
         bool live;
         {
             const int idx = base + tid;
-            // a warp = 4 column blocks x 8 row groups: a missing row or column then touches
-            // most lanes of the warps it crosses (less divergence in the mask code)
+            // a warp = 4 column blocks x 8 row groups
             const int npair = 2 * ((P.G + 3) >> 2);
             const int rest = idx >> 3, pr = rest % npair, M = rest / npair;
             g = (pr >> 1) * 4 + (pr & 1) + 2 * ((idx >> 2) & 1);
@@ -411,25 +397,30 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             live = idx < nitems && g < P.G && m < P.NBc;
             if (!live) g = m = 0;
         }
-        const int Xp0 = xb + skew_shift(g) * P.skew + RT * m;  // X' of output column t = 0
-        const int cxa = skew_shift(g) * P.skew + RT * m;       // aligned tile column of x[0]
+        const int cxa = skew_shift(g) * P.skew + RT * m;  // aligned tile column of x[0]
+        const int X0 = TX + cxa + kwa;                    // image column of window t = 0
         const int Yg = Y0 + RU * g;
-        // blocks without any valid output pixel are skipped
-        bool any = false;
+        const int fc0 = cxa + off;                        // tile column of footprint column 0
+        // valid windows of the block, bit k = u * RT + t
+        unsigned okb = 0u;
         if (live) {
+#pragma unroll
             for (int u = 0; u < RU; ++u) {
                 const int Y = Yg + u;
-                if (Y >= P.oy1) continue;
-                const int Xlo = max(P.ox0, Y + P.odlo), Xhi = min(P.ox1 - 1, Y + P.odhi);
-                const int Xa = Xp0 + P.dlo;
-                if (Xa + RT - 1 >= Xlo && Xa <= Xhi) any = true;
+                const int tlo = max(max(P.ox0, Y + P.odlo) - X0, 0);
+                const int thi = min(min(P.ox1 - 1, Y + P.odhi) - X0, RT - 1);
+                if (Y < P.oy1 && thi >= tlo)
+                    okb |= (((2u << thi) - 1u) & ~((1u << tlo) - 1u)) << (u * RT);
             }
         }
-        // per-window results of the two passes, parked in shared memory: the epilogue runs as
-        // compact loops.  [k], [NWB + k], [2 NWB + k] with k = u * RT + t.
-        constexpr int NWB = RU * RT;
-        float *mystat = statS + tid;
+        const bool any = okb != 0u;
+        unsigned slow = 0u;  // windows for the exact path
         float pl = 0.f;
+        // sum S' K' of the windows of row u = 0 (s3a) and u = 1 (s3b)
+        static_assert(RU == 2, "the epilogue is written for two window rows per thread");
+        float s3a[RT], s3b[RT];
+#pragma unroll
+        for (int t = 0; t < RT; ++t) s3a[t] = s3b[t] = 0.f;
         if (any) {                                                           // [sec:pivot]
             // block pivot: mean of the middle footprint row.  Sums and products are formed on
             // S - pl (any pivot is algebraically exact; a close one keeps float32 accurate).
@@ -446,7 +437,12 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             }
             pl = sacc * (1.0f / (float)XW);
         }
-        if (any && !(P.dbg & 8)) {                                           // [sec:main]
+#ifdef CS_ABLATE
+        if (any && !(P.dbg & 8))
+#else
+        if (any)
+#endif
+        {                                                                    // [sec:main]
             const unsigned long long npl2 = pack2(-pl, -pl);
             // one packed accumulator per window: .lo and .hi collect alternate taps
             unsigned long long acc[RU][RT];
@@ -493,21 +489,22 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 }
             }
 #pragma unroll
-            for (int u = 0; u < RU; ++u)
-#pragma unroll
-                for (int t = 0; t < RT; ++t) {
-                    float lo, hi;
-                    unpack2(acc[u][t], lo, hi);
-                    mystat[(u * RT + t) * nthr] = lo + hi;
-                }
+            for (int t = 0; t < RT; ++t) {
+                float lo, hi;
+                unpack2(acc[0][t], lo, hi);
+                s3a[t] = lo + hi;
+                unpack2(acc[1][t], lo, hi);
+                s3b[t] = lo + hi;
+            }
         }
-        if (any && !(P.dbg & 4)) {                                           // [sec:sums]
-            // window sums of (S - pl) and (S - pl)^2: column sums over KH rows in packed
-            // registers, then KW-wide sliding sums along the row
-            const unsigned long long npl2 = pack2(-pl, -pl);
-            unsigned long long cs[2 * NQ], cq[2 * NQ];
+
+        // ---- sums, mask sums and scores, one row of RT windows at a time ---------------
+        const unsigned long long npl2 = pack2(-pl, -pl);
+        unsigned long long cs[2 * NQ], cq[2 * NQ];
 #pragma unroll
-            for (int q = 0; q < 2 * NQ; ++q) cs[q] = cq[q] = 0ull;
+        for (int q = 0; q < 2 * NQ; ++q) cs[q] = cq[q] = 0ull;
+        if (any) {                                                           // [sec:sums]
+            // column sums of (S - pl) and (S - pl)^2 over the KH rows of window row u = 0
 #pragma unroll 1
             for (int iy = 0; iy < KH; ++iy) {
                 const ulonglong2 *rp =
@@ -522,29 +519,153 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     fma2(cq[2 * qd + 1], b, b);
                 }
             }
+        }
+        // mask geometry of the block                                        [sec:masksum]
+        uint32_t Rfp = 0u;             // missing rows of the footprint (bit = footprint row)
+        unsigned long long Cfp = 0ull; // missing columns of the footprint
+        unsigned long long bor0 = 0ull, bor1 = 0ull;  // MODE_BITS: columns with a missing pixel, per window row
+        bool stripz = false;
+        const int d00 = X0 - Yg;       // diagonal of window (u = 0, t = 0)
+        if (MODE == MODE_GEO && any) {
+            constexpr unsigned long long FWMASK = (XW >= 64) ? ~0ull : ((1ull << XW) - 1ull);
+            const int fr = KH + RU - 1;
+            Rfp = bits32(rbw, RU * g) & ((fr >= 32) ? 0xffffffffu : ((1u << fr) - 1u));
+            Cfp = bits64(cbw, fc0) & FWMASK;
+            // windows whose diagonal touches the strip tables
+            stripz = (d00 + RT - 1 >= P.st_base) && (d00 - (RU - 1) < P.st_base + P.st_n);
+        }
+        if (MODE == MODE_BITS && any) {
+            constexpr unsigned long long FWMASK = (XW >= 64) ? ~0ull : ((1ull << XW) - 1ull);
+            unsigned long long mid = 0ull;
+            const int fr = KH + RU - 1;
+#pragma unroll 1
+            for (int r = 0; r < fr; ++r) {
+                const unsigned long long b = bits64(bits, (RU * g + r) * IC + fc0) & FWMASK;
+                if (r == 0) bor0 = b;
+                else if (r == fr - 1) bor1 = b;
+                else mid |= b;
+            }
+            // window row 0 = footprint rows 0..KH-1, window row 1 = rows 1..KH
+            bor0 |= mid;
+            bor1 |= mid;
+        }
+
+#pragma unroll 1
+        for (int u = 0; u < RU; ++u) {
+            const int Y = Yg + u;
+            if (u > 0 && any) {
+                // rows [u, u + KH): row u + KH - 1 enters, row u - 1 leaves
+                const ulonglong2 *rin = reinterpret_cast<const ulonglong2 *>(
+                    tile + (RU * g + u + KH - 1) * IC + cxa);
+                const ulonglong2 *rout =
+                    reinterpret_cast<const ulonglong2 *>(tile + (RU * g + u - 1) * IC + cxa);
+                const unsigned long long pl2 = pack2(pl, pl);
 #pragma unroll
-            for (int u = 0; u < RU; ++u) {
-                if (u > 0) {
-                    // rows [u, u + KH): row u + KH - 1 enters, row u - 1 leaves
-                    const ulonglong2 *rin = reinterpret_cast<const ulonglong2 *>(
-                        tile + (RU * g + u + KH - 1) * IC + cxa);
-                    const ulonglong2 *rout =
-                        reinterpret_cast<const ulonglong2 *>(tile + (RU * g + u - 1) * IC + cxa);
-                    const unsigned long long pl2 = pack2(pl, pl);
+                for (int qd = 0; qd < NQ; ++qd) {
+                    const ulonglong2 vi = rin[qd], vo = rout[qd];
+                    const unsigned long long a = add2(vi.x, npl2), b = add2(vi.y, npl2);
+                    const unsigned long long c = add2(vo.x, npl2), d = add2(vo.y, npl2);
+                    const unsigned long long nc = sub2(pl2, vo.x), nd = sub2(pl2, vo.y);
+                    cs[2 * qd] = add2(add2(cs[2 * qd], a), nc);
+                    cs[2 * qd + 1] = add2(add2(cs[2 * qd + 1], b), nd);
+                    fma2(cq[2 * qd], a, a);
+                    fma2(cq[2 * qd + 1], b, b);
+                    fma2(cq[2 * qd], nc, c);  // - (x - pl)^2
+                    fma2(cq[2 * qd + 1], nd, d);
+                }
+            }
+            const unsigned ob = (okb >> (u * RT)) & ((1u << RT) - 1u);
+            if (ob) {
+                // ---- missing count and mask-kernel sums of the RT windows of this row
+                int nm[RT];
+                float sK[RT], sK2[RT];
 #pragma unroll
-                    for (int qd = 0; qd < NQ; ++qd) {
-                        const ulonglong2 vi = rin[qd], vo = rout[qd];
-                        const unsigned long long a = add2(vi.x, npl2), b = add2(vi.y, npl2);
-                        const unsigned long long c = add2(vo.x, npl2), d = add2(vo.y, npl2);
-                        const unsigned long long nc = sub2(pl2, vo.x), nd = sub2(pl2, vo.y);
-                        cs[2 * qd] = add2(add2(cs[2 * qd], a), nc);
-                        cs[2 * qd + 1] = add2(add2(cs[2 * qd + 1], b), nd);
-                        fma2(cq[2 * qd], a, a);
-                        fma2(cq[2 * qd + 1], b, b);
-                        fma2(cq[2 * qd], nc, c);  // - (x - pl)^2
-                        fma2(cq[2 * qd + 1], nd, d);
+                for (int t = 0; t < RT; ++t) {
+                    nm[t] = 0;
+                    sK[t] = sK2[t] = 0.f;
+                }
+                unsigned slowu = 0u;
+                if (MODE == MODE_GEO) {
+                    const uint32_t KHMASK = (KH >= 32) ? 0xffffffffu : ((1u << KH) - 1u);
+                    const uint32_t Rs = (Rfp >> u) & KHMASK;
+                    const int Yw = Y - kh;  // image row of window row 0
+                    if (stripz) {                                            // [sec:strip]
+#pragma unroll
+                        for (int t = 0; t < RT; ++t) {
+                            const unsigned sd = (unsigned)(d00 + t - u - P.st_base);
+                            if (sd < (unsigned)P.st_n) {
+                                const float4 s = ST[sd];
+                                nm[t] = (int)s.x;
+                                sK[t] = s.y;
+                                sK2[t] = s.z;
+                            }
+                        }
+                    }
+                    // missing rows: the taps of kernel row i inside the row's flagged span   [sec:rects]
+                    for (uint32_t rs = Rs; rs; rs &= rs - 1) {
+                        const int i = __ffs(rs) - 1;
+                        const int Yr = Yw + i;
+                        const int xlo = max(Yr + P.mlo, P.mx0) - (X0 - kw);
+                        const int xhi1 = min(Yr + P.mhi, P.mx1 - 1) + 1 - (X0 - kw);
+                        const float2 *pr = PR + i * KW1;
+#pragma unroll
+                        for (int t = 0; t < RT; ++t) {
+                            const int jlo = min(max(xlo - t, 0), KW);
+                            const int jhi = min(max(xhi1 - t, 0), KW);
+                            if (jhi > jlo) {
+                                const float2 p1 = pr[jhi], p0 = pr[jlo];
+                                nm[t] += jhi - jlo;
+                                sK[t] += p1.x - p0.x;
+                                sK2[t] += p1.y - p0.y;
+                            }
+                        }
+                    }
+                    // missing columns: the taps of kernel column j inside the column's flagged span,
+                    // minus the pixels on missing rows (counted above)
+                    for (unsigned long long cc = Cfp; cc; cc &= cc - 1) {
+                        const int c = __ffsll((long long)cc) - 1;
+                        const int Xc = X0 - kw + c;
+                        const int ilo = min(max(max(Xc - P.mhi, P.my0) - Yw, 0), KH);
+                        const int ihi = min(max(min(Xc - P.mlo, P.my1 - 1) + 1 - Yw, 0), KH);
+                        if (ihi <= ilo) continue;
+                        const uint32_t rsel =
+                            Rs & (((ihi >= 32) ? 0xffffffffu : ((1u << ihi) - 1u)) & ~((1u << ilo) - 1u));
+                        const int nc = (ihi - ilo) - __popc(rsel);
+#pragma unroll
+                        for (int t = 0; t < RT; ++t) {
+                            const int j = c - t;
+                            if (j >= 0 && j < KW) {
+                                const float2 p1 = PC[j * (KH + 1) + ihi], p0 = PC[j * (KH + 1) + ilo];
+                                float xk = p1.x - p0.x, xk2 = p1.y - p0.y;
+                                for (uint32_t rr2 = rsel; rr2; rr2 &= rr2 - 1) {
+                                    const float2 *q = PR + (__ffs(rr2) - 1) * KW1 + j;
+                                    xk -= q[1].x - q[0].x;
+                                    xk2 -= q[1].y - q[0].y;
+                                }
+                                nm[t] += nc;
+                                sK[t] += xk;
+                                sK2[t] += xk2;
+                            }
+                        }
+                    }
+                    // windows on the frame's margins: exact path (per-pixel predicate)
+                    if (P.margin_mode != 0) {
+                        if ((Yw < P.my0) || (Yw + KH > P.my1)) slowu = (1u << RT) - 1u;
+                        const int tlo = P.mx0 - (X0 - kw);          // t < tlo: left margin
+                        const int thi = P.mx1 - KW - (X0 - kw);     // t > thi: right margin
+                        if (tlo > 0) slowu |= (tlo >= RT) ? ((1u << RT) - 1u) : ((1u << tlo) - 1u);
+                        if (thi < RT - 1) slowu |= (thi < 0) ? ((1u << RT) - 1u) : (((1u << RT) - 1u) & ~((2u << thi) - 1u));
                     }
                 }
+                if (MODE == MODE_BITS) {
+                    // windows with a missing pixel: exact path
+                    const unsigned long long bu = u ? bor1 : bor0;
+#pragma unroll
+                    for (int t = 0; t < RT; ++t)
+                        if ((unsigned)(bu >> t) & KWMASK) slowu |= 1u << t;
+                }
+
+                // ---- window sums by sliding along the row, scores            [sec:score]
                 float col[4 * NQ], cqq[4 * NQ];
 #pragma unroll
                 for (int q = 0; q < 2 * NQ; ++q) {
@@ -557,223 +678,176 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     g1 += col[e];
                     g2 += cqq[e];
                 }
+                float rr[RT];
+                int nn[RT];
+                const float cm = MASK ? ((MODE == MODE_GEO ? P.fillc : 0.f) - pl) : 0.f;  // S' of a missing pixel
+                const bool raw = P.raw_xcorr != 0;
 #pragma unroll
                 for (int t = 0; t < RT; ++t) {
                     if (t > 0) {
                         g1 += col[off + t + KW - 1] - col[off + t - 1];
                         g2 += cqq[off + t + KW - 1] - cqq[off + t - 1];
                     }
-                    mystat[(NWB + u * RT + t) * nthr] = g1;
-                    mystat[(2 * NWB + u * RT + t) * nthr] = g2;
+                    // sums over the present pixels (centred): P1 = sum S', P2 = sum S'^2, Q3 = sum S' K'
+                    const float nf = (float)nm[t];
+                    const int npres = P.N - nm[t];
+                    const float np = (float)npres;
+                    float P1 = g1, P2 = g2, Q3 = s3a[t];
+                    if (MASK) {
+                        P1 = fmaf(-cm, nf, g1);
+                        P2 = fmaf(-cm * cm, nf, g2);
+                        Q3 = fmaf(-cm, sK[t], Q3);
+                    }
+                    // the three raw correlations xcorr2 thresholds at 1e-4 (det:716), over the
+                    // whole window (missing pixels are zeros)
+                    const float kp = MASK ? (P.sumKp - sK[t]) : P.sumKp;  // sum K' over present
+                    const float U1 = fmaf(np, pl, P1);                                   // sum S
+                    const float U2 = fmaf(2.f * pl, P1, fmaf(np * pl, pl, P2));          // sum S^2
+                    const float U3 = fmaf(P.qf, U1, fmaf(pl, kp, Q3));                   // sum S K_corr
+                    const float E = P.escale * (1.f + fmaf(pl, pl, g2 * invN));
+                    const float A1 = fabsf(U1 * invN), A2 = fabsf(U2 * invN), A3 = fabsf(U3 * invN);
+                    const float zone = fmaf(P.thr, 1e-3f, E);
+                    const float a = MASK ? (P.ksump - sK[t]) : P.ksump;
+                    const float b = MASK ? (P.k2sump - sK2[t]) : P.k2sump;
+                    const float invn = MASK ? rcp_fast(np) : invN;
+                    const float tt = P1 * invn;
+                    const float C = fmaf(pl, P.delta, fmaf(-tt, a, Q3));   // n cov
+                    const float VS = fmaf(-P1, tt, P2);                    // n var S
+                    const float VK = fmaf(-a * invn, a, b);                // n var K
+                    const float den2 = VS * VK;
+                    bool ok = true;
+                    if (MASK)
+                        ok = nm[t] == 0 || (npres >= P.min_present && npres > 0 && !P.kmean_zero);
+                    // det:1088-1091: |sqrt(var S var K)| < 1e-10 -> 0
+                    const bool dok = den2 > P.den_floor * np * np;
+                    float r = fminf(1.f, fmaxf(-1.f, C * rsqrtf(den2)));
+                    // a mean of squares thresholded to 0 makes the variance <= 0: score 0
+                    const bool zero2 = A2 < P.thr - zone;
+                    bool hard = !zero2 && ok &&
+                                (!dok ||                                       // flat window
+                                 fminf(fminf(A1, A2), A3) < P.thr + zone ||    // a threshold within rounding distance
+                                 g2 * P.sumKp2 > kAmpLimit2 * den2);           // ill-conditioned float32 sums
+                    if (zero2 || !ok || !dok) r = 0.f;
+                    int nmo = (MASK && P.nobs_full && r != 0.f) ? nm[t] : 0;
+                    if (raw) {
+                        // xcorr2: the thresholded raw correlation itself
+                        const float au = fabsf(U3);
+                        r = au < P.thr ? 0.f : U3;
+                        hard = fabsf(au - P.thr) <= fmaf(P.thr, 1e-3f, E * (float)P.N);
+                        nmo = 0;
+                    }
+#ifdef CS_ABLATE
+                    if (P.dbg & 32) hard = false;
+#endif
+                    if (hard) slowu |= 1u << t;
+                    rr[t] = r;
+                    nn[t] = nmo;
                 }
-            }
-        }
+                slow |= (slowu & ob) << (u * RT);
 
-        // footprint mask summary.  colfull: columns missing on every footprint row.  The other
-        // missing pixels: consecutive rows with the same pattern form one rectangle group
-        // (a missing row, the visible part of a missing column at the edge of the mask band,
-        // a frame margin); footprints with more groups than fit fall back to row-by-row.
-        const int fc0 = cxa + off;  // tile column of footprint column 0
-        unsigned long long colfull = 0ull, rowsel = 0ull, bor = 0ull;                // [sec:masksum]
-        int ng = 0;
-        if (MASK && any && !(P.dbg & 1)) {
-            constexpr unsigned long long FWMASK = (XW >= 64) ? ~0ull : ((1ull << XW) - 1ull);
-            unsigned long long band = FWMASK;
-            const int fr = KH + RU - 1;
-            for (int r = 0; r < fr; ++r) {
-                const unsigned long long b = row_bits(bits, (RU * g + r) * IC + fc0) & FWMASK;
-                band &= b;
-                bor |= b;
-            }
-            if (bor != 0ull) {
-                colfull = band;
-                if (bor & ~band) {
-                    unsigned long long prev = 0ull;
-                    int start = 0;
-                    for (int r = 0; r <= fr; ++r) {
-                        unsigned long long b = 0ull;
-                        if (r < fr) b = row_bits(bits, (RU * g + r) * IC + fc0) & FWMASK & ~band;
-                        if (b) rowsel |= 1ull << r;
-                        if (b != prev) {
-                            if (prev) {
-                                if (ng < kMaxGroups)  // pattern (< 40 bits) | first row | end row
-                                    grpS[ng * nthr + tid] = prev | ((unsigned long long)start << 40) |
-                                                            ((unsigned long long)r << 48);
-                                ++ng;
-                            }
-                            start = r;
-                            prev = b;
-                        }
-                    }
-                }
-            }
-        }
-
-        // valid windows of the block, bit k = u * RT + t
-        unsigned okb = 0u;
-        if (any) {
-#pragma unroll
-            for (int u = 0; u < RU; ++u) {
-                const int Y = Yg + u;
-                // columns of the row: [max(ox0, Y + odlo), min(ox1 - 1, Y + odhi)] as t range
-                const int tlo = max(max(P.ox0, Y + P.odlo) - (Xp0 + P.dlo), 0);
-                const int thi = min(min(P.ox1 - 1, Y + P.odhi) - (Xp0 + P.dlo), RT - 1);
-                if (Y < P.oy1 && thi >= tlo)
-                    okb |= (((2u << thi) - 1u) & ~((1u << tlo) - 1u)) << (u * RT);
-            }
-        }
-        if (P.cnt && MASK && any) {
-            constexpr unsigned long long FWM2 = (XW >= 64) ? ~0ull : ((1ull << XW) - 1ull);
-            atomicAdd(&P.cnt[0], 1ull);                       // blocks
-            if (bor) atomicAdd(&P.cnt[1], 1ull);              // blocks with any missing pixel
-            if (ng > 0) atomicAdd(&P.cnt[2], 1ull);           // blocks with groups
-            if (ng > kMaxGroups) atomicAdd(&P.cnt[3], 1ull);  // blocks on the row-by-row path
-            atomicAdd(&P.cnt[4], (unsigned long long)ng);     // groups
-            for (int k = 0; k < min(ng, kMaxGroups); ++k) {
-                const unsigned long long gp = grpS[k * nthr + tid];
-                if ((gp & ((1ull << 40) - 1ull)) == (FWM2 & ~colfull)) atomicAdd(&P.cnt[5], 1ull);  // full rows
-                atomicAdd(&P.cnt[6], (unsigned long long)((int)(gp >> 48) - (int)((gp >> 40) & 255)));  // rows in groups
-            }
-            if (colfull) atomicAdd(&P.cnt[7], 1ull);          // blocks with full columns
-        }
-        if (P.dbg & 512) bor = 0ull;  // timing experiment: summary computed, window sums skipped
-#pragma unroll 1
-        for (int u = 0; u < RU; ++u) {
-            const int Y = Yg + u;
-#pragma unroll 1
-            for (int t = 0; t < RT; ++t) {
-                const int X = Xp0 + t + P.dlo;
-                const int d = X - Y;
-                const bool wok = (okb >> (u * RT + t)) & 1u;
-                int nmiss = 0;
-                double sKm = 0.0, sKm2 = 0.0;
-                if (MASK && wok) {                                           // [sec:strip]
-                    // the declared-missing diagonal strip: a function of the window's diagonal
-                    const unsigned sd = (unsigned)(d - P.st_base);
-                    if (sd < (unsigned)P.st_n) {
-                        nmiss = (int)StC[sd];
-                        sKm = StK[sd];
-                        sKm2 = StK2[sd];
-                    }
-                }
-                if (MASK && wok && ((unsigned)(bor >> t) & KWMASK)) {        // [sec:rects]
-                    // columns missing over the whole footprint: whole kernel columns
-                    const unsigned cbw = (P.dbg & 1024) ? 0u : ((unsigned)(colfull >> t) & KWMASK);
-                    nmiss += KH * __popc(cbw);
-                    for (unsigned c = cbw; c; c &= c - 1) {
-                        const int j = __ffs(c) - 1;
-                        sKm += Kcol[j];
-                        sKm2 += K2col[j];
-                    }
-                    if (P.dbg & 2048) {
-                    } else if (ng <= kMaxGroups) {
-                        // remaining missing pixels as rectangles: rows [i0, i1) x runs of taps
-                        for (int k = 0; k < ng; ++k) {
-                            const unsigned long long gp = grpS[k * nthr + tid];
-                            const int i0 = max((int)((gp >> 40) & 255) - u, 0);
-                            const int i1 = min((int)(gp >> 48) - u, KH);
-                            const unsigned wb = (unsigned)(gp >> t) & KWMASK;
-                            if (i0 < i1 && wb) {
-                                nmiss += (i1 - i0) * __popc(wb);
-                                add_rects(wb, i0, i1, IK, IK2, KW1, sKm, sKm2);
-                            }
-                        }
-                    } else {
-                        // row by row
-                        const unsigned KHMASK = (KH >= 32) ? 0xffffffffu : ((1u << KH) - 1u);
-                        for (unsigned rs = (unsigned)(rowsel >> u) & KHMASK; rs; rs &= rs - 1) {
-                            const int i = __ffs(rs) - 1;
-                            const unsigned wb =
-                                (unsigned)(row_bits(bits, (RU * g + u + i) * IC + fc0) >> t) &
-                                KWMASK & ~cbw;
-                            nmiss += __popc(wb);
-                            add_rects(wb, i, i + 1, IK, IK2, KW1, sKm, sKm2);
-                        }
-                    }
-                }
-                int nobs = P.N;                                              // [sec:score]
-                bool redo = false;
-                float r = 0.f;
-                if (wok) {
-                    const int k = u * RT + t;
-                    const double s3 = (double)mystat[k * nthr];
-                    const double g1 = (double)mystat[(NWB + k) * nthr];
-                    const double g2 = (double)mystat[(2 * NWB + k) * nthr];
-                    if (P.dbg & 2)
-                        r = (float)(s3 + g1 + g2);
-                    else
-                        r = score_from_sums<MASK>(P, (double)pl, g1, g2, g2, nmiss, s3, sKm, sKm2,
-                                                  nobs, redo);
-                    if (P.dbg & 32) redo = false;
-                }
-                // ill-conditioned windows (flat signal or mostly missing): the warp redoes the
-                // window sums in float64 from the tile, 32 pixels at a time      [sec:redo]
-                const int woff = (RU * g + u) * IC + fc0 + t;
-                for (unsigned todo = __ballot_sync(0xffffffffu, redo); todo; todo &= todo - 1) {
-                    const int src = __ffs(todo) - 1;
-                    const float *wp = tile + __shfl_sync(0xffffffffu, woff, src);
-                    double h1 = 0.0, h2 = 0.0, s3 = 0.0;
-                    for (int idx = lane; idx < KH * KW; idx += 32) {
-                        const int i = idx / KW, j = idx - i * KW;
-                        const double sv = (double)wp[i * IC + j];
-                        h1 += sv;
-                        h2 = fma(sv, sv, h2);
-                        s3 = fma(sv, (double)Ktab[i * 2 * KWP2 + j], s3);
-                    }
-                    for (int o = 16; o > 0; o >>= 1) {
-                        h1 += __shfl_xor_sync(0xffffffffu, h1, o);
-                        h2 += __shfl_xor_sync(0xffffffffu, h2, o);
-                        s3 += __shfl_xor_sync(0xffffffffu, s3, o);
-                    }
-                    if (lane == src) {
-                        bool again;
-                        r = score_from_sums<MASK>(P, 0.0, h1, h2, h2, nmiss, s3, sKm, sKm2, nobs,
-                                                  again);
-                    }
-                }
-                if (wok) {
-                    // score and observation count replace s3 and g1 in the window's slots
-                    mystat[(u * RT + t) * nthr] = r;
-                    mystat[(NWB + u * RT + t) * nthr] = __int_as_float(nobs);
-                }
-            }
-        }
-        // ---- scores (and observation counts) to the output band, 16 bytes at a time where
-        // the row of eight windows is complete and aligned                     [sec:store]
-        if (!(P.dbg & 64)) {
-#pragma unroll
-            for (int u = 0; u < RU; ++u) {
-                const unsigned ob = (okb >> (u * RT)) & ((1u << RT) - 1u);
-                if (!ob) continue;
-                const int Y = Yg + u;
+                // ---- scores (and missing counts) to the output band, 16 bytes at a time where
+                // the row of eight windows is complete and aligned             [sec:store]
                 const long long oi0 =
-                    (long long)(Y - P.osy) * P.out_pitch + ((Xp0 + P.dlo - P.osx) - P.out_dlo);
-                float rr[RT];
-                int nn[RT];
-#pragma unroll
-                for (int t = 0; t < RT; ++t) {
-                    rr[t] = mystat[(u * RT + t) * nthr];
-                    nn[t] = __float_as_int(mystat[(NWB + u * RT + t) * nthr]);
-                }
+                    (long long)(Y - P.osy) * P.out_pitch + ((X0 - P.osx) - P.out_dlo);
                 if (ob == ((1u << RT) - 1u) && (oi0 & 3) == 0) {
 #pragma unroll
                     for (int t = 0; t < RT; t += 4)
                         *reinterpret_cast<float4 *>(P.out + oi0 + t) =
                             make_float4(rr[t], rr[t + 1], rr[t + 2], rr[t + 3]);
-                    if (P.nobs) {
+                    if (P.nmiss) {
+                        if (P.nmiss16) {
 #pragma unroll
-                        for (int t = 0; t < RT; t += 4)
-                            *reinterpret_cast<uint2 *>(P.nobs + oi0 + t) = make_uint2(
-                                (unsigned)nn[t] | ((unsigned)nn[t + 1] << 16),
-                                (unsigned)nn[t + 2] | ((unsigned)nn[t + 3] << 16));
+                            for (int t = 0; t < RT; t += 4)
+                                *reinterpret_cast<uint2 *>((unsigned short *)P.nmiss + oi0 + t) = make_uint2(
+                                    (unsigned)nn[t] | ((unsigned)nn[t + 1] << 16),
+                                    (unsigned)nn[t + 2] | ((unsigned)nn[t + 3] << 16));
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < RT; t += 4)
+                                *reinterpret_cast<unsigned *>((unsigned char *)P.nmiss + oi0 + t) =
+                                    (unsigned)nn[t] | ((unsigned)nn[t + 1] << 8) |
+                                    ((unsigned)nn[t + 2] << 16) | ((unsigned)nn[t + 3] << 24);
+                        }
                     }
                 } else {
 #pragma unroll
                     for (int t = 0; t < RT; ++t)
                         if ((ob >> t) & 1u) {
                             P.out[oi0 + t] = rr[t];
-                            if (P.nobs) P.nobs[oi0 + t] = (unsigned short)nn[t];
+                            if (P.nmiss) {
+                                if (P.nmiss16) ((unsigned short *)P.nmiss)[oi0 + t] = (unsigned short)nn[t];
+                                else ((unsigned char *)P.nmiss)[oi0 + t] = (unsigned char)nn[t];
+                            }
                         }
+                }
+            }
+            // the next row's products
+#pragma unroll
+            for (int t = 0; t < RT; ++t) s3a[t] = s3b[t];
+        }
+
+        // ---- exact path: the warp redoes the flagged windows in float64 from the tile,
+        // 32 pixels at a time, with the per-pixel mask predicate                [sec:redo]
+#ifdef CS_ABLATE
+        if (P.cnt && slow) atomicAdd(&P.cnt[0], (unsigned long long)__popc(slow));
+#endif
+        for (unsigned todo = __ballot_sync(0xffffffffu, slow != 0u); todo; todo &= todo - 1) {
+            const int src = __ffs(todo) - 1;
+            unsigned sl = __shfl_sync(0xffffffffu, slow, src);
+            const int sYg = __shfl_sync(0xffffffffu, Yg, src);
+            const int sX0 = __shfl_sync(0xffffffffu, X0, src);
+            const int sg = __shfl_sync(0xffffffffu, g, src);
+            const int sfc0 = __shfl_sync(0xffffffffu, fc0, src);
+            for (; sl; sl &= sl - 1) {
+                const int k = __ffs(sl) - 1;
+                const int u = k / RT, t = k - u * RT;
+                const int Y = sYg + u, X = sX0 + t;
+                const int trow = RU * sg + u, tcol = sfc0 + t;  // tile position of the window's corner
+                double h1 = 0.0, h2 = 0.0, q3 = 0.0, sKm = 0.0, sKm2 = 0.0;
+                int nmiss = 0;
+                for (int idx = lane; idx < KH * KW; idx += 32) {
+                    const int i = idx / KW, j = idx - i * KW;
+                    bool miss = false;
+                    if (MODE == MODE_GEO) {
+                        const bool rbit = (rbw[(trow + i) >> 5] >> ((trow + i) & 31)) & 1u;
+                        const bool cbit = (cbw[(tcol + j) >> 5] >> ((tcol + j) & 31)) & 1u;
+                        miss = geo_missing(P, Y - kh + i, X - kw + j, rbit, cbit);
+                    }
+                    if (MODE == MODE_BITS) {
+                        const int pos = (trow + i) * IC + tcol + j;
+                        miss = (bits[pos >> 5] >> (pos & 31)) & 1u;
+                    }
+                    if (miss) {
+                        ++nmiss;
+                        sKm += P.dK[P.N + idx];
+                        sKm2 += P.dK[2 * P.N + idx];
+                        continue;
+                    }
+                    const double sv = (double)tile[(trow + i) * IC + tcol + j];
+                    h1 += sv;
+                    h2 = fma(sv, sv, h2);
+                    q3 = fma(sv, P.dK[idx], q3);
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+                    h2 += __shfl_xor_sync(0xffffffffu, h2, o);
+                    q3 += __shfl_xor_sync(0xffffffffu, q3, o);
+                    if (MASK) {
+                        sKm += __shfl_xor_sync(0xffffffffu, sKm, o);
+                        sKm2 += __shfl_xor_sync(0xffffffffu, sKm2, o);
+                        nmiss += __shfl_xor_sync(0xffffffffu, nmiss, o);
+                    }
+                }
+                if (lane == 0) {
+                    int nmo;
+                    const float r = exact_score<MASK>(P, h1, h2, q3, nmiss, sKm, sKm2, nmo);
+                    const long long oi =
+                        (long long)(Y - P.osy) * P.out_pitch + ((X - P.osx) - P.out_dlo);
+                    P.out[oi] = r;
+                    if (P.nmiss) {
+                        if (P.nmiss16) ((unsigned short *)P.nmiss)[oi] = (unsigned short)nmo;
+                        else ((unsigned char *)P.nmiss)[oi] = (unsigned char)nmo;
+                    }
                 }
             }
         }
@@ -789,7 +863,6 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
 struct WideParams {
     const float *img;
     int pitch, dlo, dhi, dense;
-    const double *kc, *km, *k2m;  // K_corr, K_mask, K2_mask [KH * KW]
 };
 
 template <bool MASK>
@@ -815,15 +888,15 @@ pearson_wide(const PearsonParams P, const WideParams W) {
                 if (!(v == v)) {  // missing pixel: counts as S = 0
                     if (MASK) {
                         ++nmiss;
-                        sKm += W.km[idx];
-                        sKm2 += W.k2m[idx];
+                        sKm += P.dK[P.N + idx];
+                        sKm2 += P.dK[2 * P.N + idx];
                     }
                     continue;
                 }
                 const double sv = (double)v;
                 h1 += sv;
                 h2 = fma(sv, sv, h2);
-                s3 = fma(sv, W.kc[idx], s3);
+                s3 = fma(sv, P.dK[idx], s3);
             }
             for (int o = 16; o > 0; o >>= 1) {
                 h1 += __shfl_xor_sync(0xffffffffu, h1, o);
@@ -836,15 +909,15 @@ pearson_wide(const PearsonParams P, const WideParams W) {
                 }
             }
             if (lane == 0) {
-                int nobs;
-                bool redo;
-                // raw sums: pivot 0 and (P.q = 0) the unshifted kernel
-                const float r = score_from_sums<MASK>(P, 0.0, h1, h2, h2, nmiss, s3, sKm, sKm2, nobs,
-                                                      redo);
+                int nmo;
+                const float r = exact_score<MASK>(P, h1, h2, s3, nmiss, sKm, sKm2, nmo);
                 const long long oi =
                     (long long)(Y - P.osy) * P.out_pitch + ((X - P.osx) - P.out_dlo);
                 P.out[oi] = r;
-                if (P.nobs) P.nobs[oi] = (unsigned short)nobs;
+                if (P.nmiss) {
+                    if (P.nmiss16) ((unsigned short *)P.nmiss)[oi] = (unsigned short)nmo;
+                    else ((unsigned char *)P.nmiss)[oi] = (unsigned char)nmo;
+                }
             }
         }
     }
@@ -869,10 +942,10 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-template <int KW, bool MASK>
+template <int KW, int MODE>
 static int launch_kw(const CUtensorMap &tmap, const PearsonParams &P, int grid, int threads,
                      size_t smem, cudaStream_t st) {
-    auto kern = pearson_tiles<KW, MASK>;
+    auto kern = pearson_tiles<KW, MODE>;
     CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, threads, smem, st>>>(tmap, P);
     CS_LAUNCHED();
@@ -880,13 +953,13 @@ static int launch_kw(const CUtensorMap &tmap, const PearsonParams &P, int grid, 
     return CS_OK;
 }
 
-template <bool MASK>
-static int launch_mask(int KW, const CUtensorMap &tmap, const PearsonParams &P, int grid,
+template <int MODE>
+static int launch_mode(int KW, const CUtensorMap &tmap, const PearsonParams &P, int grid,
                        int threads, size_t smem, cudaStream_t st) {
     switch (KW) {
 #define CS_CASE(n) \
     case n:        \
-        return launch_kw<n, MASK>(tmap, P, grid, threads, smem, st);
+        return launch_kw<n, MODE>(tmap, P, grid, threads, smem, st);
         CS_CASE(3) CS_CASE(5) CS_CASE(7) CS_CASE(9) CS_CASE(11) CS_CASE(13) CS_CASE(15) CS_CASE(17)
         CS_CASE(19) CS_CASE(21) CS_CASE(23) CS_CASE(25) CS_CASE(27) CS_CASE(29) CS_CASE(31)
 #undef CS_CASE
@@ -902,93 +975,122 @@ struct KtabRing {
     void *buf[8] = {nullptr};
     size_t cap[8] = {0};
     int next = 0;
+    int get(size_t bytes, void **out) {
+        const int slot = next;
+        next = (next + 1) % 8;
+        if (cap[slot] < bytes) {
+            if (buf[slot]) cudaFree(buf[slot]);
+            buf[slot] = nullptr;
+            cap[slot] = 0;
+            if (cudaMalloc(&buf[slot], bytes) != cudaSuccess) {
+                set_error("cudaMalloc of the kernel tables failed");
+                return CS_ERR_NOMEM;
+            }
+            cap[slot] = bytes;
+        }
+        *out = buf[slot];
+        return CS_OK;
+    }
 };
 static thread_local KtabRing g_ring;
+
+static inline size_t align16(size_t v) { return (v + 15) / 16 * 16; }
 
 }  // namespace cs
 
 using namespace cs;
 
+// constants shared by the tiled and the wide kernel; returns the mask mode
+static int common_params(PearsonParams &P, const cs_kernel_desc *K, const cs_pearson_opts *opts) {
+    const int nk = K->kh * K->kw;
+    P.KH = K->kh, P.KW = K->kw, P.N = nk;
+    P.osy = opts->out_row_shift, P.osx = opts->out_col_shift;
+    P.ksum = K->k_sum, P.k2sum = K->k2_sum, P.kmean = K->k_mean, P.kstd = K->k_std;
+    P.thr_d = opts->xcorr_threshold;
+    P.thr = (float)opts->xcorr_threshold;
+    P.invN_d = 1.0 / (double)nk;
+    P.invN = (float)P.invN_d;
+    P.vK0 = opts->mask_mode ? (K->k2_sum / (double)nk - K->k_mean * K->k_mean) : K->k_std * K->k_std;
+    P.min_present = (int)((1.0 - opts->missing_tol) * (double)nk);
+    P.kmean_zero = (K->k_mean == 0.0);
+    P.raw_xcorr = opts->raw_xcorr;
+    P.nobs_full = opts->nobs_full;
+    P.den_floor = 1e-20f;
+    return opts->mask_mode;
+}
+
+static int check_output(PearsonParams &P, const cs_layout *Lo, int oy0, int oy1, int ox0, int ox1) {
+    P.out_pitch = Lo->pitch;
+    P.out_dlo = Lo->dense ? 0 : Lo->dlo;
+    bool ok = oy0 - P.osy >= 0 && ox0 - P.osx >= 0 && Lo->rows >= oy1 - P.osy &&
+              Lo->cols >= ox1 - P.osx;
+    const int sh = P.osx - P.osy;
+    // output pixel (y, x) = (Y - osy, X - osx); its diagonal is d - (osx - osy)
+    if (ok && !Lo->dense) ok = Lo->dlo <= P.odlo - sh && Lo->dhi >= P.odhi - sh;
+    if (!ok) {
+        set_error("output image does not cover scores on diagonals [%d,%d]", P.odlo - sh,
+                  P.odhi - sh);
+        return CS_ERR_INVALID;
+    }
+    return CS_OK;
+}
+
+// float64 copies of K_corr, K_mask, K2_mask behind `extra` bytes of other tables
+static int upload_tables(const cs_kernel_desc *K, bool has_mask, const unsigned char *ftab,
+                         size_t fbytes, cudaStream_t st, const unsigned char **d_ftab,
+                         const double **d_dK) {
+    const int nk = K->kh * K->kw;
+    const size_t dbytes = (size_t)3 * nk * sizeof(double);
+    const size_t total = align16(fbytes) + dbytes;
+    std::vector<unsigned char> h(total, 0);
+    if (fbytes) memcpy(h.data(), ftab, fbytes);
+    double *hd = (double *)(h.data() + align16(fbytes));
+    for (int i = 0; i < nk; ++i) {
+        hd[i] = K->k_corr[i];
+        hd[nk + i] = has_mask ? K->k_mask[i] : 0.0;
+        hd[2 * nk + i] = has_mask ? K->k2_mask[i] : 0.0;
+    }
+    void *buf = nullptr;
+    int rc = g_ring.get(total, &buf);
+    if (rc) return rc;
+    // pageable source: the copy is staged by the runtime before the call returns
+    CS_CUDA(cudaMemcpyAsync(buf, h.data(), total, cudaMemcpyHostToDevice, st));
+    *d_ftab = (const unsigned char *)buf;
+    *d_dK = (const double *)((const unsigned char *)buf + align16(fbytes));
+    return CS_OK;
+}
+
 // kernels wider than 31: the one-warp-per-window kernel
 static int pearson_wide_launch(const cs_layout *Li, const float *d_img, const cs_kernel_desc *K,
                                const cs_pearson_opts *opts, int32_t oy0, int32_t oy1, int32_t ox0,
                                int32_t ox1, int32_t odlo, int32_t odhi, const cs_layout *Lo,
-                               float *d_out, uint16_t *d_nobs, cudaStream_t st) {
+                               float *d_out, void *d_nmiss, cudaStream_t st) {
     PearsonParams P;
     memset(&P, 0, sizeof(P));
-    const int nk = K->kh * K->kw;
     P.oy0 = oy0, P.oy1 = oy1, P.ox0 = ox0, P.ox1 = ox1;
     const int dmin_poss = ox0 - (oy1 - 1), dmax_poss = (ox1 - 1) - oy0;
     P.odlo = odlo < dmin_poss ? dmin_poss : odlo;
     P.odhi = odhi > dmax_poss ? dmax_poss : odhi;
     CS_REQUIRE(P.odhi >= P.odlo, "empty output diagonal range");
-    P.KH = K->kh, P.KW = K->kw, P.N = nk;
-    P.osy = opts->out_row_shift, P.osx = opts->out_col_shift;
-    P.out = d_out, P.nobs = d_nobs;
-    P.out_pitch = Lo->pitch;
-    P.out_dlo = Lo->dense ? 0 : Lo->dlo;
-    {
-        bool ok = oy0 - P.osy >= 0 && ox0 - P.osx >= 0 && Lo->rows >= oy1 - P.osy &&
-                  Lo->cols >= ox1 - P.osx;
-        const int sh = P.osx - P.osy;
-        if (ok && !Lo->dense) ok = Lo->dlo <= P.odlo - sh && Lo->dhi >= P.odhi - sh;
-        if (!ok) {
-            set_error("output image does not cover scores on diagonals [%d,%d]", P.odlo - sh,
-                      P.odhi - sh);
-            return CS_ERR_INVALID;
-        }
-    }
-    if (opts->has_mask) CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
-    double sumK = 0.0;
-    for (int i = 0; i < nk; ++i) sumK += K->k_corr[i];
-    P.q = 0.0;
-    P.sumKp = sumK;
-    P.sumKp2 = 0.0;
-    P.ksum = K->k_sum, P.k2sum = K->k2_sum, P.kmean = K->k_mean, P.kstd = K->k_std;
-    P.thr = opts->xcorr_threshold;
-    P.invN = 1.0 / (double)nk;
-    P.vK0 = opts->has_mask ? (K->k2_sum / (double)nk - K->k_mean * K->k_mean) : K->k_std * K->k_std;
-    P.min_present = (int)((1.0 - opts->missing_tol) * (double)nk);
-    P.kmean_zero = (K->k_mean == 0.0);
-    P.has_mask = opts->has_mask;
-    P.raw_xcorr = opts->raw_xcorr;
-    P.nobs_full = opts->nobs_full;
-    // tables: K_corr, K_mask, K2_mask as float64
-    const size_t tbytes = (size_t)3 * nk * sizeof(double);
-    std::vector<double> h((size_t)3 * nk, 0.0);
-    for (int i = 0; i < nk; ++i) {
-        h[i] = K->k_corr[i];
-        if (opts->has_mask) {
-            h[nk + i] = K->k_mask[i];
-            h[2 * nk + i] = K->k2_mask[i];
-        }
-    }
-    KtabRing &ring = g_ring;
-    const int slot = ring.next;
-    ring.next = (ring.next + 1) % 8;
-    if (ring.cap[slot] < tbytes) {
-        if (ring.buf[slot]) cudaFree(ring.buf[slot]);
-        ring.buf[slot] = nullptr;
-        ring.cap[slot] = 0;
-        CS_CUDA(cudaMalloc(&ring.buf[slot], tbytes));
-        ring.cap[slot] = tbytes;
-    }
-    CS_CUDA(cudaMemcpyAsync(ring.buf[slot], h.data(), tbytes, cudaMemcpyHostToDevice, st));
-    CS_CUDA(cudaStreamSynchronize(st));  // `h` is pageable and local
+    const int mode = common_params(P, K, opts);
+    CS_REQUIRE(mode != 2, "kernels wider than 31 columns need the mask as NaN sentinels");
+    P.out = d_out, P.nmiss = d_nmiss, P.nmiss16 = opts->nmiss_bytes == 2;
+    int rc = check_output(P, Lo, oy0, oy1, ox0, ox1);
+    if (rc) return rc;
+    if (mode) CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
+    const unsigned char *d_f = nullptr;
+    if ((rc = upload_tables(K, mode != 0, nullptr, 0, st, &d_f, &P.dK))) return rc;
     WideParams Wp;
     Wp.img = d_img;
     Wp.pitch = Li->pitch;
     Wp.dense = Li->dense;
     Wp.dlo = Li->dense ? 0 : Li->dlo;
     Wp.dhi = Li->dense ? 0 : Li->dhi;
-    Wp.kc = (const double *)ring.buf[slot];
-    Wp.km = Wp.kc + nk;
-    Wp.k2m = Wp.km + nk;
     const int nrows = oy1 - oy0;
     const int Wo = P.odhi - P.odlo + 1, ncols = ox1 - ox0;
     const int per_row = Wo < ncols ? Wo : ncols;
     dim3 grid((unsigned)(nrows < (1 << 20) ? nrows : (1 << 20)), (unsigned)((per_row + 7) / 8 > 64 ? 64 : (per_row + 7) / 8));
-    if (opts->has_mask)
+    if (mode)
         pearson_wide<true><<<grid, 256, 0, st>>>(P, Wp);
     else
         pearson_wide<false><<<grid, 256, 0, st>>>(P, Wp);
@@ -1001,7 +1103,7 @@ static int pearson_wide_launch(const cs_layout *Li, const float *d_img, const cs
 static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel_desc *K,
                         const cs_pearson_opts *opts, int32_t oy0, int32_t oy1, int32_t ox0,
                         int32_t ox1, int32_t odlo, int32_t odhi, const cs_layout *Lo, float *d_out,
-                        uint16_t *d_nobs, void *stream, bool plan_only, int32_t *tile_rows_out) {
+                        void *d_nmiss, void *stream, bool plan_only, int32_t *tile_rows_out) {
     cudaStream_t st = (cudaStream_t)stream;
     CS_REQUIRE(Li && K && opts && (plan_only || (d_img && Lo && d_out)),
                "cs_pearson_f32: null argument");
@@ -1010,6 +1112,7 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
     CS_REQUIRE(K->kh <= 255 && K->kw <= 255, "kernel %dx%d too large (255x255 at most)", K->kh,
                K->kw);
     CS_REQUIRE(oy1 > oy0 && ox1 > ox0, "empty output region");
+    CS_REQUIRE(opts->mask_mode >= 0 && opts->mask_mode <= 2, "bad mask mode");
     const int kh = (K->kh - 1) / 2, kw = (K->kw - 1) / 2;
     CS_REQUIRE(oy0 - kh >= 0 && oy1 + kh <= Li->rows && ox0 - kw >= 0 && ox1 + kw <= Li->cols,
                "output region needs windows outside the image");
@@ -1019,7 +1122,7 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
             return CS_OK;
         }
         return pearson_wide_launch(Li, d_img, K, opts, oy0, oy1, ox0, ox1, odlo, odhi, Lo, d_out,
-                                   d_nobs, st);
+                                   d_nmiss, st);
     }
     PFN_encodeTiled enc = get_encode();
     if (!enc) {
@@ -1045,81 +1148,104 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
     CS_REQUIRE(odhi >= odlo, "empty output diagonal range");
     P.odlo = odlo;
     P.odhi = odhi;
-    P.KH = K->kh;
-    P.KW = K->kw;
+    const int mode = common_params(P, K, opts);
     P.KWP2 = round_up(K->kw + 1, 4);
-    P.N = K->kh * K->kw;
     const int kwa = round_up(kw, 4);
     const int nrows_out = oy1 - oy0;
+    const int nk = K->kh * K->kw;
+    if (mode) {
+        CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
+        // the centred algebra of the float32 path takes one kernel for the signal and the mask
+        for (int i = 0; i < nk; ++i)
+            CS_REQUIRE(K->k_mask[i] == K->k_corr[i], "k_mask must equal k_corr");
+    }
 
     // ---- tables -------------------------------------------------------------------
-    // float: K' = K_corr - q as two padded rows per kernel row (see Ktab), [KH][2][KWP2]
-    // double (mask): row prefix sums of K_mask and K2_mask [KH][KW+1] each, column sums [KW] each
-    const int nk = K->kh * K->kw;
+    // float: K' = K_corr - q as two padded rows per kernel row (see Ktab), [KH][2][KWP2];
+    // mask modes: row / column prefix tables of (K', K2') pairs, strip table per diagonal
     double qd = 0.0;
     for (int i = 0; i < nk; ++i) qd += K->k_corr[i];
+    const double sumKc = qd;
     qd /= nk;
     const float qf = (float)qd;
-    P.n_ftab = 2 * K->kh * P.KWP2;
-    // declared-missing strip: tables over the output diagonals whose windows touch it
+    const double q = (double)qf;
+    const int n_ktab = 2 * K->kh * P.KWP2;
     P.sdlo = 0;
     P.sdhi = -1;
     P.st_base = 0;
     P.st_n = 0;
-    if (opts->has_mask && opts->strip_dhi >= opts->strip_dlo) {
-        P.sdlo = opts->strip_dlo;
-        P.sdhi = opts->strip_dhi;
-        P.st_base = P.sdlo - (kh + kw);
-        P.st_n = (P.sdhi + (kh + kw)) - P.st_base + 1;
+    if (mode == MODE_GEO) {
+        P.sdlo = opts->geo.strip_dlo;
+        P.sdhi = opts->geo.strip_dhi;
+        if (P.sdhi >= P.sdlo) {
+            P.st_base = P.sdlo - (kh + kw);
+            P.st_n = (P.sdhi + (kh + kw)) - P.st_base + 1;
+        } else {
+            P.sdlo = 0, P.sdhi = -1;
+        }
     }
-    P.n_dtab = opts->has_mask ? (2 * (K->kh + 1) * (K->kw + 1) + 2 * K->kw + 3 * P.st_n) : 0;
-    if (opts->has_mask) CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
-    const size_t fbytes = (size_t)round_up(P.n_ftab, 4) * sizeof(float);
-    const size_t kbytes = (fbytes + (size_t)P.n_dtab * sizeof(double) + 15) / 16 * 16;
-    P.tab_bytes = (int)kbytes;
-    unsigned char *hk = (unsigned char *)malloc(kbytes);
-    if (!hk) return CS_ERR_NOMEM;
-    memset(hk, 0, kbytes);
-    float *hf = (float *)hk;
-    double *hd = (double *)(hk + fbytes);
-    double sumKp = 0.0, sumKp2 = 0.0;
+    const int kw1 = K->kw + 1, kh1 = K->kh + 1;
+    const size_t b_ktab = align16((size_t)n_ktab * sizeof(float));
+    const size_t b_pr = mode == MODE_GEO ? align16((size_t)K->kh * kw1 * sizeof(float2)) : 0;
+    const size_t b_pc = mode == MODE_GEO ? align16((size_t)K->kw * kh1 * sizeof(float2)) : 0;
+    const size_t b_st = mode == MODE_GEO ? align16((size_t)P.st_n * sizeof(float4)) : 0;
+    const size_t fbytes = b_ktab + b_pr + b_pc + b_st;
+    P.tab_bytes = (int)fbytes;
+    std::vector<unsigned char> hk(fbytes, 0);
+    float *hf = (float *)hk.data();
+    double sumKp = 0.0, sumKp2 = 0.0, sumAbsKp = 0.0;
     for (int i = 0; i < K->kh; ++i)
         for (int j = 0; j < K->kw; ++j) {
-            const float v = (float)(K->k_corr[i * K->kw + j] - (double)qf);
+            const float v = (float)(K->k_corr[i * K->kw + j] - q);
             hf[(2 * i) * P.KWP2 + j] = v;          // (k0,k1),(k2,k3),...
             hf[(2 * i + 1) * P.KWP2 + j + 1] = v;  // (0,k0),(k1,k2),...
             sumKp += (double)v;
             sumKp2 += (double)v * (double)v;
+            sumAbsKp += fabs((double)v);
         }
-    if (opts->has_mask) {
-        const int kw1 = K->kw + 1;
-        double *ik = hd, *ik2 = ik + (K->kh + 1) * kw1;
-        double *kc = ik2 + (K->kh + 1) * kw1, *k2c = kc + K->kw;
-        double *stk = k2c + K->kw, *stk2 = stk + P.st_n, *stc = stk2 + P.st_n;
-        // 2-D prefix tables: ik[i][j] = sum of k_mask[i' < i][j' < j]
+    if (mode == MODE_GEO) {
+        // centred mask kernels, consistent with the float32 taps: K' as rounded above,
+        // K2' = K2_mask - 2 q K_mask + q^2
+        auto kp = [&](int i, int j) { return (double)hf[(2 * i) * P.KWP2 + j]; };
+        auto k2p = [&](int i, int j) {
+            const double km = K->k_mask[i * K->kw + j];
+            return K->k2_mask[i * K->kw + j] - 2.0 * q * km + q * q;
+        };
+        float2 *pr = (float2 *)(hk.data() + b_ktab);
+        float2 *pc = (float2 *)(hk.data() + b_ktab + b_pr);
+        float4 *stt = (float4 *)(hk.data() + b_ktab + b_pr + b_pc);
         for (int i = 0; i < K->kh; ++i) {
             double a = 0.0, b = 0.0;
+            pr[i * kw1] = make_float2(0.f, 0.f);
             for (int j = 0; j < K->kw; ++j) {
-                a += K->k_mask[i * K->kw + j];
-                b += K->k2_mask[i * K->kw + j];
-                ik[(i + 1) * kw1 + j + 1] = ik[i * kw1 + j + 1] + a;
-                ik2[(i + 1) * kw1 + j + 1] = ik2[i * kw1 + j + 1] + b;
-                kc[j] += K->k_mask[i * K->kw + j];
-                k2c[j] += K->k2_mask[i * K->kw + j];
+                a += kp(i, j);
+                b += k2p(i, j);
+                pr[i * kw1 + j + 1] = make_float2((float)a, (float)b);
+            }
+        }
+        for (int j = 0; j < K->kw; ++j) {
+            double a = 0.0, b = 0.0;
+            pc[j * kh1] = make_float2(0.f, 0.f);
+            for (int i = 0; i < K->kh; ++i) {
+                a += kp(i, j);
+                b += k2p(i, j);
+                pc[j * kh1 + i + 1] = make_float2((float)a, (float)b);
             }
         }
         // window centred on diagonal d: tap (i, j) sits on diagonal d + (j - kw) - (i - kh)
         for (int sd = 0; sd < P.st_n; ++sd) {
             const int d = P.st_base + sd;
+            double a = 0.0, b = 0.0, c = 0.0;
             for (int i = 0; i < K->kh; ++i)
                 for (int j = 0; j < K->kw; ++j) {
                     const int dt = d + (j - kw) - (i - kh);
                     if (dt >= P.sdlo && dt <= P.sdhi) {
-                        stk[sd] += K->k_mask[i * K->kw + j];
-                        stk2[sd] += K->k2_mask[i * K->kw + j];
-                        stc[sd] += 1.0;
+                        a += kp(i, j);
+                        b += k2p(i, j);
+                        c += 1.0;
                     }
                 }
+            stt[sd] = make_float4((float)c, (float)a, (float)b, 0.f);
         }
     }
 
@@ -1129,14 +1255,15 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
     // banded traversal when the output band is narrow relative to the region
     P.skew = (Wo + 16 < ncols_out) ? 1 : 0;
     int TR = opts->tile_rows > 0 ? round_up(opts->tile_rows, RU) : 32;
+#ifdef CS_ABLATE
     if (const char *e = getenv("CS_TILE_ROWS"))  // tuning knob for experiments
         if (atoi(e) > 0) TR = round_up(atoi(e), RU);
+#endif
     if (TR > round_up(nrows_out, RU)) TR = round_up(nrows_out, RU);
     size_t smem = 0;
     int NBc = 0, nchunks = 0, IC = 0, IR = 0, NW = 0, threads = 0;
     for (;; TR -= RU) {
         if (TR < RU) {
-            free(hk);
             set_error("kernel %dx%d does not fit in shared memory", K->kh, K->kw);
             return CS_ERR_INVALID;
         }
@@ -1158,28 +1285,24 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
         if (threads > 256) threads = 256;
         if (threads < 64) threads = 64;
         NW = (IC * IR + 31) / 32 + 4;  // words of the linear bit array
-        size_t o = (size_t)IC * IR * sizeof(float);
-        o = (o + 15) / 16 * 16;
+        size_t o = align16((size_t)IC * IR * sizeof(float));
         P.off_bits = (int)o;
-        if (opts->has_mask) o += (size_t)NW * sizeof(uint32_t);
-        o = (o + 15) / 16 * 16;
+        if (mode == MODE_BITS) o += align16((size_t)NW * sizeof(uint32_t));
         P.off_K = (int)o;
+        P.off_PR = (int)(o + b_ktab);
+        P.off_PC = (int)(o + b_ktab + b_pr);
+        P.off_ST = (int)(o + b_ktab + b_pr + b_pc);
         o += fbytes;
-        P.off_D = (int)o;
-        o += (size_t)P.n_dtab * sizeof(double);
-        o = (o + 15) / 16 * 16;
-        P.off_stat = (int)o;
-        o += (size_t)3 * RU * RT * threads * sizeof(float);
-        o = (o + 15) / 16 * 16;
-        P.off_grp = (int)o;
-        if (opts->has_mask) o += (size_t)kMaxGroups * threads * sizeof(unsigned long long);
+        P.off_rb = (int)o;
+        if (mode == MODE_GEO) o += align16((size_t)((IR + 31) / 32 + 3) * sizeof(uint32_t));
+        P.off_cb = (int)o;
+        if (mode == MODE_GEO) o += align16((size_t)((IC + 31) / 32 + 4) * sizeof(uint32_t));
         P.off_bar = (int)o;
         o += 16;
         smem = o;
         if (smem <= 113 * 1024 || (TR == RU && smem <= 227 * 1024)) break;
     }
     if (plan_only) {
-        free(hk);
         if (tile_rows_out) *tile_rows_out = TR;
         return CS_OK;
     }
@@ -1193,66 +1316,48 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
     const int nrb = (nrows_out + TR - 1) / TR;
     const long long grid_ll = (long long)nrb * nchunks;
     if (grid_ll >= (1ll << 31)) {
-        free(hk);
         set_error("grid too large");
         return CS_ERR_INVALID;
     }
 
     // ---- output -----------------------------------------------------------------
-    P.osy = opts->out_row_shift;
-    P.osx = opts->out_col_shift;
     P.out = d_out;
-    P.nobs = d_nobs;
-    P.out_pitch = Lo->pitch;
-    P.out_dlo = Lo->dense ? 0 : Lo->dlo;
-    {
-        bool ok = oy0 - P.osy >= 0 && ox0 - P.osx >= 0 && Lo->rows >= oy1 - P.osy &&
-                  Lo->cols >= ox1 - P.osx;
-        const int sh = P.osx - P.osy;
-        // output pixel (y, x) = (Y - osy, X - osx); its diagonal is d - (osx - osy)
-        if (ok && !Lo->dense) ok = Lo->dlo <= odlo - sh && Lo->dhi >= odhi - sh;
-        if (!ok) {
-            free(hk);
-            set_error("output image does not cover scores on diagonals [%d,%d]", odlo - sh,
-                      odhi - sh);
-            return CS_ERR_INVALID;
-        }
-    }
+    P.nmiss = d_nmiss;
+    P.nmiss16 = opts->nmiss_bytes == 2;
+    if (d_nmiss) CS_REQUIRE(opts->nmiss_bytes == 1 || opts->nmiss_bytes == 2, "nmiss_bytes must be 1 or 2");
+    if (d_nmiss && opts->nmiss_bytes == 1)
+        CS_REQUIRE(P.N - (P.min_present > 1 ? P.min_present : 1) <= 255,
+                   "missing counts of this kernel need a 16-bit plane");
+    int rc = check_output(P, Lo, oy0, oy1, ox0, ox1);
+    if (rc) return rc;
 
-    KtabRing &ring = g_ring;
-    const int slot = ring.next;
-    ring.next = (ring.next + 1) % 8;
-    if (ring.cap[slot] < kbytes) {
-        if (ring.buf[slot]) cudaFree(ring.buf[slot]);
-        ring.buf[slot] = nullptr;
-        ring.cap[slot] = 0;
-        if (cudaMalloc(&ring.buf[slot], kbytes) != cudaSuccess) {
-            free(hk);
-            set_error("cudaMalloc of the kernel tables failed");
-            return CS_ERR_NOMEM;
-        }
-        ring.cap[slot] = kbytes;
+    if ((rc = upload_tables(K, mode != 0, hk.data(), fbytes, st, &P.tab, &P.dK))) return rc;
+    P.qf = qf;
+    P.sumKp = (float)sumKp;
+    P.sumKp2 = (float)sumKp2;
+    P.sumKc_d = sumKc;
+    P.ksump = (float)(K->k_sum - (double)nk * q);
+    P.k2sump = (float)(K->k2_sum - 2.0 * q * K->k_sum + (double)nk * q * q);
+    P.delta = (float)(sumKc - K->k_sum);
+    P.fillc = opts->geo.fill_value;
+    {
+        // error scale of the three raw correlations in float32 (see the kernel): 4e-7 x the
+        // kernel's magnitude
+        const double kappa = sqrt(sumKp2 / nk) + fabs(q) + fabs(sumKp) / nk + sumAbsKp / nk;
+        P.escale = (float)(4e-7 * (1.0 + kappa));
     }
-    // pageable source: the copy is staged by the runtime before the call returns
-    cudaError_t ce = cudaMemcpyAsync(ring.buf[slot], hk, kbytes, cudaMemcpyHostToDevice, st);
-    free(hk);
-    CS_CUDA(ce);
-    P.ftab = (const float *)ring.buf[slot];
-    P.dtab = (const double *)((const unsigned char *)ring.buf[slot] + fbytes);
-    P.q = (double)qf;
-    P.sumKp = sumKp;
-    P.sumKp2 = sumKp2;
-    P.ksum = K->k_sum;
-    P.k2sum = K->k2_sum;
-    P.kmean = K->k_mean;
-    P.kstd = K->k_std;
-    P.thr = opts->xcorr_threshold;
-    P.invN = 1.0 / (double)P.N;
-    P.vK0 = opts->has_mask ? (K->k2_sum / (double)P.N - K->k_mean * K->k_mean)
-                           : K->k_std * K->k_std;
-    P.min_present = (int)((1.0 - opts->missing_tol) * (double)P.N);
-    P.kmean_zero = (K->k_mean == 0.0);
-    P.has_mask = opts->has_mask;
+    if (mode == MODE_GEO) {
+        CS_REQUIRE(opts->geo.d_row_bits && opts->geo.d_col_bits, "geometric mask: bit vectors missing");
+        P.rbits = (const uint32_t *)opts->geo.d_row_bits;
+        P.cbits = (const uint32_t *)opts->geo.d_col_bits;
+        P.mlo = opts->geo.mask_dlo;
+        P.mhi = opts->geo.mask_dhi;
+        P.my0 = opts->geo.mat_y0, P.my1 = opts->geo.mat_y1, P.mx0 = opts->geo.mat_x0, P.mx1 = opts->geo.mat_x1;
+        P.margin_mode = opts->geo.margin_mode;
+        P.top_x1 = opts->geo.top_x1;
+        P.right_y0 = opts->geo.right_y0;
+    }
+#ifdef CS_ABLATE
     P.dbg = getenv("CS_DEBUG_SKIP") ? atoi(getenv("CS_DEBUG_SKIP")) : 0;
     P.cnt = nullptr;
     static unsigned long long *g_cnt = nullptr;
@@ -1261,8 +1366,7 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
         cudaMemsetAsync(g_cnt, 0, 16 * sizeof(unsigned long long), st);
         P.cnt = g_cnt;
     }
-    P.raw_xcorr = opts->raw_xcorr;
-    P.nobs_full = opts->nobs_full;
+#endif
 
     // ---- tensor map -----------------------------------------------------------------
     CUtensorMap tmap;
@@ -1284,25 +1388,29 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
             return CS_ERR_CUDA;
         }
     }
-    int lrc = opts->has_mask ? launch_mask<true>(K->kw, tmap, P, (int)grid_ll, threads, smem, st)
-                             : launch_mask<false>(K->kw, tmap, P, (int)grid_ll, threads, smem, st);
+    int lrc;
+    if (mode == MODE_GEO)
+        lrc = launch_mode<MODE_GEO>(K->kw, tmap, P, (int)grid_ll, threads, smem, st);
+    else if (mode == MODE_BITS)
+        lrc = launch_mode<MODE_BITS>(K->kw, tmap, P, (int)grid_ll, threads, smem, st);
+    else
+        lrc = launch_mode<MODE_NOMASK>(K->kw, tmap, P, (int)grid_ll, threads, smem, st);
+#ifdef CS_ABLATE
     if (P.cnt && lrc == CS_OK) {
         unsigned long long h[16];
         cudaMemcpyAsync(h, P.cnt, sizeof(h), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
-        fprintf(stderr,
-                "mask stats: blocks %llu, with missing %llu, with groups %llu, row-by-row %llu, groups "
-                "%llu (full rows %llu, rows in groups %llu), blocks with full columns %llu\n",
-                h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+        fprintf(stderr, "pearson stats: windows on the exact path %llu\n", h[0]);
     }
+#endif
     return lrc;
 }
 
 extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_kernel_desc *K,
                               const cs_pearson_opts *opts, int32_t oy0, int32_t oy1, int32_t ox0,
                               int32_t ox1, int32_t odlo, int32_t odhi, const cs_layout *Lo,
-                              float *d_out, uint16_t *d_nobs, void *stream) {
-    return pearson_impl(Li, d_img, K, opts, oy0, oy1, ox0, ox1, odlo, odhi, Lo, d_out, d_nobs,
+                              float *d_out, void *d_nmiss, void *stream) {
+    return pearson_impl(Li, d_img, K, opts, oy0, oy1, ox0, ox1, odlo, odhi, Lo, d_out, d_nmiss,
                         stream, false, nullptr);
 }
 

@@ -120,7 +120,7 @@ __global__ void scan_add(int64_t *a, int n, const int64_t *totals, long long bas
 }
 
 __global__ void emit_rows(ScoreView S, const float *__restrict__ sc,
-                          const unsigned short *__restrict__ nobs, int nobs_const,
+                          NmissPlane nobs,
                           const int64_t *__restrict__ indptr, int32_t *indices, double *data,
                           double *log10p, int r0, int r1) {
     const int lane = threadIdx.x & 31;
@@ -143,7 +143,7 @@ __global__ void emit_rows(ScoreView S, const float *__restrict__ sc,
                 indices[o] = x;
                 data[o] = (double)v;
                 if (log10p) {
-                    const float n = nobs ? (float)nobs[i] : (float)nobs_const;
+                    const float n = nobs_at(nobs, i);
                     log10p[o] = log10_pval(v, n);
                 }
             }
@@ -153,7 +153,7 @@ __global__ void emit_rows(ScoreView S, const float *__restrict__ sc,
 }
 
 __global__ void emit_candidates(ScoreView S, const float *__restrict__ sc,
-                                const unsigned short *__restrict__ nobs, int nobs_const,
+                                NmissPlane nobs,
                                 float threshold, cs_candidate *out, long long cap,
                                 unsigned long long *count) {
     const int lane = threadIdx.x & 31;
@@ -183,7 +183,7 @@ __global__ void emit_candidates(ScoreView S, const float *__restrict__ sc,
                     c.row = y;
                     c.col = x;
                     c.score = v;
-                    const float n = nobs ? (float)nobs[i] : (float)nobs_const;
+                    const float n = nobs_at(nobs, i);
                     c.log10p = (float)log10_pval(v, n);
                     out[o] = c;
                 }
@@ -385,15 +385,16 @@ int scores_finish_rows(const cs_layout *Lo, int64_t *d_indptr, int32_t r0, int32
     return CS_OK;
 }
 
-int scores_emit_rows(const cs_layout *Lo, const float *d_out, const uint16_t *d_nobs,
-                     int32_t nobs_const, int32_t dmin, int32_t dmax, const int64_t *d_indptr,
+int scores_emit_rows(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
+                     int32_t nmiss_bytes, int32_t n_window, int32_t dmin, int32_t dmax,
+                     const int64_t *d_indptr,
                      int32_t r0, int32_t r1, int32_t *d_indices, double *d_data, double *d_log10p,
                      cudaStream_t st) {
     if (r1 <= r0) return CS_OK;
     ScoreView S = make_view(Lo, dmin, dmax);
     int grid = (r1 - r0 + 7) / 8;
     if (grid > 148 * 16) grid = 148 * 16;
-    emit_rows<<<grid, 256, 0, st>>>(S, d_out, d_nobs, nobs_const, d_indptr, d_indices, d_data,
+    emit_rows<<<grid, 256, 0, st>>>(S, d_out, NmissPlane{d_nmiss, nmiss_bytes, n_window}, d_indptr, d_indices, d_data,
                                     d_log10p, r0, r1);
     CS_LAUNCHED();
     CS_CUDA(cudaGetLastError());
@@ -424,17 +425,18 @@ extern "C" int cs_scores_count(const cs_layout *Lo, const float *d_out, int32_t 
     return CS_OK;
 }
 
-extern "C" int cs_scores_emit(const cs_layout *Lo, const float *d_out, const uint16_t *d_nobs,
-                              int32_t nobs_const, int32_t dmin, int32_t dmax,
+extern "C" int cs_scores_emit(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
+                              int32_t nmiss_bytes, int32_t n_window, int32_t dmin, int32_t dmax,
                               const int64_t *d_indptr, int32_t *d_indices, double *d_data,
                               double *d_log10p, void *stream) {
     CS_REQUIRE(Lo && d_out && d_indptr && d_indices && d_data, "cs_scores_emit: null argument");
-    return scores_emit_rows(Lo, d_out, d_nobs, nobs_const, dmin, dmax, d_indptr, 0, Lo->rows,
+    return scores_emit_rows(Lo, d_out, d_nmiss, nmiss_bytes, n_window, dmin, dmax, d_indptr, 0, Lo->rows,
                             d_indices, d_data, d_log10p, (cudaStream_t)stream);
 }
 
-extern "C" int cs_scores_candidates(const cs_layout *Lo, const float *d_out, const uint16_t *d_nobs,
-                                    int32_t nobs_const, int32_t dmin, int32_t dmax, float threshold,
+extern "C" int cs_scores_candidates(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
+                                    int32_t nmiss_bytes, int32_t n_window, int32_t dmin,
+                                    int32_t dmax, float threshold,
                                     cs_candidate *d_cand, int64_t cap, int64_t *d_count,
                                     int64_t *n_host, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -443,7 +445,7 @@ extern "C" int cs_scores_candidates(const cs_layout *Lo, const float *d_out, con
     CS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
     int grid = (S.rows + 7) / 8;
     if (grid > 148 * 16) grid = 148 * 16;
-    emit_candidates<<<grid, 256, 0, st>>>(S, d_out, d_nobs, nobs_const, threshold, d_cand,
+    emit_candidates<<<grid, 256, 0, st>>>(S, d_out, NmissPlane{d_nmiss, nmiss_bytes, n_window}, threshold, d_cand,
                                           (long long)cap, (unsigned long long *)d_count);
     CS_LAUNCHED();
     CS_CUDA(cudaGetLastError());

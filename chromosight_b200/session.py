@@ -47,14 +47,19 @@ class Session:
             _lib.check(self._lib.cs_session_set_stream(self._h, C.c_void_p(st) if st else None))
 
     def upload(self, signal, kernel, max_dist=None, sym_upper=False, full=False, missing_mask=None,
-               missing_tol=0.75, tsvd=None, pval=False, trim_to_max_dist=False):
-        """Plan a normxcorr2 call (same arguments, det:807-817) and copy its inputs to HBM."""
+               missing_tol=0.75, tsvd=None, pval=False, trim_to_max_dist=False, mask_geometry=None):
+        """Plan a normxcorr2 call (same arguments, det:807-817) and copy its inputs to HBM.
+        `mask_geometry` = preprocessing.missing_geometry(...) stands for the mask
+        make_missing_mask would build, without building it."""
         kernel = np.asarray(kernel, dtype=np.float64)
         _det._validate(signal, kernel, missing_mask)
         csr = _det._canonical_csr(signal, np.float64)
-        mask_csr = _det._mask_csr(missing_mask)
+        mask_csr = None
+        if mask_geometry is None:
+            mask_csr, mask_geometry = _det._mask_forms(missing_mask, sym_upper)
         a, keep = _det._build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol,
-                                   tsvd, pval, trim_to_max_dist=trim_to_max_dist, device=self.device)
+                                   tsvd, pval, trim_to_max_dist=trim_to_max_dist, device=self.device,
+                                   geometry=mask_geometry)
         self._bind_stream()
         _lib.check(self._lib.cs_session_upload(self._h, C.byref(a)))
         del keep

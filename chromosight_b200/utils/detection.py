@@ -20,6 +20,9 @@ from . import preprocessing as preproc
 
 # statistics of the last hot-path call (device-side timings, windows evaluated)
 last_call_stats = {}
+# "auto": masks that make_missing_mask can build reach the device as two bit vectors, any other
+# as its pixel list; "pixels" forces the pixel list (tests compare the two device paths)
+MASK_FORM = "auto"
 
 
 def _device_index():
@@ -65,8 +68,11 @@ def _kernel_desc(kernel, tsvd, keep):
 
 
 def _build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsvd, pval,
-                raw_xcorr=False, threshold=1e-4, trim_to_max_dist=False, device=None):
-    """cs_normxcorr2_args of one call; the second value keeps the host arrays alive."""
+                raw_xcorr=False, threshold=1e-4, trim_to_max_dist=False, device=None,
+                geometry=None):
+    """cs_normxcorr2_args of one call; the second value keeps the host arrays alive.
+    The missing mask is either a pixel mask (`mask_csr`) or the ingredients of
+    make_missing_mask (`geometry` = (miss_rows, miss_cols, dlo, dhi), pre:535-633)."""
     keep = []
     a = _lib.Normxcorr2Args()
     a.rows, a.cols = csr.shape
@@ -76,7 +82,17 @@ def _build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, t
     keep.extend([indptr, indices, data])
     a.indptr, a.indices, a.data = indptr.ctypes.data, indices.ctypes.data, data.ctypes.data
     a.has_mask = 0
-    if mask_csr is not None:
+    if geometry is not None:
+        miss_r = np.ascontiguousarray(geometry[0], dtype=np.uint8)
+        miss_c = np.ascontiguousarray(geometry[1], dtype=np.uint8)
+        if miss_r.shape != (csr.shape[0],) or miss_c.shape != (csr.shape[1],):
+            raise ValueError("Signal and missing mask do not have the same shape")
+        keep.extend([miss_r, miss_c])
+        a.has_mask = 2
+        a.miss_row, a.miss_col = miss_r.ctypes.data, miss_c.ctypes.data
+        a.mask_dlo = -(2 ** 31) if geometry[2] is None else int(geometry[2])
+        a.mask_dhi = 2 ** 31 - 1 if geometry[3] is None else int(geometry[3])
+    elif mask_csr is not None:
         m_indptr = np.ascontiguousarray(mask_csr.indptr, dtype=np.int64)
         m_indices = np.ascontiguousarray(mask_csr.indices, dtype=np.int32)
         keep.extend([m_indptr, m_indices])
@@ -154,11 +170,11 @@ def _result_to_csr(res, shape, pval):
 
 
 def _run_host(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsvd, pval,
-              raw_xcorr=False, threshold=1e-4, trim_to_max_dist=False):
+              raw_xcorr=False, threshold=1e-4, trim_to_max_dist=False, geometry=None):
     """One call of cs_normxcorr2_host -> (corr csr, log10 p csr or None)."""
     lib = _lib.load()
     a, keep = _build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsvd,
-                          pval, raw_xcorr, threshold, trim_to_max_dist)
+                          pval, raw_xcorr, threshold, trim_to_max_dist, geometry=geometry)
     res = _lib.CsrResult()
     _lib.check(lib.cs_normxcorr2_host(C.byref(a), C.byref(res)))
     last_call_stats.clear()
@@ -195,6 +211,18 @@ def _validate(signal, kernel, missing_mask):
         raise ValueError("Cannot have flat kernel.")
     _check_kernel_shape(kernel)
     return kernel
+
+
+def _mask_forms(missing_mask, sym_upper):
+    """(pixel mask CSR, geometry): the geometric form when the mask is one
+    make_missing_mask can build (two bit vectors reach the device instead of the pixel
+    list), else the canonical CSR pattern."""
+    if missing_mask is None:
+        return None, None
+    geometry = None if MASK_FORM == "pixels" else preproc.mask_geometry(missing_mask, sym_upper)
+    if geometry is not None:
+        return None, geometry
+    return _mask_csr(missing_mask), None
 
 
 def _mask_csr(missing_mask):
@@ -256,9 +284,9 @@ def normxcorr2(
     kernel = _validate(signal, kernel, missing_mask)
     dense_in = not sp.issparse(signal)
     csr = _canonical_csr(np.asarray(signal) if dense_in else signal, np.float64)
-    mask_csr = _mask_csr(missing_mask)
+    mask_csr, geometry = _mask_forms(missing_mask, sym_upper)
     corr, pvals = _run_host(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsvd,
-                            pval, trim_to_max_dist=trim_to_max_dist)
+                            pval, trim_to_max_dist=trim_to_max_dist, geometry=geometry)
     if dense_in:
         return corr.toarray(), (pvals.toarray() if pvals is not None else None)
     return corr, pvals
@@ -335,15 +363,17 @@ def pattern_detector(contact_map, kernel_config, kernel_matrix, coords=None, dum
     if min(shape) <= max(kernel_matrix.shape):           # det:237-238
         return None, None
     inter = bool(contact_map.inter)
-    missing_mask = None
-    if full:                                             # det:241-250
-        missing_mask = preproc.make_missing_mask(
-            shape, valid_rows=contact_map.detectable_bins[0], valid_cols=contact_map.detectable_bins[1],
+    geometry = None
+    if full:
+        # det:241-250 builds the pixel mask of the missing bins; the device only needs its
+        # ingredients (two bit vectors and the flagged diagonals)
+        geometry = preproc.missing_geometry(
+            shape, contact_map.detectable_bins[0], contact_map.detectable_bins[1],
             max_dist=contact_map.max_dist, sym_upper=not inter)
     sess = Session()
     try:
         sess.upload(contact_map.matrix, kernel_matrix, max_dist=contact_map.max_dist,
-                    sym_upper=not inter, full=full, missing_mask=missing_mask, tsvd=tsvd, pval=True,
+                    sym_upper=not inter, full=full, mask_geometry=geometry, tsvd=tsvd, pval=True,
                     missing_tol=kernel_config["max_perc_undetected"] / 100)
         sess.run()
         dmax = 2 ** 30 if inter else int(contact_map.max_dist)

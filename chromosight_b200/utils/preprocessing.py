@@ -53,12 +53,34 @@ def zero_pad_sparse(mat, margin_h, margin_v, fmt="coo"):
     return out.tocsr()
 
 
+def missing_geometry(shape, valid_rows, valid_cols, max_dist=None, sym_upper=False):
+    """The ingredients of make_missing_mask (pre:535-633) without the matrix: boolean
+    vectors of missing rows / columns and the diagonals col - row on which a missing bin
+    flags its pixels (None = unbounded).  This is what the device needs of the mask."""
+    sm, sn = shape
+    if sym_upper and (sm != sn or len(valid_rows) != len(valid_cols)):
+        raise ValueError("Rectangular matrices cannot be upper symmetric")
+    fr = np.ones(sm, dtype=bool)
+    fr[np.asarray(valid_rows, dtype=np.int64)] = False
+    if sym_upper:
+        if max_dist is None:
+            max_dist = min(shape)
+        return fr, fr, 0, int(max_dist)
+    fc = np.ones(sn, dtype=bool)
+    fc[np.asarray(valid_cols, dtype=np.int64)] = False
+    return fr, fc, None, None
+
+
 def make_missing_mask(shape, valid_rows, valid_cols, max_dist=None, sym_upper=False):
-    """Sparse boolean mask of the pixels that belong to missing bins (pre:535-633)."""
+    """Sparse boolean mask of the pixels that belong to missing bins (pre:535-633).
+
+    The returned matrix remembers how it was made (`_cs_geometry`): normxcorr2 then hands
+    the device two bit vectors instead of the pixel list."""
     sm, sn = shape
     if sym_upper and (sm != sn or len(valid_rows) != len(valid_cols)):
         raise ValueError("Rectangular matrices cannot be upper symmetric")
     miss_r = valid_to_missing(valid_rows, sm)
+    geometry = missing_geometry(shape, valid_rows, valid_cols, max_dist, sym_upper)
     if sym_upper:
         if max_dist is None:
             max_dist = min(shape)
@@ -71,12 +93,11 @@ def make_missing_mask(shape, valid_rows, valid_cols, max_dist=None, sym_upper=Fa
         ok = (rows >= 0) & (rows < sm) & (cols >= 0) & (cols < sm)
         mask = sp.coo_matrix((np.ones(ok.sum(), dtype=bool), (rows[ok], cols[ok])),
                              shape=shape, dtype=bool).tocsr()
+        mask._cs_geometry = geometry + (mask.nnz,)
         return mask
     miss_c = valid_to_missing(valid_cols, sn)
     fr = np.zeros(sm, dtype=bool)
     fr[miss_r] = True
-    fc = np.zeros(sn, dtype=bool)
-    fc[miss_c] = True
     # whole rows, then the remaining pixels of whole columns
     r1 = np.repeat(miss_r, sn)
     c1 = np.tile(np.arange(sn), len(miss_r))
@@ -85,8 +106,53 @@ def make_missing_mask(shape, valid_rows, valid_cols, max_dist=None, sym_upper=Fa
     c2 = np.repeat(miss_c, len(good_rows))
     rows = np.concatenate([r1, r2])
     cols = np.concatenate([c1, c2])
-    return sp.coo_matrix((np.ones(len(rows), dtype=bool), (rows, cols)), shape=shape,
+    mask = sp.coo_matrix((np.ones(len(rows), dtype=bool), (rows, cols)), shape=shape,
                          dtype=bool).tocsr()
+    mask._cs_geometry = geometry + (mask.nnz,)
+    return mask
+
+
+def mask_geometry(mask, sym_upper=False):
+    """(miss_rows, miss_cols, dlo, dhi) if `mask` (scipy sparse, bool) is exactly a mask
+    make_missing_mask can build, else None.  Masks made by this module carry the answer;
+    foreign ones (e.g. the reference's own make_missing_mask) are recognised from their
+    pattern in O(nnz)."""
+    tag = getattr(mask, "_cs_geometry", None)
+    if tag is not None and tag[4] == mask.nnz and len(tag[0]) == mask.shape[0] \
+            and len(tag[1]) == mask.shape[1]:
+        return tag[:4]
+    csr = mask.tocsr()
+    if not csr.has_canonical_format:
+        csr = csr.copy()
+        csr.sum_duplicates()
+    if csr.nnz and not np.all(csr.data):
+        csr = csr.copy()
+        csr.eliminate_zeros()
+    sm, sn = csr.shape
+    counts = np.diff(csr.indptr)
+    rows = np.repeat(np.arange(sm), counts)
+    cols = csr.indices
+    if csr.nnz == 0:
+        return np.zeros(sm, bool), np.zeros(sn, bool), (0 if sym_upper else None), (0 if sym_upper else None)
+    d = cols.astype(np.int64) - rows
+    if sm == sn and d.min() >= 0:
+        # banded upper-triangular generator: bin b is missing iff pixel (b, b) is flagged
+        miss = np.zeros(sm, dtype=bool)
+        miss[rows[d == 0]] = True
+        md = int(d.max())
+        cum = np.concatenate([[0], np.cumsum(miss)])
+        r = np.arange(sm)
+        last = np.minimum(r + md, sm - 1)
+        expect = np.where(miss, last - r + 1, cum[last + 1] - cum[r])
+        if np.array_equal(expect, counts) and np.all(miss[rows] | miss[cols]):
+            return miss, miss, 0, md
+    # whole rows and whole columns
+    fr = counts == sn
+    fc = np.bincount(cols, minlength=sn) == sm
+    n_r, n_c = int(fr.sum()), int(fc.sum())
+    if csr.nnz == n_r * sn + n_c * (sm - n_r) and np.all(fr[rows] | fc[cols]):
+        return fr, fc, None, None
+    return None
 
 
 def frame_missing_mask(mask, kernel_shape, sym_upper=False, max_dist=None):

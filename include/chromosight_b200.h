@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define CS_ABI_VERSION 1
+#define CS_ABI_VERSION 2
 
 typedef enum cs_status {
     CS_OK = 0,
@@ -55,17 +55,47 @@ int cs_layout_band(cs_layout *L, int32_t rows, int32_t cols, int32_t dlo, int32_
 int cs_layout_dense(cs_layout *L, int32_t rows, int32_t cols);
 
 /* ------------------------------------------------------------------------
+ * Missing-pixel masks.  Two representations reach the device:
+ *   mask_mode 1  an arbitrary pixel mask (CSR pattern).  Missing pixels are written
+ *                into the image as NaN sentinels.
+ *   mask_mode 2  the mask preprocessing.make_missing_mask (pre:535-633) builds from the
+ *                detectable bins and frame_missing_mask (pre:404-498) frames: a pixel
+ *                inside the matrix is missing iff its row or its column is a missing
+ *                bin and it lies on diagonals mask_dlo..mask_dhi; plus the frame's
+ *                margins and the strip of sub-diagonals (pre:483-497).  It is given by
+ *                two bit vectors and a few integers (cs_geo_mask, IMAGE coordinates);
+ *                missing pixels hold `fill_value` in the image (any constant is
+ *                algebraically exact; one close to the signal's mean keeps the float32
+ *                sums of heavily masked windows well conditioned; NaN for kernels wider
+ *                than 31 columns, which take the one-warp-per-window kernel).
+ * ------------------------------------------------------------------------ */
+typedef struct cs_geo_mask {
+    /* device bit vectors, bit i of word i / 32 = image row (column) i is a missing bin
+     * inside the matrix; at least 2 zero words before word 0 and after the last word */
+    const void *d_row_bits;
+    const void *d_col_bits;
+    int32_t mask_dlo, mask_dhi;   /* flagged diagonals X - Y (image coordinates) */
+    int32_t mat_y0, mat_y1;       /* the matrix inside the frame: rows mat_y0 <= Y < mat_y1 */
+    int32_t mat_x0, mat_x1;       /* and columns mat_x0 <= X < mat_x1 */
+    int32_t margin_mode;          /* 0 no frame, 1 banded frame (pre:461-477), 2 all four margins */
+    int32_t top_x1;               /* banded frame: top margin missing for X < top_x1 */
+    int32_t right_y0;             /* banded frame: right margin missing for Y >= right_y0 */
+    int32_t strip_dlo, strip_dhi; /* diagonals entirely missing (pre:483-497); empty if dhi < dlo */
+    float fill_value;
+} cs_geo_mask;
+
+/* ------------------------------------------------------------------------
  * Framing + densification: detection.py:979-991 (zero frame around the
  * signal), preprocessing.py:404-498 (frame_missing_mask) and
  * preprocessing.py:501-532 (check_missing_mask).
  *
  * Scatters the CSR signal (n_rows x n_cols, float64 values, int32 column
  * indices, int64 row pointers) into the float32 image `d_img` (layout L) at
- * offset (row_off, col_off), writes the missing mask as NaN sentinels
- * (user mask pixels from a CSR pattern, then the geometric frame of
- * frame_missing_mask when frame_mk > 0), and counts signal pixels that are
- * non-zero under the mask into *d_err (int32, device).
- *   mask_mode: 0 no mask, 1 mask given.
+ * offset (row_off, col_off), writes the missing mask (mode 1: user mask pixels
+ * from a CSR pattern, then the geometric frame of frame_missing_mask when
+ * frame_mk > 0, as NaN sentinels; mode 2: `geo`), and counts signal pixels that
+ * are non-zero under the mask into *d_err (int32[2], device).
+ *   mask_mode: 0 no mask, 1 pixel mask (CSR), 2 geometric mask (geo).
  *   sym_upper / max_dist (-1 = None): as in frame_missing_mask.
  *   frame_mk, frame_nk: kernel shape when the image is framed (full=True), 0 otherwise.
  * ------------------------------------------------------------------------ */
@@ -74,7 +104,7 @@ int cs_image_fill_f32(const cs_layout *L, float *d_img,
                       const double *d_sig_data, int32_t n_rows, int32_t n_cols,
                       int32_t row_off, int32_t col_off,
                       int32_t mask_mode, const int64_t *d_mask_indptr,
-                      const int32_t *d_mask_indices,
+                      const int32_t *d_mask_indices, const cs_geo_mask *geo,
                       int32_t sym_upper, int32_t max_dist,
                       int32_t frame_mk, int32_t frame_nk,
                       int32_t *d_err, void *stream);
@@ -87,9 +117,10 @@ int cs_image_fill_f32(const cs_layout *L, float *d_img,
  * Output pixel set (image coordinates): oy0 <= Y < oy1, ox0 <= X < ox1 and
  * odlo <= X - Y <= odhi.  Results go to the float32 image `d_out` with layout
  * Lout, whose pixel (Y - out_row_shift, X - out_col_shift) receives the score of
- * window (Y, X) (the shifts undo the frame, det:1124-1129).  `d_nobs` (uint16, same
- * layout, may be NULL) receives the number of observations of each window
- * (det:1110-1116).
+ * window (Y, X) (the shifts undo the frame, det:1124-1129).  `d_nmiss` (uint8 or
+ * uint16 per opts->nmiss_bytes, same layout, may be NULL) receives the number of
+ * missing pixels of each window when nobs_full (0 otherwise): the number of
+ * observations of det:1110-1116 is kh*kw - nmiss.
  * ------------------------------------------------------------------------ */
 typedef struct cs_kernel_desc {
     int32_t kh, kw;          /* kernel shape (mk, nk), both odd */
@@ -101,7 +132,7 @@ typedef struct cs_kernel_desc {
 } cs_kernel_desc;
 
 typedef struct cs_pearson_opts {
-    int32_t has_mask;        /* image carries NaN sentinels (masked branch) */
+    int32_t mask_mode;       /* 0 no mask, 1 NaN sentinels in the image, 2 geometric (geo) */
     double missing_tol;      /* det:1069-1072 */
     double xcorr_threshold;  /* 1e-4, det:595 */
     int32_t raw_xcorr;       /* 1: write thresholded raw cross-correlation instead of Pearson */
@@ -109,18 +140,15 @@ typedef struct cs_pearson_opts {
     int32_t tile_rows;       /* 0 = auto */
     int32_t out_row_shift;   /* score of window (Y, X) is written to pixel           */
     int32_t out_col_shift;   /* (Y - out_row_shift, X - out_col_shift) of the output */
-    /* Diagonals strip_dlo <= X - Y <= strip_dhi of the image that the caller declares
-     * entirely missing (the sub-diagonals frame_missing_mask adds for sym_upper,
-     * pre:483-497); handled analytically instead of pixel by pixel.  Empty when
-     * strip_dhi < strip_dlo. */
-    int32_t strip_dlo, strip_dhi;
+    int32_t nmiss_bytes;     /* element size of d_nmiss: 1 or 2 */
+    cs_geo_mask geo;         /* mask_mode 2 */
 } cs_pearson_opts;
 
 int cs_pearson_f32(const cs_layout *Limg, const float *d_img,
                    const cs_kernel_desc *K, const cs_pearson_opts *opts,
                    int32_t oy0, int32_t oy1, int32_t ox0, int32_t ox1,
                    int32_t odlo, int32_t odhi,
-                   const cs_layout *Lout, float *d_out, uint16_t *d_nobs,
+                   const cs_layout *Lout, float *d_out, void *d_nmiss,
                    void *stream);
 /* Height (output rows) of the tiles cs_pearson_f32 would use for this call.  A caller that
  * splits one region into row ranges (the slab pipeline of cs_normxcorr2_host) cuts at
@@ -143,8 +171,10 @@ int64_t cs_scan_scratch(int32_t rows);
 int cs_scores_count(const cs_layout *Lout, const float *d_out,
                     int32_t dmin, int32_t dmax, /* keep only dmin <= col-row <= dmax */
                     int64_t *d_indptr, int64_t *nnz_host, void *stream);
-int cs_scores_emit(const cs_layout *Lout, const float *d_out, const uint16_t *d_nobs,
-                   int32_t nobs_const, int32_t dmin, int32_t dmax,
+/* d_nmiss / nmiss_bytes / n_window: the missing-count plane cs_pearson_f32 wrote (NULL: every
+ * window has n_window = kh*kw observations). */
+int cs_scores_emit(const cs_layout *Lout, const float *d_out, const void *d_nmiss,
+                   int32_t nmiss_bytes, int32_t n_window, int32_t dmin, int32_t dmax,
                    const int64_t *d_indptr, int32_t *d_indices, double *d_data,
                    double *d_log10p /* may be NULL */, void *stream);
 
@@ -156,8 +186,9 @@ typedef struct cs_candidate {
     float score;
     float log10p;
 } cs_candidate;
-int cs_scores_candidates(const cs_layout *Lout, const float *d_out, const uint16_t *d_nobs,
-                         int32_t nobs_const, int32_t dmin, int32_t dmax, float threshold,
+int cs_scores_candidates(const cs_layout *Lout, const float *d_out, const void *d_nmiss,
+                         int32_t nmiss_bytes, int32_t n_window, int32_t dmin, int32_t dmax,
+                         float threshold,
                          cs_candidate *d_cand, int64_t cap, int64_t *d_count,
                          int64_t *n_host, void *stream);
 
@@ -203,8 +234,9 @@ typedef struct cs_gather_args {
 int cs_window_gather(const cs_gather_args *a, const int32_t *d_coords, int64_t n_coords,
                      double *d_windows /* n_coords * win_h * win_w */, uint8_t *d_valid,
                      void *stream);
-int cs_scores_lookup(const cs_layout *Lout, const float *d_out, const uint16_t *d_nobs,
-                     int32_t nobs_const, int32_t dmin, int32_t dmax, const int32_t *d_coords,
+int cs_scores_lookup(const cs_layout *Lout, const float *d_out, const void *d_nmiss,
+                     int32_t nmiss_bytes, int32_t n_window, int32_t dmin, int32_t dmax,
+                     const int32_t *d_coords,
                      int64_t n_coords, double *d_score, double *d_log10p /* may be NULL */,
                      void *stream);
 
@@ -251,9 +283,17 @@ typedef struct cs_normxcorr2_args {
     const int64_t *indptr;
     const int32_t *indices;
     const double *data;
-    int32_t has_mask;
+    int32_t has_mask;          /* 0 none, 1 pixel mask (CSR pattern), 2 geometric (below) */
     const int64_t *mask_indptr;
     const int32_t *mask_indices;
+    /* has_mask == 2: the mask make_missing_mask(shape, valid_rows, valid_cols, max_dist,
+     * sym_upper) would build (pre:535-633), given by its ingredients: uint8[rows] / uint8[cols]
+     * (1 = missing bin) and the diagonals col - row on which missing bins flag their pixels
+     * (INT32_MIN / INT32_MAX = unbounded).  The frame of frame_missing_mask is added by the
+     * library when full. */
+    const uint8_t *miss_row;
+    const uint8_t *miss_col;
+    int32_t mask_dlo, mask_dhi;
     int32_t sym_upper;
     int32_t max_dist; /* -1 = None */
     int32_t full;

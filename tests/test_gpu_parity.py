@@ -112,13 +112,32 @@ def test_detrend_golden():
             assert np.allclose(out.toarray(), ref, rtol=1e-12)
 
 
+@pytest.fixture
+def mask_form(request):
+    """Run a test with the mask reaching the device in one of its forms: "auto" (a mask made
+    by this package: geometry attached), "foreign" (the same pixels without the tag, as the
+    reference's make_missing_mask returns them: recognised from the pattern), "pixels"
+    (geometry ignored: NaN sentinels + per-pixel exact path)."""
+    from chromosight_b200.utils import detection as cud
+    form = request.param
+    old = cud.MASK_FORM
+    cud.MASK_FORM = "pixels" if form == "pixels" else "auto"
+    yield form
+    cud.MASK_FORM = old
+
+
+def _as_form(mask, form):
+    return mask.copy() if form == "foreign" else mask
+
+
+@pytest.mark.parametrize("mask_form", ["auto", "foreign", "pixels"], indirect=True)
 @pytest.mark.parametrize("seed,n,D,kname,tol", [
     (21, 700, 60, "loops", 0.5), (22, 513, 25, "loops_small", 0.5),
     (23, 400, 90, "hairpins", 0.75), (24, 333, 40, "borders", 0.75),
 ])
-def test_production_call_vs_oracle(seed, n, D, kname, tol, presets):
+def test_production_call_vs_oracle(seed, n, D, kname, tol, presets, mask_form):
     """pattern_detector's call (det:242-263) on seeded synthetic maps, checked
-    against the oracle on every window."""
+    against the oracle on every window, strictly to 1e-5."""
     from chromosight_b200 import synthetic
     from chromosight_b200.utils import detection as cud, preprocessing as cup
     from oracle import pearson_oracle as po
@@ -129,12 +148,13 @@ def test_production_call_vs_oracle(seed, n, D, kname, tol, presets):
     mat = cup.diag_trim(mat.tocsr(), D + k)
     mat.data[np.isnan(mat.data)] = 0
     mat.eliminate_zeros()
-    mask = cup.make_missing_mask(mat.shape, detect, detect, max_dist=D, sym_upper=True)
+    mask = _as_form(cup.make_missing_mask(mat.shape, detect, detect, max_dist=D, sym_upper=True), mask_form)
+    assert hasattr(mask, "_cs_geometry") == (mask_form != "foreign")
     kw = dict(max_dist=D, sym_upper=True, full=True, missing_tol=tol, pval=True)
     r, p = cud.normxcorr2(mat, kernel, missing_mask=mask, **kw)
     r0, p0, nob = po.normxcorr2_dense(mat.toarray(), kernel, missing_mask=mask.toarray(),
                                       return_nobs=True, **kw)
-    _compare(r, p, r0, p0, nob)
+    _compare(r, p, r0, p0, nob, strict=True)
     # the extension that skips scores beyond max_dist equals a diag_trim of the full
     # result (same windows; another tiling, hence another float32 rounding)
     rt, _ = cud.normxcorr2(mat, kernel, missing_mask=mask, trim_to_max_dist=True, **kw)
@@ -143,22 +163,23 @@ def test_production_call_vs_oracle(seed, n, D, kname, tol, presets):
     assert np.abs(rt - full_trim).max() <= 5e-6
 
 
-def test_inter_and_odd_shapes_vs_oracle(presets):
+@pytest.mark.parametrize("mask_form", ["auto", "foreign", "pixels"], indirect=True)
+def test_inter_and_odd_shapes_vs_oracle(presets, mask_form):
     from chromosight_b200 import synthetic
     from chromosight_b200.utils import detection as cud, preprocessing as cup
     from oracle import pearson_oracle as po
     kernel = presets.loops["kernels"][0][3:14, :]           # 11 x 17 rectangle
     imat, (vr, vc) = synthetic.inter_counts(301, 187, seed=31, density=0.2, missing_frac=0.05)
-    mask = cup.make_missing_mask(imat.shape, vr, vc, sym_upper=False)
+    mask = _as_form(cup.make_missing_mask(imat.shape, vr, vc, sym_upper=False), mask_form)
     for full in (True, False):
         kw = dict(max_dist=None, sym_upper=False, full=full, missing_tol=0.6, pval=True)
         r, p = cud.normxcorr2(imat, kernel, missing_mask=mask, **kw)
         r0, p0, nob = po.normxcorr2_dense(imat.toarray(), kernel, missing_mask=mask.toarray(),
                                           return_nobs=True, **kw)
-        _compare(r, p, r0, p0, nob)
+        _compare(r, p, r0, p0, nob, strict=True)
     r, p = cud.normxcorr2(imat, kernel, full=True, pval=True)
     r0, p0 = po.normxcorr2_dense(imat.toarray(), kernel, full=True, pval=True)
-    _compare(r, p, r0, p0)
+    _compare(r, p, r0, p0, strict=True)
 
 
 def test_error_behaviour(presets):
@@ -289,7 +310,7 @@ def test_full_size_map_against_oracle_crops(kname, ksize, tol, pearson, presets)
             gp[far] = 0
             p0 = p0.copy()
             p0[lo:hi][far] = 0
-        _compare(got, gp, exp, p0[lo:hi], nob[lo:hi])
+        _compare(got, gp, exp, p0[lo:hi], nob[lo:hi], strict=True)
 
 
 from conftest import DummyMap, detector_case_names, load_detector_case  # noqa: E402

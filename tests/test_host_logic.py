@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.cs_version() == 1
+    assert lib.cs_version() == _lib.ABI_VERSION == int(re.search(r"#define CS_ABI_VERSION (\d+)", header).group(1))
     assert lib.cs_launch_count() == 0
 
 

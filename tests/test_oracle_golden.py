@@ -105,3 +105,55 @@ def test_detector_oracle_matches_reference(name):
     assert np.allclose(windows, exp["windows"], rtol=1e-12, atol=0, equal_nan=True)
     assert np.allclose(score, exp["score"], rtol=0, atol=1e-9, equal_nan=True)
     assert np.allclose(np.log10(pvalue), np.log10(exp["pvalue"]), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_sparse_port_matches_reference(name):
+    """oracle/sparse_port.py (the timed CPU port of bench.py) against the reference's outputs on
+    every sparse fixture.  Stored round-off noise of exactly flat windows (|r| < 1e-6) may
+    differ between the two summation orders, everything else agrees to 1e-8 (1e-14 typically;
+    the near-flat windows of the zoomed hairpin template amplify fp64 round-off)."""
+    from oracle import sparse_port as spt
+    signal, kernel, kw, dense, corr_ref, pval_ref = load_case(name)
+    if dense:
+        pytest.skip("dense fixture: the port follows the sparse path (det:917-1131)")
+    r, p = spt.normxcorr2_sparse(signal, kernel, **kw)
+    r = r.toarray()
+    d = np.abs(r - corr_ref)
+    sig = (np.abs(corr_ref) > 1e-6) | (np.abs(r) > 1e-6)
+    assert d.max() < 1e-6
+    assert d[sig].max(initial=0) < 1e-8
+    if pval_ref is not None:
+        p = p.toarray()
+        fin = sig & (corr_ref != 0) & np.isfinite(pval_ref)
+        assert np.allclose(p[fin], pval_ref[fin], rtol=1e-6, atol=1e-7)
+
+
+def test_oracle_matches_live_reference_when_present():
+    """Where oracle/_ref (the unmodified reference, oracle/make_ref.sh) travelled with the
+    repository, the dense oracle and the sparse port are checked against it live on a seeded
+    production-style call -- not only through the stored fixtures."""
+    from oracle import ref_loader, sparse_port as spt
+    ref = ref_loader.load()
+    if ref is None:
+        pytest.skip("oracle/_ref absent (run oracle/make_ref.sh in the build container)")
+    det, pre, _ = ref
+    from chromosight_b200 import kernels, synthetic
+    kernel = kernels.loops["kernels"][0]
+    n, D, k = 400, 40, kernel.shape[0]
+    raw, detect = synthetic.band_counts(n, D + k, seed=9, missing_frac=0.04, max_dist=D)
+    mat = pre.detrend(raw.tocsr(), detectable_bins=detect, max_dist=D + k, max_val=10)
+    mat = pre.diag_trim(mat.tocsr(), D + k)
+    mat.data[np.isnan(mat.data)] = 0
+    mat.eliminate_zeros()
+    assert np.allclose(mat.toarray(), np.triu(np.tril(po.detrend_dense(raw.toarray(), detect, D + k, 10), D + k)),
+                       rtol=1e-12)
+    mask = pre.make_missing_mask(mat.shape, detect, detect, max_dist=D, sym_upper=True)
+    kw = dict(max_dist=D, sym_upper=True, full=True, missing_tol=0.5, pval=True)
+    r_ref, p_ref = det.normxcorr2(mat, kernel, missing_mask=mask, **kw)
+    r0, p0 = po.normxcorr2_dense(mat.toarray(), kernel, missing_mask=mask.toarray(), **kw)
+    assert np.abs(r_ref.toarray() - r0).max() < 1e-10
+    r1, p1 = spt.normxcorr2_sparse(mat, kernel, missing_mask=mask, **kw)
+    assert np.abs(r_ref.toarray() - r1.toarray()).max() < 1e-10
+    nz = r0 != 0
+    assert np.allclose(p_ref.toarray()[nz], p0[nz], rtol=1e-8, atol=1e-9)
