@@ -51,7 +51,7 @@ struct PearsonParams {
     // output pixel set (image coordinates)
     int oy0, oy1, ox0, ox1, odlo, odhi;
     // tiling
-    int TR, G, NBc, nchunks, skew;
+    int TR, G, NBc, nchunks, skew, nrb;
     int IC, IR, NW;
     // kernel geometry
     int KH, KW, KWP2, N;
@@ -275,8 +275,11 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + P.off_bar);
 
     const int tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
-    const int rb = blockIdx.x / P.nchunks;
-    const int ch = blockIdx.x - rb * P.nchunks;
+    // row tiles are taken alternately from both ends of the region: the tiles on the frame's
+    // margins (many exact-path windows) start first instead of forming the tail of the grid
+    const int rbi = blockIdx.x / P.nchunks;
+    const int ch = blockIdx.x - rbi * P.nchunks;
+    const int rb = (rbi & 1) ? (P.nrb - 1 - (rbi >> 1)) : (rbi >> 1);
     const int KH = P.KH;
     const int kh = (KH - 1) / 2;
     const int Y0 = P.oy0 + rb * P.TR;
@@ -366,6 +369,9 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
     } else if (!P.dense) {
         // only the aliases of the box outside the stored band: two triangles of at most
         // IR + 3 columns at the ends of the rows; one warp per tile row
+#ifdef CS_ABLATE
+        if (!(P.dbg & 16))
+#endif
         for (int iy = tid >> 5; iy < IR; iy += nthr >> 5) {
             const int dbase = TX - (TY + iy);
             const int clo = min(max(P.dlo - dbase, 0), IC);
@@ -533,6 +539,9 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             Cfp = bits64(cbw, fc0) & FWMASK;
             // windows whose diagonal touches the strip tables
             stripz = (d00 + RT - 1 >= P.st_base) && (d00 - (RU - 1) < P.st_base + P.st_n);
+#ifdef CS_ABLATE
+            if (P.dbg & 1) Rfp = 0u, Cfp = 0ull, stripz = false;
+#endif
         }
         if (MODE == MODE_BITS && any) {
             constexpr unsigned long long FWMASK = (XW >= 64) ? ~0ull : ((1ull << XW) - 1ull);
@@ -648,13 +657,19 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                             }
                         }
                     }
-                    // windows on the frame's margins: exact path (per-pixel predicate)
+                    // windows on a masked part of the frame: exact path (per-pixel predicate).
+                    // All four margins when margin_mode = 2; with a banded frame only the top
+                    // margin and the lower part of the right margin are masked (pre:461-477).
                     if (P.margin_mode != 0) {
-                        if ((Yw < P.my0) || (Yw + KH > P.my1)) slowu = (1u << RT) - 1u;
+                        const bool top = Yw < P.my0;
+                        const bool bottom = P.margin_mode == 2 && Yw + KH > P.my1;
+                        if (top || bottom) slowu = (1u << RT) - 1u;
                         const int tlo = P.mx0 - (X0 - kw);          // t < tlo: left margin
                         const int thi = P.mx1 - KW - (X0 - kw);     // t > thi: right margin
-                        if (tlo > 0) slowu |= (tlo >= RT) ? ((1u << RT) - 1u) : ((1u << tlo) - 1u);
-                        if (thi < RT - 1) slowu |= (thi < 0) ? ((1u << RT) - 1u) : (((1u << RT) - 1u) & ~((2u << thi) - 1u));
+                        if (P.margin_mode == 2 && tlo > 0)
+                            slowu |= (tlo >= RT) ? ((1u << RT) - 1u) : ((1u << tlo) - 1u);
+                        if (thi < RT - 1 && (P.margin_mode == 2 || Yw + KH > P.right_y0))
+                            slowu |= (thi < 0) ? ((1u << RT) - 1u) : (((1u << RT) - 1u) & ~((2u << thi) - 1u));
                     }
                 }
                 if (MODE == MODE_BITS) {
@@ -740,6 +755,9 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     if (P.dbg & 32) hard = false;
 #endif
                     if (hard) slowu |= 1u << t;
+#ifdef CS_ABLATE
+                    if (P.dbg & 2) r = Q3 + g1 + g2;
+#endif
                     rr[t] = r;
                     nn[t] = nmo;
                 }
@@ -805,6 +823,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 const int trow = RU * sg + u, tcol = sfc0 + t;  // tile position of the window's corner
                 double h1 = 0.0, h2 = 0.0, q3 = 0.0, sKm = 0.0, sKm2 = 0.0;
                 int nmiss = 0;
+#pragma unroll 2
                 for (int idx = lane; idx < KH * KW; idx += 32) {
                     const int i = idx / KW, j = idx - i * KW;
                     bool miss = false;
@@ -817,16 +836,17 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                         const int pos = (trow + i) * IC + tcol + j;
                         miss = (bits[pos >> 5] >> (pos & 31)) & 1u;
                     }
-                    if (miss) {
-                        ++nmiss;
-                        sKm += P.dK[P.N + idx];
-                        sKm2 += P.dK[2 * P.N + idx];
-                        continue;
-                    }
-                    const double sv = (double)tile[(trow + i) * IC + tcol + j];
+                    const double kc = __ldg(P.dK + idx);
+                    const double sv = miss ? 0.0 : (double)tile[(trow + i) * IC + tcol + j];
                     h1 += sv;
                     h2 = fma(sv, sv, h2);
-                    q3 = fma(sv, P.dK[idx], q3);
+                    q3 = fma(sv, kc, q3);
+                    if (MASK) {
+                        const double km = __ldg(P.dK + P.N + idx), k2m = __ldg(P.dK + 2 * P.N + idx);
+                        nmiss += miss ? 1 : 0;
+                        sKm += miss ? km : 0.0;
+                        sKm2 += miss ? k2m : 0.0;
+                    }
                 }
                 for (int o = 16; o > 0; o >>= 1) {
                     h1 += __shfl_xor_sync(0xffffffffu, h1, o);
@@ -1314,6 +1334,7 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
     P.IR = IR;
     P.NW = NW;
     const int nrb = (nrows_out + TR - 1) / TR;
+    P.nrb = nrb;
     const long long grid_ll = (long long)nrb * nchunks;
     if (grid_ll >= (1ll << 31)) {
         set_error("grid too large");
