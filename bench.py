@@ -282,6 +282,8 @@ def run_b200(a, kernel):
     raw, detect = raw_map(n, D, k, seed=rank)
     mat = cup.detrend(raw, detectable_bins=detect, max_dist=D + k, max_val=10)
     mat, mask = finish_map(mat, detect, D, k, cup.diag_trim, cup.make_missing_mask)
+
+    detrend_leg = detrend_device_leg(raw, detect, D + k, torch) if rank == 0 else None
     del raw
 
     sess = Session(local)
@@ -354,6 +356,7 @@ def run_b200(a, kernel):
 
     # ---- e2e: the reference-facing call, host matrices in and out
     e2e = None
+    detector_e2e = None
     if not a.no_e2e:
         ke = a.e2e_steps or min(a.steps, 8)
         from chromosight_b200 import _cuda
@@ -372,22 +375,58 @@ def run_b200(a, kernel):
             torch.cuda.synchronize()
             return (time.perf_counter() - t0) / ke, r, p, cs
 
-        te_pageable, r, p, _ = timed(mat, mask)
+        # the drop-in case leads: ordinary (pageable) scipy matrices, staged through the
+        # library's pinned buffers; page-locked inputs (direct DMA) are timed next to it
+        te, r, p, checksum = timed(mat, mask)
+        s = dict(cud.last_call_stats)
+        nnz_e2e = int(r.nnz)
         del r, p
-        te, r, p, checksum = timed(_cuda.pin_sparse(mat), _cuda.pin_sparse(mask))
-        t = torch.tensor([te], dtype=torch.float64, device=dev)
+        te_pinned, r, p, _ = timed(_cuda.pin_sparse(mat), _cuda.pin_sparse(mask))
+        del r, p
+        t = torch.tensor([te, te_pinned], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        te = float(t.item())
-        s = cud.last_call_stats
+        te, te_pinned = float(t[0].item()), float(t[1].item())
         e2e = {"value": world * nwin / te, "unit": UNIT,
                "h2d_bytes_per_step": int(s.get("h2d_bytes", 0)), "d2h_bytes_per_step": int(s.get("d2h_bytes", 0)),
                "ms_per_step": te * 1e3, "steps": ke, "timer": "host wall clock around the API call, max over ranks",
-               "inputs": "scipy CSR matrices with page-locked arrays (direct DMA)",
-               "pageable_inputs_ms_per_step": te_pageable * 1e3,
+               "inputs": "pageable scipy CSR matrices (signal float64 + missing mask), staged through pinned buffers",
+               "outputs": "two scipy CSR float64 matrices (scores, log10 p) of every non-zero score, as the reference returns",
+               "wire_format": "float32 score + float32 log10p + uint8 diagonal offset per stored score, widened to "
+                              "float64 / int32 on the host (csrc/host_expand.cpp)",
+               "pinned_inputs_ms_per_step": te_pinned * 1e3,
                "overlapped_span_ms": s.get("ms_kernels"),
-               "result_nnz": int(r.nnz), "checksum": checksum}
-        del r, p
+               "result_nnz": nnz_e2e, "checksum": checksum}
+
+        # ---- detector e2e: the reference's real call site (pattern_detector, det:177-345):
+        # host matrix in, table of loops + their windows out; only foci leave the device
+        from chromosight_b200 import kernels as presets
+        cfg = dict(getattr(presets, a.kernel))
+        cfg["pearson"] = a.pearson
+
+        class _Map:  # the attributes pattern_detector reads of a ContactMap (det:230-257)
+            matrix, detectable_bins, max_dist, inter, name = mat, (detect, detect), D, False, "bench"
+
+        def detect_once():
+            return cud.pattern_detector(_Map, cfg, kernel, full=True)
+
+        for _ in range(2):
+            tab, wins = detect_once()
+        barrier()
+        kd = max(3, min(ke, 5))
+        t0 = time.perf_counter()
+        for _ in range(kd):
+            tab, wins = detect_once()
+        td = (time.perf_counter() - t0) / kd
+        t = torch.tensor([td], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        td = float(t.item())
+        detector_e2e = {"value": world * nwin / td, "unit": UNIT, "ms_per_step": td * 1e3, "steps": kd,
+                        "call": "chromosight_b200.utils.detection.pattern_detector(contact_map, config, kernel, full=True)",
+                        "patterns": 0 if tab is None else int(len(tab)),
+                        "h2d_bytes_per_step": int(s.get("h2d_bytes", 0)),
+                        "d2h": "foci records, k x k float64 windows and the score / p-value at the foci"}
 
     if rank != 0:
         if world > 1:
@@ -397,9 +436,11 @@ def run_b200(a, kernel):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "dtype_detail": "float32 image and sums (centred), float64 score formulas; CSR results float64",
+        "dtype_detail": "float32 image, sums and score (centred algebra), float64 exact path for ill-conditioned / "
+                        "near-threshold windows; CSR results float64",
         "data": "synthetic", "config": workload_config(a, kernel),
-        "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "e2e": e2e, "detector_e2e": detector_e2e, "detrend": detrend_leg,
+        "gpu_launches": int(launches), "clocks": clocks,
         "step_breakdown_ms": {"fill": float(np.mean(ms_fill)), "pearson": float(np.mean(ms_pearson)),
                               "compact_csr_pvalues": float(np.mean(ms_compact))},
         "candidates_per_map": state["ncand"], "result_nnz": int(st["nnz"]),
@@ -411,6 +452,56 @@ def run_b200(a, kernel):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def detrend_device_leg(raw, detect, max_dist, torch, reps=10):
+    """K0a (csrc/detrend.cu: distance law + division, pre:129-310) with the raw CSR resident in
+    HBM: CUDA events around the two library calls, algorithmic bytes 20 B per stored pixel read
+    (8 B value + 4 B column twice: law pass and division pass... counted once each) + 8 B written."""
+    import ctypes as C
+    from chromosight_b200 import _cuda, _lib
+    lib = _lib.load()
+    csr = raw.tocsr()
+    n = csr.shape[0]
+    n_diags = int(min(n, max_dist + 1))
+    flags = np.zeros(n, dtype=np.uint8)
+    flags[np.asarray(detect)] = 1
+    d = dict(indptr=_cuda.to_device(csr.indptr, np.int64), indices=_cuda.to_device(csr.indices, np.int32),
+             data=_cuda.to_device(csr.data, np.float64), det=_cuda.to_device(flags))
+    d_sum, d_cnt = _cuda.empty(n_diags, torch.float64), _cuda.empty(n_diags, torch.int64)
+    d_law, d_out = _cuda.empty(n, torch.float64), _cuda.empty(csr.nnz, torch.float64)
+
+    def once():
+        _lib.check(lib.cs_distance_law(_cuda.ptr(d["indptr"]), _cuda.ptr(d["indices"]), _cuda.ptr(d["data"]), n,
+                                       _cuda.ptr(d["det"]), n_diags, _cuda.ptr(d_sum), _cuda.ptr(d_cnt),
+                                       _cuda.ptr(d_law), _cuda.stream_ptr()))
+        _lib.check(lib.cs_detrend_apply(_cuda.ptr(d["indptr"]), _cuda.ptr(d["indices"]), _cuda.ptr(d["data"]),
+                                        _cuda.ptr(d_out), n, _cuda.ptr(d_law), n, C.c_double(10.0),
+                                        _cuda.stream_ptr()))
+
+    for _ in range(3):
+        once()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        once()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nnz = int(csr.nnz)
+    algo = 32 * nnz   # law pass reads value + column (12 B), division pass reads 12 B and writes 8 B
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    return {"kernel": "diag_accumulate + law_finalize + detrend_rows (csrc/detrend.cu)", "ms": ms, "nnz": nnz,
+            "value": nnz / (ms * 1e-3), "unit": "stored pixels/s",
+            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": algo / (ms * 1e-3) / 1e9 / peak, "bytes_per_nnz": 32,
+                         "note": "two passes over the CSR entries (law: 12 B read; division: 12 B read + 8 B written)"}}
 
 
 def traffic_from_profile():

@@ -163,6 +163,7 @@ _PROTOS = {
                                        C.c_double, C.c_int32, _P, _P, _P, _P]),
     "cs_distance_law": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P, _P, _P, _P]),
     "cs_detrend_apply": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.c_double, _P]),
+    "cs_expand_rows": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int32]),
     "cs_normxcorr2_host": (C.c_int, [C.POINTER(Normxcorr2Args), C.POINTER(CsrResult)]),
     "cs_result_free": (None, [C.POINTER(CsrResult)]),
     "cs_session_create": (C.c_int, [C.c_int32, C.POINTER(C.c_void_p)]),
@@ -170,6 +171,7 @@ _PROTOS = {
     "cs_session_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cs_session_upload": (C.c_int, [C.c_void_p, C.POINTER(Normxcorr2Args)]),
     "cs_session_run": (C.c_int, [C.c_void_p, C.POINTER(RunStats)]),
+    "cs_session_run_scores": (C.c_int, [C.c_void_p, C.POINTER(RunStats)]),
     "cs_foci_work_bytes": (C.c_int64, [C.POINTER(Layout)]),
     "cs_scores_foci": (C.c_int, [C.POINTER(Layout), _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, _P, _P,
                                   C.c_int64, _P, C.POINTER(C.c_int64), _P]),

@@ -13,7 +13,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["image.cu", "pearson.cu", "scores.cu", "detrend.cu", "gather.cu", "host_api.cu"]
+SOURCES = ["image.cu", "pearson.cu", "scores.cu", "detrend.cu", "gather.cu", "host_api.cu", "host_expand.cpp"]
+CXX = os.environ.get("CXX", "g++")
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "chromosight_b200.h")]
 LIB = os.path.join(PKG, "libchromosight_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -31,15 +32,19 @@ def _stale(target, deps):
 
 
 def _compile(src, verbose, ablate=False):
-    obj = os.path.join(HERE, "build", src.replace(".cu", ".abl.o" if ablate else ".o"))
+    stem, ext = os.path.splitext(src)
+    obj = os.path.join(HERE, "build", stem + (".abl.o" if ablate else ".o"))
     deps = [os.path.join(HERE, src)] + [os.path.join(HERE, h) for h in HEADERS]
     if not _stale(obj, deps):
         return obj, ""
-    cmd = [NVCC] + FLAGS + (["-DCS_ABLATE"] if ablate else []) + (["-Xptxas", "-v"] if verbose else []) \
-        + ["-c", os.path.join(HERE, src), "-o", obj]
+    if ext == ".cpp":  # plain host code
+        cmd = [CXX, "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", os.path.join(HERE, src), "-o", obj]
+    else:
+        cmd = [NVCC] + FLAGS + (["-DCS_ABLATE"] if ablate else []) + (["-Xptxas", "-v"] if verbose else []) \
+            + ["-c", os.path.join(HERE, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        raise RuntimeError(f"compiler failed for {src}:\n{r.stdout}\n{r.stderr}")
     return obj, r.stderr
 
 

@@ -56,6 +56,20 @@ int scores_emit_rows(const cs_layout *Lo, const float *d_out, const void *d_nmis
                      int32_t r0, int32_t r1, int32_t *d_indices, double *d_data, double *d_log10p,
                      cudaStream_t st);
 
+// the narrow wire format of the host path (scores.cu) and its expansion on the host
+// (host_expand.cpp): rows [r0, r1) of a band result, entries indptr[r0]..indptr[r1]
+int scores_emit_rows_narrow(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
+                            int32_t nmiss_bytes, int32_t n_window, const int64_t *d_indptr,
+                            int32_t r0, int32_t r1, float *d_score, float *d_log10p,
+                            uint8_t *d_off, cudaStream_t st);
+// score / log10p / off: wire arrays indexed like the CSR entries; indptr: final row pointers
+// (host); writes data, logp (may be null), indices, indices2 (may be null) for the entries of
+// rows [r0, r1); col = row + dlo + off.  Uses up to `threads` host threads.
+void expand_rows(const float *score, const float *log10p, const uint8_t *off,
+                 const int64_t *indptr, int32_t r0, int32_t r1, int32_t dlo, double *data,
+                 double *logp, int32_t *indices, int32_t *indices2, int threads);
+int expand_threads_default();
+
 #define CS_LAUNCHED() (cs::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }

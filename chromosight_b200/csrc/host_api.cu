@@ -212,6 +212,17 @@ static void pin_release(void *p) {
 
 using namespace cs;
 
+extern "C" int cs_expand_rows(const float *score, const float *log10p, const uint8_t *off,
+                              const int64_t *indptr, int32_t r0, int32_t r1, int32_t dlo,
+                              double *data, double *logp, int32_t *indices, int32_t *indices2,
+                              int32_t threads) {
+    CS_REQUIRE(score && off && indptr && data && indices && r1 >= r0, "cs_expand_rows: bad arguments");
+    CS_REQUIRE((log10p != nullptr) == (logp != nullptr), "cs_expand_rows: log10p and logp go together");
+    expand_rows(score, log10p, off, indptr, r0, r1, dlo, data, logp, indices, indices2,
+                threads > 0 ? threads : expand_threads_default());
+    return CS_OK;
+}
+
 extern "C" void cs_result_free(cs_csr_result *r) {
     if (!r) return;
     pin_release(r->indptr);
@@ -241,11 +252,12 @@ struct cs_session {
     // device-resident inputs, images and results of this session
     DevBuf sig_indptr, sig_indices, sig_data, m_indptr, m_indices, img, out, nobs, r_indptr,
         r_indices, r_data, r_p, err, g_coords, g_win, g_flag, g_score, g_p, g_vrow, g_vcol, f_work,
-        f_rec, geo_bits;
+        f_rec, geo_bits, w_score, w_logp, w_off;
+    bool narrow = false;   // result held in the narrow wire format (band of <= 256 diagonals)
     cs_geo_mask geo;       // has_mask == 2: the mask's geometry in image coordinates
     int pearson_mask = 0;  // mask mode handed to the Pearson kernel (0 / 1 NaN sentinels / 2 geometric)
     int nmiss_bytes = 1;   // element size of the missing-count plane
-    bool uploaded = false, ran = false, empty = false;
+    bool uploaded = false, ran = false, empty = false, compacted = false;
     cs_normxcorr2_args a;
     std::vector<double> k_corr, k_mask, k2_mask;
     cs_layout Li, Lo;
@@ -276,7 +288,8 @@ extern "C" void cs_session_destroy(cs_session *s) {
                       &s->img,        &s->out,         &s->nobs,     &s->r_indptr, &s->r_indices,
                       &s->r_data,     &s->r_p,         &s->err,      &s->g_coords, &s->g_win,
                       &s->g_flag,     &s->g_score,     &s->g_p,      &s->g_vrow,   &s->g_vcol,
-                      &s->f_work,     &s->f_rec,       &s->geo_bits};
+                      &s->f_work,     &s->f_rec,       &s->geo_bits,
+                      &s->w_score,    &s->w_logp,      &s->w_off};
     cudaSetDevice(s->c->device);
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -402,6 +415,9 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
     rc = band_out ? cs_layout_band(&s->Lo, a->rows, a->cols, (int)(od_lo - sh), (int)(od_hi - sh))
                   : cs_layout_dense(&s->Lo, a->rows, a->cols);
     if (rc) return rc;
+    // band results of at most 256 diagonals travel as float32 score / float32 log10 p / uint8
+    // diagonal offset and are widened on the host (host_expand.cpp)
+    s->narrow = band_out && (od_hi - od_lo) < 256 && !getenv("CS_WIDE_RESULT");
     for (int Y = s->oy0; Y < s->oy1; ++Y) {
         long long lo = (long long)Y + od_lo, hi = (long long)Y + od_hi;
         if (lo < s->ox0) lo = s->ox0;
@@ -534,7 +550,9 @@ extern "C" int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a) {
 }
 
 // fill -> Pearson -> CSR compaction, all on the device, inputs already resident.
-extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
+static int session_compact(cs_session *s, cudaStream_t st, int64_t *nnz_out);
+
+static int session_run_impl(cs_session *s, cs_run_stats *stats, bool compact) {
     CS_REQUIRE(s && s->uploaded, "cs_session_run: nothing uploaded");
     HostCtx *c = s->c;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -569,12 +587,14 @@ extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
     if (rc) return rc;
     CS_CUDA(cudaEventRecord(s->ev[4], st));
     int64_t nnz = 0;
-    rc = cs_scores_count(&s->Lo, (const float *)s->out.p, -(1 << 30), (1 << 30),
-                         (int64_t *)s->r_indptr.p, &nnz, st);
-    if (rc) return rc;
     int32_t herr[2] = {0, 0};
     CS_CUDA(cudaMemcpyAsync(herr, s->err.p, sizeof(herr), cudaMemcpyDeviceToHost, st));
-    CS_CUDA(cudaStreamSynchronize(st));
+    s->compacted = false;
+    if (compact) {
+        if ((rc = session_compact(s, st, &nnz))) return rc;
+    } else {
+        CS_CUDA(cudaStreamSynchronize(st));
+    }
     if (herr[0] > 0 && a.has_mask) {
         set_error("There are %d non-zero elements reported as missing.", herr[0]);
         return CS_ERR_MASKED_SIGNAL;
@@ -583,18 +603,6 @@ extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
     if (herr[1] > 0 && !a.trim_to_max_dist) {
         set_error("internal: %d signal pixels fell outside the stored band", herr[1]);
         return CS_ERR_INVALID;
-    }
-    if ((rc = s->r_indices.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(int32_t)))) return rc;
-    if ((rc = s->r_data.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(double)))) return rc;
-    if (a.pval)
-        if ((rc = s->r_p.ensure((size_t)(nnz > 0 ? nnz : 1) * sizeof(double)))) return rc;
-    if (nnz > 0) {
-        rc = cs_scores_emit(&s->Lo, (const float *)s->out.p,
-                            s->want_nobs ? s->nobs.p : nullptr, s->nmiss_bytes, K.kh * K.kw,
-                            -(1 << 30), (1 << 30), (const int64_t *)s->r_indptr.p,
-                            (int32_t *)s->r_indices.p, (double *)s->r_data.p,
-                            a.pval ? (double *)s->r_p.p : nullptr, st);
-        if (rc) return rc;
     }
     CS_CUDA(cudaEventRecord(s->ev[5], st));
     CS_CUDA(cudaStreamSynchronize(st));
@@ -614,10 +622,64 @@ extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
         stats->nnz = nnz;
         stats->launches = g_launches.load() - l0;
         stats->h2d_bytes = (int64_t)s->h2d_bytes;
-        stats->d2h_bytes = (int64_t)(((size_t)a.rows + 1) * sizeof(int64_t) +
-                                     (size_t)nnz * (sizeof(int32_t) + sizeof(double) +
-                                                    (a.pval ? sizeof(double) : 0)));
+        const size_t per_nz = s->narrow ? (sizeof(float) + 1 + (a.pval ? sizeof(float) : 0))
+                                        : (sizeof(int32_t) + sizeof(double) + (a.pval ? sizeof(double) : 0));
+        stats->d2h_bytes = (int64_t)(((size_t)a.rows + 1) * sizeof(int64_t) + (size_t)nnz * per_nz);
     }
+    return CS_OK;
+}
+
+extern "C" int cs_session_run(cs_session *s, cs_run_stats *stats) {
+    return session_run_impl(s, stats, true);
+}
+
+// fill -> Pearson only: the scores stay an image in HBM (candidates, foci, validate and lookups
+// read it); the CSR compaction and the p-values of every stored score are left to a later
+// cs_session_download, which pattern_detector never needs (det:337-339 reads p at the foci)
+extern "C" int cs_session_run_scores(cs_session *s, cs_run_stats *stats) {
+    return session_run_impl(s, stats, false);
+}
+
+// K2 of the last run: non-zero scores -> CSR (narrow wire format for bands of <= 256 diagonals)
+static int session_compact(cs_session *s, cudaStream_t st, int64_t *nnz_out) {
+    const cs_normxcorr2_args &a = s->a;
+    const cs_kernel_desc &K = a.kernel;
+    int64_t nnz = 0;
+    int rc = cs_scores_count(&s->Lo, (const float *)s->out.p, -(1 << 30), (1 << 30),
+                             (int64_t *)s->r_indptr.p, &nnz, st);
+    if (rc) return rc;
+    const size_t nz1 = (size_t)(nnz > 0 ? nnz : 1);
+    if (s->narrow) {
+        if ((rc = s->w_score.ensure(nz1 * sizeof(float)))) return rc;
+        if ((rc = s->w_off.ensure(nz1))) return rc;
+        if (a.pval)
+            if ((rc = s->w_logp.ensure(nz1 * sizeof(float)))) return rc;
+        if (nnz > 0) {
+            rc = scores_emit_rows_narrow(&s->Lo, (const float *)s->out.p,
+                                         s->want_nobs ? s->nobs.p : nullptr, s->nmiss_bytes,
+                                         K.kh * K.kw, (const int64_t *)s->r_indptr.p, 0, a.rows,
+                                         (float *)s->w_score.p,
+                                         a.pval ? (float *)s->w_logp.p : nullptr,
+                                         (uint8_t *)s->w_off.p, st);
+            if (rc) return rc;
+        }
+    } else {
+        if ((rc = s->r_indices.ensure(nz1 * sizeof(int32_t)))) return rc;
+        if ((rc = s->r_data.ensure(nz1 * sizeof(double)))) return rc;
+        if (a.pval)
+            if ((rc = s->r_p.ensure(nz1 * sizeof(double)))) return rc;
+        if (nnz > 0) {
+            rc = cs_scores_emit(&s->Lo, (const float *)s->out.p,
+                                s->want_nobs ? s->nobs.p : nullptr, s->nmiss_bytes, K.kh * K.kw,
+                                -(1 << 30), (1 << 30), (const int64_t *)s->r_indptr.p,
+                                (int32_t *)s->r_indices.p, (double *)s->r_data.p,
+                                a.pval ? (double *)s->r_p.p : nullptr, st);
+            if (rc) return rc;
+        }
+    }
+    s->nnz_out = nnz;
+    s->compacted = true;
+    *nnz_out = nnz;
     return CS_OK;
 }
 
@@ -701,12 +763,58 @@ extern "C" int cs_session_download(cs_session *s, cs_csr_result *res) {
         if (h_ip2) memset(h_ip2, 0, n_ip * sizeof(int64_t));
         return CS_OK;
     }
+    if (!s->compacted) {  // the last run kept the scores as an image only
+        int64_t nz = 0;
+        if ((rc = session_compact(s, st, &nz))) return rc;
+    }
     const int64_t nnz = s->nnz_out;
     if ((rc = pin_alloc(c, (size_t)nnz * sizeof(int32_t), &h_ix))) return rc;
     if ((rc = pin_alloc(c, (size_t)nnz * sizeof(double), &h_d))) return rc;
     if (a.pval) {
         if ((rc = pin_alloc(c, (size_t)nnz * sizeof(double), &h_p))) return rc;
         if ((rc = pin_alloc(c, (size_t)nnz * sizeof(int32_t), &h_ix2))) return rc;
+    }
+    if (s->narrow) {
+        // wire arrays to pinned scratch, then widened by host threads
+        void *h_ws = nullptr, *h_wp = nullptr, *h_wo = nullptr;
+        if ((rc = pin_alloc(c, (size_t)nnz * sizeof(float), &h_ws))) return rc;
+        if ((rc = pin_alloc(c, (size_t)nnz, &h_wo))) return rc;
+        if (a.pval)
+            if ((rc = pin_alloc(c, (size_t)nnz * sizeof(float), &h_wp))) return rc;
+        struct WGuard {
+            void *a, *b, *c;
+            ~WGuard() {
+                pin_release_unlocked(a);
+                pin_release_unlocked(b);
+                pin_release_unlocked(c);
+            }
+        } wguard{h_ws, h_wp, h_wo};
+        CS_CUDA(cudaEventRecord(s->ev[0], st));
+        CS_CUDA(cudaMemcpyAsync(h_ip, s->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        if (nnz > 0) {
+            CS_CUDA(cudaMemcpyAsync(h_ws, s->w_score.p, (size_t)nnz * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CS_CUDA(cudaMemcpyAsync(h_wo, s->w_off.p, (size_t)nnz, cudaMemcpyDeviceToHost, st));
+            if (a.pval)
+                CS_CUDA(cudaMemcpyAsync(h_wp, s->w_logp.p, (size_t)nnz * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        CS_CUDA(cudaEventRecord(s->ev[1], st));
+        CS_CUDA(cudaStreamSynchronize(st));
+        if (nnz > 0)
+            expand_rows((const float *)h_ws, (const float *)h_wp, (const uint8_t *)h_wo,
+                        (const int64_t *)h_ip, 0, a.rows, s->Lo.dlo, (double *)h_d, (double *)h_p,
+                        (int32_t *)h_ix, (int32_t *)h_ix2, expand_threads_default());
+        if (a.pval) memcpy(h_ip2, h_ip, n_ip * sizeof(int64_t));
+        float msn = 0.f;
+        cudaEventElapsedTime(&msn, s->ev[0], s->ev[1]);
+        res->ms_d2h = msn;
+        res->nnz = nnz;
+        res->indices = (int32_t *)h_ix;
+        res->data = (double *)h_d;
+        res->log10p = (double *)h_p;
+        res->p_indices = (int32_t *)h_ix2;
+        res->d2h_bytes = (int64_t)(n_ip * sizeof(int64_t) +
+                                   (size_t)nnz * (sizeof(float) + 1 + (a.pval ? sizeof(float) : 0)));
+        return CS_OK;
     }
     CS_CUDA(cudaEventRecord(s->ev[0], st));
     CS_CUDA(cudaMemcpyAsync(h_ip, s->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -775,12 +883,33 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
     res->n_windows = s->n_windows;
     // worst-case result buffers: every window non-zero
     const size_t cap = (size_t)s->n_windows;
-    if ((rc = s->r_indices.ensure(cap * sizeof(int32_t)))) return rc;
-    if ((rc = s->r_data.ensure(cap * sizeof(double)))) return rc;
-    if (A.pval)
-        if ((rc = s->r_p.ensure(cap * sizeof(double)))) return rc;
+    const bool narrow = s->narrow;
     void *h_ip = nullptr, *h_ix = nullptr, *h_d = nullptr, *h_p = nullptr, *h_ip2 = nullptr,
-         *h_ix2 = nullptr, *h_tot = nullptr;
+         *h_ix2 = nullptr, *h_tot = nullptr, *h_ws = nullptr, *h_wp = nullptr, *h_wo = nullptr;
+    if (narrow) {
+        if ((rc = s->w_score.ensure(cap * sizeof(float)))) return rc;
+        if ((rc = s->w_off.ensure(cap))) return rc;
+        if (A.pval)
+            if ((rc = s->w_logp.ensure(cap * sizeof(float)))) return rc;
+        // pinned landing buffers of the wire arrays (scratch of this call)
+        if ((rc = pin_alloc(c, cap * sizeof(float), &h_ws))) return rc;
+        if ((rc = pin_alloc(c, cap, &h_wo))) return rc;
+        if (A.pval)
+            if ((rc = pin_alloc(c, cap * sizeof(float), &h_wp))) return rc;
+    } else {
+        if ((rc = s->r_indices.ensure(cap * sizeof(int32_t)))) return rc;
+        if ((rc = s->r_data.ensure(cap * sizeof(double)))) return rc;
+        if (A.pval)
+            if ((rc = s->r_p.ensure(cap * sizeof(double)))) return rc;
+    }
+    struct WireGuard {
+        void *a, *b, *c;
+        ~WireGuard() {
+            pin_release_unlocked(a);
+            pin_release_unlocked(b);
+            pin_release_unlocked(c);
+        }
+    } wireguard{h_ws, h_wp, h_wo};
     if ((rc = pin_alloc(c, n_ip * sizeof(int64_t), &h_ip))) return rc;
     res->indptr = (int64_t *)h_ip;
     if ((rc = pin_alloc(c, cap * sizeof(int32_t), &h_ix))) return rc;
@@ -816,52 +945,76 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
         }
     } evguard{ev_tot, ev_emit, ev_up};
 
-    // The p-value matrix owns a second copy of the column indices (the two returned matrices
-    // share no storage).  It is made on the host, by a helper thread that follows the
-    // downloads slab by slab, instead of crossing PCIe twice: the download is the floor of
-    // this call and the indices are a sixth of it.  CS_HOST_INDEX_COPY=0 restores the DMA.
-    bool host_ix2 = A.pval;
-    // several ranks on one box compete for host memory bandwidth: measured at 2 ranks, the host
-    // copy costs more than the DMA it saves (36 ms instead of 26 ms per call), so it is used by
-    // single-rank processes only
+    // A helper thread follows the downloads slab by slab.
+    // Narrow format: it widens the wire arrays of each slab into the float64 / int32 arrays of
+    // the two result matrices (expand_rows, a few threads with streaming stores).
+    // Wide format: the p-value matrix owns a second copy of the column indices (the two
+    // returned matrices share no storage); it is made on the host instead of crossing PCIe
+    // twice (single-rank processes only: with several ranks per box the host copies compete
+    // for memory bandwidth; CS_HOST_INDEX_COPY overrides).
+    bool host_ix2 = A.pval && !narrow;
     if (const char *w = getenv("LOCAL_WORLD_SIZE"))
         if (atoi(w) > 1) host_ix2 = false;
-    if (const char *e = getenv("CS_HOST_INDEX_COPY")) host_ix2 = A.pval && atoi(e) != 0;
-    struct IxCopier {
-        std::vector<cudaEvent_t> ev;          // slab's index download has landed
+    if (const char *e = getenv("CS_HOST_INDEX_COPY")) host_ix2 = A.pval && !narrow && atoi(e) != 0;
+    struct Follower {
+        std::vector<cudaEvent_t> ev;          // slab's download has landed
         std::vector<int64_t> off, cnt;
+        std::vector<int> r0, r1;
         std::atomic<int> n_enq{0};
         std::atomic<bool> stop{false};
         std::thread th;
-        ~IxCopier() {
+        ~Follower() {
             stop.store(true);
             if (th.joinable()) th.join();
             for (auto e : ev) cudaEventDestroy(e);
         }
-    } ixc;
-    if (host_ix2) {
-        ixc.ev.resize(nslab);
-        ixc.off.assign(nslab, 0);
-        ixc.cnt.assign(nslab, 0);
+    } fol;
+    if (host_ix2 || narrow) {
+        fol.ev.resize(nslab);
+        fol.off.assign(nslab, 0);
+        fol.cnt.assign(nslab, 0);
+        fol.r0.assign(nslab, 0);
+        fol.r1.assign(nslab, 0);
         for (int i = 0; i < nslab; ++i)
-            CS_CUDA(cudaEventCreateWithFlags(&ixc.ev[i], cudaEventDisableTiming));
+            CS_CUDA(cudaEventCreateWithFlags(&fol.ev[i], cudaEventDisableTiming));
         const int dev = c->device;
-        int32_t *src = (int32_t *)h_ix, *dst = (int32_t *)h_ix2;
-        IxCopier *ic = &ixc;
+        Follower *fp = &fol;
         const int ns = nslab;
-        ixc.th = std::thread([ic, src, dst, dev, ns] {
-            cudaSetDevice(dev);
-            for (int k = 0; k < ns; ++k) {
-                while (ic->n_enq.load(std::memory_order_acquire) <= k) {
-                    if (ic->stop.load()) return;
-                    std::this_thread::sleep_for(std::chrono::microseconds(20));
+        if (narrow) {
+            const float *ws = (const float *)h_ws, *wp = (const float *)h_wp;
+            const uint8_t *wo = (const uint8_t *)h_wo;
+            const int64_t *ip = (const int64_t *)h_ip;
+            double *dd = (double *)h_d, *dp = (double *)h_p;
+            int32_t *ix = (int32_t *)h_ix, *ix2 = (int32_t *)h_ix2;
+            const int dlo = s->Lo.dlo, nthreads = expand_threads_default();
+            fol.th = std::thread([=] {
+                cudaSetDevice(dev);
+                for (int k = 0; k < ns; ++k) {
+                    while (fp->n_enq.load(std::memory_order_acquire) <= k) {
+                        if (fp->stop.load()) return;
+                        std::this_thread::sleep_for(std::chrono::microseconds(20));
+                    }
+                    if (fp->cnt[k] == 0) continue;
+                    if (cudaEventSynchronize(fp->ev[k]) != cudaSuccess) return;
+                    expand_rows(ws, wp, wo, ip, fp->r0[k], fp->r1[k], dlo, dd, dp, ix, ix2, nthreads);
                 }
-                if (ic->cnt[k] == 0) continue;
-                if (cudaEventSynchronize(ic->ev[k]) != cudaSuccess) return;
-                // a few threads: one core does not keep up with the DMA it follows
-                memcpy_mt(dst + ic->off[k], src + ic->off[k], (size_t)ic->cnt[k] * sizeof(int32_t));
-            }
-        });
+            });
+        } else {
+            int32_t *src = (int32_t *)h_ix, *dst = (int32_t *)h_ix2;
+            fol.th = std::thread([fp, src, dst, dev, ns] {
+                cudaSetDevice(dev);
+                for (int k = 0; k < ns; ++k) {
+                    while (fp->n_enq.load(std::memory_order_acquire) <= k) {
+                        if (fp->stop.load()) return;
+                        std::this_thread::sleep_for(std::chrono::microseconds(20));
+                    }
+                    if (fp->cnt[k] == 0) continue;
+                    if (cudaEventSynchronize(fp->ev[k]) != cudaSuccess) return;
+                    // a few threads: one core does not keep up with the DMA it follows
+                    memcpy_mt(dst + fp->off[k], src + fp->off[k], (size_t)fp->cnt[k] * sizeof(int32_t));
+                }
+            });
+        }
     }
 
     // CS_TRACE=1: per-slab timeline on stderr (host clock and device events, ms from the start)
@@ -931,23 +1084,49 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
                                    scan_slot(cr0, k));
         if (r) return r;
         if (nnz_k > 0) {
-            r = scores_emit_rows(&s->Lo, (const float *)s->out.p, nb, s->nmiss_bytes, K.kh * K.kw, -(1 << 30),
-                                 1 << 30, (const int64_t *)s->r_indptr.p, cr0, cr1,
-                                 (int32_t *)s->r_indices.p, (double *)s->r_data.p,
-                                 A.pval ? (double *)s->r_p.p : nullptr, st_e);
+            if (narrow)
+                r = scores_emit_rows_narrow(&s->Lo, (const float *)s->out.p, nb, s->nmiss_bytes,
+                                            K.kh * K.kw, (const int64_t *)s->r_indptr.p, cr0, cr1,
+                                            (float *)s->w_score.p,
+                                            A.pval ? (float *)s->w_logp.p : nullptr,
+                                            (uint8_t *)s->w_off.p, st_e);
+            else
+                r = scores_emit_rows(&s->Lo, (const float *)s->out.p, nb, s->nmiss_bytes, K.kh * K.kw,
+                                     -(1 << 30), 1 << 30, (const int64_t *)s->r_indptr.p, cr0, cr1,
+                                     (int32_t *)s->r_indices.p, (double *)s->r_data.p,
+                                     A.pval ? (double *)s->r_p.p : nullptr, st_e);
             if (r) return r;
         }
         CS_CUDA(cudaEventRecord(ev_emit[k], st_e));
         CS_CUDA(cudaStreamWaitEvent(st_d, ev_emit[k], 0));
         if (trace) CS_CUDA(cudaEventRecord(tev[4 * k + 2], st_d));
-        if (nnz_k > 0) {
-            const size_t o = (size_t)base, n = (size_t)nnz_k;
+        const size_t o = (size_t)base, n = (size_t)nnz_k;
+        if (narrow) {
+            // the slab's final row pointers (the expansion needs them), then its wire arrays
+            CS_CUDA(cudaMemcpyAsync((int64_t *)h_ip + cr0, (int64_t *)s->r_indptr.p + cr0,
+                                    (size_t)(cr1 - cr0 + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                    st_d));
+            if (nnz_k > 0) {
+                CS_CUDA(cudaMemcpyAsync((float *)h_ws + o, (float *)s->w_score.p + o, n * sizeof(float),
+                                        cudaMemcpyDeviceToHost, st_d));
+                CS_CUDA(cudaMemcpyAsync((uint8_t *)h_wo + o, (uint8_t *)s->w_off.p + o, n,
+                                        cudaMemcpyDeviceToHost, st_d));
+                if (A.pval)
+                    CS_CUDA(cudaMemcpyAsync((float *)h_wp + o, (float *)s->w_logp.p + o,
+                                            n * sizeof(float), cudaMemcpyDeviceToHost, st_d));
+                CS_CUDA(cudaEventRecord(fol.ev[k], st_d));
+            }
+            fol.off[k] = (int64_t)o;
+            fol.cnt[k] = (int64_t)n;
+            fol.r0[k] = cr0;
+            fol.r1[k] = cr1;
+        } else if (nnz_k > 0) {
             CS_CUDA(cudaMemcpyAsync((int32_t *)h_ix + o, (int32_t *)s->r_indices.p + o,
                                     n * sizeof(int32_t), cudaMemcpyDeviceToHost, st_d));
             if (host_ix2) {
-                CS_CUDA(cudaEventRecord(ixc.ev[k], st_d));
-                ixc.off[k] = (int64_t)o;
-                ixc.cnt[k] = (int64_t)n;
+                CS_CUDA(cudaEventRecord(fol.ev[k], st_d));
+                fol.off[k] = (int64_t)o;
+                fol.cnt[k] = (int64_t)n;
             }
             CS_CUDA(cudaMemcpyAsync((double *)h_d + o, (double *)s->r_data.p + o, n * sizeof(double),
                                     cudaMemcpyDeviceToHost, st_d));
@@ -959,7 +1138,7 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
                                             n * sizeof(int32_t), cudaMemcpyDeviceToHost, st_d));
             }
         }
-        if (host_ix2) ixc.n_enq.store(k + 1, std::memory_order_release);
+        if (host_ix2 || narrow) fol.n_enq.store(k + 1, std::memory_order_release);
         if (trace) CS_CUDA(cudaEventRecord(tev[4 * k + 3], st_d));
         base += nnz_k;
         return CS_OK;
@@ -1038,19 +1217,23 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
         if ((rc = finalize(n_final))) return rc;
     int32_t *herr = (int32_t *)(tot + nslab);  // last slot of the pinned totals block
     CS_CUDA(cudaMemcpyAsync(herr, s->err.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    // row pointers: final once every slab has been finalized (the copy stream follows them all)
-    CS_CUDA(cudaMemcpyAsync(h_ip, s->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost,
-                            st_d));
-    if (A.pval)
-        CS_CUDA(cudaMemcpyAsync(h_ip2, s->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost,
+    // row pointers: final once every slab has been finalized (the copy stream follows them
+    // all); the narrow path has downloaded them slab by slab
+    if (!narrow) {
+        CS_CUDA(cudaMemcpyAsync(h_ip, s->r_indptr.p, n_ip * sizeof(int64_t), cudaMemcpyDeviceToHost,
                                 st_d));
+        if (A.pval)
+            CS_CUDA(cudaMemcpyAsync(h_ip2, s->r_indptr.p, n_ip * sizeof(int64_t),
+                                    cudaMemcpyDeviceToHost, st_d));
+    }
     // the span ends when the last download has landed
     CS_CUDA(cudaEventRecord(ev_emit[0], st_d));
     CS_CUDA(cudaStreamWaitEvent(st, ev_emit[0], 0));
     CS_CUDA(cudaEventRecord(s->ev[5], st));
     CS_CUDA(cudaStreamSynchronize(st));
     CS_CUDA(cudaStreamSynchronize(st_d));
-    if (host_ix2 && ixc.th.joinable()) ixc.th.join();  // the last slab's index copy
+    if (narrow && A.pval) memcpy(h_ip2, h_ip, n_ip * sizeof(int64_t));
+    if (fol.th.joinable()) fol.th.join();  // the last slab's expansion / index copy
     if (trace) {
         fprintf(stderr, "slab  host:enq0  enq1  fin_wait0 fin_wait1 | dev:compute0 compute1 d2h0 d2h1 (ms)\n");
         for (int k = 0; k < nslab; ++k) {
@@ -1080,9 +1263,13 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
     cudaEventElapsedTime(&ms, s->ev[2], s->ev[5]);
     res->ms_kernels = ms;  // upload, kernels and most of the download overlap inside this span
     res->h2d_bytes = (int64_t)s->h2d_bytes;
-    res->d2h_bytes = (int64_t)(n_ip * sizeof(int64_t) * (A.pval ? 2 : 1) +
-                               (size_t)base * (sizeof(int32_t) * ((A.pval && !host_ix2) ? 2 : 1) +
-                                               sizeof(double) * (A.pval ? 2 : 1)));
+    if (narrow)
+        res->d2h_bytes = (int64_t)(n_ip * sizeof(int64_t) +
+                                   (size_t)base * (sizeof(float) + 1 + (A.pval ? sizeof(float) : 0)));
+    else
+        res->d2h_bytes = (int64_t)(n_ip * sizeof(int64_t) * (A.pval ? 2 : 1) +
+                                   (size_t)base * (sizeof(int32_t) * ((A.pval && !host_ix2) ? 2 : 1) +
+                                                   sizeof(double) * (A.pval ? 2 : 1)));
     return CS_OK;
 }
 

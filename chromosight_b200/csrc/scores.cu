@@ -152,6 +152,41 @@ __global__ void emit_rows(ScoreView S, const float *__restrict__ sc,
     }
 }
 
+// The same rows in the narrow wire format of the host path: float32 score, float32 log10 p
+// and the column as a uint8 offset from the first stored diagonal of the row (bands of at
+// most 256 diagonals): 9 bytes per stored score instead of 20.  The float64 CSR arrays scipy
+// gets are expanded from these on the host (host_expand.cpp), losslessly: the scores are
+// float32 on the device anyway and the p-values are evaluated in float32.
+__global__ void emit_rows_narrow(ScoreView S, const float *__restrict__ sc, NmissPlane nobs,
+                                 const int64_t *__restrict__ indptr, float *score, float *log10p,
+                                 unsigned char *off, int r0, int r1) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    for (int y = r0 + blockIdx.x * wpb + (threadIdx.x >> 5); y < r1; y += gridDim.x * wpb) {
+        int x0, x1;
+        row_range(S, y, x0, x1);
+        int64_t pos = indptr[y];
+        const int xbase = y + S.dlo;  // column of offset 0
+        for (int xb = x0; xb < x1; xb += 32) {
+            const int x = xb + lane;
+            float v = 0.f;
+            long long i = 0;
+            if (x < x1) {
+                i = sidx(S, y, x);
+                v = sc[i];
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, v != 0.f);
+            if (v != 0.f) {
+                const int64_t o = pos + __popc(m & ((1u << lane) - 1u));
+                score[o] = v;
+                off[o] = (unsigned char)(x - xbase);
+                if (log10p) log10p[o] = (float)log10_pval(v, nobs_at(nobs, i));
+            }
+            pos += __popc(m);
+        }
+    }
+}
+
 __global__ void emit_candidates(ScoreView S, const float *__restrict__ sc,
                                 NmissPlane nobs,
                                 float threshold, cs_candidate *out, long long cap,
@@ -407,6 +442,22 @@ using namespace cs;
 
 // Row ranges scanned independently (the slabs of the host pipeline) own disjoint parts of
 // the scratch: a range starting at row r0, the k-th of a call, uses cs_scan_slot(r0, k).
+int cs::scores_emit_rows_narrow(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
+                                int32_t nmiss_bytes, int32_t n_window, const int64_t *d_indptr,
+                                int32_t r0, int32_t r1, float *d_score, float *d_log10p,
+                                uint8_t *d_off, cudaStream_t st) {
+    if (r1 <= r0) return CS_OK;
+    CS_REQUIRE(!Lo->dense && Lo->dhi - Lo->dlo < 256, "narrow result format needs a band of <= 256 diagonals");
+    ScoreView S = make_view(Lo, -(1 << 30), 1 << 30);
+    int grid = (r1 - r0 + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    emit_rows_narrow<<<grid, 256, 0, st>>>(S, d_out, NmissPlane{d_nmiss, nmiss_bytes, n_window},
+                                           d_indptr, d_score, d_log10p, d_off, r0, r1);
+    CS_LAUNCHED();
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
 extern "C" int64_t cs_scan_scratch(int32_t rows) {
     return (int64_t)((rows + cs::kScanChunk - 1) / cs::kScanChunk) + 2 + 256;
 }

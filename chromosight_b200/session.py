@@ -68,11 +68,14 @@ class Session:
         self.pval = bool(pval)
         return self
 
-    def run(self):
-        """fill -> Pearson -> CSR compaction on the device; returns the run statistics."""
+    def run(self, compact=True):
+        """fill -> Pearson -> CSR compaction (+ p-values of every stored score) on the device;
+        returns the run statistics.  compact=False stops after the Pearson kernel: candidates,
+        foci and validate only read the score image (download compacts on demand)."""
         self._bind_stream()
         st = _lib.RunStats()
-        _lib.check(self._lib.cs_session_run(self._h, C.byref(st)))
+        fn = self._lib.cs_session_run if compact else self._lib.cs_session_run_scores
+        _lib.check(fn(self._h, C.byref(st)))
         self.stats = {f: getattr(st, f) for f, _ in _lib.RunStats._fields_}
         return self.stats
 
@@ -94,7 +97,9 @@ class Session:
         if out is None:
             out = t.empty((cap, 4), dtype=t.int32, device=dev)
         cap = out.shape[0]
-        cnt = t.zeros(1, dtype=t.int64, device=dev)
+        # (the library zeroes the counter on its own stream: no torch-side fill that could
+        # land after it when the session runs on the library stream)
+        cnt = t.empty(1, dtype=t.int64, device=dev)
         n = C.c_int64(0)
         _lib.check(self._lib.cs_session_candidates(self._h, C.c_float(threshold), int(dmin),
                                                    int(min(dmax, 2 ** 30)), _cuda.ptr(out), cap,

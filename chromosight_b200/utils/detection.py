@@ -375,7 +375,9 @@ def pattern_detector(contact_map, kernel_config, kernel_matrix, coords=None, dum
         sess.upload(contact_map.matrix, kernel_matrix, max_dist=contact_map.max_dist,
                     sym_upper=not inter, full=full, mask_geometry=geometry, tsvd=tsvd, pval=True,
                     missing_tol=kernel_config["max_perc_undetected"] / 100)
-        sess.run()
+        # the detector reads the score image only (foci, lookups at coordinates): the CSR
+        # compaction and the p-values of every stored score are skipped unless dumped
+        sess.run(compact=bool(dump))
         dmax = 2 ** 30 if inter else int(contact_map.max_dist)
         dmin = -(2 ** 30) if inter else 0
         if dump:

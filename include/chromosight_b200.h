@@ -259,6 +259,19 @@ int cs_detrend_apply(const int64_t *d_indptr, const int32_t *d_indices, const do
                      double max_val, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Narrow result format of the host path.  Band results of at most 256 diagonals leave the
+ * device as float32 score, float32 log10 p and the column as a uint8 offset from the row's
+ * first stored diagonal (9 B per stored score over PCIe instead of 20); this HOST function
+ * widens rows [r0, r1) of it into the float64 / int32 arrays of the CSR matrices
+ * (det:1098-1131) with up to `threads` threads (0 = default).  log10p / logp / indices2 may
+ * be NULL.  Exposed for tests; cs_normxcorr2_host and cs_session_download call it.
+ * ------------------------------------------------------------------------ */
+int cs_expand_rows(const float *score, const float *log10p, const uint8_t *off,
+                   const int64_t *indptr, int32_t r0, int32_t r1, int32_t dlo,
+                   double *data, double *logp, int32_t *indices, int32_t *indices2,
+                   int32_t threads);
+
+/* ------------------------------------------------------------------------
  * Host-buffer, whole-call entry point: what chromosight.utils.detection.
  * normxcorr2 (det:807-914) does for a sparse signal, from host CSR arrays to
  * host CSR arrays, including host<->device copies through pinned staging.
@@ -330,6 +343,10 @@ void cs_session_destroy(cs_session *s);
 int cs_session_set_stream(cs_session *s, void *stream);
 int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a);
 int cs_session_run(cs_session *s, cs_run_stats *stats);
+/* fill -> Pearson only: the scores stay a float32 image in HBM, which is all that
+ * cs_session_candidates / _foci / _validate read (pattern_detector, det:265-345, needs
+ * p-values at the foci only); cs_session_download compacts on demand. */
+int cs_session_run_scores(cs_session *s, cs_run_stats *stats);
 int cs_session_candidates(cs_session *s, float threshold, int32_t dmin, int32_t dmax,
                           cs_candidate *d_cand, int64_t cap, int64_t *d_count, int64_t *n_host);
 int cs_session_download(cs_session *s, cs_csr_result *res);

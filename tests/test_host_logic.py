@@ -184,3 +184,44 @@ def test_global_host_filters_match_reference():
     assert i == 4
     assert np.allclose(cud.pileup_patterns(z["pile_in"]), z["pile_out"], equal_nan=True)
     assert np.allclose(cus.fdr_correction(z["fdr_in"]), z["fdr_out"])
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_expand_rows_narrow_format(threads):
+    """Host side of the narrow result format (csrc/host_expand.cpp): float32 score / log10 p and
+    uint8 diagonal offsets -> float64 data and int32 column indices, bit for bit."""
+    from chromosight_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(threads)
+    rows, dlo = 5000, -3
+    counts = rng.integers(0, 240, size=rows)
+    counts[rng.random(rows) < 0.1] = 0
+    indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    n = int(indptr[-1])
+    score = rng.standard_normal(n).astype(np.float32)
+    logp = (-np.abs(rng.standard_normal(n)) * 5).astype(np.float32)
+    logp[::97] = -np.inf
+    off = np.concatenate([np.sort(rng.choice(256, size=c, replace=False)) for c in counts]).astype(np.uint8)
+    for r0, r1 in ((0, rows), (123, 4001)):
+        data = np.full(n + 3, 7.0)[3:]           # deliberately not 64-byte aligned
+        lp = np.full(n, 7.0)
+        idx = np.full(n, -1, dtype=np.int32)
+        idx2 = np.full(n, -1, dtype=np.int32)
+        rc = lib.cs_expand_rows(score.ctypes.data, logp.ctypes.data, off.ctypes.data, indptr.ctypes.data,
+                                r0, r1, dlo, data.ctypes.data, lp.ctypes.data, idx.ctypes.data,
+                                idx2.ctypes.data, threads)
+        assert rc == 0
+        a, b = int(indptr[r0]), int(indptr[r1])
+        row_of = np.repeat(np.arange(rows), counts)
+        assert np.array_equal(data[a:b], score[a:b].astype(np.float64))
+        assert np.array_equal(lp[a:b], logp[a:b].astype(np.float64))
+        exp_idx = (row_of + dlo + off.astype(np.int64)).astype(np.int32)
+        assert np.array_equal(idx[a:b], exp_idx[a:b]) and np.array_equal(idx2[a:b], exp_idx[a:b])
+        # nothing outside the row range is touched
+        assert np.all(data[:a] == 7.0) and np.all(data[b:] == 7.0) and np.all(idx[:a] == -1) and np.all(idx[b:] == -1)
+    # without p-values / second index array
+    data = np.zeros(n)
+    idx = np.zeros(n, dtype=np.int32)
+    assert lib.cs_expand_rows(score.ctypes.data, None, off.ctypes.data, indptr.ctypes.data, 0, rows, dlo,
+                              data.ctypes.data, None, idx.ctypes.data, None, threads) == 0
+    assert np.array_equal(data, score.astype(np.float64))
