@@ -60,6 +60,9 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=50_000, help="rows of the CPU-baseline slab")
     ap.add_argument("--ref-rows", type=int, default=2_000, help="rows per worker per step (--impl reference)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 8)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one chromosome per GPU (independent sub-matrices); strong: ONE chromosome cut "
+                         "into row slabs over the GPUs (rowslab.py: law all-reduce + candidate gather)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -194,7 +197,9 @@ def workload_config(a, kernel, sample=None):
         "windows_per_map": synthetic.n_windows(a.n, a.max_dist),
         "missing_bins": "2%", "seed": 0,
         "l2": "inputs_exceed_l2 (CSR input, fp32 band and score band are each > 126 MB)",
-        "parallelism": f"{a.gpus} x one chromosome per GPU (independent sub-matrices)",
+        "parallelism": (f"one chromosome cut into {a.gpus} row slabs (halo k above, D+3k below; distance law by one all-reduce)"
+                        if getattr(a, "scaling", "weak") == "strong" and a.gpus > 1
+                        else f"{a.gpus} x one chromosome per GPU (independent sub-matrices)"),
     }
     if sample:
         cfg["sample"] = sample
@@ -278,12 +283,23 @@ def run_b200(a, kernel):
     kw = call_kwargs(D)
     nwin = synthetic.n_windows(n, D)
 
-    # ---- inputs: one chromosome per rank (weak scaling), detrended with the CUDA path (a8)
-    raw, detect = raw_map(n, D, k, seed=rank)
-    mat = cup.detrend(raw, detectable_bins=detect, max_dist=D + k, max_val=10)
-    mat, mask = finish_map(mat, detect, D, k, cup.diag_trim, cup.make_missing_mask)
-
-    detrend_leg = detrend_device_leg(raw, detect, D + k, torch) if rank == 0 else None
+    strong = a.scaling == "strong" and world > 1
+    plan = None
+    if strong:
+        # ---- ONE chromosome over all ranks: row slabs with halos, global distance law by one
+        # all-reduce of the per-diagonal sums
+        from chromosight_b200 import rowslab
+        raw, detect_all = raw_map(n, D, k, seed=0)
+        plan = rowslab.slab_plan(n, world, k, D)[rank]
+        law = rowslab.global_law(raw, detect_all, D + k, plan[0], plan[1])
+        mat, detect = rowslab.slab_inputs(raw, detect_all, law, plan, D, k)
+        mask = cup.make_missing_mask(mat.shape, detect, detect, max_dist=D, sym_upper=True)
+    else:
+        # ---- one chromosome per rank (weak scaling), detrended with the CUDA path (a8)
+        raw, detect = raw_map(n, D, k, seed=rank)
+        mat = cup.detrend(raw, detectable_bins=detect, max_dist=D + k, max_val=10)
+        mat, mask = finish_map(mat, detect, D, k, cup.diag_trim, cup.make_missing_mask)
+    detrend_leg = detrend_device_leg(raw, detect_all if strong else detect, D + k, torch) if rank == 0 else None
     del raw
 
     sess = Session(local)
@@ -291,16 +307,28 @@ def run_b200(a, kernel):
     cap = 1 << 22
     cand_buf = torch.empty((cap, 4), dtype=torch.int32, device=dev)
     state = {"ncand": 0, "gathered": 0}
+    gather_cap = 1 << 16   # records exchanged per rank by the final gather (1 MB)
 
     def step():
         st = sess.run()
         _, nc = sess.candidates(a.pearson, 0, D, out=cand_buf)
         state["ncand"] = nc
-        if world > 1:
-            # the one collective of the path: candidate records of every sub-matrix
-            _, counts = sharding.gather_candidates(cand_buf, nc)
-            state["gathered"] = int(counts.sum().item())
         return st
+
+    def final_gather():
+        # the one collective of the path (north_star): the candidate records of every rank, once,
+        # at the end of the run; fixed size, no host synchronisation
+        if world > 1:
+            send, nc = cand_buf, state["ncand"]
+            if strong:
+                from chromosight_b200 import rowslab
+                from chromosight_b200.session import records_to_numpy
+                mine = rowslab.owned_candidates(records_to_numpy(cand_buf, nc), plan)
+                nc = len(mine)
+                send = torch.zeros((gather_cap, 4), dtype=torch.int32, device=dev)
+                send[:nc] = torch.from_numpy(mine.view(np.int32).reshape(-1, 4)).to(dev)
+            gathered, counts = sharding.gather_candidates(send, nc, cap=gather_cap)
+            state["gathered_t"] = (gathered, counts)
 
     def barrier():
         torch.cuda.synchronize()
@@ -324,8 +352,11 @@ def run_b200(a, kernel):
         ms_pearson.append(st["ms_pearson"])
         ms_fill.append(st["ms_fill"])
         ms_compact.append(st["ms_compact"])
+    final_gather()
     ev1.record()
     barrier()
+    if world > 1:
+        state["gathered"] = int(state["gathered_t"][1].sum().item())
     launches = _lib.launch_count() - l0
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
@@ -333,7 +364,7 @@ def run_b200(a, kernel):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / a.steps
-    value = world * nwin / (ms_step * 1e-3)
+    value = (1 if strong else world) * nwin / (ms_step * 1e-3)
     n_eval = int(st["n_windows"])
     peaks = {}
     try:
@@ -387,7 +418,7 @@ def run_b200(a, kernel):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         te, te_pinned = float(t[0].item()), float(t[1].item())
-        e2e = {"value": world * nwin / te, "unit": UNIT,
+        e2e = {"value": (1 if strong else world) * nwin / te, "unit": UNIT,
                "h2d_bytes_per_step": int(s.get("h2d_bytes", 0)), "d2h_bytes_per_step": int(s.get("d2h_bytes", 0)),
                "ms_per_step": te * 1e3, "steps": ke, "timer": "host wall clock around the API call, max over ranks",
                "inputs": "pageable scipy CSR matrices (signal float64 + missing mask), staged through pinned buffers",
@@ -422,7 +453,7 @@ def run_b200(a, kernel):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         td = float(t.item())
-        detector_e2e = {"value": world * nwin / td, "unit": UNIT, "ms_per_step": td * 1e3, "steps": kd,
+        detector_e2e = {"value": (1 if strong else world) * nwin / td, "unit": UNIT, "ms_per_step": td * 1e3, "steps": kd,
                         "call": "chromosight_b200.utils.detection.pattern_detector(contact_map, config, kernel, full=True)",
                         "patterns": 0 if tab is None else int(len(tab)),
                         "h2d_bytes_per_step": int(s.get("h2d_bytes", 0)),
@@ -435,7 +466,7 @@ def run_b200(a, kernel):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32",
         "dtype_detail": "float32 image, sums and score (centred algebra), float64 exact path for ill-conditioned / "
                         "near-threshold windows; CSR results float64",
         "data": "synthetic", "config": workload_config(a, kernel),
@@ -443,7 +474,10 @@ def run_b200(a, kernel):
         "gpu_launches": int(launches), "clocks": clocks,
         "step_breakdown_ms": {"fill": float(np.mean(ms_fill)), "pearson": float(np.mean(ms_pearson)),
                               "compact_csr_pvalues": float(np.mean(ms_compact))},
-        "candidates_per_map": state["ncand"], "result_nnz": int(st["nnz"]),
+        "candidates_per_map": state["ncand"], "candidates_gathered": state["gathered"],
+        "collective": "one all-gather of the candidate records (fixed 65536 x 16 B per rank) after the last step"
+                      if world > 1 else None,
+        "result_nnz": int(st["nnz"]),
     }
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(a.cpu_rows, D, kernel)

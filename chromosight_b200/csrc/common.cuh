@@ -70,6 +70,29 @@ void expand_rows(const float *score, const float *log10p, const uint8_t *off,
                  double *logp, int32_t *indices, int32_t *indices2, int threads);
 int expand_threads_default();
 
+// exact float64 recomputation, from the CSR signal, of the scores at / near a Pearson threshold
+// (pearson.cu): makes the candidate set of pick_foci independent of float32 rounding
+struct RefineArgs {
+    const cs_kernel_desc *K;
+    const cs_pearson_opts *opts;  // mask mode, frame geometry, missing_tol, nobs_full, nmiss_bytes
+    const int64_t *d_indptr;      // signal CSR (matrix coordinates)
+    const int32_t *d_indices;
+    const double *d_data;
+    int rows, cols, pr, pc;       // matrix shape and its offset in the framed image
+    const int64_t *d_m_indptr;    // pixel mask CSR (mask mode 1)
+    const int32_t *d_m_indices;
+    int trim_lo, trim_hi;         // diagonals of the pixel mask kept by the frame
+    const cs_layout *Lo;          // score image (matrix coordinates)
+    float *d_out;
+    void *d_nmiss;
+    double threshold;
+    int dmin, dmax;
+    int2 *d_list;                 // scratch: cap pixels + one counter
+    long long cap;
+    unsigned long long *d_count;
+};
+int exact_refine(const RefineArgs &R, cudaStream_t st, long long *n_refined);
+
 #define CS_LAUNCHED() (cs::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }

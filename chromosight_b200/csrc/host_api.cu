@@ -252,11 +252,15 @@ struct cs_session {
     // device-resident inputs, images and results of this session
     DevBuf sig_indptr, sig_indices, sig_data, m_indptr, m_indices, img, out, nobs, r_indptr,
         r_indices, r_data, r_p, err, g_coords, g_win, g_flag, g_score, g_p, g_vrow, g_vcol, f_work,
-        f_rec, geo_bits, w_score, w_logp, w_off;
+        f_rec, geo_bits, w_score, w_logp, w_off, x_list;
+    long long n_refined = 0;
     bool narrow = false;   // result held in the narrow wire format (band of <= 256 diagonals)
     cs_geo_mask geo;       // has_mask == 2: the mask's geometry in image coordinates
     int pearson_mask = 0;  // mask mode handed to the Pearson kernel (0 / 1 NaN sentinels / 2 geometric)
     int nmiss_bytes = 1;   // element size of the missing-count plane
+    int trim_lo = 0, trim_hi = 0;  // diagonals of a pixel mask the frame keeps (pre:452-454)
+    double refined_thr = 0.0;      // threshold the scores were last refined for
+    bool refined = false;
     bool uploaded = false, ran = false, empty = false, compacted = false;
     cs_normxcorr2_args a;
     std::vector<double> k_corr, k_mask, k2_mask;
@@ -289,7 +293,8 @@ extern "C" void cs_session_destroy(cs_session *s) {
                       &s->r_data,     &s->r_p,         &s->err,      &s->g_coords, &s->g_win,
                       &s->g_flag,     &s->g_score,     &s->g_p,      &s->g_vrow,   &s->g_vcol,
                       &s->f_work,     &s->f_rec,       &s->geo_bits,
-                      &s->w_score,    &s->w_logp,      &s->w_off};
+                      &s->w_score,    &s->w_logp,      &s->w_off,
+                      &s->x_list};
     cudaSetDevice(s->c->device);
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -442,31 +447,19 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
         s->nmiss_bytes = (N - (min_present > 1 ? min_present : 1) <= 255) ? 1 : 2;
     }
     size_t geo_h2d = 0;
-    if (a->has_mask == 2) {
-        CS_REQUIRE(a->miss_row && a->miss_col, "geometric mask: missing-bin vectors missing");
-        // bit vectors over image rows / columns, 4 zero words of padding on both sides
-        const int nwr = (H + 31) / 32 + 8, nwc = (W + 31) / 32 + 8;
-        std::vector<uint32_t> hb((size_t)nwr + nwc, 0u);
-        uint32_t *hr = hb.data() + 4, *hc = hb.data() + nwr + 4;
-        for (int r = 0; r < a->rows; ++r)
-            if (a->miss_row[r]) hr[(r + pr) >> 5] |= 1u << ((r + pr) & 31);
-        for (int cidx = 0; cidx < a->cols; ++cidx)
-            if (a->miss_col[cidx]) hc[(cidx + pc) >> 5] |= 1u << ((cidx + pc) & 31);
-        if ((rc = s->geo_bits.ensure(hb.size() * sizeof(uint32_t)))) return rc;
-        // pageable source: staged by the runtime before the call returns
-        CS_CUDA(cudaMemcpyAsync(s->geo_bits.p, hb.data(), hb.size() * sizeof(uint32_t),
-                                cudaMemcpyHostToDevice, st));
-        geo_h2d = hb.size() * sizeof(uint32_t);
+    s->trim_lo = -(1 << 29), s->trim_hi = 1 << 29;
+    if (a->has_mask) {
+        // the frame of frame_missing_mask (pre:404-498) in image coordinates, for both mask forms
         cs_geo_mask &g = s->geo;
-        g.d_row_bits = (const uint32_t *)s->geo_bits.p + 4;
-        g.d_col_bits = (const uint32_t *)s->geo_bits.p + nwr + 4;
         const bool banded = a->sym_upper && a->max_dist >= 0;
         const int big_k = mk > nk ? mk : nk;
-        long long lo = a->mask_dlo, hi = a->mask_dhi;
+        long long lo = a->has_mask == 2 ? (long long)a->mask_dlo : -(1ll << 40);
+        long long hi = a->has_mask == 2 ? (long long)a->mask_dhi : (1ll << 40);
         if (a->full && banded) {
             // pre:452-454: the mask is diag-trimmed to max_dist + max(mk, nk) before framing
             if (lo < 0) lo = 0;
             if (hi > (long long)a->max_dist + big_k) hi = (long long)a->max_dist + big_k;
+            s->trim_lo = 0, s->trim_hi = a->max_dist + big_k;
         }
         const long long lim = 1ll << 29;
         lo += pc - pr, hi += pc - pr;
@@ -488,6 +481,24 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
         }
         // detrended maps have mean 1 on every diagonal; the wide kernel wants NaN sentinels
         g.fill_value = wide ? __builtin_nanf("") : 1.0f;
+    }
+    if (a->has_mask == 2) {
+        CS_REQUIRE(a->miss_row && a->miss_col, "geometric mask: missing-bin vectors missing");
+        // bit vectors over image rows / columns, 4 zero words of padding on both sides
+        const int nwr = (H + 31) / 32 + 8, nwc = (W + 31) / 32 + 8;
+        std::vector<uint32_t> hb((size_t)nwr + nwc, 0u);
+        uint32_t *hr = hb.data() + 4, *hc = hb.data() + nwr + 4;
+        for (int r = 0; r < a->rows; ++r)
+            if (a->miss_row[r]) hr[(r + pr) >> 5] |= 1u << ((r + pr) & 31);
+        for (int cidx = 0; cidx < a->cols; ++cidx)
+            if (a->miss_col[cidx]) hc[(cidx + pc) >> 5] |= 1u << ((cidx + pc) & 31);
+        if ((rc = s->geo_bits.ensure(hb.size() * sizeof(uint32_t)))) return rc;
+        // pageable source: staged by the runtime before the call returns
+        CS_CUDA(cudaMemcpyAsync(s->geo_bits.p, hb.data(), hb.size() * sizeof(uint32_t),
+                                cudaMemcpyHostToDevice, st));
+        geo_h2d = hb.size() * sizeof(uint32_t);
+        s->geo.d_row_bits = (const uint32_t *)s->geo_bits.p + 4;
+        s->geo.d_col_bits = (const uint32_t *)s->geo_bits.p + nwr + 4;
     }
     if (a->has_mask == 1) {
         CS_REQUIRE(a->mask_indptr && a->mask_indices, "mask arrays missing");
@@ -560,6 +571,7 @@ static int session_run_impl(cs_session *s, cs_run_stats *stats, bool compact) {
     cudaStream_t st = s->stream();
     if (stats) memset(stats, 0, sizeof(*stats));
     s->ran = false;
+    s->refined = false;
     if (s->empty) {
         s->nnz_out = 0;
         s->ran = true;
@@ -683,6 +695,49 @@ static int session_compact(cs_session *s, cudaStream_t st, int64_t *nnz_out) {
     return CS_OK;
 }
 
+// Exact scores at and near `threshold` (see exact_refine): run once per (run, threshold)
+// before the thresholding of pick_foci, so that candidates and foci do not depend on float32
+// rounding.  CS_NO_REFINE=1 skips it (timing experiments).
+static int session_refine(cs_session *s, double threshold, int32_t dmin, int32_t dmax, cudaStream_t st) {
+    if (s->refined && s->refined_thr == threshold) return CS_OK;
+    static const bool off = getenv("CS_NO_REFINE") != nullptr;
+    if (off || s->a.raw_xcorr) return CS_OK;
+    const cs_normxcorr2_args &a = s->a;
+    cs_pearson_opts po;
+    session_pearson_opts(s, &po);
+    po.mask_mode = a.has_mask;  // the predicate of the exact path, whatever the image holds
+    const long long cap = 1 << 20;
+    int rc;
+    if ((rc = s->x_list.ensure((size_t)cap * sizeof(int2) + 64))) return rc;
+    RefineArgs R;
+    memset(&R, 0, sizeof(R));
+    R.K = &a.kernel;
+    R.opts = &po;
+    R.d_indptr = (const int64_t *)s->sig_indptr.p;
+    R.d_indices = (const int32_t *)s->sig_indices.p;
+    R.d_data = (const double *)s->sig_data.p;
+    R.rows = a.rows, R.cols = a.cols, R.pr = s->pr, R.pc = s->pc;
+    R.d_m_indptr = (const int64_t *)s->m_indptr.p;
+    R.d_m_indices = (const int32_t *)s->m_indices.p;
+    R.trim_lo = s->trim_lo, R.trim_hi = s->trim_hi;
+    R.Lo = &s->Lo;
+    R.d_out = (float *)s->out.p;
+    R.d_nmiss = s->want_nobs ? s->nobs.p : nullptr;
+    R.threshold = threshold;
+    R.dmin = dmin, R.dmax = dmax;
+    R.d_list = (int2 *)s->x_list.p;
+    R.cap = cap;
+    R.d_count = (unsigned long long *)((char *)s->x_list.p + (size_t)cap * sizeof(int2));
+    long long n = 0;
+    if ((rc = exact_refine(R, st, &n))) return rc;
+    s->refined = true;
+    s->refined_thr = threshold;
+    s->n_refined = n;
+    // the CSR result (if any) was compacted from the unrefined image
+    if (n > 0) s->compacted = false;
+    return CS_OK;
+}
+
 // Candidate pixels (score >= threshold) of the last run, written to a caller-owned
 // device buffer (e.g. the send buffer of the final all-gather).
 extern "C" int cs_session_candidates(cs_session *s, float threshold, int32_t dmin, int32_t dmax,
@@ -696,6 +751,7 @@ extern "C" int cs_session_candidates(cs_session *s, float threshold, int32_t dmi
         *n_host = 0;
         return CS_OK;
     }
+    if (int rrc = session_refine(s, (double)threshold, dmin, dmax, s->stream())) return rrc;
     return cs_scores_candidates(&s->Lo, (const float *)s->out.p,
                                 s->want_nobs ? s->nobs.p : nullptr, s->nmiss_bytes,
                                 s->a.kernel.kh * s->a.kernel.kw, dmin, dmax, threshold, d_cand, cap,
@@ -719,6 +775,7 @@ extern "C" int cs_session_foci(cs_session *s, double threshold, int32_t dmin, in
     if ((rc = s->f_rec.ensure((size_t)dcap * sizeof(cs_focus) + 64))) return rc;
     int64_t *d_count = (int64_t *)((char *)s->f_rec.p + (size_t)dcap * sizeof(cs_focus));
     d_count = (int64_t *)(((uintptr_t)d_count + 7) & ~(uintptr_t)7);
+    if ((rc = session_refine(s, threshold, dmin, dmax, st))) return rc;
     int64_t n = 0;
     rc = cs_scores_foci(&s->Lo, (const float *)s->out.p, dmin, dmax, threshold, min_size,
                         s->f_work.p, (cs_focus *)s->f_rec.p, dcap, d_count, &n, st);
@@ -1258,6 +1315,8 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
     }
     s->nnz_out = base;
     s->ran = true;
+    s->refined = false;
+    s->compacted = false;  // the pipeline's CSR arrays are not the resident session's
     res->nnz = base;
     float ms = 0.f;
     cudaEventElapsedTime(&ms, s->ev[2], s->ev[5]);

@@ -176,11 +176,11 @@ constexpr float kAmpLimit2 = 8.0f;
 // raw window sums: h1, h2 = sum S, sum S^2 (missing pixels count as S = 0), s3 = sum S * K_corr,
 // nmiss, sKm / sKm2 = sums of the mask kernels (K and K^2) over the missing pixels.
 template <bool MASK>
-__device__ __forceinline__ float exact_score(const PearsonParams &P, double h1, double h2,
-                                             double s3, int nmiss, double sKm, double sKm2,
-                                             int &nmiss_out) {
+__device__ __forceinline__ double exact_score_core(const PearsonParams &P, double h1, double h2,
+                                                   double s3, int nmiss, double sKm, double sKm2,
+                                                   int &nmiss_out) {
     nmiss_out = 0;
-    if (P.raw_xcorr) return (float)thr0(s3, P.thr_d);
+    if (P.raw_xcorr) return thr0(s3, P.thr_d);
     const double A1 = thr0(h1 * P.invN_d, P.thr_d);
     const double A2 = thr0(h2 * P.invN_d, P.thr_d);
     const double A3 = thr0(s3 * P.invN_d, P.thr_d);
@@ -206,15 +206,19 @@ __device__ __forceinline__ float exact_score(const PearsonParams &P, double h1, 
         if (P.nobs_full && npres != 0) nmiss_out = nmiss;
     }
     // det:1066,1088-1091: denom = sqrt(den2); |denom| < 1e-10 or NaN -> 0
-    float r = 0.f;
+    double r = 0.0;
     if (ok && den2 >= 1e-20 && den2 < 1e300) {
-        const double rr = cov / sqrt(den2);
-        r = (float)fmin(1.0, fmax(-1.0, rr));
-        if (!(r == r)) r = 0.f;
+        r = fmin(1.0, fmax(-1.0, cov / sqrt(den2)));
+        if (!(r == r)) r = 0.0;
     }
     return r;
 }
-
+template <bool MASK>
+__device__ __forceinline__ float exact_score(const PearsonParams &P, double h1, double h2,
+                                             double s3, int nmiss, double sKm, double sKm2,
+                                             int &nmiss_out) {
+    return (float)exact_score_core<MASK>(P, h1, h2, s3, nmiss, sKm, sKm2, nmiss_out);
+}
 // `nb` (<= 64) bits of a bit array (one bit per position, 32 per word) from bit `pos` on
 __device__ __forceinline__ unsigned long long bits64(const uint32_t *bits, int pos) {  // [sec:maskfn]
     const int w = pos >> 5, sh = pos & 31;
@@ -943,6 +947,137 @@ pearson_wide(const PearsonParams P, const WideParams W) {
     }
 }
 
+// ---------------------------------------------------------------- exact scores from the CSR
+// Scores that decide something (pixels at or near the Pearson threshold of pick_foci,
+// det:417-421) are recomputed from the float64 CSR signal with the per-pixel mask predicate
+// and the reference's float64 formulas, so that the candidate set -- and with it the foci --
+// does not depend on float32 rounding.  One warp per listed pixel.
+struct ExactArgs {
+    // signal (matrix coordinates) and its place in the framed image
+    const int64_t *indptr;
+    const int32_t *indices;
+    const double *data;
+    int rows, cols, pr, pc;
+    // pixel mask (mask_mode 1): CSR pattern, diagonals kept by the frame's trim
+    const int64_t *m_indptr;
+    const int32_t *m_indices;
+    int trim_lo, trim_hi;
+    int mask_mode;
+    // score image (matrix coordinates)
+    float *out;
+    void *nmiss;
+    int nmiss16, out_pitch, out_dlo, out_dense;
+    double thr_pearson;
+};
+
+__device__ __forceinline__ bool csr_find(const int64_t *indptr, const int32_t *indices, int r, int c,
+                                         int64_t &pos) {
+    int64_t lo = indptr[r], hi = indptr[r + 1];
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (indices[mid] < c) lo = mid + 1;
+        else hi = mid;
+    }
+    pos = lo;
+    return lo < indptr[r + 1] && indices[lo] == c;
+}
+
+__global__ void collect_near(ExactArgs A, int rows, int cols, int dlo, int dhi, int dmin, int dmax,
+                             float lo, float hi, int2 *list, long long cap,
+                             unsigned long long *count) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int y = blockIdx.x * wpb + (threadIdx.x >> 5); y < rows; y += gridDim.x * wpb) {
+        long long a = (long long)y + dmin, b = (long long)y + dmax;
+        if (!A.out_dense) {
+            a = a < (long long)y + dlo ? (long long)y + dlo : a;
+            b = b > (long long)y + dhi ? (long long)y + dhi : b;
+        }
+        if (a < 0) a = 0;
+        if (b > cols - 1) b = cols - 1;
+        for (long long x = a + lane; x <= b; x += 32) {
+            const float v = A.out[(long long)y * A.out_pitch + (x - A.out_dlo)];
+            if (v != 0.f && v >= lo && v <= hi) {
+                const unsigned long long o = atomicAdd(count, 1ull);
+                if ((long long)o < cap) list[o] = make_int2(y, (int)x);
+            }
+        }
+    }
+}
+
+template <int MASKMODE>
+__global__ void exact_windows(const PearsonParams P, const ExactArgs A, const int2 *list, long long n) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int KH = P.KH, KW = P.KW, kh = (KH - 1) / 2, kw = (KW - 1) / 2;
+    for (long long w = blockIdx.x * (long long)wpb + (threadIdx.x >> 5); w < n;
+         w += (long long)gridDim.x * wpb) {
+        const int y = list[w].x, x = list[w].y;
+        const int Y = y + A.pr, X = x + A.pc;  // image coordinates of the window centre
+        double h1 = 0.0, h2 = 0.0, q3 = 0.0, sKm = 0.0, sKm2 = 0.0;
+        int nmiss = 0;
+        for (int idx = lane; idx < KH * KW; idx += 32) {
+            const int i = idx / KW, j = idx - i * KW;
+            const int Yp = Y - kh + i, Xp = X - kw + j;
+            const int r = Yp - A.pr, c = Xp - A.pc;
+            const bool inside = r >= 0 && r < A.rows && c >= 0 && c < A.cols;
+            bool miss = false;
+            if (MASKMODE == MODE_GEO) {
+                bool rbit = false, cbit = false;
+                if (inside) {
+                    rbit = (P.rbits[Yp >> 5] >> (Yp & 31)) & 1u;
+                    cbit = (P.cbits[Xp >> 5] >> (Xp & 31)) & 1u;
+                }
+                miss = geo_missing(P, Yp, Xp, rbit, cbit);
+            }
+            if (MASKMODE == MODE_BITS) {
+                bool bit = false;
+                if (inside && c - r >= A.trim_lo && c - r <= A.trim_hi) {
+                    int64_t pos;
+                    bit = csr_find(A.m_indptr, A.m_indices, r, c, pos);
+                }
+                // the frame (margins, strip) of frame_missing_mask around the pixel mask
+                miss = geo_missing(P, Yp, Xp, bit, false);
+            }
+            if (miss) {
+                ++nmiss;
+                sKm += __ldg(P.dK + P.N + idx);
+                sKm2 += __ldg(P.dK + 2 * P.N + idx);
+                continue;
+            }
+            if (!inside) continue;
+            int64_t pos;
+            if (csr_find(A.indptr, A.indices, r, c, pos)) {
+                const double sv = A.data[pos];
+                h1 += sv;
+                h2 = fma(sv, sv, h2);
+                q3 = fma(sv, __ldg(P.dK + idx), q3);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+            h2 += __shfl_xor_sync(0xffffffffu, h2, o);
+            q3 += __shfl_xor_sync(0xffffffffu, q3, o);
+            sKm += __shfl_xor_sync(0xffffffffu, sKm, o);
+            sKm2 += __shfl_xor_sync(0xffffffffu, sKm2, o);
+            nmiss += __shfl_xor_sync(0xffffffffu, nmiss, o);
+        }
+        if (lane == 0) {
+            // the double itself (not its float32 rounding) is compared with the threshold
+            int nmo;
+            const double rx = exact_score_core<MASKMODE != MODE_NOMASK>(P, h1, h2, q3, nmiss, sKm, sKm2, nmo);
+            float r = (float)rx;
+            // keep the side of the threshold the double value is on (pick_foci compares float64)
+            if (rx >= A.thr_pearson && (double)r < A.thr_pearson) r = nextafterf(r, 2.f);
+            if (rx < A.thr_pearson && (double)r >= A.thr_pearson) r = nextafterf(r, -2.f);
+            const long long oi = (long long)y * A.out_pitch + (x - A.out_dlo);
+            A.out[oi] = r;
+            if (A.nmiss) {
+                if (A.nmiss16) ((unsigned short *)A.nmiss)[oi] = (unsigned short)nmo;
+                else ((unsigned char *)A.nmiss)[oi] = (unsigned char)nmo;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                     const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -1425,6 +1560,75 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
     }
 #endif
     return lrc;
+}
+
+// Pixels of the score image with a score >= threshold - 2e-5 on diagonals dmin..dmax (all
+// candidates of pick_foci plus the borderline ones below the threshold; if they overflow the
+// scratch list, only the borderline band of +-2e-5) are recomputed exactly from the CSR.
+int cs::exact_refine(const RefineArgs &R, cudaStream_t st, long long *n_refined) {
+    *n_refined = 0;
+    const cs_kernel_desc *K = R.K;
+    PearsonParams P;
+    memset(&P, 0, sizeof(P));
+    const int mode = common_params(P, K, R.opts);
+    if (mode) CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
+    P.mlo = -(1 << 29), P.mhi = 1 << 29;
+    P.sdlo = 0, P.sdhi = -1;
+    if (mode) {
+        const cs_geo_mask &g = R.opts->geo;
+        P.rbits = (const uint32_t *)g.d_row_bits;
+        P.cbits = (const uint32_t *)g.d_col_bits;
+        if (mode == MODE_GEO) P.mlo = g.mask_dlo, P.mhi = g.mask_dhi;
+        P.my0 = g.mat_y0, P.my1 = g.mat_y1, P.mx0 = g.mat_x0, P.mx1 = g.mat_x1;
+        P.margin_mode = g.margin_mode;
+        P.top_x1 = g.top_x1, P.right_y0 = g.right_y0;
+        if (g.strip_dhi >= g.strip_dlo) P.sdlo = g.strip_dlo, P.sdhi = g.strip_dhi;
+    }
+    const unsigned char *d_f = nullptr;
+    int rc = upload_tables(K, mode != 0, nullptr, 0, st, &d_f, &P.dK);
+    if (rc) return rc;
+    ExactArgs A;
+    memset(&A, 0, sizeof(A));
+    A.indptr = R.d_indptr, A.indices = R.d_indices, A.data = R.d_data;
+    A.rows = R.rows, A.cols = R.cols, A.pr = R.pr, A.pc = R.pc;
+    A.m_indptr = R.d_m_indptr, A.m_indices = R.d_m_indices;
+    A.trim_lo = R.trim_lo, A.trim_hi = R.trim_hi;
+    A.mask_mode = mode;
+    A.out = R.d_out;
+    A.nmiss = R.d_nmiss;
+    A.nmiss16 = R.opts->nmiss_bytes == 2;
+    A.out_pitch = R.Lo->pitch;
+    A.out_dlo = R.Lo->dense ? 0 : R.Lo->dlo;
+    A.out_dense = R.Lo->dense;
+    A.thr_pearson = R.threshold;
+    const float eps = 2e-5f;
+    int grid = (R.Lo->rows + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    unsigned long long n = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const float lo = (float)R.threshold - eps;
+        const float hi = pass == 0 ? 3.0e38f : (float)R.threshold + eps;
+        CS_CUDA(cudaMemsetAsync(R.d_count, 0, sizeof(unsigned long long), st));
+        collect_near<<<grid, 256, 0, st>>>(A, R.Lo->rows, R.Lo->cols, R.Lo->dlo, R.Lo->dhi, R.dmin,
+                                           R.dmax, lo, hi, R.d_list, R.cap, R.d_count);
+        CS_LAUNCHED();
+        CS_CUDA(cudaMemcpyAsync(&n, R.d_count, sizeof(n), cudaMemcpyDeviceToHost, st));
+        CS_CUDA(cudaStreamSynchronize(st));
+        if ((long long)n <= R.cap) break;
+    }
+    if ((long long)n > R.cap || n == 0) return CS_OK;  // nothing to do / too many to redo
+    long long blocks = ((long long)n + 7) / 8;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (mode == MODE_GEO)
+        exact_windows<MODE_GEO><<<(int)blocks, 256, 0, st>>>(P, A, R.d_list, (long long)n);
+    else if (mode == MODE_BITS)
+        exact_windows<MODE_BITS><<<(int)blocks, 256, 0, st>>>(P, A, R.d_list, (long long)n);
+    else
+        exact_windows<MODE_NOMASK><<<(int)blocks, 256, 0, st>>>(P, A, R.d_list, (long long)n);
+    CS_LAUNCHED();
+    CS_CUDA(cudaGetLastError());
+    *n_refined = (long long)n;
+    return CS_OK;
 }
 
 extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_kernel_desc *K,

@@ -3,9 +3,12 @@
 (cli:738-755), SURVEY 8e / 8f-4.
 
 Every rank runs `pattern_detector` (GPU) on its share of the sub-matrices; the per-sub-matrix
-tables -- a few KB -- are exchanged with one `all_gather_object` per kernel iteration, after
-which every rank holds the same global table and does the reference's global host steps
-(neighbour removal, minimum distance, FDR; cli:807-848) redundantly.
+tables -- a few KB -- are exchanged as float64 record tensors (sharding.gather_rows: NCCL on
+the device, gloo in the CPU tests; nothing is pickled) once per kernel iteration, after which
+every rank holds the same global table and does the reference's global host steps (neighbour
+removal, minimum distance, FDR; cli:807-848) redundantly.  Windows travel the same way, or
+stay on their rank (`gather_windows=False`: only their mean, which the next iteration uses as
+kernel, is all-reduced).
 """
 import numpy as np
 import pandas as pd
@@ -38,10 +41,11 @@ def _world():
     return 0, 1, None
 
 
-def detect_sub_matrices(hic_genome, cfg, kernel_matrix, full=True, tsvd=None):
+def detect_sub_matrices(hic_genome, cfg, kernel_matrix, full=True, tsvd=None, gather_windows=True):
     """One pass of `_detect_sub_mat` (cli:601-622) over all sub-matrices, sharded over the
     ranks.  Returns the list of result dicts {coords, windows, chr1, chr2} in sub-matrix
-    order, identical on every rank."""
+    order; the tables are identical on every rank, the windows too unless
+    gather_windows=False (then `windows` is None for the sub-matrices of other ranks)."""
     rank, world, dist = _world()
     mine = sharding.partition_units(unit_costs(hic_genome), world)[rank]
     local = {}
@@ -53,37 +57,89 @@ def detect_sub_matrices(hic_genome, cfg, kernel_matrix, full=True, tsvd=None):
         cm.destroy_mat()
         local[u] = {"coords": coords, "windows": windows, "chr1": row.chr1, "chr2": row.chr2}
     if world > 1:
-        parts = [None] * world
-        dist.all_gather_object(parts, local)
-        local = {}
-        for p in parts:
-            local.update(p)
+        km, kn = np.asarray(kernel_matrix).shape
+        have = [u for u in mine if local[u]["coords"] is not None and len(local[u]["coords"])]
+        # float64 records (unit, bin1, bin2, score, pvalue): the integers are exact
+        rec = np.concatenate([np.column_stack([np.full(len(local[u]["coords"]), float(u)),
+                                               local[u]["coords"][["bin1", "bin2", "score", "pvalue"]]
+                                               .to_numpy(dtype=np.float64)]) for u in have]) \
+            if have else np.zeros((0, 5))
+        parts = sharding.gather_rows(rec)
+        wparts = None
+        if gather_windows:
+            w = np.concatenate([np.asarray(local[u]["windows"], dtype=np.float64).reshape(-1, km * kn)
+                                for u in have]) if have else np.zeros((0, km * kn))
+            wparts = sharding.gather_rows(w)
+        out = {}
+        for r, p in enumerate(parts):
+            units = p[:, 0].astype(np.int64)
+            for u in np.unique(units):
+                sel = units == u
+                srow = hic_genome.sub_mats.iloc[int(u)]
+                tab = pd.DataFrame({"bin1": p[sel, 1].astype(np.int64), "bin2": p[sel, 2].astype(np.int64),
+                                    "score": p[sel, 3], "pvalue": p[sel, 4]})
+                wins = wparts[r][sel].reshape(-1, km, kn) if wparts is not None else \
+                    (local[int(u)]["windows"] if r == rank else None)
+                out[int(u)] = {"coords": tab, "windows": wins, "chr1": srow.chr1, "chr2": srow.chr2}
+        for u in range(len(hic_genome.sub_mats)):
+            if u not in out:
+                srow = hic_genome.sub_mats.iloc[u]
+                out[u] = {"coords": None, "windows": None, "chr1": srow.chr1, "chr2": srow.chr2}
+        local = out
     return [local[u] for u in sorted(local)]
 
 
-def detect(hic_genome, cfg, full=True, tsvd=None):
+def _global_pileup(windows_list, shape):
+    """nanmean over the windows of every rank (cli:791, det:158-174) from per-rank NaN-aware
+    sums and counts: one all-reduce of 2 k^2 numbers instead of moving the windows."""
+    import torch
+    rank, world, dist = _world()
+    tot = np.zeros(shape)
+    cnt = np.zeros(shape)
+    for w in windows_list:
+        if w is not None and len(w):
+            w = np.asarray(w, dtype=np.float64)
+            tot += np.nansum(w, axis=0)
+            cnt += (~np.isnan(w)).sum(axis=0)
+    if world > 1:
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" \
+            else torch.device("cpu")
+        buf = torch.from_numpy(np.stack([tot, cnt])).to(dev)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        tot, cnt = buf.cpu().numpy()
+    with np.errstate(all="ignore"):
+        return tot / cnt
+
+
+def detect(hic_genome, cfg, full=True, tsvd=None, gather_windows=True):
     """Pattern detection on every sub-matrix with every kernel of `cfg`, then the global
     filters (cli:720-860).  Returns (table, windows) or (None, None) when nothing is found;
-    the table has the columns the reference writes (chrom1 ... qvalue)."""
+    the table has the columns the reference writes (chrom1 ... qvalue).  With
+    gather_windows=False the windows stay on the rank that cut them: the second value then
+    holds NaN windows for the patterns of other ranks."""
     if hic_genome.sub_mats is None:
         hic_genome.make_sub_matrices()
     all_coords, all_windows = [], []
     for kernel_id, kernel_matrix in enumerate(cfg["kernels"]):
         kernel_matrix = np.asarray(kernel_matrix, dtype=np.float64)
         for it in range(cfg["max_iterations"]):
-            results = detect_sub_matrices(hic_genome, cfg, kernel_matrix, full=full, tsvd=tsvd)
+            results = detect_sub_matrices(hic_genome, cfg, kernel_matrix, full=full, tsvd=tsvd,
+                                          gather_windows=gather_windows)
             coords = [hic_genome.get_full_mat_pattern(d["chr1"], d["chr2"], d["coords"])
                       for d in results if d["coords"] is not None]
-            wins = [d["windows"] for d in results if d["windows"] is not None]
-            if not wins:
+            if not coords:
                 break  # nothing found with this kernel: next kernel (cli:786-788)
+            kshape = kernel_matrix.shape
+            wins = [d["windows"] if d["windows"] is not None else np.full((len(d["coords"]),) + kshape, np.nan)
+                    for d in results if d["coords"] is not None]
+            pile = _global_pileup([d["windows"] for d in results], kshape) if not gather_windows else None
             wins = np.concatenate(wins, axis=0)
             tab = pd.concat(coords, axis=0).reset_index(drop=True)
             tab["kernel_id"] = kernel_id
             tab["iteration"] = it
             all_coords.append(tab)
             all_windows.append(wins)
-            kernel_matrix = cud.pileup_patterns(wins)  # cli:791
+            kernel_matrix = cud.pileup_patterns(wins) if pile is None else pile  # cli:791
     if not all_coords:
         return None, None
     tab = pd.concat(all_coords, axis=0).reset_index(drop=True)
@@ -123,12 +179,14 @@ def _chrom_positions(positions, hic_genome, chr1, chr2):
     return sel[ok], coords
 
 
-def quantify(hic_genome, cfg, bed2d, tsvd=None, return_windows=True):
+def quantify(hic_genome, cfg, bed2d, tsvd=None, return_windows=True, gather_windows=True):
     """Correlation score of every position of `bed2d` (DataFrame chrom1, start1, end1, chrom2,
     start2, end2) with the kernels of `cfg`: the loop of cmd_quantify (cli:295-496), sharded by
     sub-matrix.  `cfg` is modified like the reference does (max_dist = furthest pair,
     min_dist = 0).  Returns (table sorted by bins with score / pvalue / qvalue, windows of the
-    best kernel per position or None)."""
+    best kernel per position or None).  Scores and p-values of all ranks are exchanged as
+    float64 record tensors; windows too (gather_windows=True) or they stay on their rank
+    (NaN windows for the positions of other ranks)."""
     rank, world, dist = _world()
     bed2d = bed2d.reset_index(drop=True).copy()
     furthest = int(np.max(bed2d.start2 - bed2d.start1))
@@ -169,12 +227,19 @@ def quantify(hic_genome, cfg, bed2d, tsvd=None, return_windows=True):
             if return_windows:
                 wins[u] = (idx, windows)
         if world > 1:
-            parts = [None] * world
-            dist.all_gather_object(parts, (np.flatnonzero(~np.isnan(score) | ~np.isnan(pval)),
-                                           score, pval, wins if return_windows else {}))
-            for sel, sc, pv, w in parts:
-                score[sel], pval[sel] = sc[sel], pv[sel]
-                wins.update(w)
+            sel = np.flatnonzero(~np.isnan(score) | ~np.isnan(pval))
+            rec = np.column_stack([sel.astype(np.float64), score[sel], pval[sel]])
+            for p in sharding.gather_rows(rec):
+                ix = p[:, 0].astype(np.int64)
+                score[ix], pval[ix] = p[:, 1], p[:, 2]
+            if return_windows and gather_windows:
+                mine_idx = np.concatenate([i for i, _ in wins.values()]) if wins else np.zeros(0, np.int64)
+                mine_w = np.concatenate([w.reshape(len(w), -1) for _, w in wins.values()]) if wins \
+                    else np.zeros((0, km * kn))
+                idx_parts = sharding.gather_rows(mine_idx.reshape(-1, 1).astype(np.float64))
+                win_parts = sharding.gather_rows(np.asarray(mine_w, dtype=np.float64))
+                wins = {r: (ip[:, 0].astype(np.int64), wp.reshape(-1, km, kn))
+                        for r, (ip, wp) in enumerate(zip(idx_parts, win_parts)) if len(ip)}
         # the best kernel of each position (cli:442-450: highest score; NaN never wins)
         better = (~np.isnan(score)) & (np.isnan(best_score) | (score >= best_score))
         first = np.isnan(best_score) & np.isnan(score) & np.isnan(best_p)

@@ -47,26 +47,58 @@ def row_slabs(n_rows, world_size, halo):
     return out
 
 
-def gather_candidates(records, count, group=None):
+def gather_candidates(records, count, group=None, cap=None):
     """All-gather of variable-length candidate records.
 
-    records : int32 tensor [cap, 4] (device tensor for NCCL, host tensor for gloo) whose
+    records : int32 tensor [n, 4] (device tensor for NCCL, host tensor for gloo) whose
               first `count` rows are valid cs_candidate records.
-    Returns (tensor [world, max_count, 4], counts tensor [world] on the same device)."""
+    cap     : None -- two collectives sized by the largest count (one host read of the counts
+              in between); an int -- ONE fixed-size exchange of `cap` records per rank plus the
+              counts, without any host synchronisation (the caller checks counts <= cap when
+              it reads them).
+    Returns (tensor [world, max_count or cap, 4], counts tensor [world] on the same device)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     dev = records.device
     counts = torch.zeros(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(counts, torch.tensor([count], dtype=torch.int64, device=dev), group=group)
-    mx = max(int(counts.max().item()), 1)
+    mine = count if torch.is_tensor(count) else torch.tensor([count], dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, mine.reshape(1).to(torch.int64), group=group)
+    mx = int(cap) if cap is not None else max(int(counts.max().item()), 1)
     send = records[:mx]
-    if send.shape[0] < mx:  # the local buffer is shorter than another rank's count
+    if send.shape[0] < mx:  # the local buffer is shorter than the exchanged size
         pad = torch.zeros((mx - send.shape[0], 4), dtype=records.dtype, device=dev)
         send = torch.cat([send, pad])
     out = torch.empty((world * mx, 4), dtype=records.dtype, device=dev)
     dist.all_gather_into_tensor(out, send.contiguous(), group=group)
     return out.view(world, mx, 4), counts
+
+
+def gather_rows(rows, group=None):
+    """Variable-length all-gather of the rows of a 2-D numeric array (same dtype and column
+    count on every rank): tensors over NCCL (device) or gloo (host), no pickling.
+    Returns the list of per-rank numpy arrays (every rank gets all of them)."""
+    import torch
+    import torch.distributed as dist
+    rows = np.ascontiguousarray(rows)
+    if rows.ndim != 2:
+        raise ValueError("gather_rows wants a 2-D array")
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return [rows]
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
+        else torch.device("cpu")
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts, torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev), group=group)
+    counts = counts.cpu().numpy()
+    mx = max(int(counts.max()), 1)
+    send = torch.zeros((mx, rows.shape[1]), dtype=torch.from_numpy(rows[:0]).dtype, device=dev)
+    if rows.shape[0]:
+        send[: rows.shape[0]] = torch.from_numpy(rows).to(dev)
+    out = torch.empty((world * mx, rows.shape[1]), dtype=send.dtype, device=dev)
+    dist.all_gather_into_tensor(out, send, group=group)
+    out = out.cpu().numpy().reshape(world, mx, rows.shape[1])
+    return [out[r, : int(counts[r])].copy() for r in range(world)]
 
 
 def merge_candidates(gathered, counts, row_offsets=None):
@@ -76,6 +108,8 @@ def merge_candidates(gathered, counts, row_offsets=None):
     c = counts.cpu().numpy()
     parts = []
     for r in range(g.shape[0]):
+        if int(c[r]) > g.shape[1]:
+            raise ValueError(f"rank {r} found {int(c[r])} candidates, more than the {g.shape[1]} exchanged")
         rec = np.ascontiguousarray(g[r, : int(c[r])]).view(_lib.CANDIDATE_DTYPE).reshape(-1).copy()
         if row_offsets is not None:
             rec["row"] += int(row_offsets[r])

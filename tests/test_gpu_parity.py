@@ -260,14 +260,6 @@ def test_full_size_map_against_oracle_crops(kname, ksize, tol, pearson, presets)
     assert st["n_windows"] >= synthetic.n_windows(n, D)
     assert r.shape == (n, n) and r.nnz == st["nnz"] and abs(r.data).max() <= 1.0
     assert r.nnz > 0.9 * synthetic.n_windows(n, D)
-    # candidates on the device == thresholding of the downloaded map (det:417-421)
-    cand, nc = s.candidates(pearson, 0, D)
-    rec = records_to_numpy(cand, nc)
-    rt = cup.diag_trim(r, D).tocoo()
-    sel = (rt.data >= pearson)
-    assert nc == int(sel.sum())
-    key = np.sort(rec["row"].astype(np.int64) * n + rec["col"])
-    assert np.array_equal(key, np.sort(rt.row[sel].astype(np.int64) * n + rt.col[sel]))
     # the one-shot host call (slab-pipelined for a map of this size: uploads, kernels and
     # downloads overlap) returns exactly what the resident session does
     from chromosight_b200.utils import detection as cud
@@ -283,10 +275,25 @@ def test_full_size_map_against_oracle_crops(kname, ksize, tol, pearson, presets)
         assert np.array_equal(a_.indptr, b_.indptr) and np.array_equal(a_.indices, b_.indices)
         assert np.array_equal(a_.data, b_.data)
     del r_h, p_h
+    # candidates and foci: scores at / near the threshold are recomputed in float64 from the
+    # CSR first (exact_refine), so the candidate set does not depend on float32 rounding
+    cand, nc = s.candidates(pearson, 0, D)
+    rec = records_to_numpy(cand, nc)
+    foci = s.foci(pearson, 0, D, min_size=2)
+    r2, p2 = s.download()                     # re-compacted from the refined image
+    assert abs(r2 - r).max() <= SCORE_TOL
+    rt = cup.diag_trim(r2, D).tocoo()
+    sel = (rt.data >= pearson)
+    assert nc == int(sel.sum())               # det:417-421 on the downloaded map
+    key = np.sort(rec["row"].astype(np.int64) * n + rec["col"])
+    assert np.array_equal(key, np.sort(rt.row[sel].astype(np.int64) * n + rt.col[sel]))
+    foci_key = set((foci["row"].astype(np.int64) * n + foci["col"]).tolist())
+    assert len(foci_key) == len(foci)
     # oracle on crops
     rng = np.random.default_rng(5)
     W = D + 3 * k
     starts = [0, n - 400 - W] + list(rng.integers(100, n - 400 - W - 100, size=6))
+    n_foci_checked = 0
     for a0 in starts:
         a0 = int(a0)
         a1 = a0 + 400 + W
@@ -299,18 +306,46 @@ def test_full_size_map_against_oracle_crops(kname, ksize, tol, pearson, presets)
         lo = 0 if a0 == 0 else k
         hi = (a1 - a0) if a1 == n else (a1 - a0) - W
         got = r[a0 + lo:a0 + hi, a0:a1].toarray()
+        got2 = r2[a0 + lo:a0 + hi, a0:a1].toarray()
         exp = r0[lo:hi, :].copy()
         gp = p[a0 + lo:a0 + hi, a0:a1].toarray()
+        p0 = p0.copy()
         if a1 != n:
             # windows reaching beyond the crop's right edge are not comparable
             cols = np.arange(a1 - a0)[None, :] - (np.arange(lo, hi)[:, None])
             far = cols > D + 2 * k
             got[far] = 0
+            got2[far] = 0
             exp[far] = 0
             gp[far] = 0
-            p0 = p0.copy()
             p0[lo:hi][far] = 0
         _compare(got, gp, exp, p0[lo:hi], nob[lo:hi], strict=True)
+        # refined scores: the candidates of the crop carry the float64 result itself
+        cpx = np.triu(np.tril(exp, D)) >= pearson
+        cpx &= exp != 0
+        g2t = np.triu(np.tril(got2, D))
+        assert np.array_equal((g2t >= pearson) & (g2t != 0), cpx)   # the candidate set, exactly
+        assert np.abs(got2[cpx] - exp[cpx].astype(np.float32)).max(initial=0) <= 1.2e-7
+        # foci of the crop interior == pick_foci of the oracle (det:387-456): foci whose
+        # pixels all lie at least 3 rows inside the compared rows are complete in the crop
+        ex_trim = sp.coo_matrix(np.triu(np.tril(exp, D)))
+        coords0, lab0 = cud.pick_foci(ex_trim, pearson)
+        if coords0 is not None:
+            lab0 = lab0.tocoo()
+            for fid, (fy, fx) in zip(np.unique(lab0.data), coords0):
+                rows_f = lab0.row[lab0.data == fid]
+                if rows_f.min() < 3 or rows_f.max() >= (hi - lo) - 3:
+                    continue
+                assert (int(fy) + a0 + lo) * n + (int(fx) + a0) in foci_key, (a0, fy, fx)
+                n_foci_checked += 1
+        # and the device foci centred well inside the crop are the oracle's
+        inside = [(fr, fc) for fr, fc in zip(foci["row"], foci["col"])
+                  if a0 + lo + 6 <= fr < a0 + hi - 6]
+        if inside:
+            exp_set = set() if coords0 is None else {(int(y) + a0 + lo, int(x) + a0) for y, x in coords0}
+            for fr, fc in inside:
+                assert (int(fr), int(fc)) in exp_set, (a0, fr, fc)
+    assert n_foci_checked > 0
 
 
 from conftest import DummyMap, detector_case_names, load_detector_case  # noqa: E402
@@ -413,3 +448,53 @@ def test_device_foci_match_host_pick_foci(thr, presets):
     assert np.array_equal(ids, np.sort(ids)) and len(np.unique(ids)) == len(ids)
     sizes = np.bincount(labelled.data.astype(np.int64))[ids.astype(np.int64)]
     assert np.array_equal(sizes, foci["size"])
+
+
+def test_row_slabs_match_single_run(presets):
+    """SURVEY 8e, one chromosome over several GPUs: the row-slab path (rowslab.py; here the
+    slabs of a 3-rank plan run one after the other on one device) yields exactly the candidate
+    pixels and foci of a single run over the whole map.  Exact because scores at / near the
+    threshold are recomputed in float64 from the CSR on both sides."""
+    from chromosight_b200 import rowslab, synthetic
+    from chromosight_b200.session import Session, records_to_numpy
+    from chromosight_b200.utils import detection as cud, preprocessing as cup
+    kernel = presets.loops["kernels"][0]
+    k, n, D, thr, world = kernel.shape[0], 30_000, 200, 0.3, 3
+    raw, detect = synthetic.band_counts(n, D + k, seed=17, missing_frac=0.02, max_dist=D)
+    kw = dict(max_dist=D, sym_upper=True, full=True, missing_tol=0.5, pval=True)
+
+    def candidates_of(mat, det):
+        s = Session()
+        try:
+            s.upload(mat, kernel, mask_geometry=cup.missing_geometry(mat.shape, det, det, D, True), **kw)
+            s.run(compact=False)
+            rec, nc = s.candidates(thr, 0, D)
+            return records_to_numpy(rec, nc).copy()
+        finally:
+            s.close()
+
+    # single run
+    mat = cup.detrend(raw, detectable_bins=detect, max_dist=D + k, max_val=10)
+    mat = cup.diag_trim(mat.tocsr(), D + k)
+    mat.data[np.isnan(mat.data)] = 0
+    mat.eliminate_zeros()
+    whole = rowslab.merge_sorted([candidates_of(mat, detect)])
+    # slabs: partial law sums of the owned rows, summed like the all-reduce does
+    plans = rowslab.slab_plan(n, world, k, D)
+    sums = [rowslab.law_sums(rowslab.owned_rows(raw, p[0], p[1]), detect, D + k) for p in plans]
+    tot_s = sum(s_.cpu().numpy() for s_, _ in sums)
+    tot_c = sum(c_.cpu().numpy() for _, c_ in sums)
+    law = rowslab.law_from_sums(tot_s, tot_c, n)
+    assert np.allclose(law[: D + k + 1], np.nan_to_num(cup.distance_law(raw, detect, D + k, smooth=False))[: D + k + 1],
+                       rtol=1e-12)
+    parts = []
+    for p in plans:
+        sub, det = rowslab.slab_inputs(raw, detect, law, p, D, k)
+        parts.append(rowslab.owned_candidates(candidates_of(sub, det), p))
+    merged = rowslab.merge_sorted(parts)
+    assert len(whole) > 100
+    assert np.array_equal(merged["row"], whole["row"]) and np.array_equal(merged["col"], whole["col"])
+    assert np.abs(merged["score"] - whole["score"]).max() <= 2e-7
+    c_m = rowslab.foci_of_candidates(merged, (n, n), thr)
+    c_w = rowslab.foci_of_candidates(whole, (n, n), thr)
+    assert np.array_equal(c_m, c_w)

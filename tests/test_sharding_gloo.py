@@ -201,3 +201,114 @@ def test_detect_driver_world2_gloo_matches_single_process():
     for r in both:
         assert r[1] == single[1]
         assert r[2] == single[2]
+
+
+# --------------------------------------------------------------------------- row slabs (strong scaling)
+def _slab_worker(rank, world, port, q):
+    """One rank of the row-slab path with the oracle standing in for the device kernels: partial
+    distance-law sums of the owned rows -> ONE all-reduce -> slab detrend -> Pearson map of the
+    slab's square sub-matrix -> candidates of the owned rows -> fixed-size gather."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import scipy.sparse as sp
+        from chromosight_b200 import kernels, rowslab, synthetic
+        from chromosight_b200.utils import preprocessing as cup
+        from oracle import pearson_oracle as po
+        kernel = kernels.loops_small["kernels"][0]
+        k, n, D, thr = kernel.shape[0], 260, 24, 0.3
+        raw, detect = synthetic.band_counts(n, D + k, seed=4, missing_frac=0.04, max_dist=D)
+        raw = raw.tocsr()
+        plan = rowslab.slab_plan(n, world, k, D)[rank]
+        r0, r1, in0, in1 = plan
+        # partial law sums of the owned rows (what K0a accumulates on the device)
+        own = rowslab.owned_rows(raw, r0, r1).toarray()
+        ok = np.zeros(n, bool)
+        ok[detect] = True
+        nd = min(n, D + k + 1)
+        psum, pcnt = np.zeros(nd), np.zeros(nd)
+        for d in range(nd):
+            v = np.diagonal(own, d)[ok[: n - d] & ok[d:]]
+            v = v[v > 0]
+            psum[d], pcnt[d] = v.sum(), len(v)
+        buf = torch.from_numpy(np.concatenate([psum, pcnt]))
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        law = rowslab.law_from_sums(buf[:nd].numpy(), buf[nd:].numpy(), n)
+        ref_law = po.distance_law_dense(raw.toarray(), detect, D + k)
+        ref_law[np.isnan(ref_law)] = 0
+        assert np.allclose(law, ref_law, rtol=1e-13)
+        # slab inputs (host arithmetic of slab_inputs, division by the global law)
+        sub = raw[in0:in1, in0:in1].toarray()
+        rr, cc = np.indices(sub.shape)
+        with np.errstate(all="ignore"):
+            mat = np.where(sub != 0, sub / law[np.abs(rr - cc)], 0.0)
+        mat[mat >= 10] = 1.0
+        mat = np.triu(np.tril(mat, D + k))
+        mat[np.isnan(mat)] = 0
+        det = np.asarray(detect)
+        det = det[(det >= in0) & (det < in1)] - in0
+        mask = po.make_missing_mask_dense(mat.shape, det, det, max_dist=D, sym_upper=True)
+        kw = dict(max_dist=D, sym_upper=True, full=True, missing_tol=0.5)
+        r, _ = po.normxcorr2_dense(mat, kernel, missing_mask=mask, **kw)
+        r = np.triu(np.tril(r, D))
+        ys, xs = np.nonzero((r >= thr) & (r != 0))
+        rec = np.zeros(len(ys), dtype=_lib.CANDIDATE_DTYPE)
+        rec["row"], rec["col"], rec["score"] = ys, xs, r[ys, xs]
+        mine = rowslab.owned_candidates(rec, plan)
+        cap = 4096
+        sendbuf = torch.zeros((cap, 4), dtype=torch.int32)
+        sendbuf[: len(mine)] = torch.from_numpy(mine.view(np.int32).reshape(-1, 4))
+        gathered, counts = sharding.gather_candidates(sendbuf, len(mine), cap=cap)
+        merged = rowslab.merge_sorted([sharding.merge_candidates(gathered, counts)])
+        q.put((rank, merged))
+    except Exception as e:
+        q.put((rank, repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_slab_path_world2_gloo():
+    """Row slabs of ONE chromosome over two ranks give the candidate pixels of a single run
+    over the whole map (the law all-reduce, the halos and the merge are what is tested; the
+    device kernels are replaced by the oracle)."""
+    import scipy.sparse as sp
+    from chromosight_b200 import kernels, rowslab, synthetic
+    from oracle import pearson_oracle as po
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_slab_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert not isinstance(res[0][1], str), res[0][1]
+    # single run over the whole map
+    kernel = kernels.loops_small["kernels"][0]
+    k, n, D, thr = kernel.shape[0], 260, 24, 0.3
+    raw, detect = synthetic.band_counts(n, D + k, seed=4, missing_frac=0.04, max_dist=D)
+    mat = np.triu(np.tril(po.detrend_dense(raw.toarray(), detect, D + k, 10), D + k))
+    mat[np.isnan(mat)] = 0
+    mask = po.make_missing_mask_dense(mat.shape, detect, detect, max_dist=D, sym_upper=True)
+    r, _ = po.normxcorr2_dense(mat, kernel, missing_mask=mask, max_dist=D, sym_upper=True, full=True,
+                               missing_tol=0.5)
+    r = np.triu(np.tril(r, D))
+    ys, xs = np.nonzero((r >= thr) & (r != 0))
+    for rank in range(2):
+        merged = res[rank][1]
+        assert np.array_equal(merged["row"], ys) and np.array_equal(merged["col"], xs)
+        assert np.allclose(merged["score"], r[ys, xs].astype(np.float32), atol=1e-6)
+    assert len(ys) > 20
+    # foci of the merged pixels = foci of the whole map
+    coords = rowslab.foci_of_candidates(res[0][1], r.shape, thr)
+    from chromosight_b200.utils.detection import pick_foci
+    coords0, _ = pick_foci(sp.coo_matrix(r), thr)
+    assert np.array_equal(coords, coords0)
+    # plan arithmetic
+    plan = rowslab.slab_plan(200_000, 8, 17, 200)
+    assert plan[0][:3] == (0, 25_000, 0) and plan[-1][1] == plan[-1][3] == 200_000
+    assert all(p[2] == p[0] - 17 for p in plan[1:]) and all(p[3] == p[1] + 200 + 51 for p in plan[:-1])
