@@ -215,3 +215,40 @@ def test_driver_host_plumbing(fx):
     assert list(idx) == [1] and coords.tolist() == [[0, 126]]
     idx, coords = driver._chrom_positions(pos, hg, "chr3", "chr3")
     assert len(idx) == 0 and coords.shape == (0, 2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,expected_n", [("loops_default", 89), ("loops_nb", 59), ("borders", 57),
+                                             ("hairpins", 55)])
+def test_detect_driver_reference_held_answers(fx, presets, case, expected_n):
+    """SURVEY 8f-4 against known answers the reference itself holds: `chromosight test` reports
+    "89 patterns detected" (cli:185-199) and docs/notebooks/detect/example_{loops,borders,
+    hairpins}.tsv list 59 / 57 / 55 patterns (plot_output.ipynb:13-15).  The fixture
+    (tests/golden/make_golden_cli.py) is the same chain driven through the unmodified reference's
+    functions; it reproduces those four answers exactly, coordinates and scores included.  The
+    sharded driver must return the same table: same patterns in the same order, scores to 1e-5,
+    p- and q-values to 1e-4 relative in log10."""
+    from chromosight_b200 import driver
+    from chromosight_b200.contacts_map import HicGenome
+    z = np.load(os.path.join(GOLDEN, "cli_example.npz"), allow_pickle=False)
+    cfg = dict(getattr(presets, str(z[f"{case}_pattern"])))
+    cfg.update(eval(str(z[f"{case}_override"]), {"__builtins__": {}}))
+    cfg["kernels"] = [np.array(k) for k in cfg["kernels"]]
+    hg = HicGenome(cool_from_fixture(fx), inter=False, kernel_config=cfg)
+    hg.normalize()
+    table, windows = driver.detect(hg, cfg, full=True)
+    assert len(table) == expected_n == len(z[f"{case}_bin1"]) == len(windows)
+    assert np.array_equal(table.bin1.values, z[f"{case}_bin1"])
+    assert np.array_equal(table.bin2.values, z[f"{case}_bin2"])
+    assert np.array_equal(table.kernel_id.values, z[f"{case}_kernel_id"])
+    assert np.array_equal(table.iteration.values, z[f"{case}_iteration"])
+    assert np.abs(table.score.values - z[f"{case}_score"]).max() <= 1e-5
+    for col in ("pvalue", "qvalue"):
+        a, b = np.log10(table[col].values), np.log10(z[f"{case}_{col}"])
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), fin)
+        assert np.allclose(a[fin], b[fin], rtol=2e-4, atol=1e-4)
+    if f"{case}_held_bin1" in z.files:
+        # the TSV in the reference's repository: identical pattern coordinates
+        held = set(zip(z[f"{case}_held_bin1"].tolist(), z[f"{case}_held_bin2"].tolist()))
+        assert held == set(zip(table.bin1.tolist(), table.bin2.tolist()))

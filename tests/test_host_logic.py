@@ -225,3 +225,19 @@ def test_expand_rows_narrow_format(threads):
     assert lib.cs_expand_rows(score.ctypes.data, None, off.ctypes.data, indptr.ctypes.data, 0, rows, dlo,
                               data.ctypes.data, None, idx.ctypes.data, None, threads) == 0
     assert np.array_equal(data, score.astype(np.float64))
+
+
+def test_cli_fixture_reproduces_reference_held_answers():
+    """tests/golden/cli_example.npz (the `chromosight detect` chain driven through the unmodified
+    reference's functions, make_golden_cli.py) against the answers the reference's repository
+    holds: 89 patterns of `chromosight test` (cli:185-199) and the 59 / 57 / 55 rows of
+    docs/notebooks/detect/example_*.tsv -- same coordinates, scores to 1e-9."""
+    z = np.load(os.path.join(GOLDEN, "cli_example.npz"), allow_pickle=False)
+    assert len(z["loops_default_bin1"]) == 89
+    for case, n in (("loops_nb", 59), ("borders", 57), ("hairpins", 55)):
+        assert len(z[f"{case}_bin1"]) == n == len(z[f"{case}_held_bin1"])
+        o = np.lexsort((z[f"{case}_bin2"], z[f"{case}_bin1"]))
+        h = np.lexsort((z[f"{case}_held_bin2"], z[f"{case}_held_bin1"]))
+        assert np.array_equal(z[f"{case}_bin1"][o], z[f"{case}_held_bin1"][h])
+        assert np.array_equal(z[f"{case}_bin2"][o], z[f"{case}_held_bin2"][h])
+        assert np.abs(z[f"{case}_score"][o] - z[f"{case}_held_score"][h]).max() < 1e-9
