@@ -434,6 +434,9 @@ def run_b200(a, kernel):
         from chromosight_b200 import kernels as presets
         cfg = dict(getattr(presets, a.kernel))
         cfg["pearson"] = a.pearson
+        # the synthetic generator thins the map out with distance (half the pixels are zeros at
+        # 0.5 Mb): keep the zero-pixel filter of validate_patterns from discarding every loop
+        cfg["max_perc_zero"] = 100.0
 
         class _Map:  # the attributes pattern_detector reads of a ContactMap (det:230-257)
             matrix, detectable_bins, max_dist, inter, name = mat, (detect, detect), D, False, "bench"

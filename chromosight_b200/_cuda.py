@@ -63,4 +63,6 @@ def pin_sparse(mat):
 
     out = sp.csr_matrix((pin(csr.data), pin(csr.indices), pin(csr.indptr)), shape=csr.shape, copy=False)
     out.has_canonical_format = True
+    if hasattr(mat, "_cs_geometry"):  # a mask of make_missing_mask stays recognisable
+        out._cs_geometry = mat._cs_geometry
     return out

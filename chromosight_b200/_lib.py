@@ -172,6 +172,7 @@ _PROTOS = {
     "cs_session_upload": (C.c_int, [C.c_void_p, C.POINTER(Normxcorr2Args)]),
     "cs_session_run": (C.c_int, [C.c_void_p, C.POINTER(RunStats)]),
     "cs_session_run_scores": (C.c_int, [C.c_void_p, C.POINTER(RunStats)]),
+    "cs_session_upload_run_scores": (C.c_int, [C.c_void_p, C.POINTER(Normxcorr2Args), C.POINTER(RunStats)]),
     "cs_foci_work_bytes": (C.c_int64, [C.POINTER(Layout)]),
     "cs_scores_foci": (C.c_int, [C.POINTER(Layout), _P, C.c_int32, C.c_int32, C.c_double, C.c_int32, _P, _P,
                                   C.c_int64, _P, C.POINTER(C.c_int64), _P]),

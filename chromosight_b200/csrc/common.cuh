@@ -69,6 +69,14 @@ void expand_rows(const float *score, const float *log10p, const uint8_t *off,
                  const int64_t *indptr, int32_t r0, int32_t r1, int32_t dlo, double *data,
                  double *logp, int32_t *indices, int32_t *indices2, int threads);
 int expand_threads_default();
+}  // namespace cs
+#include <functional>
+namespace cs {
+// fn(0..n-1) on one of the library's persistent host worker pools (host_expand.cpp; 0: widening
+// of results, 1: staging copies of uploads); the caller runs share 0
+void parallel_for(int n, const std::function<void(int)> &fn, int which);
+int upload_threads_default();
+void copy_stream(void *dst, const void *src, size_t n);
 
 // exact float64 recomputation, from the CSR signal, of the scores at / near a Pearson threshold
 // (pearson.cu): makes the candidate set of pick_foci independent of float32 rounding

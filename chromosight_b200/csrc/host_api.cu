@@ -39,19 +39,21 @@ struct PinBlock {
     bool busy;
 };
 
-constexpr size_t kStageBytes = 32u << 20;
-static const size_t kStageChunk = [] {  // one DMA per chunk; two buffers alternate
+constexpr int kStageBufs = 4;  // staging buffers in rotation: host copies run ahead of the DMA
+constexpr size_t kStageBytes = 16u << 20;
+static const size_t kStageChunk = [] {  // one DMA per chunk
     const char *e = getenv("CS_STAGE_CHUNK_MB");
-    size_t mb = (e && atoi(e) > 0) ? (size_t)atoi(e) : 32;
-    if (mb > 32) mb = 32;
+    size_t mb = (e && atoi(e) > 0) ? (size_t)atoi(e) : 16;
+    if (mb > 16) mb = 16;
     return mb << 20;
 }();
 
 struct HostCtx {
     int device = -1;
     cudaStream_t st = nullptr, st_copy = nullptr, st_emit = nullptr, st_up = nullptr;
-    void *stage[2] = {nullptr, nullptr};
-    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    void *stage[kStageBufs] = {nullptr};
+    cudaEvent_t stage_ev[kStageBufs] = {nullptr};
+    int stage_next = 0;  // rotation continues across calls of h2d_staged
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<PinBlock> pool;
     std::mutex mu;       // device work of one call phase
@@ -80,7 +82,7 @@ static int get_ctx(int device, HostCtx **out) {
         CS_CUDA(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
         CS_CUDA(cudaStreamCreateWithPriority(&c->st_emit, cudaStreamNonBlocking, hi_pri));
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kStageBufs; ++i) {
         CS_CUDA(cudaHostAlloc(&c->stage[i], kStageBytes, cudaHostAllocDefault));
         CS_CUDA(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
     }
@@ -90,40 +92,29 @@ static int get_ctx(int device, HostCtx **out) {
     return CS_OK;
 }
 
-// memcpy split over a few host threads.  Measured on the B200 boxes (scripts/pipe_ab.sh): the
-// staging copy competes with the download DMA for host memory bandwidth, and two or three
-// threads are as good as more.  CS_COPY_THREADS overrides the count.
+// memcpy split over the upload pool's threads (up to 4; CS_COPY_THREADS overrides): the staging
+// copy of pageable inputs is on the device's critical path.
 static void memcpy_mt(void *dst, const void *src, size_t n) {
-    const size_t kMin = 4u << 20;
-    static const int maxt = [] {
-        const char *e = getenv("CS_COPY_THREADS");
-        if (e && atoi(e) > 0) return atoi(e);
-        int n = 3;
-        // the ranks of one box share its cores
-        const unsigned hw = std::thread::hardware_concurrency();
-        if (const char *w = getenv("LOCAL_WORLD_SIZE"))
-            if (atoi(w) > 1 && hw) {
-                const int share = (int)hw / (2 * atoi(w));
-                n = share < 1 ? 1 : (share < n ? share : n);
-            }
-        return n;
-    }();
+    const size_t kMin = 1u << 20;
+    const int maxt = upload_threads_default();
     int nt = (int)(n / kMin);
     if (nt > maxt) nt = maxt;
+    static const bool plain = getenv("CS_STAGE_PLAIN_MEMCPY") != nullptr;
+    auto cp = [](void *d, const void *s_, size_t m) {
+        if (plain) memcpy(d, s_, m);
+        else copy_stream(d, s_, m);
+    };
     if (nt <= 1) {
-        memcpy(dst, src, n);
+        cp(dst, src, n);
         return;
     }
     const size_t per = ((n / nt) + 4095) & ~(size_t)4095;
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t) {
-        const size_t o = per * t;
-        if (o >= n) break;
+    parallel_for(nt, [&](int t) {
+        const size_t o = per * (size_t)t;
+        if (o >= n) return;
         const size_t len = (o + per > n) ? n - o : per;
-        th.emplace_back([=] { memcpy((char *)dst + o, (const char *)src + o, len); });
-    }
-    memcpy(dst, src, per < n ? per : n);
-    for (auto &t : th) t.join();
+        cp((char *)dst + o, (const char *)src + o, len);
+    }, 1);
 }
 
 // true when `p` lies in page-locked host memory CUDA knows about (cudaHostAlloc /
@@ -139,11 +130,19 @@ static bool is_pinned(const void *p) {
 
 // pageable host -> device through the two pinned staging buffers (CPU memcpy of chunk
 // i+1 overlaps the DMA of chunk i)
+struct StageTimes {  // CS_TRACE: where the staging thread's time goes (ms)
+    double wait = 0, copy = 0, api = 0;
+};
+static thread_local StageTimes *g_stage_times = nullptr;
+static inline double ms_now() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 template <typename Poll>
 static int h2d_staged(HostCtx *c, cudaStream_t st, void *dst, const void *src, size_t bytes,
                       Poll poll) {
     size_t done = 0;
-    int k = 0;
+    int k = c->stage_next;
     if (bytes >= (1u << 16) && is_pinned(src) && is_pinned((const char *)src + bytes - 1)) {
         if (int prc = poll()) return prc;
         CS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
@@ -152,13 +151,23 @@ static int h2d_staged(HostCtx *c, cudaStream_t st, void *dst, const void *src, s
     while (done < bytes) {
         const size_t n = bytes - done < kStageChunk ? bytes - done : kStageChunk;
         if (int prc = poll()) return prc;
+        const double t0 = g_stage_times ? ms_now() : 0.0;
         CS_CUDA(cudaEventSynchronize(c->stage_ev[k]));
+        const double t1 = g_stage_times ? ms_now() : 0.0;
         memcpy_mt(c->stage[k], (const char *)src + done, n);
+        const double t2 = g_stage_times ? ms_now() : 0.0;
         CS_CUDA(cudaMemcpyAsync((char *)dst + done, c->stage[k], n, cudaMemcpyHostToDevice, st));
         CS_CUDA(cudaEventRecord(c->stage_ev[k], st));
+        if (g_stage_times) {
+            const double t3 = ms_now();
+            g_stage_times->wait += t1 - t0;
+            g_stage_times->copy += t2 - t1;
+            g_stage_times->api += t3 - t2;
+        }
         done += n;
-        k ^= 1;
+        k = (k + 1) % kStageBufs;
     }
+    c->stage_next = k;
     return CS_OK;
 }
 static int h2d_staged(HostCtx *c, cudaStream_t st, void *dst, const void *src, size_t bytes) {
@@ -706,7 +715,7 @@ static int session_refine(cs_session *s, double threshold, int32_t dmin, int32_t
     cs_pearson_opts po;
     session_pearson_opts(s, &po);
     po.mask_mode = a.has_mask;  // the predicate of the exact path, whatever the image holds
-    const long long cap = 1 << 20;
+    const long long cap = 1 << 23;  // 8 M pixels (64 MB of scratch)
     int rc;
     if ((rc = s->x_list.ensure((size_t)cap * sizeof(int2) + 64))) return rc;
     RefineArgs R;
@@ -906,6 +915,221 @@ extern "C" int cs_session_download(cs_session *s, cs_csr_result *res) {
     return CS_OK;
 }
 
+// The uploads of a slab-pipelined call run ahead on a thread of their own (the staging copies
+// of pageable inputs are host work): slab k needs the signal (and pixel mask) rows below
+// need_of[k]; `done` counts the slabs whose rows are enqueued on the upload stream, ev[k] is
+// recorded behind them.
+struct SlabUploader {
+    std::atomic<int> done{0};
+    std::atomic<int> rc{0};
+    std::atomic<bool> stop{false};
+    std::thread th;
+    ~SlabUploader() {
+        stop.store(true);
+        if (th.joinable()) th.join();
+    }
+    void start(HostCtx *c, cudaStream_t sth, const cs_normxcorr2_args *a, cs_session *s,
+               const std::vector<int> &need_of, cudaEvent_t *evs, bool utrace) {
+        const int dev = c->device, ns = (int)need_of.size();
+        const bool pixmask = a->has_mask == 1;
+        const int *needs = need_of.data();
+        int32_t *d_ix = (int32_t *)s->sig_indices.p, *d_mix = (int32_t *)s->m_indices.p;
+        double *d_dat = (double *)s->sig_data.p;
+        SlabUploader *up = this;
+        th = std::thread([=] {
+            cudaSetDevice(dev);
+            StageTimes stt;
+            if (utrace) g_stage_times = &stt;
+            const double tu0 = ms_now();
+            struct Report {
+                bool on;
+                StageTimes *t;
+                double t0;
+                ~Report() {
+                    if (on)
+                        fprintf(stderr, "uploader: %.2f ms total; waiting for a staging buffer %.2f, host copies %.2f, "
+                                        "CUDA calls %.2f\n", ms_now() - t0, t->wait, t->copy, t->api);
+                }
+            } report{utrace, &stt, tu0};
+            int from = 0;
+            for (int k = 0; k < ns && !up->stop.load(); ++k) {
+                const int to = needs[k];
+                int r = CS_OK;
+                if (to > from) {
+                    const int64_t e0 = a->indptr[from], e1 = a->indptr[to];
+                    if (e1 > e0) {
+                        r = h2d_staged(c, sth, d_ix + e0, a->indices + e0, (size_t)(e1 - e0) * sizeof(int32_t));
+                        if (!r)
+                            r = h2d_staged(c, sth, d_dat + e0, a->data + e0, (size_t)(e1 - e0) * sizeof(double));
+                    }
+                    if (!r && pixmask) {
+                        const int64_t m0 = a->mask_indptr[from], m1 = a->mask_indptr[to];
+                        if (m1 > m0)
+                            r = h2d_staged(c, sth, d_mix + m0, a->mask_indices + m0,
+                                           (size_t)(m1 - m0) * sizeof(int32_t));
+                    }
+                    if (!r && cudaEventRecord(evs[k], sth) != cudaSuccess) r = CS_ERR_CUDA;
+                    from = to;
+                }
+                if (r) {
+                    up->rc.store(r);
+                    return;
+                }
+                up->done.store(k + 1, std::memory_order_release);
+            }
+        });
+    }
+};
+
+// slab boundaries in image rows (multiples of the tile height; with `ramp` the first slabs are
+// small so that the download -- the longest leg -- starts early) and the signal rows each needs
+static void plan_slabs(const cs_session *s, int TRp, int nslab, bool ramp, std::vector<int> &Yb,
+                       std::vector<int> &need_of) {
+    Yb.assign(nslab + 1, 0);
+    std::vector<double> w(nslab, 1.0);
+    if (ramp && nslab >= 6) w[0] = 0.15, w[1] = 0.3, w[2] = 0.6;
+    double tot_w = 0.0, acc_w = 0.0;
+    for (double v : w) tot_w += v;
+    const int R = s->oy1 - s->oy0;
+    Yb[0] = s->oy0;
+    for (int i = 1; i <= nslab; ++i) {
+        acc_w += w[i - 1];
+        long long y = (long long)((double)R * acc_w / tot_w);
+        y = (y + TRp / 2) / TRp * TRp;
+        Yb[i] = s->oy0 + (int)(y > R ? R : y);
+        if (Yb[i] < Yb[i - 1]) Yb[i] = Yb[i - 1];
+    }
+    Yb[0] = s->oy0;
+    Yb[nslab] = s->oy1;
+    const int kh = (s->a.kernel.kh - 1) / 2;
+    need_of.assign(nslab, 0);
+    int prev = 0;
+    for (int k = 0; k < nslab; ++k) {
+        int need = Yb[k + 1] + kh - s->pr;  // signal rows the slab's windows read
+        if (need > s->a.rows || k == nslab - 1) need = s->a.rows;
+        if (need < prev) need = prev;
+        need_of[k] = prev = need;
+    }
+}
+
+// Large inputs, scores only: upload, fill and Pearson tiles cut into row slabs so that the
+// staging / DMA of slab s+1 overlaps the kernels of slab s; the scores stay an image in HBM
+// (what pattern_detector reads through foci / validate).
+static int session_upload_run_pipelined(cs_session *s, const cs_normxcorr2_args *a, int nslab,
+                                        cs_run_stats *stats) {
+    int rc = session_upload_impl(s, a, true);
+    if (rc) return rc;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    s->ran = false;
+    s->refined = false;
+    s->compacted = false;
+    if (s->empty) {
+        s->nnz_out = 0;
+        s->ran = true;
+        return CS_OK;
+    }
+    HostCtx *c = s->c;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = s->stream(), st_h = c->st_up;
+    const cs_normxcorr2_args &A = s->a;
+    const cs_kernel_desc &K = A.kernel;
+    const long long l0 = g_launches.load();
+    std::vector<cudaEvent_t> ev_up(nslab);
+    for (int i = 0; i < nslab; ++i) CS_CUDA(cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming));
+    struct EvGuard {
+        std::vector<cudaEvent_t> &a;
+        ~EvGuard() {
+            for (auto e : a) cudaEventDestroy(e);
+        }
+    } evguard{ev_up};
+    CS_CUDA(cudaEventRecord(s->ev[2], st));
+    rc = fill_begin(&s->Li, (float *)s->img.p, A.rows, A.cols, A.has_mask, A.sym_upper, A.max_dist,
+                    A.full ? K.kh : 0, A.full ? K.kw : 0, (int32_t *)s->err.p, st);
+    if (rc) return rc;
+    CS_CUDA(cudaMemsetAsync(s->out.p, 0, (size_t)s->Lo.n_elems * sizeof(float), st));
+    cs_pearson_opts po;
+    session_pearson_opts(s, &po);
+    int32_t TRp = 32;
+    if ((rc = cs_pearson_tile_rows(&s->Li, &K, &po, s->oy0, s->oy1, s->ox0, s->ox1, s->od_lo,
+                                   s->od_hi, &TRp)))
+        return rc;
+    po.tile_rows = TRp;
+    std::vector<int> Yb, need_of;
+    plan_slabs(s, TRp, nslab, false, Yb, need_of);
+    // the upload stream must not run ahead of the row pointers (uploaded on `st` by the plan)
+    CS_CUDA(cudaEventRecord(s->ev[3], st));
+    CS_CUDA(cudaStreamWaitEvent(st_h, s->ev[3], 0));
+    SlabUploader upl;
+    upl.start(c, st_h, a, s, need_of, ev_up.data(), false);
+    int up_end = 0;
+    for (int k = 0; k < nslab; ++k) {
+        while (upl.done.load(std::memory_order_acquire) <= k) {
+            if (upl.rc.load()) {
+                set_error("upload of the input failed");
+                return upl.rc.load();
+            }
+            std::this_thread::sleep_for(std::chrono::microseconds(10));
+        }
+        const int need = need_of[k];
+        if (need > up_end) {
+            CS_CUDA(cudaStreamWaitEvent(st, ev_up[k], 0));
+            rc = fill_rows(&s->Li, (float *)s->img.p, (const int64_t *)s->sig_indptr.p,
+                           (const int32_t *)s->sig_indices.p, (const double *)s->sig_data.p, A.rows,
+                           up_end, need, s->pr, s->pc, A.has_mask, (const int64_t *)s->m_indptr.p,
+                           (const int32_t *)s->m_indices.p, &s->geo, A.sym_upper, A.max_dist,
+                           A.full ? K.kh : 0, A.full ? K.kw : 0, (int32_t *)s->err.p, st);
+            if (rc) return rc;
+            up_end = need;
+        }
+        if (Yb[k + 1] > Yb[k]) {
+            rc = cs_pearson_f32(&s->Li, (const float *)s->img.p, &K, &po, Yb[k], Yb[k + 1], s->ox0,
+                                s->ox1, s->od_lo, s->od_hi, &s->Lo, (float *)s->out.p,
+                                s->want_nobs ? s->nobs.p : nullptr, st);
+            if (rc) return rc;
+        }
+    }
+    int32_t herr[2] = {0, 0};
+    CS_CUDA(cudaMemcpyAsync(herr, s->err.p, sizeof(herr), cudaMemcpyDeviceToHost, st));
+    CS_CUDA(cudaEventRecord(s->ev[5], st));
+    CS_CUDA(cudaStreamSynchronize(st));
+    if (herr[0] > 0 && A.has_mask) {
+        set_error("There are %d non-zero elements reported as missing.", herr[0]);
+        return CS_ERR_MASKED_SIGNAL;
+    }
+    if (herr[1] > 0 && !A.trim_to_max_dist) {
+        set_error("internal: %d signal pixels fell outside the stored band", herr[1]);
+        return CS_ERR_INVALID;
+    }
+    s->nnz_out = 0;
+    s->ran = true;
+    if (stats) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s->ev[2], s->ev[5]);
+        stats->ms_total = ms;
+        stats->n_windows = s->n_windows;
+        stats->launches = g_launches.load() - l0;
+        stats->h2d_bytes = (int64_t)s->h2d_bytes;
+    }
+    return CS_OK;
+}
+
+// Upload + scores in one call: slab-pipelined for large inputs, else cs_session_upload followed
+// by cs_session_run_scores.
+extern "C" int cs_session_upload_run_scores(cs_session *s, const cs_normxcorr2_args *a,
+                                            cs_run_stats *stats) {
+    CS_REQUIRE(s && a && a->indptr, "cs_session_upload_run_scores: null argument");
+    long long rows_out = a->full ? a->rows : a->rows - (a->kernel.kh - 1);
+    const int64_t nnz_in = a->indptr[a->rows];
+    int nslab = 8;
+    if (const char *e = getenv("CS_PIPELINE_SLABS")) nslab = atoi(e);
+    if (nslab > 1 && nnz_in >= (4 << 20) && rows_out >= 64 * nslab)
+        return session_upload_run_pipelined(s, a, nslab, stats);
+    int rc = cs_session_upload(s, a);
+    if (rc) return rc;
+    return cs_session_run_scores(s, stats);
+}
+
 // Large calls: the same work as upload + run + download, cut into row slabs so that the
 // upload of slab s+1, the kernels of slab s and the download of slab s-1 overlap (PCIe is
 // full duplex; the CSR result is 5x the input).  Per slab, on the compute stream:
@@ -924,12 +1148,6 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
     std::lock_guard<std::mutex> lk(c->mu);
     CS_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = s->stream(), st_d = c->st_copy, st_e = c->st_emit, st_h = c->st_up;
-    {
-        // uploads normally run in line with the kernels; CS_UPLOAD_STREAM=1 lets them run ahead on
-        // their own stream (measured: no difference, the download is the floor either way)
-        const char *e = getenv("CS_UPLOAD_STREAM");
-        if (!e || atoi(e) == 0) st_h = st;
-    }
     const cs_normxcorr2_args &A = s->a;
     const cs_kernel_desc &K = A.kernel;
     const int kh = (K.kh - 1) / 2;
@@ -1105,26 +1323,8 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
                                    s->od_hi, &TRp)))
         return rc;
     po.tile_rows = TRp;
-    // slab boundaries in image rows (multiples of the tile height); the first slabs are small
-    // so that the download -- the longest leg -- starts early
-    std::vector<int> Yb(nslab + 1);
-    {
-        std::vector<double> w(nslab, 1.0);
-        if (nslab >= 6) w[0] = 0.15, w[1] = 0.3, w[2] = 0.6;
-        double tot_w = 0.0, acc_w = 0.0;
-        for (double v : w) tot_w += v;
-        const int R = s->oy1 - s->oy0;
-        Yb[0] = s->oy0;
-        for (int i = 1; i <= nslab; ++i) {
-            acc_w += w[i - 1];
-            long long y = (long long)((double)R * acc_w / tot_w);
-            y = (y + TRp / 2) / TRp * TRp;
-            Yb[i] = s->oy0 + (int)(y > R ? R : y);
-            if (Yb[i] < Yb[i - 1]) Yb[i] = Yb[i - 1];
-        }
-    }
-    Yb[0] = s->oy0;
-    Yb[nslab] = s->oy1;
+    std::vector<int> Yb, need_of;
+    plan_slabs(s, TRp, nslab, true, Yb, need_of);
     auto csr_row = [&](int i) { return i == 0 ? 0 : (i == nslab ? A.rows : Yb[i] - s->pr); };
     int up_end = 0;
     int64_t base = 0;
@@ -1210,35 +1410,28 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
         }
         return CS_OK;
     };
+    // the uploads run ahead on a thread of their own; the enqueueing thread only waits for the
+    // rows a slab needs and keeps finalizing finished slabs meanwhile
+    SlabUploader upl;
+    st_h = c->st_up;  // always a stream of its own
+    upl.start(c, st_h, a, s, need_of, ev_up.data(), trace);
     for (int k = 0; k < nslab; ++k) {
         const int Y0 = Yb[k], Y1 = Yb[k + 1];
         if (trace) {
             th0[k] = now() - t_begin;
             CS_CUDA(cudaEventRecord(tev[4 * k], st));
         }
-        // signal rows the windows of this slab read: image rows < Y1 + kh
-        int need = Y1 + kh - s->pr;
-        if (need > A.rows || k == nslab - 1) need = A.rows;
+        const int need = need_of[k];
+        // wait for the slab's rows to be on their way, finalizing finished slabs meanwhile
+        while (upl.done.load(std::memory_order_acquire) <= k) {
+            if (upl.rc.load()) {
+                set_error("upload of the input failed");
+                return upl.rc.load();
+            }
+            if ((rc = poll())) return rc;
+            std::this_thread::sleep_for(std::chrono::microseconds(10));
+        }
         if (need > up_end) {
-            const int64_t e0 = a->indptr[up_end], e1 = a->indptr[need];
-            if (e1 > e0) {
-                if ((rc = h2d_staged(c, st_h, (int32_t *)s->sig_indices.p + e0, a->indices + e0,
-                                     (size_t)(e1 - e0) * sizeof(int32_t), poll)))
-                    return rc;
-                if ((rc = h2d_staged(c, st_h, (double *)s->sig_data.p + e0, a->data + e0,
-                                     (size_t)(e1 - e0) * sizeof(double), poll)))
-                    return rc;
-            }
-            if (A.has_mask == 1) {
-                const int64_t m0 = a->mask_indptr[up_end], m1 = a->mask_indptr[need];
-                if (m1 > m0)
-                    if ((rc = h2d_staged(c, st_h, (int32_t *)s->m_indices.p + m0,
-                                         a->mask_indices + m0, (size_t)(m1 - m0) * sizeof(int32_t),
-                                         poll)))
-                        return rc;
-            }
-            // uploads run ahead on their own stream; the slab's kernels wait for its rows only
-            CS_CUDA(cudaEventRecord(ev_up[k], st_h));
             CS_CUDA(cudaStreamWaitEvent(st, ev_up[k], 0));
             rc = fill_rows(&s->Li, (float *)s->img.p, (const int64_t *)s->sig_indptr.p,
                            (const int32_t *)s->sig_indices.p, (const double *)s->sig_data.p, A.rows,

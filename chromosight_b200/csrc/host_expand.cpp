@@ -7,11 +7,96 @@
 #include <immintrin.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
 namespace cs {
+
+// A small persistent worker pool: spawning threads per slab costs more than the slab's work
+// (a new thread needs a good part of a millisecond before it runs).  Callers from several
+// threads share it; parallel_for runs one share on the calling thread.
+class WorkerPool {
+public:
+    explicit WorkerPool(int n) {
+        for (int i = 0; i < n; ++i) th_.emplace_back([this] { loop(); });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int size() const { return (int)th_.size(); }
+    void parallel_for(int n, const std::function<void(int)> &fn) {
+        if (n <= 1) {
+            if (n == 1) fn(0);
+            return;
+        }
+        std::atomic<int> left{n - 1};
+        std::mutex dmu;
+        std::condition_variable dcv;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (int i = 1; i < n; ++i)
+                q_.emplace_back([&, i] {
+                    fn(i);
+                    if (left.fetch_sub(1) == 1) {
+                        std::lock_guard<std::mutex> dl(dmu);
+                        dcv.notify_one();
+                    }
+                });
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> dl(dmu);
+        dcv.wait(dl, [&] { return left.load() == 0; });
+    }
+
+private:
+    void loop() {
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+                if (stop_ && q_.empty()) return;
+                job = std::move(q_.front());
+                q_.pop_front();
+            }
+            job();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::deque<std::function<void()>> q_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
+int expand_threads_default();
+int upload_threads_default();
+
+// two pools, so that the staging copies of the upload (on the critical path of the device)
+// never queue behind the widening of results (leaked on purpose: worker threads must not be
+// joined from a static destructor at exit)
+static WorkerPool &pool(int which) {
+    static WorkerPool *p[2] = {new WorkerPool(std::max(expand_threads_default(), 2) - 1),
+                               new WorkerPool(std::max(upload_threads_default(), 2) - 1)};
+    return *p[which];
+}
+
+void parallel_for(int n, const std::function<void(int)> &fn, int which) {
+    pool(which).parallel_for(n, fn);
+}
 
 static void expand_scalar(const float *score, const float *log10p, const uint8_t *off,
                           const int64_t *indptr, int32_t r0, int32_t r1, int32_t dlo,
@@ -53,21 +138,39 @@ CS_AVX512 static void expand_avx512(const float *score, const float *log10p, con
     const int64_t k0 = indptr[r0], k1 = indptr[r1];
     widen_avx512(score, data, k0, k1);
     if (logp) widen_avx512(log10p, logp, k0, k1);
-    // indices: per row (col = row + dlo + offset)
+    // indices: per row (col = row + dlo + offset).  A masked head up to the next 64-byte
+    // boundary of the destination, streaming stores over the aligned middle, a masked tail.
+    const bool same_align = indices2 == nullptr || ((((uintptr_t)indices) ^ ((uintptr_t)indices2)) & 63) == 0;
     for (int32_t r = r0; r < r1; ++r) {
         const __m512i base = _mm512_set1_epi32(r + dlo);
         int64_t k = indptr[r];
         const int64_t e = indptr[r + 1];
+        if (k >= e) continue;
+        int head = (int)((16 - (((uintptr_t)(indices + k) >> 2) & 15)) & 15);
+        if (head > e - k) head = (int)(e - k);
+        if (head) {
+            const __mmask16 m = (__mmask16)((1u << head) - 1u);
+            const __m512i c = _mm512_add_epi32(
+                _mm512_cvtepu8_epi32(_mm_maskz_loadu_epi8(m, (const void *)(off + k))), base);
+            _mm512_mask_storeu_epi32((void *)(indices + k), m, c);
+            if (indices2) _mm512_mask_storeu_epi32((void *)(indices2 + k), m, c);
+            k += head;
+        }
         for (; k + 16 <= e; k += 16) {
             const __m512i c = _mm512_add_epi32(
                 _mm512_cvtepu8_epi32(_mm_loadu_si128((const __m128i *)(off + k))), base);
-            _mm512_storeu_si512((void *)(indices + k), c);
-            if (indices2) _mm512_storeu_si512((void *)(indices2 + k), c);
+            _mm512_stream_si512((__m512i *)(indices + k), c);
+            if (indices2) {
+                if (same_align) _mm512_stream_si512((__m512i *)(indices2 + k), c);
+                else _mm512_storeu_si512((void *)(indices2 + k), c);
+            }
         }
-        for (; k < e; ++k) {
-            const int32_t c = r + dlo + (int32_t)off[k];
-            indices[k] = c;
-            if (indices2) indices2[k] = c;
+        if (k < e) {  // the row's tail, one masked vector
+            const __mmask16 m = (__mmask16)((1u << (int)(e - k)) - 1u);
+            const __m512i c = _mm512_add_epi32(
+                _mm512_cvtepu8_epi32(_mm_maskz_loadu_epi8(m, (const void *)(off + k))), base);
+            _mm512_mask_storeu_epi32((void *)(indices + k), m, c);
+            if (indices2) _mm512_mask_storeu_epi32((void *)(indices2 + k), m, c);
         }
     }
     _mm_sfence();
@@ -85,6 +188,57 @@ int expand_threads_default() {
             if (atoi(w) > 1) ranks = atoi(w);
         int t = hw / (2 * ranks);
         return std::max(1, std::min(t, 8));
+    }();
+    return n;
+}
+
+#if defined(__x86_64__)
+CS_AVX512 static void copy_stream_avx512(void *dst, const void *src, size_t n) {
+    char *d = (char *)dst;
+    const char *s = (const char *)src;
+    size_t k = 0;
+    while (k < n && ((uintptr_t)(d + k) & 63)) {
+        d[k] = s[k];
+        ++k;
+    }
+    for (; k + 256 <= n; k += 256) {
+        const __m512i a = _mm512_loadu_si512((const void *)(s + k));
+        const __m512i b = _mm512_loadu_si512((const void *)(s + k + 64));
+        const __m512i c = _mm512_loadu_si512((const void *)(s + k + 128));
+        const __m512i e = _mm512_loadu_si512((const void *)(s + k + 192));
+        _mm512_stream_si512((__m512i *)(d + k), a);
+        _mm512_stream_si512((__m512i *)(d + k + 64), b);
+        _mm512_stream_si512((__m512i *)(d + k + 128), c);
+        _mm512_stream_si512((__m512i *)(d + k + 192), e);
+    }
+    for (; k < n; ++k) d[k] = s[k];
+    _mm_sfence();
+}
+#endif
+
+// memcpy whose stores bypass the cache: the destination (a pinned staging buffer) is read next
+// by the DMA engine, not by a CPU
+void copy_stream(void *dst, const void *src, size_t n) {
+#if defined(__x86_64__)
+    static const bool has512 = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+    if (has512 && n >= 4096) {
+        copy_stream_avx512(dst, src, n);
+        return;
+    }
+#endif
+    memcpy(dst, src, n);
+}
+
+int upload_threads_default() {
+    static const int n = [] {
+        if (const char *e = getenv("CS_COPY_THREADS"))
+            if (atoi(e) > 0) return atoi(e);
+        int hw = (int)std::thread::hardware_concurrency();
+        if (hw <= 0) hw = 4;
+        int ranks = 1;
+        if (const char *w = getenv("LOCAL_WORLD_SIZE"))
+            if (atoi(w) > 1) ranks = atoi(w);
+        return std::max(1, std::min(hw / (4 * ranks), 4));
     }();
     return n;
 }
@@ -122,11 +276,9 @@ void expand_rows(const float *score, const float *log10p, const uint8_t *off,
         cut[t] = (int32_t)(std::lower_bound(indptr + r0, indptr + r1, want) - indptr);
         if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
     }
-    std::vector<std::thread> th;
-    for (int t = 1; t < nt; ++t)
-        if (cut[t + 1] > cut[t]) th.emplace_back(run, cut[t], cut[t + 1]);
-    run(cut[0], cut[1]);
-    for (auto &x : th) x.join();
+    parallel_for(nt, [&](int t) {
+        if (cut[t + 1] > cut[t]) run(cut[t], cut[t + 1]);
+    }, 0);
 }
 
 }  // namespace cs

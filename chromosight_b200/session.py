@@ -47,10 +47,13 @@ class Session:
             _lib.check(self._lib.cs_session_set_stream(self._h, C.c_void_p(st) if st else None))
 
     def upload(self, signal, kernel, max_dist=None, sym_upper=False, full=False, missing_mask=None,
-               missing_tol=0.75, tsvd=None, pval=False, trim_to_max_dist=False, mask_geometry=None):
+               missing_tol=0.75, tsvd=None, pval=False, trim_to_max_dist=False, mask_geometry=None,
+               run_scores=False):
         """Plan a normxcorr2 call (same arguments, det:807-817) and copy its inputs to HBM.
         `mask_geometry` = preprocessing.missing_geometry(...) stands for the mask
-        make_missing_mask would build, without building it."""
+        make_missing_mask would build, without building it.  run_scores=True also computes the
+        scores (as run(compact=False) would), overlapping the upload of large inputs with the
+        kernels slab by slab."""
         kernel = np.asarray(kernel, dtype=np.float64)
         _det._validate(signal, kernel, missing_mask)
         csr = _det._canonical_csr(signal, np.float64)
@@ -61,7 +64,12 @@ class Session:
                                    tsvd, pval, trim_to_max_dist=trim_to_max_dist, device=self.device,
                                    geometry=mask_geometry)
         self._bind_stream()
-        _lib.check(self._lib.cs_session_upload(self._h, C.byref(a)))
+        if run_scores:
+            st = _lib.RunStats()
+            _lib.check(self._lib.cs_session_upload_run_scores(self._h, C.byref(a), C.byref(st)))
+            self.stats = {f: getattr(st, f) for f, _ in _lib.RunStats._fields_}
+        else:
+            _lib.check(self._lib.cs_session_upload(self._h, C.byref(a)))
         del keep
         self.shape = csr.shape
         self.kernel_shape = kernel.shape

@@ -342,6 +342,22 @@ def validate_patterns(coords, matrix, conv_mat, detectable_bins, kernel_matrix, 
     return table, windows
 
 
+_sessions = {}
+
+
+def _detector_session():
+    """One device-resident session per (process, device): pattern_detector is called once per
+    sub-matrix and kernel (cli:738-792); allocating ~1.5 GB of device buffers per call would
+    cost more than the call."""
+    import threading
+    from ..session import Session
+    dev = _device_index()
+    s = _sessions.get(dev)
+    if s is None:
+        s = _sessions[dev] = (Session(dev), threading.Lock())
+    return s
+
+
 def pattern_detector(contact_map, kernel_config, kernel_matrix, coords=None, dump=None, full=False,
                      tsvd=None):
     """Detect (or, with `coords`, quantify) one pattern kernel on one sub-matrix
@@ -370,14 +386,17 @@ def pattern_detector(contact_map, kernel_config, kernel_matrix, coords=None, dum
         geometry = preproc.missing_geometry(
             shape, contact_map.detectable_bins[0], contact_map.detectable_bins[1],
             max_dist=contact_map.max_dist, sym_upper=not inter)
-    sess = Session()
+    sess, lock = _detector_session()
+    lock.acquire()
     try:
+        # the detector reads the score image only (foci, lookups at coordinates): upload and
+        # kernels overlap slab by slab, the CSR compaction and the p-values of every stored
+        # score are skipped unless dumped
         sess.upload(contact_map.matrix, kernel_matrix, max_dist=contact_map.max_dist,
                     sym_upper=not inter, full=full, mask_geometry=geometry, tsvd=tsvd, pval=True,
-                    missing_tol=kernel_config["max_perc_undetected"] / 100)
-        # the detector reads the score image only (foci, lookups at coordinates): the CSR
-        # compaction and the p-values of every stored score are skipped unless dumped
-        sess.run(compact=bool(dump))
+                    missing_tol=kernel_config["max_perc_undetected"] / 100, run_scores=not dump)
+        if dump:
+            sess.run(compact=True)
         dmax = 2 ** 30 if inter else int(contact_map.max_dist)
         dmin = -(2 ** 30) if inter else 0
         if dump:
@@ -420,7 +439,7 @@ def pattern_detector(contact_map, kernel_config, kernel_matrix, coords=None, dum
             coords, contact_map.detectable_bins[0], contact_map.detectable_bins[1], inter,
             kernel_config["max_perc_zero"] / 100, kernel_config["max_perc_undetected"] / 100, dmax)
     finally:
-        sess.close()
+        lock.release()  # the session (and its device buffers) is reused by the next call
     score = np.where(valid, score, np.nan)
     table = pd.DataFrame({"bin1": coords[:, 0], "bin2": coords[:, 1], "score": score,
                           "pvalue": 10.0 ** logp})

@@ -347,6 +347,10 @@ int cs_session_run(cs_session *s, cs_run_stats *stats);
  * cs_session_candidates / _foci / _validate read (pattern_detector, det:265-345, needs
  * p-values at the foci only); cs_session_download compacts on demand. */
 int cs_session_run_scores(cs_session *s, cs_run_stats *stats);
+/* cs_session_upload + cs_session_run_scores in one call; large inputs are cut into row slabs so
+ * that the staging / DMA of slab s+1 overlaps the kernels of slab s (what pattern_detector
+ * issues per sub-matrix, det:253-263). */
+int cs_session_upload_run_scores(cs_session *s, const cs_normxcorr2_args *a, cs_run_stats *stats);
 int cs_session_candidates(cs_session *s, float threshold, int32_t dmin, int32_t dmax,
                           cs_candidate *d_cand, int64_t cap, int64_t *d_count, int64_t *n_host);
 int cs_session_download(cs_session *s, cs_csr_result *res);

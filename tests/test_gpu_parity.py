@@ -325,7 +325,8 @@ def test_full_size_map_against_oracle_crops(kname, ksize, tol, pearson, presets)
         cpx &= exp != 0
         g2t = np.triu(np.tril(got2, D))
         assert np.array_equal((g2t >= pearson) & (g2t != 0), cpx)   # the candidate set, exactly
-        assert np.abs(got2[cpx] - exp[cpx].astype(np.float32)).max(initial=0) <= 1.2e-7
+        # (all of them when they fit the refinement list of 8 M pixels)
+        assert np.abs(got2[cpx] - exp[cpx].astype(np.float32)).max(initial=0) <= (1.2e-7 if nc < (1 << 23) else SCORE_TOL)
         # foci of the crop interior == pick_foci of the oracle (det:387-456): foci whose
         # pixels all lie at least 3 rows inside the compared rows are complete in the crop
         ex_trim = sp.coo_matrix(np.triu(np.tril(exp, D)))
