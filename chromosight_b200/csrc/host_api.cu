@@ -400,7 +400,9 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
     const int sh = pc - pr;
     long long od_lo = (long long)sig_dmin + sh - (kh + kw);
     long long od_hi = (long long)sig_dmax + sh + (kh + kw);
-    if (a->sym_upper && od_lo < sh) od_lo = sh;  // det:1098-1099 (triu of the cropped map)
+    // det:1098-1099: sp.triu of the FRAMED map (before the crop of det:1124-1129) keeps the
+    // image diagonals X - Y >= 0; for non-square kernels that is matrix diagonal -(nk - mk)
+    if (a->sym_upper && od_lo < 0) od_lo = 0;
     if (a->trim_to_max_dist && a->max_dist >= 0 && od_hi > (long long)a->max_dist + sh)
         od_hi = (long long)a->max_dist + sh;
     if (!s->empty) {

@@ -13,6 +13,7 @@
 #include <condition_variable>
 #include <deque>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -41,24 +42,28 @@ public:
             if (n == 1) fn(0);
             return;
         }
-        std::atomic<int> left{n - 1};
-        std::mutex dmu;
-        std::condition_variable dcv;
+        // completion state shared with the tasks (kept alive by them: the last worker may still
+        // be inside notify when the caller wakes up)
+        struct Done {
+            std::mutex mu;
+            std::condition_variable cv;
+            int left;
+        };
+        auto done = std::make_shared<Done>();
+        done->left = n - 1;
         {
             std::lock_guard<std::mutex> lk(mu_);
             for (int i = 1; i < n; ++i)
-                q_.emplace_back([&, i] {
+                q_.emplace_back([done, &fn, i] {
                     fn(i);
-                    if (left.fetch_sub(1) == 1) {
-                        std::lock_guard<std::mutex> dl(dmu);
-                        dcv.notify_one();
-                    }
+                    std::lock_guard<std::mutex> dl(done->mu);
+                    if (--done->left == 0) done->cv.notify_one();
                 });
         }
         cv_.notify_all();
         fn(0);
-        std::unique_lock<std::mutex> dl(dmu);
-        dcv.wait(dl, [&] { return left.load() == 0; });
+        std::unique_lock<std::mutex> dl(done->mu);
+        done->cv.wait(dl, [&] { return done->left == 0; });
     }
 
 private:

@@ -304,21 +304,50 @@ def _law_device(csr, d_csr, detectable_bins, max_dist):
     return d_law, d_cnt, n_diags
 
 
+def _law_host_fun(csr, detectable_bins, max_dist, fun):
+    """Distance law with an arbitrary reduction `fun` (pre:129-136 lets the caller pass any
+    callable): the qualifying pixels of each diagonal (upper, <= max_dist, strictly positive,
+    both bins detectable; pre:178-188) are grouped on the host and reduced by `fun` itself --
+    an arbitrary Python callable cannot run on the device.  The default (np.nanmean) never
+    comes here."""
+    n = csr.shape[0]
+    if max_dist is None:
+        max_dist = n
+    n_diags = int(min(n, max_dist + 1))
+    coo = csr.tocoo()
+    d = coo.col.astype(np.int64) - coo.row
+    ok = (d >= 0) & (d < n_diags) & (coo.data > 0)
+    if detectable_bins is not None:
+        good = np.zeros(n, dtype=bool)
+        good[np.asarray(detectable_bins)] = True
+        ok &= good[coo.row] & good[coo.col]
+    d, v = d[ok], coo.data[ok]
+    order = np.argsort(d, kind="stable")
+    d, v = d[order], v[order]
+    starts = np.searchsorted(d, np.arange(n_diags + 1))
+    law = np.zeros(n)
+    for k in range(n_diags):
+        seg = v[starts[k]:starts[k + 1]]
+        law[k] = fun(seg) if len(seg) else np.nan
+    return law, n_diags
+
+
 def distance_law(matrix, detectable_bins=None, max_dist=None, smooth=True, fun=np.nanmean):
     """Average contact value per upper diagonal (pre:129-197)."""
-    if fun is not np.nanmean:
-        raise NotImplementedError("the CUDA distance law implements fun=np.nanmean only")
     csr = sp.csr_matrix(matrix)
     if not csr.has_canonical_format:
         csr = csr.copy()
         csr.sum_duplicates()
     n = csr.shape[0]
-    d_law, d_cnt, n_diags = _law_device(csr, _csr_device(csr), detectable_bins, max_dist)
-    law = d_law.cpu().numpy()
-    cnt = d_cnt.cpu().numpy()
-    # the reference reports NaN for diagonals without any usable pixel (nanmean of
-    # an empty slice); the device array already holds the 0 that detrend needs
-    law[:n_diags][cnt == 0] = np.nan
+    if fun is not np.nanmean:
+        law, n_diags = _law_host_fun(csr, detectable_bins, max_dist, fun)
+    else:
+        d_law, d_cnt, n_diags = _law_device(csr, _csr_device(csr), detectable_bins, max_dist)
+        law = d_law.cpu().numpy()
+        cnt = d_cnt.cpu().numpy()
+        # the reference reports NaN for diagonals without any usable pixel (nanmean of
+        # an empty slice); the device array already holds the 0 that detrend needs
+        law[:n_diags][cnt == 0] = np.nan
     if smooth and n > 2:
         from sklearn.isotonic import IsotonicRegression
         law[~np.isfinite(law)] = 0
@@ -328,8 +357,6 @@ def distance_law(matrix, detectable_bins=None, max_dist=None, smooth=True, fun=n
 
 def detrend(matrix, detectable_bins=None, max_dist=None, smooth=False, fun=np.nanmean, max_val=10):
     """Divide each pixel by the distance law of its diagonal (pre:256-310)."""
-    if fun is not np.nanmean:
-        raise NotImplementedError("the CUDA detrend implements fun=np.nanmean only")
     t = _cuda.require_cuda()
     lib = _lib.load()
     csr = sp.csr_matrix(matrix, dtype=np.float64)
@@ -338,8 +365,10 @@ def detrend(matrix, detectable_bins=None, max_dist=None, smooth=False, fun=np.na
         csr.sum_duplicates()
     n = csr.shape[0]
     d_csr = _csr_device(csr)
-    if smooth:
-        law = distance_law(csr, detectable_bins, max_dist, smooth=True)
+    if smooth or fun is not np.nanmean:
+        # isotonic smoothing (sklearn) and custom reductions are host code, as in the reference;
+        # the division by the law still runs on the device
+        law = distance_law(csr, detectable_bins, max_dist, smooth=smooth, fun=fun)
         law[np.isnan(law)] = 0.0
         d_law = _cuda.to_device(law, np.float64)
     else:

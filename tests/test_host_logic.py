@@ -241,3 +241,27 @@ def test_cli_fixture_reproduces_reference_held_answers():
         assert np.array_equal(z[f"{case}_bin1"][o], z[f"{case}_held_bin1"][h])
         assert np.array_equal(z[f"{case}_bin2"][o], z[f"{case}_held_bin2"][h])
         assert np.abs(z[f"{case}_score"][o] - z[f"{case}_held_score"][h]).max() < 1e-9
+
+
+def test_distance_law_custom_fun_host_reduction():
+    """distance_law(fun=...) with a reduction other than nanmean (pre:129-136): grouped on the
+    host; checked against a dense restatement of pre:178-188 (and the live reference when
+    oracle/_ref is present)."""
+    from chromosight_b200 import synthetic
+    from chromosight_b200.utils import preprocessing as cup
+    from oracle import ref_loader
+    raw, detect = synthetic.band_counts(300, 45, seed=6, missing_frac=0.05, max_dist=40)
+    A = raw.toarray()
+    ok = np.zeros(300, bool)
+    ok[detect] = True
+    ref = ref_loader.load()
+    for fun in (np.nanmedian, np.nanmax):
+        law, n_diags = cup._law_host_fun(raw.tocsr(), detect, 40, fun)
+        assert n_diags == 41 and np.all(law[41:] == 0)
+        for d in range(41):
+            v = np.diagonal(A, d)[ok[: 300 - d] & ok[d:]]
+            v = v[v > 0]
+            assert (np.isnan(law[d]) and len(v) == 0) or np.isclose(law[d], fun(v))
+        if ref is not None:
+            exp = ref[1].distance_law(raw.tocsr(), detectable_bins=detect, max_dist=40, smooth=False, fun=fun)
+            assert np.allclose(law[:41], exp[:41], equal_nan=True)
