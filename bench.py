@@ -63,6 +63,13 @@ def parse_args():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: one chromosome per GPU (independent sub-matrices); strong: ONE chromosome cut "
                          "into row slabs over the GPUs (rowslab.py: law all-reduce + candidate gather)")
+    ap.add_argument("--config", type=int, default=0, choices=[0, 4, 5],
+                    help="4: quantify loops at --positions bed2d positions on 4 chromosomes x 50k bins, sharded "
+                         "by chromosome; 5: detect loops --inter on a synthetic 23-chromosome / 500k-bin genome, "
+                         "sharded by sub-matrix (BASELINE.json configs[3], [4]); 0: the metric workload")
+    ap.add_argument("--positions", type=int, default=1_000_000)
+    ap.add_argument("--genome-bins", type=int, default=500_000, help="config 5: bins of the whole genome")
+    ap.add_argument("--chroms", type=int, default=23, help="config 5: chromosomes (sizes ~ hg38)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -541,6 +548,123 @@ def detrend_device_leg(raw, detect, max_dist, torch, reps=10):
                          "note": "two passes over the CSR entries (law: 12 B read; division: 12 B read + 8 B written)"}}
 
 
+# --------------------------------------------------------------------------- configs 4 and 5
+HG38_MB = [248, 242, 198, 190, 182, 171, 159, 145, 138, 134, 135, 133, 114, 107, 102, 90, 83, 80, 59, 64, 47, 51, 156]
+
+
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the hot path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    return world, rank, dist, sync
+
+
+def run_config4(a):
+    """BASELINE.json configs[3]: quantify loops at 1 M bed2d positions on the 200k map cut into 4
+    chromosomes of 50k bins, sharded by chromosome (driver.quantify = cmd_quantify, cli:295-496)."""
+    import pandas as pd
+    from chromosight_b200 import driver, kernels, synthetic
+    from chromosight_b200.contacts_map import HicGenome
+    from chromosight_b200.utils import detection as cud
+    world, rank, dist, sync = _dist_setup()
+    binsize, D, nb = 10_000, a.max_dist, a.n // 4
+    t0 = time.perf_counter()
+    clr = synthetic.genome_cool([nb] * 4, binsize=binsize, n_diags=D + 17, seed=0, density_floor=1.0)
+    t_gen = time.perf_counter() - t0
+    rng = np.random.default_rng(1)
+    P = a.positions
+    chrom = rng.integers(0, 4, size=P)
+    b1 = rng.integers(0, nb - D, size=P)
+    b2 = b1 + rng.integers(2, D + 1, size=P)
+    names = np.array(clr.chromnames)[chrom]
+    bed = pd.DataFrame({"chrom1": names, "start1": b1 * binsize, "end1": (b1 + 1) * binsize,
+                        "chrom2": names, "start2": b2 * binsize, "end2": (b2 + 1) * binsize})
+    cfg = dict(kernels.loops)
+    cfg["kernels"] = [np.array(k) for k in cfg["kernels"]]
+    hg = HicGenome(clr, inter=False, kernel_config=cfg)
+    hg.normalize()
+    driver.quantify(hg, cfg, bed.iloc[:2000].copy(), return_windows=False)   # warm-up
+    for key in cud.detector_totals:
+        cud.detector_totals[key] = 0
+    sync()
+    t0 = time.perf_counter()
+    table, windows = driver.quantify(hg, cfg, bed, return_windows=True, gather_windows=False)
+    sync()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        tot = cud.detector_totals
+        print(json.dumps({
+            "config": 4, "what": "quantify loops (driver.quantify, cli:295-496)", "positions": P, "chroms": 4,
+            "bins_per_chrom": nb, "n_gpus": world, "seconds": dt, "positions_per_s": P / dt,
+            "scored": int(table.score.notna().sum()),
+            "windows": "k x k float64 window per position, kept on the rank that cut it",
+            "rank0_pattern_detector": {"calls": tot["calls"], "wall_s": tot["wall_ms"] / 1e3,
+                                       "device_s": tot["device_ms"] / 1e3},
+            "host_share": "the rest of `seconds`: sub-matrix extraction and balancing from the pixel table, "
+                          "detrend round trip, pandas bookkeeping of cmd_quantify",
+            "reference_estimate": "validate_patterns alone: 207 us per position (SURVEY 6) = %.0f s" % (P * 207e-6),
+            "genome_generation_s": t_gen}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_config5(a):
+    """BASELINE.json configs[4]: detect loops --inter on a synthetic 23-chromosome genome of 500k
+    bins (sizes proportional to hg38), 23 intra + 253 inter sub-matrices sharded over the ranks
+    by window count (driver.detect = cmd_detect, cli:625-860)."""
+    from chromosight_b200 import driver, kernels, synthetic
+    from chromosight_b200.contacts_map import HicGenome
+    from chromosight_b200.utils import detection as cud
+    world, rank, dist, sync = _dist_setup()
+    w = np.array(HG38_MB[: a.chroms], dtype=np.float64)
+    sizes = np.maximum((w / w.sum() * a.genome_bins).astype(int), 200)
+    t0 = time.perf_counter()
+    clr = synthetic.genome_cool([int(x) for x in sizes], binsize=10_000, n_diags=a.max_dist + 17, seed=10,
+                                inter_density=1e-4, density_floor=1.0)
+    t_gen = time.perf_counter() - t0
+    cfg = dict(kernels.loops)
+    cfg["kernels"] = [np.array(k) for k in cfg["kernels"]]
+    hg = HicGenome(clr, inter=True, kernel_config=cfg)
+    hg.normalize()
+    hg.make_sub_matrices()
+    costs = driver.unit_costs(hg)
+    for key in cud.detector_totals:
+        cud.detector_totals[key] = 0
+    sync()
+    t0 = time.perf_counter()
+    table, windows = driver.detect(hg, cfg, full=True, gather_windows=False)
+    sync()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        tot = cud.detector_totals
+        n_inter = 0 if table is None else int((table.chrom1.astype(str) != table.chrom2.astype(str)).sum())
+        print(json.dumps({
+            "config": 5, "what": "detect loops --inter (driver.detect, cli:625-860)", "chroms": int(a.chroms),
+            "genome_bins": int(sizes.sum()), "sub_matrices": len(costs), "windows_total": float(np.sum(costs)),
+            "n_gpus": world, "seconds": dt, "windows_per_s": float(np.sum(costs)) / dt,
+            "patterns": 0 if table is None else len(table), "inter_patterns": n_inter,
+            "rank0_pattern_detector": {"calls": tot["calls"], "wall_s": tot["wall_ms"] / 1e3,
+                                       "device_s": tot["device_ms"] / 1e3},
+            "host_share": "the rest of `seconds`: sub-matrix extraction from the pixel table, inter "
+                          "normalisation, table bookkeeping of cmd_detect",
+            "genome_generation_s": t_gen}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def traffic_from_profile():
     """DRAM bytes per launch of the Pearson kernel from the committed ncu capture
     (profiles/pearson_traffic.json, written by scripts/summarize_ncu.py), else null."""
@@ -559,6 +683,10 @@ def main():
         kernel = hostpre.resize_kernel(kernel, factor=a.win_size / kernel.shape[0])
     if a.impl == "reference":
         run_reference(a, kernel)
+    elif a.config == 4:
+        run_config4(a)
+    elif a.config == 5:
+        run_config5(a)
     else:
         run_b200(a, kernel)
 

@@ -45,9 +45,8 @@ class ContactMap:
         (s1, e1), (s2, e2) = self.extent
         self.matrix = self.clr.matrix(sparse=True, balance=self.use_norm)[s1:e1, s2:e2]
         if self.inter:
-            # cm:598-601
-            self.matrix.data[np.isnan(self.matrix.data)] = 0.0
-            self.matrix.data = self.matrix.data / np.nanmedian(self.matrix.data)
+            # cm:598-601: stored values (NaN -> 0) divided by their median, on the device
+            self.matrix.data = preproc.divide_by_median(self.matrix.data)
         else:
             # cm:607-624: distance-law detrend (GPU) then band trim
             self.matrix = preproc.detrend(

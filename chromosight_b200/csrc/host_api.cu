@@ -601,6 +601,8 @@ static int session_run_impl(cs_session *s, cs_run_stats *stats, bool compact) {
     if (rc) return rc;
     // scores outside the computed set must read as 0
     CS_CUDA(cudaMemsetAsync(s->out.p, 0, (size_t)s->Lo.n_elems * sizeof(float), st));
+    if (s->want_nobs)  // missing counts: only windows that have one are written by the kernel
+        CS_CUDA(cudaMemsetAsync(s->nobs.p, 0, (size_t)s->Lo.n_elems * (size_t)s->nmiss_bytes, st));
     cs_pearson_opts po;
     session_pearson_opts(s, &po);
     CS_CUDA(cudaEventRecord(s->ev[3], st));
@@ -1050,6 +1052,8 @@ static int session_upload_run_pipelined(cs_session *s, const cs_normxcorr2_args 
                     A.full ? K.kh : 0, A.full ? K.kw : 0, (int32_t *)s->err.p, st);
     if (rc) return rc;
     CS_CUDA(cudaMemsetAsync(s->out.p, 0, (size_t)s->Lo.n_elems * sizeof(float), st));
+    if (s->want_nobs)  // missing counts: only windows that have one are written by the kernel
+        CS_CUDA(cudaMemsetAsync(s->nobs.p, 0, (size_t)s->Lo.n_elems * (size_t)s->nmiss_bytes, st));
     cs_pearson_opts po;
     session_pearson_opts(s, &po);
     int32_t TRp = 32;
@@ -1317,6 +1321,8 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
                     A.max_dist, A.full ? K.kh : 0, A.full ? K.kw : 0, (int32_t *)s->err.p, st);
     if (rc) return rc;
     CS_CUDA(cudaMemsetAsync(s->out.p, 0, (size_t)s->Lo.n_elems * sizeof(float), st));
+    if (s->want_nobs)  // missing counts: only windows that have one are written by the kernel
+        CS_CUDA(cudaMemsetAsync(s->nobs.p, 0, (size_t)s->Lo.n_elems * (size_t)s->nmiss_bytes, st));
     cs_pearson_opts po;
     session_pearson_opts(s, &po);
     const void *nb = s->want_nobs ? s->nobs.p : nullptr;

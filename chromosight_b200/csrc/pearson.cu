@@ -771,12 +771,17 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 // the row of eight windows is complete and aligned             [sec:store]
                 const long long oi0 =
                     (long long)(Y - P.osy) * P.out_pitch + ((X0 - P.osx) - P.out_dlo);
+                // the missing-count plane is zeroed by the caller: only rows with a count are written
+                int anyn = 0;
+#pragma unroll
+                for (int t = 0; t < RT; ++t) anyn |= nn[t];
+                const bool wn = P.nmiss != nullptr && anyn != 0;
                 if (ob == ((1u << RT) - 1u) && (oi0 & 3) == 0) {
 #pragma unroll
                     for (int t = 0; t < RT; t += 4)
                         *reinterpret_cast<float4 *>(P.out + oi0 + t) =
                             make_float4(rr[t], rr[t + 1], rr[t + 2], rr[t + 3]);
-                    if (P.nmiss) {
+                    if (wn) {
                         if (P.nmiss16) {
 #pragma unroll
                             for (int t = 0; t < RT; t += 4)
@@ -796,7 +801,7 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     for (int t = 0; t < RT; ++t)
                         if ((ob >> t) & 1u) {
                             P.out[oi0 + t] = rr[t];
-                            if (P.nmiss) {
+                            if (wn) {
                                 if (P.nmiss16) ((unsigned short *)P.nmiss)[oi0 + t] = (unsigned short)nn[t];
                                 else ((unsigned char *)P.nmiss)[oi0 + t] = (unsigned char)nn[t];
                             }

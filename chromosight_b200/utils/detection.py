@@ -343,6 +343,8 @@ def validate_patterns(coords, matrix, conv_mat, detectable_bins, kernel_matrix, 
 
 
 _sessions = {}
+# running totals over pattern_detector calls (bench.py --config 4 / 5 report the device share)
+detector_totals = {"calls": 0, "device_ms": 0.0, "wall_ms": 0.0}
 
 
 def _detector_session():
@@ -386,8 +388,10 @@ def pattern_detector(contact_map, kernel_config, kernel_matrix, coords=None, dum
         geometry = preproc.missing_geometry(
             shape, contact_map.detectable_bins[0], contact_map.detectable_bins[1],
             max_dist=contact_map.max_dist, sym_upper=not inter)
+    import time as _time
     sess, lock = _detector_session()
     lock.acquire()
+    _t0 = _time.perf_counter()
     try:
         # the detector reads the score image only (foci, lookups at coordinates): upload and
         # kernels overlap slab by slab, the CSR compaction and the p-values of every stored
@@ -439,6 +443,9 @@ def pattern_detector(contact_map, kernel_config, kernel_matrix, coords=None, dum
             coords, contact_map.detectable_bins[0], contact_map.detectable_bins[1], inter,
             kernel_config["max_perc_zero"] / 100, kernel_config["max_perc_undetected"] / 100, dmax)
     finally:
+        detector_totals["calls"] += 1
+        detector_totals["device_ms"] += float(sess.stats.get("ms_total", 0.0))
+        detector_totals["wall_ms"] += 1e3 * (_time.perf_counter() - _t0)
         lock.release()  # the session (and its device buffers) is reused by the next call
     score = np.where(valid, score, np.nan)
     table = pd.DataFrame({"bin1": coords[:, 0], "bin2": coords[:, 1], "score": score,

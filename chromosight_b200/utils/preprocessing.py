@@ -272,6 +272,21 @@ def ztransform(matrix):
 
 
 # --------------------------------------------------------------------------- CUDA path
+def divide_by_median(data):
+    """Inter-chromosomal normalisation (cm:598-601): NaN -> 0, then every stored value divided by
+    the median of the stored values (np.nanmedian semantics: mean of the two middle values),
+    sorted and divided on the device."""
+    t = _cuda.require_cuda()
+    d = _cuda.to_device(np.asarray(data, dtype=np.float64))
+    d = t.nan_to_num(d, nan=0.0)
+    n = d.numel()
+    if n == 0:
+        return np.asarray(data, dtype=np.float64)
+    srt = t.sort(d).values
+    med = (srt[(n - 1) // 2] + srt[n // 2]) / 2.0
+    return (d / med).cpu().numpy()
+
+
 def _csr_device(csr):
     indptr = _cuda.to_device(csr.indptr, np.int64)
     indices = _cuda.to_device(csr.indices, np.int32)

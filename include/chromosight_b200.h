@@ -119,8 +119,9 @@ int cs_image_fill_f32(const cs_layout *L, float *d_img,
  * Lout, whose pixel (Y - out_row_shift, X - out_col_shift) receives the score of
  * window (Y, X) (the shifts undo the frame, det:1124-1129).  `d_nmiss` (uint8 or
  * uint16 per opts->nmiss_bytes, same layout, may be NULL) receives the number of
- * missing pixels of each window when nobs_full (0 otherwise): the number of
- * observations of det:1110-1116 is kh*kw - nmiss.
+ * missing pixels of each window when nobs_full: the number of observations of
+ * det:1110-1116 is kh*kw - nmiss.  The caller ZEROES the plane first: only windows with a
+ * count are written.
  * ------------------------------------------------------------------------ */
 typedef struct cs_kernel_desc {
     int32_t kh, kw;          /* kernel shape (mk, nk), both odd */

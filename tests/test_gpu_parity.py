@@ -202,6 +202,13 @@ def test_sym_upper_non_square_kernels_vs_oracle(presets, kshape):
     for use_mask in (True, False):
         kw = dict(max_dist=D, sym_upper=True, full=True, missing_tol=0.6, pval=True)
         mm = mask if use_mask else None
+        if use_mask and kshape[0] > kshape[1]:
+            # a kernel taller than wide: the max(mk, nk) sub-diagonals of the FRAMED map that
+            # frame_missing_mask flags (pre:483-497) reach the signal's main diagonals, and
+            # check_missing_mask refuses the call (pre:501-532) -- in the reference as here
+            with pytest.raises(ValueError):
+                cud.normxcorr2(mat, kernel, missing_mask=mm, **kw)
+            continue
         r, p = cud.normxcorr2(mat, kernel, missing_mask=mm, **kw)
         r0, p0, nob = po.normxcorr2_dense(mat.toarray(), kernel, return_nobs=True,
                                           missing_mask=None if mm is None else mm.toarray(), **kw)
@@ -358,15 +365,16 @@ def test_full_size_map_against_oracle_crops(kname, ksize, tol, pearson, presets)
             p0[lo:hi][far] = 0
         _compare(got, gp, exp, p0[lo:hi], nob[lo:hi], strict=True)
         # refined scores: the candidates of the crop carry the float64 result itself
-        cpx = np.triu(np.tril(exp, D)) >= pearson
+        # (row i of `exp` is row lo + i of the crop: map diagonals 0..D are its diagonals lo..D+lo)
+        cpx = np.triu(np.tril(exp, D + lo), lo) >= pearson
         cpx &= exp != 0
-        g2t = np.triu(np.tril(got2, D))
+        g2t = np.triu(np.tril(got2, D + lo), lo)
         assert np.array_equal((g2t >= pearson) & (g2t != 0), cpx)   # the candidate set, exactly
         # (all of them when they fit the refinement list of 8 M pixels)
         assert np.abs(got2[cpx] - exp[cpx].astype(np.float32)).max(initial=0) <= (1.2e-7 if nc < (1 << 23) else SCORE_TOL)
         # foci of the crop interior == pick_foci of the oracle (det:387-456): foci whose
         # pixels all lie at least 3 rows inside the compared rows are complete in the crop
-        ex_trim = sp.coo_matrix(np.triu(np.tril(exp, D)))
+        ex_trim = sp.coo_matrix(np.triu(np.tril(exp, D + lo), lo))
         coords0, lab0 = cud.pick_foci(ex_trim, pearson)
         exp_set = set()
         if coords0 is not None:
