@@ -138,6 +138,8 @@ _PROTOS = {
     "cs_last_error": (C.c_char_p, []),
     "cs_launch_count": (C.c_int64, []),
     "cs_layout_band": (C.c_int, [C.POINTER(Layout), C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "cs_layout_band_padded": (C.c_int, [C.POINTER(Layout), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32]),
     "cs_layout_dense": (C.c_int, [C.POINTER(Layout), C.c_int32, C.c_int32]),
     "cs_image_fill_f32": (C.c_int, [C.POINTER(Layout), _P, _P, _P, _P, C.c_int32, C.c_int32,
                                      C.c_int32, C.c_int32, C.c_int32, _P, _P, C.POINTER(GeoMask),
@@ -148,6 +150,9 @@ _PROTOS = {
     "cs_pearson_tile_rows": (C.c_int, [C.POINTER(Layout), C.POINTER(KernelDesc), C.POINTER(PearsonOpts),
                                         C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.POINTER(C.c_int32)]),
+    "cs_pearson_plan": (C.c_int, [C.POINTER(Layout), C.POINTER(KernelDesc), C.POINTER(PearsonOpts),
+                                   C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "cs_scan_scratch": (C.c_int64, [C.c_int32]),
     "cs_scores_count": (C.c_int, [C.POINTER(Layout), _P, C.c_int32, C.c_int32, _P,
                                    C.POINTER(C.c_int64), _P]),

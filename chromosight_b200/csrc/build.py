@@ -31,16 +31,20 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+VARIANT = os.environ.get("CS_BUILD_VARIANT", "")     # experiments: a tagged library built with
+VARIANT_DEFS = os.environ.get("CS_BUILD_DEFS", "").split()  # extra -D flags (scripts/gpu_r2.sh)
+
+
 def _compile(src, verbose, ablate=False):
     stem, ext = os.path.splitext(src)
-    obj = os.path.join(HERE, "build", stem + (".abl.o" if ablate else ".o"))
+    obj = os.path.join(HERE, "build", stem + (".abl.o" if ablate else (f".{VARIANT}.o" if VARIANT else ".o")))
     deps = [os.path.join(HERE, src)] + [os.path.join(HERE, h) for h in HEADERS]
     if not _stale(obj, deps):
         return obj, ""
     if ext == ".cpp":  # plain host code
         cmd = [CXX, "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", os.path.join(HERE, src), "-o", obj]
     else:
-        cmd = [NVCC] + FLAGS + (["-DCS_ABLATE"] if ablate else []) + (["-Xptxas", "-v"] if verbose else []) \
+        cmd = [NVCC] + FLAGS + (["-DCS_ABLATE"] if ablate else []) + VARIANT_DEFS + (["-Xptxas", "-v"] if verbose else []) \
             + ["-c", os.path.join(HERE, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -62,7 +66,7 @@ def build(force=False, verbose=False, ablate=False):
     if verbose:
         for _, log in results:
             sys.stderr.write(log)
-    lib = LIB.replace(".so", "_ablate.so") if ablate else LIB
+    lib = LIB.replace(".so", "_ablate.so") if ablate else (LIB.replace(".so", f"_{VARIANT}.so") if VARIANT else LIB)
     if force or _stale(lib, objs):
         cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs + ["-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -318,6 +318,8 @@ extern "C" int cs_session_set_stream(cs_session *s, void *stream) {
 }
 
 // Plan the call and copy its inputs to the device (through pinned staging).
+static void session_pearson_opts(const cs_session *s, cs_pearson_opts *po);
+
 static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool skip_payload) {
     CS_REQUIRE(s && a, "cs_session_upload: null argument");
     CS_REQUIRE(a->rows > 0 && a->cols > 0 && a->indptr && a->indices && a->data,
@@ -518,9 +520,21 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
         if ((rc = s->m_indices.ensure((size_t)(s->nnz_m > 0 ? s->nnz_m : 1) * sizeof(int32_t))))
             return rc;
     }
+    s->want_nobs = a->pval && a->has_mask && a->full && !a->raw_xcorr;
+    if (band_img) {
+        // zeros between the rows' bands as wide as the tile boxes stick out of the band: the
+        // Pearson kernel then needs no alias fix-up (cs_layout_band_padded)
+        cs_pearson_opts po;
+        session_pearson_opts(s, &po);
+        int32_t TRp = 32, gap = 0;
+        static const bool nopad = getenv("CS_NO_BAND_GAP") != nullptr;
+        if (!nopad && cs_pearson_plan(&s->Li, &s->a.kernel, &po, s->oy0, s->oy1, s->ox0, s->ox1, s->od_lo,
+                                      s->od_hi, &TRp, &gap) == CS_OK &&
+            gap > 0 && gap <= 160)
+            if ((rc = cs_layout_band_padded(&s->Li, H, W, id_lo, id_hi, gap))) return rc;
+    }
     if ((rc = s->img.ensure((size_t)s->Li.n_elems * sizeof(float)))) return rc;
     if ((rc = s->out.ensure((size_t)s->Lo.n_elems * sizeof(float)))) return rc;
-    s->want_nobs = a->pval && a->has_mask && a->full && !a->raw_xcorr;
     if (s->want_nobs)
         if ((rc = s->nobs.ensure((size_t)s->Lo.n_elems * (size_t)s->nmiss_bytes))) return rc;
     if ((rc = s->r_indptr.ensure((n_ip + (size_t)cs_scan_scratch(a->rows)) * sizeof(int64_t))))

@@ -186,8 +186,9 @@ extern "C" int cs_version(void) { return CS_ABI_VERSION; }
 extern "C" const char *cs_last_error(void) { return cs::g_err; }
 extern "C" int64_t cs_launch_count(void) { return (int64_t)cs::g_launches.load(); }
 
-extern "C" int cs_layout_band(cs_layout *L, int32_t rows, int32_t cols, int32_t dlo, int32_t dhi) {
-    CS_REQUIRE(L && rows > 0 && cols > 0 && dhi >= dlo, "cs_layout_band: bad arguments");
+extern "C" int cs_layout_band_padded(cs_layout *L, int32_t rows, int32_t cols, int32_t dlo, int32_t dhi,
+                                     int32_t gap) {
+    CS_REQUIRE(L && rows > 0 && cols > 0 && dhi >= dlo && gap >= 0, "cs_layout_band: bad arguments");
     if (dlo < -(rows - 1)) dlo = -(rows - 1);
     if (dhi > cols - 1) dhi = cols - 1;
     CS_REQUIRE(dhi >= dlo, "cs_layout_band: empty band");
@@ -196,7 +197,8 @@ extern "C" int cs_layout_band(cs_layout *L, int32_t rows, int32_t cols, int32_t 
     L->dlo = dlo;
     L->dhi = dhi;
     L->dense = 0;
-    int pitch = round_up(dhi - dlo, 4);
+    // a row holds pitch + 1 elements: the dhi - dlo + 1 stored diagonals, then >= gap zeros
+    int pitch = round_up(dhi - dlo + gap, 4);
     if (pitch < 4) pitch = 4;
     L->pitch = pitch;
     int64_t n = (int64_t)(rows - 1) * pitch + ((int64_t)cols - dlo);
@@ -204,6 +206,10 @@ extern "C" int cs_layout_band(cs_layout *L, int32_t rows, int32_t cols, int32_t 
     if (n2 > n) n = n2;
     L->n_elems = (n + 3 + 64) / 4 * 4;
     return CS_OK;
+}
+
+extern "C" int cs_layout_band(cs_layout *L, int32_t rows, int32_t cols, int32_t dlo, int32_t dhi) {
+    return cs_layout_band_padded(L, rows, cols, dlo, dhi, 0);
 }
 
 extern "C" int cs_layout_dense(cs_layout *L, int32_t rows, int32_t cols) {

@@ -53,6 +53,7 @@ struct PearsonParams {
     // tiling
     int TR, G, NBc, nchunks, skew, nrb;
     int IC, IR, NW;
+    int fixup;  // banded image: the box aliases neighbouring rows' pixels outside the band
     // kernel geometry
     int KH, KW, KWP2, N;
     // output image
@@ -370,9 +371,10 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             }
         }
         __syncthreads();
-    } else if (!P.dense) {
+    } else if (P.fixup) {
         // only the aliases of the box outside the stored band: two triangles of at most
-        // IR + 3 columns at the ends of the rows; one warp per tile row
+        // IR + 3 columns at the ends of the rows; one warp per tile row (not needed when the
+        // band is stored with a gap of zeros that wide, cs_layout_band_padded)
 #ifdef CS_ABLATE
         if (!(P.dbg & 16))
 #endif
@@ -1263,7 +1265,8 @@ static int pearson_wide_launch(const cs_layout *Li, const float *d_img, const cs
 static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel_desc *K,
                         const cs_pearson_opts *opts, int32_t oy0, int32_t oy1, int32_t ox0,
                         int32_t ox1, int32_t odlo, int32_t odhi, const cs_layout *Lo, float *d_out,
-                        void *d_nmiss, void *stream, bool plan_only, int32_t *tile_rows_out) {
+                        void *d_nmiss, void *stream, bool plan_only, int32_t *tile_rows_out,
+                        int32_t *band_gap_out = nullptr) {
     cudaStream_t st = (cudaStream_t)stream;
     CS_REQUIRE(Li && K && opts && (plan_only || (d_img && Lo && d_out)),
                "cs_pearson_f32: null argument");
@@ -1279,13 +1282,14 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
     if (K->kh > 31 || K->kw > 31) {
         if (plan_only) {
             if (tile_rows_out) *tile_rows_out = 32;
+            if (band_gap_out) *band_gap_out = 0;
             return CS_OK;
         }
         return pearson_wide_launch(Li, d_img, K, opts, oy0, oy1, ox0, ox1, odlo, odhi, Lo, d_out,
                                    d_nmiss, st);
     }
-    PFN_encodeTiled enc = get_encode();
-    if (!enc) {
+    PFN_encodeTiled enc = plan_only ? nullptr : get_encode();
+    if (!enc && !plan_only) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
         return CS_ERR_CUDA;
     }
@@ -1462,8 +1466,23 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
         smem = o;
         if (smem <= 113 * 1024 || (TR == RU && smem <= 227 * 1024)) break;
     }
+    // Width of the two triangles of a tile box that lie outside the stored band (a banded
+    // traversal keeps them bounded): left, at the last box row of chunk 0; right, at the first
+    // box row of the last chunk.  With at least that many zeros between the rows' bands
+    // (cs_layout_band_padded) the box reads zeros there and the fix-up pass is skipped.
+    int gap_need = 0;
+    if (!Li->dense && P.skew) {
+        const int Wimg = P.dhi - P.dlo + 1;
+        const int left = IR - 1 - kh + kwa + 3 - (odlo - P.dlo);
+        const int right = IC - Wimg + kh + (odlo - P.dlo) - kwa + RT * (nchunks - 1) * NBc;
+        gap_need = left > right ? left : right;
+        if (gap_need < 0) gap_need = 0;
+    }
+    P.fixup = Li->dense ? 0 : 1;
+    if (!Li->dense && P.skew && Li->pitch - (P.dhi - P.dlo) >= gap_need) P.fixup = 0;
     if (plan_only) {
         if (tile_rows_out) *tile_rows_out = TR;
+        if (band_gap_out) *band_gap_out = gap_need;
         return CS_OK;
     }
     P.TR = TR;
@@ -1642,6 +1661,14 @@ extern "C" int cs_pearson_f32(const cs_layout *Li, const float *d_img, const cs_
                               float *d_out, void *d_nmiss, void *stream) {
     return pearson_impl(Li, d_img, K, opts, oy0, oy1, ox0, ox1, odlo, odhi, Lo, d_out, d_nmiss,
                         stream, false, nullptr);
+}
+
+extern "C" int cs_pearson_plan(const cs_layout *Li, const cs_kernel_desc *K, const cs_pearson_opts *opts,
+                               int32_t oy0, int32_t oy1, int32_t ox0, int32_t ox1, int32_t odlo,
+                               int32_t odhi, int32_t *tile_rows, int32_t *band_gap) {
+    CS_REQUIRE(tile_rows && band_gap, "cs_pearson_plan: null argument");
+    return pearson_impl(Li, nullptr, K, opts, oy0, oy1, ox0, ox1, odlo, odhi, nullptr, nullptr,
+                        nullptr, nullptr, true, tile_rows, band_gap);
 }
 
 extern "C" int cs_pearson_tile_rows(const cs_layout *Li, const cs_kernel_desc *K,

@@ -52,6 +52,13 @@ typedef struct cs_layout {
 } cs_layout;
 
 int cs_layout_band(cs_layout *L, int32_t rows, int32_t cols, int32_t dlo, int32_t dhi);
+/* The same band with at least `gap` zero elements between the stored diagonals of consecutive
+ * rows (pitch = roundup4(dhi - dlo + gap)).  A tile box of the Pearson kernel that sticks out
+ * of the band by at most `gap` columns then reads zeros instead of the neighbouring rows'
+ * pixels, and the kernel skips its alias fix-up pass; cs_pearson_plan reports the gap its
+ * tiling needs.  The fill functions never write the gap (cs_image_fill_f32 zeroes it). */
+int cs_layout_band_padded(cs_layout *L, int32_t rows, int32_t cols, int32_t dlo, int32_t dhi,
+                          int32_t gap);
 int cs_layout_dense(cs_layout *L, int32_t rows, int32_t cols);
 
 /* ------------------------------------------------------------------------
@@ -159,6 +166,13 @@ int cs_pearson_tile_rows(const cs_layout *Limg, const cs_kernel_desc *K,
                          const cs_pearson_opts *opts,
                          int32_t oy0, int32_t oy1, int32_t ox0, int32_t ox1,
                          int32_t odlo, int32_t odhi, int32_t *tile_rows);
+/* The same plan, plus the gap (cs_layout_band_padded) a banded image needs for the kernel to
+ * skip its alias fix-up: 0 when the image is dense or the traversal does not follow the band
+ * (the kernel then keeps the fix-up; results are identical either way). */
+int cs_pearson_plan(const cs_layout *Limg, const cs_kernel_desc *K,
+                    const cs_pearson_opts *opts,
+                    int32_t oy0, int32_t oy1, int32_t ox0, int32_t ox1,
+                    int32_t odlo, int32_t odhi, int32_t *tile_rows, int32_t *band_gap);
 
 /* ------------------------------------------------------------------------
  * Score map -> CSR (what normxcorr2 returns, det:1098-1131): non-zero scores

@@ -29,7 +29,10 @@ benchq)
   quick borders9 --kernel borders --win-size 9 --pearson 0.15
   quick small7 --kernel loops_small --pearson 0.5;;
 count)
-  CHROMOSIGHT_B200_LIB=$PWD/chromosight_b200/libchromosight_b200_ablate.so CS_DEBUG_COUNT=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e 2>&1 >/dev/null | grep "pearson stats" | tail -2;;
+  for cfg in "" "--kernel borders --win-size 9 --pearson 0.15" "--kernel loops_small --pearson 0.5"; do
+    echo "count [$cfg]:"
+    CHROMOSIGHT_B200_LIB=$PWD/chromosight_b200/libchromosight_b200_ablate.so CS_DEBUG_COUNT=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e $cfg 2>&1 >/dev/null | grep "pearson stats" | tail -1
+  done;;
 ablate)
   for m in ${MASKS:-0 8 32 40}; do
     echo -n "skip=$m: "
@@ -37,6 +40,14 @@ ablate)
 import json,sys
 d=json.loads(sys.stdin.read()); print('pearson ms %.3f' % d['step_breakdown_ms']['pearson'])"
   done;;
+abk1)
+  # A/B of the Pearson kernel variants: persistent vs one CTA per tile, 3 CTAs/SM build for small kernels
+  echo "== default (persistent)"; quick loops17; quick borders9 --kernel borders --win-size 9 --pearson 0.15; quick small7 --kernel loops_small --pearson 0.5
+  echo "== CS_PERSIST=0"; export CS_PERSIST=0; quick loops17; quick borders9 --kernel borders --win-size 9 --pearson 0.15; quick small7 --kernel loops_small --pearson 0.5; unset CS_PERSIST
+  if [ -f chromosight_b200/libchromosight_b200_occ3.so ]; then
+    echo "== occ3 build"; export CHROMOSIGHT_B200_LIB=$PWD/chromosight_b200/libchromosight_b200_occ3.so
+    quick borders9 --kernel borders --win-size 9 --pearson 0.15; quick small7 --kernel loops_small --pearson 0.5; unset CHROMOSIGHT_B200_LIB
+  fi;;
 benchref)
   timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/benchref_$TAG.json 2> gpurun_out/benchref_$TAG.err; echo "benchref rc=$?"; cat gpurun_out/benchref_$TAG.json; nproc;;
 ncu)

@@ -36,6 +36,39 @@ def test_layout_arithmetic():
     assert b"band" in lib.cs_last_error()
 
 
+def test_band_gap_plan():
+    """cs_pearson_plan reports the gap of zeros a banded image needs for the Pearson kernel to
+    skip its alias fix-up; cs_layout_band_padded provides it (host arithmetic only)."""
+    from chromosight_b200 import _lib
+    lib = _lib.load()
+    n, D, k = 200_000, 200, 17
+    H = W = n + 2 * (k - 1)
+    od_lo, od_hi = 0, D + 2 * k - 1  # image diagonals of the scores of the bench call
+    id_lo, id_hi = od_lo - (k - 1), od_hi + (k - 1)
+    L = _lib.Layout()
+    assert lib.cs_layout_band(ctypes.byref(L), H, W, id_lo, id_hi) == 0
+    kern = np.ones((k, k))
+    kd = _lib.KernelDesc()
+    kd.kh = kd.kw = k
+    arr = np.ascontiguousarray(kern.ravel())
+    kd.k_corr = kd.k_mask = kd.k2_mask = arr.ctypes.data
+    po = _lib.PearsonOpts()
+    tr, gap = ctypes.c_int32(0), ctypes.c_int32(-1)
+    rc = lib.cs_pearson_plan(ctypes.byref(L), ctypes.byref(kd), ctypes.byref(po), k - 1, k - 1 + n, k - 1, k - 1 + n,
+                             od_lo, od_hi, ctypes.byref(tr), ctypes.byref(gap))
+    assert rc == 0, lib.cs_last_error()
+    assert tr.value == 32 and 0 < gap.value <= 64
+    pitch0 = L.pitch
+    assert lib.cs_layout_band_padded(ctypes.byref(L), H, W, id_lo, id_hi, gap.value) == 0
+    assert L.pitch % 4 == 0 and L.pitch - (id_hi - id_lo) >= gap.value and L.pitch <= pitch0 + gap.value + 4
+    assert L.n_elems >= H * (L.pitch + 1)
+    # a dense image needs none
+    assert lib.cs_layout_dense(ctypes.byref(L), 500, 500) == 0
+    rc = lib.cs_pearson_plan(ctypes.byref(L), ctypes.byref(kd), ctypes.byref(po), 8, 492, 8, 492, -483, 483,
+                             ctypes.byref(tr), ctypes.byref(gap))
+    assert rc == 0 and gap.value == 0
+
+
 def test_no_silent_cpu_fallback():
     """Without a GPU the hot path must raise, not compute on the CPU."""
     import torch
