@@ -66,3 +66,30 @@ def pin_sparse(mat):
     if hasattr(mat, "_cs_geometry"):  # a mask of make_missing_mask stays recognisable
         out._cs_geometry = mat._cs_geometry
     return out
+
+
+class DeviceCSR:
+    """A canonical CSR matrix whose column indices (int32) and values (float64) live in HBM as
+    torch tensors; the row pointers (int64) stay on the host, which plans the call from them.
+    What the device-side preprocessing of a sub-matrix (contacts_map.ContactMap.create_mat)
+    hands to Session.upload without a host round trip.  `diag_range` = (min, max) of
+    col - row over the stored entries."""
+
+    def __init__(self, shape, indptr, d_indices, d_data, diag_range):
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        self.d_indices = d_indices
+        self.d_data = d_data
+        self.diag_range = (int(diag_range[0]), int(diag_range[1]))
+        self.nnz = int(self.indptr[-1])
+        self.dtype = np.dtype(np.float64)
+
+    def to_scipy(self, drop_zeros=True):
+        """Host copy as a scipy CSR matrix (explicit zeros removed)."""
+        import scipy.sparse as sp
+        m = sp.csr_matrix((self.d_data.cpu().numpy(), self.d_indices.cpu().numpy(), self.indptr.copy()),
+                          shape=self.shape)
+        m.has_canonical_format = True
+        if drop_zeros:
+            m.eliminate_zeros()
+        return m

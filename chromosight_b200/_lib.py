@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # scripts/k1_ablate.sh times)
 LIB_PATH = os.environ.get("CHROMOSIGHT_B200_LIB") or os.path.join(_HERE, "libchromosight_b200.so")
 
-ABI_VERSION = 2  # CS_ABI_VERSION of include/chromosight_b200.h
+ABI_VERSION = 3  # CS_ABI_VERSION of include/chromosight_b200.h
 CS_OK = 0
 CS_ERR_INVALID = -1
 CS_ERR_CUDA = -2
@@ -106,6 +106,7 @@ class Normxcorr2Args(C.Structure):
         ("device", C.c_int32),
         ("raw_xcorr", C.c_int32),
         ("xcorr_threshold", C.c_double),
+        ("device_payload", C.c_int32),
     ]
 
 

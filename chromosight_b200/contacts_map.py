@@ -15,6 +15,18 @@ from . import cool as _cool
 from .utils import preprocessing as preproc
 
 
+def chrom_codes(values, names):
+    """Index of every chromosome name of `values` in `names` (-1 when absent)."""
+    codes, uniques = pd.factorize(pd.Series(values), sort=False)
+    look = {str(n): i for i, n in enumerate(names)}
+    remap = np.array([look.get(str(u), -1) for u in uniques] + [-1], dtype=np.int64)  # code -1 = missing value
+    return remap[codes]
+
+
+# the device-side fast path of ContactMap.create_mat (tests switch it off to compare both)
+FAST_CREATE_MAT = True
+
+
 class ContactMap:
     """One intra- or inter-chromosomal sub-matrix (contacts_map.py:453-638).  The attributes
     the hot path reads are `matrix`, `detectable_bins`, `max_dist`, `inter`, `name`."""
@@ -29,20 +41,69 @@ class ContactMap:
         self.use_norm = use_norm
         self.smooth = smooth
         self.name = name
-        self.matrix = None
+        self._matrix = None
+        self.device_csr = None   # the preprocessed sub-matrix in HBM (fast path of create_mat)
         self.detectable_bins = detectable_bins
         if detectable_bins is None:
             raise ValueError("detectable_bins are required (get_detectable_bins is not mirrored)")
 
     @property
+    def matrix(self):
+        """The preprocessed sub-matrix as a scipy matrix (what the reference keeps in
+        `ContactMap.matrix`).  After the device-side fast path of create_mat it is copied
+        back from HBM on first access only: pattern_detector reads `device_csr` instead."""
+        if self._matrix is None and self.device_csr is not None:
+            self._matrix = self.device_csr.to_scipy()
+        return self._matrix
+
+    @matrix.setter
+    def matrix(self, value):
+        self._matrix = value
+
+    @property
+    def shape(self):
+        (s1, e1), (s2, e2) = self.extent
+        return (e1 - s1, e2 - s2)
+
+    @property
     def keep_distance(self):
         """Diagonals kept in an intra map: scan distance plus a kernel margin (cm:629-638)."""
-        n = self.matrix.shape[0]
+        n = self.shape[0]
         return (n if self.max_dist is None else min(self.max_dist, n)) + self.largest_kernel
+
+    def _create_mat_device(self):
+        """Fast path of create_mat for balanced maps read by CoolFile: the stored (upper)
+        triangle is sliced straight into CSR arrays (no mirrored copy, no sort), uploaded once
+        and preprocessed in HBM -- distance-law detrend + clamp for an intra map (cm:607-624;
+        the band trim is implicit), median normalisation for an inter map (cm:598-601).  The
+        result stays on the device for pattern_detector.  Returns False when the file or the
+        options need the general path."""
+        if not (self.use_norm and not self.smooth and FAST_CREATE_MAT):
+            return False
+        (s1, e1), (s2, e2) = self.extent
+        if self.inter:
+            get = getattr(self.clr, "block_csr", None)
+            arrays = get(s1, e1, s2, e2, balance=True) if get else None
+            if arrays is None:
+                return False
+            self.device_csr = preproc.divide_by_median_device(*arrays, shape=(e1 - s1, e2 - s2))
+        else:
+            get = getattr(self.clr, "upper_band_csr", None)
+            keep = self.keep_distance
+            arrays = get(s1, e1, keep, balance=True) if get else None
+            if arrays is None:
+                return False
+            self.device_csr = preproc.detrend_band_device(
+                *arrays, n=e1 - s1, detectable_bins=self.detectable_bins[0], max_dist=keep, max_val=10)
+        self._matrix = None
+        return True
 
     def create_mat(self):
         """Load, balance, detrend and trim the sub-matrix (cm:527-548)."""
+        if self._create_mat_device():
+            return
         (s1, e1), (s2, e2) = self.extent
+        self.device_csr = None
         self.matrix = self.clr.matrix(sparse=True, balance=self.use_norm)[s1:e1, s2:e2]
         if self.inter:
             # cm:598-601: stored values (NaN -> 0) divided by their median, on the device
@@ -65,6 +126,7 @@ class ContactMap:
 
     def destroy_mat(self):
         self.matrix = None
+        self.device_csr = None
 
 
 class HicGenome:
@@ -147,8 +209,36 @@ class HicGenome:
 
     def coords_to_bins(self, coords):
         """Genomic positions (DataFrame[chrom, pos]) -> whole-genome bin ids, in the order of
-        the input (cm:416-450)."""
-        pos = (coords.pos // self.clr.binsize) * self.clr.binsize
+        the input, NaN where no bin starts at floor(pos / binsize) * binsize (cm:416-450).
+        Fixed-size bins are located by arithmetic; any other table by the reference's join."""
+        bs = self.clr.binsize
+        if self._uniform_bins():
+            codes = chrom_codes(coords.chrom, self._chrom_names)
+            k = np.asarray(coords.pos, dtype=np.int64) // bs
+            ok = (codes >= 0) & (k >= 0) & (k < self._chrom_nbins[np.maximum(codes, 0)])
+            out = np.full(len(k), np.nan)
+            out[ok] = self._chrom_first[codes[ok]] + k[ok]
+            return out
+        pos = (coords.pos // bs) * bs
         key = pd.MultiIndex.from_arrays([self.bins.chrom.astype(str), self.bins.start])
         look = pd.Series(np.arange(len(self.bins)), index=key)
         return look.reindex(pd.MultiIndex.from_arrays([coords.chrom.astype(str), pos])).values
+
+    def _uniform_bins(self):
+        """True when every chromosome's bins start at 0, binsize, 2 binsize, ... (cached)."""
+        if getattr(self, "_uniform", None) is None:
+            self._uniform = False
+            bs = self.clr.binsize
+            if bs:
+                chrom = self.bins.chrom.astype(str).values
+                start = self.bins.start.values.astype(np.int64)
+                names = [str(c) for c in self.clr.chromnames]
+                first = np.array([self.clr.extent(c)[0] for c in names], dtype=np.int64)
+                last = np.array([self.clr.extent(c)[1] for c in names], dtype=np.int64)
+                owner = np.searchsorted(last, np.arange(len(start)), side="right")
+                ok = owner < len(names)
+                if ok.all() and (np.asarray(names, dtype=object)[owner] == chrom).all() and \
+                        (start == (np.arange(len(start)) - first[owner]) * bs).all():
+                    self._uniform = True
+                    self._chrom_names, self._chrom_first, self._chrom_nbins = names, first, last - first
+        return self._uniform

@@ -394,6 +394,82 @@ class CoolFile:
         return sp.coo_matrix((vals, (rows, cols)), shape=(e1 - s1, e2 - s2))
 
 
+    # ---- direct CSR extraction (what ContactMap.create_mat feeds the device with) -------------
+    def _lex_sorted(self):
+        """True when the pixel table is sorted by (bin1, bin2) without duplicates, as cooler
+        writes it: row slices of it are canonical CSR rows."""
+        if getattr(self, "_lex", None) is None:
+            b1, b2 = self._pix.bin1_id.values, self._pix.bin2_id.values
+            d1 = np.diff(b1)
+            self._lex = bool(((d1 > 0) | ((d1 == 0) & (np.diff(b2) > 0))).all())
+        return self._lex
+
+    def _row_offsets(self):
+        """cooler's indexes/bin1_offset: first pixel of every bin1 (+ the total)."""
+        if getattr(self, "_bin1_offset", None) is None:
+            self._bin1_offset = np.searchsorted(self._pix.bin1_id.values,
+                                                np.arange(self.shape[0] + 1)).astype(np.int64)
+        return self._bin1_offset
+
+    def upper_band_csr(self, s, e, max_diag, balance=True):
+        """Diagonals 0..max_diag of the intra block [s:e, s:e] as canonical CSR arrays
+        (indptr int64, indices int32, data float64), balanced like `matrix(balance=True)`;
+        pixels on masked bins (NaN weight) are dropped.  cooler stores exactly this triangle,
+        sorted: one slice and one filter, no mirroring, no sort.  None when the pixel table
+        is not sorted."""
+        if not self._lex_sorted():
+            return None
+        off = self._row_offsets()
+        lo, hi = int(off[s]), int(off[e])
+        b1 = self._pix.bin1_id.values[lo:hi]
+        b2 = self._pix.bin2_id.values[lo:hi]
+        keep = (b2 < e) & (b2 - b1 <= max_diag)
+        v = self._pix["count"].values[lo:hi].astype(np.float64)
+        if balance:
+            if "weight" not in self._bins.columns:
+                raise ValueError("no 'weight' column: balance the file first")
+            w = self._bins.weight.values
+            v = v * w[b1] * w[b2]
+            keep &= np.isfinite(v)
+        sel = np.flatnonzero(keep)
+        rows = b1[sel] - s
+        indptr = np.zeros(e - s + 1, dtype=np.int64)
+        np.cumsum(np.bincount(rows, minlength=e - s), out=indptr[1:])
+        return indptr, (b2[sel] - s).astype(np.int32), v[sel]
+
+    def block_csr(self, s1, e1, s2, e2, balance=True):
+        """The inter block [s1:e1, s2:e2] with s2 >= e1 (stored as is in the upper triangle) as
+        canonical CSR arrays; NaN-weighted pixels are kept (the inter normalisation turns them
+        into zeros, cm:598-601).  The pixels of the rows s1:e1 are grouped by the chromosome
+        of bin2 once and cached, so that the blocks of one chromosome row cost one pass in
+        total.  None when the table is not sorted or the block is below the diagonal."""
+        if not self._lex_sorted() or s2 < e1:
+            return None
+        cache = getattr(self, "_rowslab", None)
+        if cache is None or cache[0] != (s1, e1):
+            off = self._row_offsets()
+            lo, hi = int(off[s1]), int(off[e1])
+            b2 = self._pix.bin2_id.values[lo:hi]
+            cid = np.searchsorted(self._chrom_offset, b2, side="right") - 1
+            order = np.argsort(cid, kind="stable")       # keeps (bin1, bin2) order inside a group
+            starts = np.searchsorted(cid[order], np.arange(len(self._chrom_offset)))
+            cache = self._rowslab = ((s1, e1), lo, order, starts)
+        _, lo, order, starts = cache
+        j = int(np.searchsorted(self._chrom_offset, s2, side="right") - 1)
+        if self._chrom_offset[j] != s2 or self._chrom_offset[j + 1] != e2:
+            return None
+        sel = order[starts[j]:starts[j + 1]] + lo
+        b1 = self._pix.bin1_id.values[sel]
+        b2 = self._pix.bin2_id.values[sel]
+        v = self._pix["count"].values[sel].astype(np.float64)
+        if balance:
+            w = self._bins.weight.values
+            v = v * w[b1] * w[b2]
+        indptr = np.zeros(e1 - s1 + 1, dtype=np.int64)
+        np.cumsum(np.bincount(b1 - s1, minlength=e1 - s1), out=indptr[1:])
+        return indptr, (b2 - s2).astype(np.int32), v
+
+
 class _Table:
     """`clr.bins()[:]`-style access to a DataFrame."""
 

@@ -365,6 +365,9 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
     }
     s->nnz_in = a->indptr[a->rows];
     int sig_dmin = a->sig_dmin, sig_dmax = a->sig_dmax;
+    if (a->device_payload)
+        CS_REQUIRE(a->sig_dmin != INT32_MIN && a->device == c->device,
+                   "device payload: sig_dmin / sig_dmax must be given, arrays on the session's device");
     if (a->sig_dmin == INT32_MIN) {
         // diagonal extent from the first and last stored column of every row (two cache
         // misses per row: split over a few threads)
@@ -544,14 +547,24 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
     // ---- H2D ----------------------------------------------------------------------
     CS_CUDA(cudaEventRecord(s->ev[0], st));
     if ((rc = h2d_staged(c, st, s->sig_indptr.p, a->indptr, n_ip * sizeof(int64_t)))) return rc;
-    if (!skip_payload) {
+    if (a->device_payload) {
+        // the CSR entries are already in HBM (device-side preprocessing): device-to-device
+        CS_REQUIRE(!skip_payload, "device payload cannot be slab-pipelined");
+        if (s->nnz_in > 0) {
+            CS_CUDA(cudaMemcpyAsync(s->sig_indices.p, a->indices, (size_t)s->nnz_in * sizeof(int32_t),
+                                    cudaMemcpyDeviceToDevice, st));
+            CS_CUDA(cudaMemcpyAsync(s->sig_data.p, a->data, (size_t)s->nnz_in * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, st));
+        }
+    } else if (!skip_payload) {
         if ((rc = h2d_staged(c, st, s->sig_indices.p, a->indices,
                              (size_t)s->nnz_in * sizeof(int32_t))))
             return rc;
         if ((rc = h2d_staged(c, st, s->sig_data.p, a->data, (size_t)s->nnz_in * sizeof(double))))
             return rc;
     }
-    s->h2d_bytes = n_ip * sizeof(int64_t) + (size_t)s->nnz_in * (sizeof(int32_t) + sizeof(double));
+    s->h2d_bytes = n_ip * sizeof(int64_t) +
+                   (a->device_payload ? 0 : (size_t)s->nnz_in * (sizeof(int32_t) + sizeof(double)));
     s->h2d_bytes += geo_h2d;
     if (a->has_mask == 1) {
         if ((rc = h2d_staged(c, st, s->m_indptr.p, a->mask_indptr, n_ip * sizeof(int64_t)))) return rc;
@@ -1143,7 +1156,7 @@ extern "C" int cs_session_upload_run_scores(cs_session *s, const cs_normxcorr2_a
     const int64_t nnz_in = a->indptr[a->rows];
     int nslab = 8;
     if (const char *e = getenv("CS_PIPELINE_SLABS")) nslab = atoi(e);
-    if (nslab > 1 && nnz_in >= (4 << 20) && rows_out >= 64 * nslab)
+    if (nslab > 1 && nnz_in >= (4 << 20) && rows_out >= 64 * nslab && !a->device_payload)
         return session_upload_run_pipelined(s, a, nslab, stats);
     int rc = cs_session_upload(s, a);
     if (rc) return rc;
@@ -1550,6 +1563,7 @@ static int normxcorr2_pipelined(cs_session *s, const cs_normxcorr2_args *a, cs_c
 // One-shot: upload + run + download on a per-device cached session.
 extern "C" int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *res) {
     CS_REQUIRE(a && res, "cs_normxcorr2_host: null argument");
+    CS_REQUIRE(!a->device_payload, "cs_normxcorr2_host takes host arrays (device payload: use a session)");
     static std::mutex mu;
     static std::vector<cs_session *> cache;
     cs_session *s = nullptr;

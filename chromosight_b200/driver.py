@@ -164,19 +164,30 @@ def detect(hic_genome, cfg, full=True, tsvd=None, gather_windows=True):
     return tab.loc[:, cols], wins
 
 
-def _chrom_positions(positions, hic_genome, chr1, chr2):
+def _locate_positions(positions, hic_genome):
+    """Chromosome codes and whole-genome bins of both ends of every position, once for all
+    sub-matrices (cli:262-293)."""
+    names = [str(c) for c in hic_genome.clr.chromnames]
+    from .contacts_map import chrom_codes
+    c1 = chrom_codes(positions.chrom1.values, names)
+    c2 = chrom_codes(positions.chrom2.values, names)
+    b1 = hic_genome.coords_to_bins(pd.DataFrame({"chrom": positions.chrom1.values, "pos": positions.pos1.values}))
+    b2 = hic_genome.coords_to_bins(pd.DataFrame({"chrom": positions.chrom2.values, "pos": positions.pos2.values}))
+    return names, c1, c2, b1, b2
+
+
+def _chrom_positions(located, hic_genome, chr1, chr2):
     """Positions falling on one sub-matrix, in sub-matrix bins (cli:262-293): (index into
-    `positions`, int array [P, 2])."""
-    sel = np.flatnonzero((positions.chrom1.values == chr1) & (positions.chrom2.values == chr2))
+    the positions, int array [P, 2])."""
+    names, c1, c2, b1, b2 = located
+    sel = np.flatnonzero((c1 == names.index(str(chr1))) & (c2 == names.index(str(chr2))))
     if len(sel) == 0:
         return sel, np.zeros((0, 2), dtype=np.int64)
-    sub = positions.iloc[sel]
-    b1 = hic_genome.coords_to_bins(pd.DataFrame({"chrom": sub.chrom1.values, "pos": sub.pos1.values}))
-    b2 = hic_genome.coords_to_bins(pd.DataFrame({"chrom": sub.chrom2.values, "pos": sub.pos2.values}))
-    ok = ~(np.isnan(b1) | np.isnan(b2))   # positions outside the map are ignored
+    ok = ~(np.isnan(b1[sel]) | np.isnan(b2[sel]))   # positions outside the map are ignored
+    sel = sel[ok]
     s1, s2 = hic_genome.clr.extent(chr1)[0], hic_genome.clr.extent(chr2)[0]
-    coords = np.stack([b1[ok] - s1, b2[ok] - s2], axis=1).astype(np.int64)
-    return sel[ok], coords
+    coords = np.stack([b1[sel] - s1, b2[sel] - s2], axis=1).astype(np.int64)
+    return sel, coords
 
 
 def quantify(hic_genome, cfg, bed2d, tsvd=None, return_windows=True, gather_windows=True):
@@ -201,9 +212,16 @@ def quantify(hic_genome, cfg, bed2d, tsvd=None, return_windows=True, gather_wind
     positions["pos2"] = (positions.start2 + positions.end2) // 2
     km, kn = np.asarray(cfg["kernels"][0]).shape
     mine = set(sharding.partition_units(unit_costs(hic_genome), world)[rank])
+    # the output is sorted by bins (cli:476-480): windows are written at their final place
+    out_bin1 = hic_genome.coords_to_bins(pd.DataFrame({"chrom": bed2d.chrom1.values, "pos": bed2d.start1.values}))
+    out_bin2 = hic_genome.coords_to_bins(pd.DataFrame({"chrom": bed2d.chrom2.values, "pos": bed2d.start2.values}))
+    order = np.lexsort((out_bin2, out_bin1))
+    rank_of = np.empty(n, dtype=np.int64)
+    rank_of[order] = np.arange(n)
+    located = _locate_positions(positions, hic_genome)
     best_score = np.full(n, np.nan)
     best_p = np.full(n, np.nan)
-    best_win = np.full((n, km, kn), np.nan) if return_windows else None
+    best_win = np.full((n, km, kn), np.nan) if return_windows else None   # in output order
     for kernel_matrix in cfg["kernels"]:
         kernel_matrix = np.asarray(kernel_matrix, dtype=np.float64)
         score = np.full(n, np.nan)
@@ -212,7 +230,7 @@ def quantify(hic_genome, cfg, bed2d, tsvd=None, return_windows=True, gather_wind
         for u, (_, row) in enumerate(hic_genome.sub_mats.iterrows()):
             if u not in mine:
                 continue
-            idx, coords = _chrom_positions(positions, hic_genome, row.chr1, row.chr2)
+            idx, coords = _chrom_positions(located, hic_genome, row.chr1, row.chr2)
             if len(idx) == 0:
                 continue            # no position on this sub-matrix: not scanned (cli:239-241)
             cm = row.contact_map
@@ -248,17 +266,17 @@ def quantify(hic_genome, cfg, bed2d, tsvd=None, return_windows=True, gather_wind
         if return_windows:
             for idx, w in wins.values():
                 take = better[idx] | first[idx]
-                best_win[idx[take]] = w[take]
+                if take.all():
+                    best_win[rank_of[idx]] = w
+                else:
+                    best_win[rank_of[idx[take]]] = w[take]
     out = bed2d.loc[:, ["chrom1", "start1", "end1", "chrom2", "start2", "end2"]].copy()
-    out["bin1"] = hic_genome.coords_to_bins(out[["chrom1", "start1"]].rename(
-        columns={"chrom1": "chrom", "start1": "pos"}))
-    out["bin2"] = hic_genome.coords_to_bins(out[["chrom2", "start2"]].rename(
-        columns={"chrom2": "chrom", "start2": "pos"}))
+    out["bin1"] = out_bin1
+    out["bin2"] = out_bin2
     out["score"] = best_score
     out["pvalue"] = best_p
     out["qvalue"] = fdr_correction(out["pvalue"])
     bad = np.isnan(out.score.values)
     out.loc[bad, ["pvalue", "qvalue"]] = np.nan
-    order = np.lexsort((out.bin2.values, out.bin1.values))     # cli:476-480
-    out = out.iloc[order].reset_index(drop=True)
-    return out, (best_win[order] if return_windows else None)
+    out = out.iloc[order].reset_index(drop=True)                # cli:476-480
+    return out, best_win

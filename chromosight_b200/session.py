@@ -55,8 +55,15 @@ class Session:
         scores (as run(compact=False) would), overlapping the upload of large inputs with the
         kernels slab by slab."""
         kernel = np.asarray(kernel, dtype=np.float64)
-        _det._validate(signal, kernel, missing_mask)
-        csr = _det._canonical_csr(signal, np.float64)
+        if isinstance(signal, _cuda.DeviceCSR):
+            # entries already in HBM; order the library stream behind the stream that made them
+            csr = signal
+            if not (self._use_torch_stream and _cuda.torch().cuda.current_stream().cuda_stream):
+                _cuda.torch().cuda.current_stream().synchronize()
+            _det._validate(signal, kernel, missing_mask)
+        else:
+            _det._validate(signal, kernel, missing_mask)
+            csr = _det._canonical_csr(signal, np.float64)
         mask_csr = None
         if mask_geometry is None:
             mask_csr, mask_geometry = _det._mask_forms(missing_mask, sym_upper)

@@ -76,11 +76,18 @@ def _build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, t
     keep = []
     a = _lib.Normxcorr2Args()
     a.rows, a.cols = csr.shape
-    indptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
-    indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
-    data = _as_f64(csr.data)
-    keep.extend([indptr, indices, data])
-    a.indptr, a.indices, a.data = indptr.ctypes.data, indices.ctypes.data, data.ctypes.data
+    on_device = hasattr(csr, "d_indices")       # _cuda.DeviceCSR: entries already in HBM
+    if on_device:
+        indptr = csr.indptr
+        keep.extend([indptr, csr.d_indices, csr.d_data])
+        a.indptr, a.indices, a.data = indptr.ctypes.data, csr.d_indices.data_ptr(), csr.d_data.data_ptr()
+        a.device_payload = 1
+    else:
+        indptr = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(csr.indices, dtype=np.int32)
+        data = _as_f64(csr.data)
+        keep.extend([indptr, indices, data])
+        a.indptr, a.indices, a.data = indptr.ctypes.data, indices.ctypes.data, data.ctypes.data
     a.has_mask = 0
     if geometry is not None:
         miss_r = np.ascontiguousarray(geometry[0], dtype=np.uint8)
@@ -105,6 +112,8 @@ def _build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, t
     a.trim_to_max_dist = int(bool(trim_to_max_dist))
     # canonical CSR (sorted rows): the library measures the diagonal extent itself
     a.sig_dmin, a.sig_dmax = -(2 ** 31), -1
+    if on_device:
+        a.sig_dmin, a.sig_dmax = csr.diag_range
     a.kernel = _kernel_desc(kernel, tsvd, keep)
     a.missing_tol = float(missing_tol)
     a.device = _device_index() if device is None else int(device)
@@ -377,7 +386,11 @@ def pattern_detector(contact_map, kernel_config, kernel_matrix, coords=None, dum
     km, kn = kernel_matrix.shape
     kh, kw = (km - 1) // 2, (kn - 1) // 2
     quantify = coords is not None
-    shape = contact_map.matrix.shape
+    # a ContactMap preprocessed on the device (contacts_map.py) hands its CSR over in HBM
+    signal = getattr(contact_map, "device_csr", None)
+    if signal is None:
+        signal = contact_map.matrix
+    shape = signal.shape
     if min(shape) <= max(kernel_matrix.shape):           # det:237-238
         return None, None
     inter = bool(contact_map.inter)
@@ -396,7 +409,7 @@ def pattern_detector(contact_map, kernel_config, kernel_matrix, coords=None, dum
         # the detector reads the score image only (foci, lookups at coordinates): upload and
         # kernels overlap slab by slab, the CSR compaction and the p-values of every stored
         # score are skipped unless dumped
-        sess.upload(contact_map.matrix, kernel_matrix, max_dist=contact_map.max_dist,
+        sess.upload(signal, kernel_matrix, max_dist=contact_map.max_dist,
                     sym_upper=not inter, full=full, mask_geometry=geometry, tsvd=tsvd, pval=True,
                     missing_tol=kernel_config["max_perc_undetected"] / 100, run_scores=not dump)
         if dump:

@@ -287,6 +287,48 @@ def divide_by_median(data):
     return (d / med).cpu().numpy()
 
 
+def detrend_band_device(indptr, indices, data, n, detectable_bins=None, max_dist=None, max_val=10):
+    """`detrend` (pre:256-310) of an upper-band CSR given as host arrays, result left in HBM:
+    -> _cuda.DeviceCSR with the detrended values (NaN -> 0, cm:537-538).  The arrays go to the
+    device once; law, division and clamp run there (csrc/detrend.cu); nothing comes back.
+    This is ContactMap.create_mat's intra branch (cm:607-624) fused with the upload of
+    pattern_detector: diag_trim is implicit (the band holds diagonals 0..max_dist only)."""
+    t = _cuda.require_cuda()
+    lib = _lib.load()
+    n = int(n)
+    d_indptr = _cuda.to_device(indptr, np.int64)
+    d_indices = _cuda.to_device(indices, np.int32)
+    d_data = _cuda.to_device(data, np.float64)
+    nnz = int(indptr[-1])
+
+    class _Shape:
+        shape = (n, n)
+    d_law, _, _ = _law_device(_Shape, (d_indptr, d_indices, d_data), detectable_bins, max_dist)
+    out = _cuda.empty(nnz, t.float64)
+    if nnz:
+        _lib.check(lib.cs_detrend_apply(_cuda.ptr(d_indptr), _cuda.ptr(d_indices), _cuda.ptr(d_data),
+                                        _cuda.ptr(out), n, _cuda.ptr(d_law), n,
+                                        C.c_double(-1.0 if max_val is None else float(max_val)),
+                                        _cuda.stream_ptr()))
+        out = t.where(t.isnan(out), t.zeros((), dtype=out.dtype, device=out.device), out)
+    dmax = n - 1 if max_dist is None else int(min(max_dist, n - 1))
+    return _cuda.DeviceCSR((n, n), indptr, d_indices, out, (0, dmax))
+
+
+def divide_by_median_device(indptr, indices, data, shape):
+    """Inter-chromosomal normalisation (cm:598-601) of a CSR block given as host arrays, result
+    left in HBM as a _cuda.DeviceCSR (see divide_by_median)."""
+    t = _cuda.require_cuda()
+    d_indices = _cuda.to_device(indices, np.int32)
+    d = _cuda.to_device(np.asarray(data, dtype=np.float64))
+    d = t.where(t.isnan(d), t.zeros((), dtype=d.dtype, device=d.device), d)
+    n = d.numel()
+    if n:
+        srt = t.sort(d).values
+        d = d / ((srt[(n - 1) // 2] + srt[n // 2]) / 2.0)
+    return _cuda.DeviceCSR(shape, indptr, d_indices, d, (-(shape[0] - 1), shape[1] - 1))
+
+
 def _csr_device(csr):
     indptr = _cuda.to_device(csr.indptr, np.int64)
     indices = _cuda.to_device(csr.indices, np.int32)

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define CS_ABI_VERSION 2
+#define CS_ABI_VERSION 3
 
 typedef enum cs_status {
     CS_OK = 0,
@@ -334,6 +334,12 @@ typedef struct cs_normxcorr2_args {
     int32_t device;
     int32_t raw_xcorr;       /* 1: xcorr2 (det:595-723) instead of normxcorr2 */
     double xcorr_threshold;  /* threshold of xcorr2 when raw_xcorr (normxcorr2 always uses 1e-4) */
+    /* 1: `indices` and `data` are DEVICE arrays on `device` (e.g. the output of
+     * cs_detrend_apply, never brought to the host); `indptr` stays a host array and sig_dmin /
+     * sig_dmax must be given.  Session calls only (cs_session_upload, _upload_run_scores):
+     * ContactMap.create_mat -> pattern_detector (cm:607-624, det:253-263) without a host
+     * round trip of the detrended sub-matrix. */
+    int32_t device_payload;
 } cs_normxcorr2_args;
 
 int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *res);

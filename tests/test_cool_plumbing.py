@@ -84,9 +84,14 @@ def test_genome_model_bookkeeping(fx):
 
 
 @pytest.mark.gpu
-def test_example_cool_detect_loops_matches_reference(fx):
+@pytest.mark.parametrize("fast", [True, False])
+def test_example_cool_detect_loops_matches_reference(fx, fast, monkeypatch):
+    """fast=True: the sub-matrix is sliced into CSR, detrended and kept in HBM
+    (ContactMap._create_mat_device); fast=False: the reference's sequence of host matrices."""
+    from chromosight_b200 import contacts_map
     from chromosight_b200.contacts_map import HicGenome
     from chromosight_b200.utils import detection as cud
+    monkeypatch.setattr(contacts_map, "FAST_CREATE_MAT", fast)
     cfg = loops_config(fx)
     kernel = cfg["kernels"][0]
     hg = HicGenome(cool_from_fixture(fx), inter=False, kernel_config=cfg)
@@ -96,6 +101,7 @@ def test_example_cool_detect_loops_matches_reference(fx):
     for _, row in hg.sub_mats.iterrows():
         chrom, cm = row.chr1, row.contact_map
         cm.create_mat()
+        assert (cm.device_csr is not None) == fast
         exp = sp.coo_matrix((fx[f"{chrom}_matrix_val"], (fx[f"{chrom}_matrix_row"], fx[f"{chrom}_matrix_col"])),
                             shape=tuple(fx[f"{chrom}_matrix_shape"])).tocsr()
         got = cm.matrix.tocsr()
@@ -113,6 +119,52 @@ def test_example_cool_detect_loops_matches_reference(fx):
         assert np.allclose(windows, fx[f"{chrom}_windows"], rtol=1e-12, atol=0, equal_nan=True)
         cm.destroy_mat()
     assert total == 135
+
+
+@pytest.mark.gpu
+def test_device_create_mat_equals_host_path_on_a_synthetic_genome(monkeypatch):
+    """Intra and inter sub-matrices of a synthetic genome: the device-resident preprocessing
+    gives the same matrix (<= 1e-12) and pattern_detector the same table and windows as the
+    host sequence of the reference (cm:527-624)."""
+    from chromosight_b200 import contacts_map, kernels, synthetic
+    from chromosight_b200.contacts_map import HicGenome
+    from chromosight_b200.utils import detection as cud
+    clr = synthetic.genome_cool([900, 700, 500], binsize=10_000, n_diags=80, seed=5, inter_density=0.02,
+                                density_floor=1.0)
+    cfg = dict(kernels.loops)
+    cfg["kernels"] = [np.array(k) for k in cfg["kernels"]]
+    cfg["max_dist"] = 60 * 10_000
+    cfg["max_perc_zero"] = 100.0
+    out = {}
+    for fast in (True, False):
+        monkeypatch.setattr(contacts_map, "FAST_CREATE_MAT", fast)
+        hg = HicGenome(clr, inter=True, kernel_config=cfg)
+        hg.normalize()
+        hg.make_sub_matrices()
+        assert len(hg.sub_mats) == 6
+        for _, row in hg.sub_mats.iterrows():
+            cm = row.contact_map
+            cm.create_mat()
+            assert (cm.device_csr is not None) == fast
+            table, windows = cud.pattern_detector(cm, cfg, cfg["kernels"][0], full=True)
+            out[(fast, cm.name)] = (cm.matrix.tocsr().copy(), table, windows)
+            cm.destroy_mat()
+    n_found = 0
+    for (fast, name), (mat, table, windows) in out.items():
+        if not fast:
+            continue
+        mat0, table0, windows0 = out[(False, name)]
+        assert mat.shape == mat0.shape and mat.nnz == mat0.nnz
+        assert abs(mat - mat0).max() <= 1e-12 * abs(mat0).max()
+        assert (table is None) == (table0 is None)
+        if table is None:
+            continue
+        n_found += len(table)
+        assert np.array_equal(table.bin1.values, table0.bin1.values)
+        assert np.array_equal(table.bin2.values, table0.bin2.values)
+        assert np.abs(table.score.values - table0.score.values).max() <= 1e-6
+        assert np.allclose(windows, windows0, rtol=1e-12, atol=0, equal_nan=True)
+    assert n_found > 0
 
 
 @pytest.mark.gpu
@@ -209,11 +261,11 @@ def test_driver_host_plumbing(fx):
     assert sorted(parts[0] + parts[1]) == list(range(6))
     pos = pd.DataFrame({"chrom1": ["chr2", "chr1", "chr2", "chr9"], "pos1": [4500, 0, 10 ** 9, 5],
                         "chrom2": ["chr2", "chr1", "chr2", "chr9"], "pos2": [9999, 126999, 10 ** 9, 9]})
-    idx, coords = driver._chrom_positions(pos, hg, "chr2", "chr2")
+    idx, coords = driver._chrom_positions(driver._locate_positions(pos, hg), hg, "chr2", "chr2")
     assert list(idx) == [0] and coords.tolist() == [[4, 9]]       # the off-map position is dropped
-    idx, coords = driver._chrom_positions(pos, hg, "chr1", "chr1")
+    idx, coords = driver._chrom_positions(driver._locate_positions(pos, hg), hg, "chr1", "chr1")
     assert list(idx) == [1] and coords.tolist() == [[0, 126]]
-    idx, coords = driver._chrom_positions(pos, hg, "chr3", "chr3")
+    idx, coords = driver._chrom_positions(driver._locate_positions(pos, hg), hg, "chr3", "chr3")
     assert len(idx) == 0 and coords.shape == (0, 2)
 
 
