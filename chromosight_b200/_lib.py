@@ -107,6 +107,7 @@ class Normxcorr2Args(C.Structure):
         ("raw_xcorr", C.c_int32),
         ("xcorr_threshold", C.c_double),
         ("device_payload", C.c_int32),
+        ("out_row0", C.c_int32), ("out_row1", C.c_int32),
     ]
 
 

@@ -363,6 +363,12 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
     } else {
         s->oy0 = kh, s->oy1 = a->rows - kh, s->ox0 = kw, s->ox1 = a->cols - kw;
     }
+    if (a->out_row1 > a->out_row0) {
+        // a row range of the result only (first matrix row = image row pr in full mode, 0 else)
+        const int base = a->full ? pr : 0;
+        if (base + a->out_row0 > s->oy0) s->oy0 = base + a->out_row0;
+        if (base + a->out_row1 < s->oy1) s->oy1 = base + a->out_row1;
+    }
     s->nnz_in = a->indptr[a->rows];
     int sig_dmin = a->sig_dmin, sig_dmax = a->sig_dmax;
     if (a->device_payload)

@@ -48,12 +48,13 @@ class Session:
 
     def upload(self, signal, kernel, max_dist=None, sym_upper=False, full=False, missing_mask=None,
                missing_tol=0.75, tsvd=None, pval=False, trim_to_max_dist=False, mask_geometry=None,
-               run_scores=False):
+               run_scores=False, out_rows=None):
         """Plan a normxcorr2 call (same arguments, det:807-817) and copy its inputs to HBM.
         `mask_geometry` = preprocessing.missing_geometry(...) stands for the mask
         make_missing_mask would build, without building it.  run_scores=True also computes the
         scores (as run(compact=False) would), overlapping the upload of large inputs with the
-        kernels slab by slab."""
+        kernels slab by slab.  out_rows=(a, b) scores the rows a <= row < b only (the owned rows
+        of a row slab, rowslab.py); the rest of the result stays empty."""
         kernel = np.asarray(kernel, dtype=np.float64)
         if isinstance(signal, _cuda.DeviceCSR):
             # entries already in HBM; order the library stream behind the stream that made them
@@ -69,7 +70,7 @@ class Session:
             mask_csr, mask_geometry = _det._mask_forms(missing_mask, sym_upper)
         a, keep = _det._build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol,
                                    tsvd, pval, trim_to_max_dist=trim_to_max_dist, device=self.device,
-                                   geometry=mask_geometry)
+                                   geometry=mask_geometry, out_rows=out_rows)
         self._bind_stream()
         if run_scores:
             st = _lib.RunStats()

@@ -69,7 +69,7 @@ def _kernel_desc(kernel, tsvd, keep):
 
 def _build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, tsvd, pval,
                 raw_xcorr=False, threshold=1e-4, trim_to_max_dist=False, device=None,
-                geometry=None):
+                geometry=None, out_rows=None):
     """cs_normxcorr2_args of one call; the second value keeps the host arrays alive.
     The missing mask is either a pixel mask (`mask_csr`) or the ingredients of
     make_missing_mask (`geometry` = (miss_rows, miss_cols, dlo, dhi), pre:535-633)."""
@@ -119,6 +119,8 @@ def _build_args(csr, kernel, mask_csr, max_dist, sym_upper, full, missing_tol, t
     a.device = _device_index() if device is None else int(device)
     a.raw_xcorr = int(bool(raw_xcorr))
     a.xcorr_threshold = float(threshold)
+    if out_rows is not None:
+        a.out_row0, a.out_row1 = int(out_rows[0]), int(out_rows[1])
     return a, keep
 
 

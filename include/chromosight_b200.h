@@ -340,6 +340,10 @@ typedef struct cs_normxcorr2_args {
      * ContactMap.create_mat -> pattern_detector (cm:607-624, det:253-263) without a host
      * round trip of the detrended sub-matrix. */
     int32_t device_payload;
+    /* Score only the output rows out_row0 <= row < out_row1 (matrix rows; out_row1 <= out_row0:
+     * all rows); the other rows of the result are empty.  A rank of the row-slab path
+     * (rowslab.py) scores its owned rows only, not the halo it received. */
+    int32_t out_row0, out_row1;
 } cs_normxcorr2_args;
 
 int cs_normxcorr2_host(const cs_normxcorr2_args *a, cs_csr_result *res);

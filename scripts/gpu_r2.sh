@@ -48,6 +48,13 @@ abk1)
     echo "== occ3 build"; export CHROMOSIGHT_B200_LIB=$PWD/chromosight_b200/libchromosight_b200_occ3.so
     quick borders9 --kernel borders --win-size 9 --pearson 0.15; quick small7 --kernel loops_small --pearson 0.5; unset CHROMOSIGHT_B200_LIB
   fi;;
+tilerows)
+  # tile height of the Pearson kernel (ablate build reads CS_TILE_ROWS)
+  export CHROMOSIGHT_B200_LIB=$PWD/chromosight_b200/libchromosight_b200_ablate.so
+  for tr in 32 48 64 96; do
+    export CS_TILE_ROWS=$tr; echo "== CS_TILE_ROWS=$tr"
+    quick loops17; quick borders9 --kernel borders --win-size 9 --pearson 0.15; quick small7 --kernel loops_small --pearson 0.5
+  done; unset CS_TILE_ROWS CHROMOSIGHT_B200_LIB;;
 benchref)
   timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/benchref_$TAG.json 2> gpurun_out/benchref_$TAG.err; echo "benchref rc=$?"; cat gpurun_out/benchref_$TAG.json; nproc;;
 ncu)

@@ -93,6 +93,43 @@ def test_xcorr2_golden():
         assert np.abs(out.toarray() - ref).max() <= 2e-5 * scale, nm
 
 
+def test_xcorr2_dense_signal():
+    """The reference's own test of the dense branch (tests/test_detection.py:241-270,
+    _xcorr2_dense det:726-804): a dense (ndarray / np.matrix) signal returns an ndarray equal
+    to the sparse result and to scipy's correlate2d thresholded at 1e-4, with its maximum at
+    the mode of the 2-D normal the signal holds."""
+    import scipy.signal as sig
+    from scipy.stats import multivariate_normal
+    from chromosight_b200.utils import detection as cud
+
+    def gauss_mat(meanx, meany, std, shape=(100, 100)):
+        k = multivariate_normal(mean=(meanx, meany), cov=np.eye(2) * std)
+        x, y = np.linspace(-10, 10, shape[0]), np.linspace(-10, 10, shape[1])
+        xx, yy = np.meshgrid(x, y)
+        return k.pdf(np.c_[xx.ravel(), yy.ravel()]).reshape(shape)
+
+    gauss_kernel = gauss_mat(0, 0, 5.0, shape=(7, 7))
+    n_checked = 0
+    for mx, my, sd in ((-1.5, -1.0, 0.3), (-1.0, 0.5, 0.9), (0.0, 1.0, 1.8), (-0.5, 1.0, 2.7)):
+        dense = gauss_mat(mx, my, sd)
+        exp_row, exp_col = np.where(dense == dense.max())
+        out_sparse = cud.xcorr2(sp.coo_matrix(dense), gauss_kernel, threshold=1e-4)
+        assert sp.issparse(out_sparse)
+        for signal in (dense, np.asmatrix(dense)):          # ndarray and what .todense() returns
+            out = cud.xcorr2(signal, gauss_kernel, threshold=1e-4)
+            assert isinstance(out, np.ndarray) and not sp.issparse(out) and out.shape == dense.shape
+            obs_row, obs_col = np.where(out == out.max())
+            assert np.all(np.isin(obs_row, exp_row)) and np.all(np.isin(obs_col, exp_col))
+            ref = np.zeros(dense.shape)
+            ref[3:-3, 3:-3] = sig.correlate2d(dense, gauss_kernel, "valid")
+            ref[ref < 1e-4] = 0
+            near = np.abs(np.abs(ref) - 1e-4) < 1e-8           # the threshold itself is float32-fuzzy
+            assert np.abs(out - ref)[~near].max() <= 2e-5 * max(1.0, np.abs(ref).max())
+            assert np.abs(out - out_sparse.toarray()).max() == 0
+            n_checked += 1
+    assert n_checked == 8
+
+
 def test_detrend_golden():
     from chromosight_b200.utils import preprocessing as cup
     z = np.load(os.path.join(GOLDEN, "preproc_cases.npz"))
@@ -529,10 +566,11 @@ def test_row_slabs_match_single_run(presets):
     raw, detect = synthetic.band_counts(n, D + k, seed=17, missing_frac=0.02, max_dist=D)
     kw = dict(max_dist=D, sym_upper=True, full=True, missing_tol=0.5, pval=True)
 
-    def candidates_of(mat, det):
+    def candidates_of(mat, det, out_rows=None):
         s = Session()
         try:
-            s.upload(mat, kernel, mask_geometry=cup.missing_geometry(mat.shape, det, det, D, True), **kw)
+            s.upload(mat, kernel, mask_geometry=cup.missing_geometry(mat.shape, det, det, D, True),
+                     out_rows=out_rows, **kw)
             s.run(compact=False)
             rec, nc = s.candidates(thr, 0, D)
             return records_to_numpy(rec, nc).copy()
@@ -556,7 +594,13 @@ def test_row_slabs_match_single_run(presets):
     parts = []
     for p in plans:
         sub, det = rowslab.slab_inputs(raw, detect, law, p, D, k)
-        parts.append(rowslab.owned_candidates(candidates_of(sub, det), p))
+        # every second slab scores its owned rows only (what bench.py --scaling strong does),
+        # the others the whole sub-matrix: the owned candidates are the same
+        rows = (p[0] - p[2], p[1] - p[2]) if len(parts) % 2 == 0 else None
+        rec = candidates_of(sub, det, rows)
+        if rows is not None:
+            assert ((rec["row"] >= rows[0]) & (rec["row"] < rows[1])).all()
+        parts.append(rowslab.owned_candidates(rec, p))
     merged = rowslab.merge_sorted(parts)
     assert len(whole) > 100
     assert np.array_equal(merged["row"], whole["row"]) and np.array_equal(merged["col"], whole["col"])
