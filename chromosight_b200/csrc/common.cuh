@@ -61,7 +61,7 @@ int scores_emit_rows(const cs_layout *Lo, const float *d_out, const void *d_nmis
 int scores_emit_rows_narrow(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
                             int32_t nmiss_bytes, int32_t n_window, const int64_t *d_indptr,
                             int32_t r0, int32_t r1, float *d_score, float *d_log10p,
-                            uint8_t *d_off, cudaStream_t st);
+                            uint8_t *d_off, cudaStream_t st, int64_t limit = INT64_MAX);
 // score / log10p / off: wire arrays indexed like the CSR entries; indptr: final row pointers
 // (host); writes data, logp (may be null), indices, indices2 (may be null) for the entries of
 // rows [r0, r1); col = row + dlo + off.  Uses up to `threads` host threads.
@@ -100,6 +100,11 @@ struct RefineArgs {
     unsigned long long *d_count;
 };
 int exact_refine(const RefineArgs &R, cudaStream_t st, long long *n_refined);
+int exact_refine_enqueue(const RefineArgs &R, cudaStream_t st);
+// emit_candidates without the read-back of the count (scores.cu)
+int scores_candidates_enqueue(const cs_layout *Lo, const float *d_out, const void *d_nmiss, int32_t nmiss_bytes,
+                              int32_t n_window, int32_t dmin, int32_t dmax, float threshold, cs_candidate *d_cand,
+                              int64_t cap, int64_t *d_count, cudaStream_t st);
 
 #define CS_LAUNCHED() (cs::g_launches.fetch_add(1, std::memory_order_relaxed))
 

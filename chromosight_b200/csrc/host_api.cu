@@ -277,6 +277,8 @@ struct cs_session {
     int oy0 = 0, oy1 = 0, ox0 = 0, ox1 = 0, od_lo = 0, od_hi = 0, pr = 0, pc = 0;
     bool want_nobs = false;
     int64_t nnz_in = 0, nnz_m = 0, nnz_out = 0, n_windows = 0;
+    int64_t nnz_hint = -1;   // non-zero scores of the last compaction of this upload (sizes the next one)
+    int64_t nnz_async = 0;   // read-back target of a compaction enqueued without synchronisation
     size_t h2d_bytes = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -329,6 +331,7 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
     CS_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = s->stream();
     s->uploaded = s->ran = false;
+    s->nnz_hint = -1;
     s->a = *a;
     const cs_kernel_desc &K = a->kernel;
     CS_REQUIRE(K.kh >= 1 && K.kw >= 1 && K.k_corr, "cs_session_upload: bad kernel");
@@ -605,7 +608,7 @@ extern "C" int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a) {
 }
 
 // fill -> Pearson -> CSR compaction, all on the device, inputs already resident.
-static int session_compact(cs_session *s, cudaStream_t st, int64_t *nnz_out);
+static int session_compact(cs_session *s, cudaStream_t st, int64_t *nnz_out, bool *deferred = nullptr);
 
 static int session_run_impl(cs_session *s, cs_run_stats *stats, bool compact) {
     CS_REQUIRE(s && s->uploaded, "cs_session_run: nothing uploaded");
@@ -648,10 +651,23 @@ static int session_run_impl(cs_session *s, cs_run_stats *stats, bool compact) {
     int32_t herr[2] = {0, 0};
     CS_CUDA(cudaMemcpyAsync(herr, s->err.p, sizeof(herr), cudaMemcpyDeviceToHost, st));
     s->compacted = false;
+    bool deferred = false;
     if (compact) {
-        if ((rc = session_compact(s, st, &nnz))) return rc;
-    } else {
-        CS_CUDA(cudaStreamSynchronize(st));
+        if ((rc = session_compact(s, st, &nnz, &deferred))) return rc;
+        if (deferred) CS_CUDA(cudaEventRecord(s->ev[5], st));
+    }
+    // (the only synchronisation of a re-run; the first compaction of an upload has one more)
+    if (!compact || deferred) CS_CUDA(cudaStreamSynchronize(st));
+    if (deferred) {
+        if (s->nnz_async > s->nnz_hint) {
+            // more scores than the arrays were sized for: compact again, counting first
+            if ((rc = session_compact(s, st, &nnz, nullptr))) return rc;
+            deferred = false;
+        } else {
+            nnz = s->nnz_async;
+            s->nnz_out = s->nnz_hint = nnz;
+            s->compacted = true;
+        }
     }
     if (herr[0] > 0 && a.has_mask) {
         set_error("There are %d non-zero elements reported as missing.", herr[0]);
@@ -662,8 +678,10 @@ static int session_run_impl(cs_session *s, cs_run_stats *stats, bool compact) {
         set_error("internal: %d signal pixels fell outside the stored band", herr[1]);
         return CS_ERR_INVALID;
     }
-    CS_CUDA(cudaEventRecord(s->ev[5], st));
-    CS_CUDA(cudaStreamSynchronize(st));
+    if (!deferred) {
+        CS_CUDA(cudaEventRecord(s->ev[5], st));
+        CS_CUDA(cudaStreamSynchronize(st));
+    }
     s->nnz_out = nnz;
     s->ran = true;
     if (stats) {
@@ -699,12 +717,35 @@ extern "C" int cs_session_run_scores(cs_session *s, cs_run_stats *stats) {
 }
 
 // K2 of the last run: non-zero scores -> CSR (narrow wire format for bands of <= 256 diagonals)
-static int session_compact(cs_session *s, cudaStream_t st, int64_t *nnz_out) {
+static int session_compact(cs_session *s, cudaStream_t st, int64_t *nnz_out, bool *deferred) {
     const cs_normxcorr2_args &a = s->a;
     const cs_kernel_desc &K = a.kernel;
     int64_t nnz = 0;
-    int rc = cs_scores_count(&s->Lo, (const float *)s->out.p, -(1 << 30), (1 << 30),
-                             (int64_t *)s->r_indptr.p, &nnz, st);
+    int rc;
+    if (deferred) *deferred = false;
+    if (deferred && s->narrow && s->nnz_hint > 0 && s->w_score.cap >= (size_t)s->nnz_hint * sizeof(float) &&
+        s->w_off.cap >= (size_t)s->nnz_hint && (!a.pval || s->w_logp.cap >= (size_t)s->nnz_hint * sizeof(float))) {
+        // a re-run of the same upload: the arrays are sized from the last compaction, so counting,
+        // scan and emission are enqueued back to back and the count is read with the run's own
+        // final synchronisation (the caller checks it against the capacity)
+        if ((rc = scores_count_rows(&s->Lo, (const float *)s->out.p, -(1 << 30), (1 << 30),
+                                    (int64_t *)s->r_indptr.p, 0, s->Lo.rows, nullptr, st)))
+            return rc;
+        if ((rc = scores_finish_rows(&s->Lo, (int64_t *)s->r_indptr.p, 0, s->Lo.rows, 0, st))) return rc;
+        if ((rc = scores_emit_rows_narrow(&s->Lo, (const float *)s->out.p, s->want_nobs ? s->nobs.p : nullptr,
+                                          s->nmiss_bytes, K.kh * K.kw, (const int64_t *)s->r_indptr.p, 0,
+                                          a.rows, (float *)s->w_score.p,
+                                          a.pval ? (float *)s->w_logp.p : nullptr, (uint8_t *)s->w_off.p, st,
+                                          s->nnz_hint)))
+            return rc;
+        CS_CUDA(cudaMemcpyAsync(&s->nnz_async, (const int64_t *)s->r_indptr.p + s->Lo.rows, sizeof(int64_t),
+                                cudaMemcpyDeviceToHost, st));
+        *deferred = true;
+        *nnz_out = s->nnz_hint;
+        return CS_OK;
+    }
+    rc = cs_scores_count(&s->Lo, (const float *)s->out.p, -(1 << 30), (1 << 30),
+                         (int64_t *)s->r_indptr.p, &nnz, st);
     if (rc) return rc;
     const size_t nz1 = (size_t)(nnz > 0 ? nnz : 1);
     if (s->narrow) {
@@ -736,6 +777,7 @@ static int session_compact(cs_session *s, cudaStream_t st, int64_t *nnz_out) {
         }
     }
     s->nnz_out = nnz;
+    s->nnz_hint = nnz;
     s->compacted = true;
     *nnz_out = nnz;
     return CS_OK;
@@ -744,21 +786,25 @@ static int session_compact(cs_session *s, cudaStream_t st, int64_t *nnz_out) {
 // Exact scores at and near `threshold` (see exact_refine): run once per (run, threshold)
 // before the thresholding of pick_foci, so that candidates and foci do not depend on float32
 // rounding.  CS_NO_REFINE=1 skips it (timing experiments).
-static int session_refine(cs_session *s, double threshold, int32_t dmin, int32_t dmax, cudaStream_t st) {
-    if (s->refined && s->refined_thr == threshold) return CS_OK;
+static const long long kRefineCap = 1 << 23;  // 8 M pixels (64 MB of scratch)
+
+static bool refine_off(const cs_session *s) {
     static const bool off = getenv("CS_NO_REFINE") != nullptr;
-    if (off || s->a.raw_xcorr) return CS_OK;
+    return off || s->a.raw_xcorr;
+}
+
+static int refine_args(cs_session *s, double threshold, int32_t dmin, int32_t dmax, cs_pearson_opts *po,
+                       RefineArgs *Rp) {
     const cs_normxcorr2_args &a = s->a;
-    cs_pearson_opts po;
-    session_pearson_opts(s, &po);
-    po.mask_mode = a.has_mask;  // the predicate of the exact path, whatever the image holds
-    const long long cap = 1 << 23;  // 8 M pixels (64 MB of scratch)
+    session_pearson_opts(s, po);
+    po->mask_mode = a.has_mask;  // the predicate of the exact path, whatever the image holds
+    const long long cap = kRefineCap;
     int rc;
     if ((rc = s->x_list.ensure((size_t)cap * sizeof(int2) + 64))) return rc;
-    RefineArgs R;
+    RefineArgs &R = *Rp;
     memset(&R, 0, sizeof(R));
     R.K = &a.kernel;
-    R.opts = &po;
+    R.opts = po;
     R.d_indptr = (const int64_t *)s->sig_indptr.p;
     R.d_indices = (const int32_t *)s->sig_indices.p;
     R.d_data = (const double *)s->sig_data.p;
@@ -774,13 +820,27 @@ static int session_refine(cs_session *s, double threshold, int32_t dmin, int32_t
     R.d_list = (int2 *)s->x_list.p;
     R.cap = cap;
     R.d_count = (unsigned long long *)((char *)s->x_list.p + (size_t)cap * sizeof(int2));
-    long long n = 0;
-    if ((rc = exact_refine(R, st, &n))) return rc;
+    return CS_OK;
+}
+
+static void refine_done(cs_session *s, double threshold, long long n) {
     s->refined = true;
     s->refined_thr = threshold;
     s->n_refined = n;
     // the CSR result (if any) was compacted from the unrefined image
     if (n > 0) s->compacted = false;
+}
+
+static int session_refine(cs_session *s, double threshold, int32_t dmin, int32_t dmax, cudaStream_t st) {
+    if (s->refined && s->refined_thr == threshold) return CS_OK;
+    if (refine_off(s)) return CS_OK;
+    cs_pearson_opts po;
+    RefineArgs R;
+    int rc = refine_args(s, threshold, dmin, dmax, &po, &R);
+    if (rc) return rc;
+    long long n = 0;
+    if ((rc = exact_refine(R, st, &n))) return rc;
+    refine_done(s, threshold, n);
     return CS_OK;
 }
 
@@ -797,11 +857,36 @@ extern "C" int cs_session_candidates(cs_session *s, float threshold, int32_t dmi
         *n_host = 0;
         return CS_OK;
     }
-    if (int rrc = session_refine(s, (double)threshold, dmin, dmax, s->stream())) return rrc;
-    return cs_scores_candidates(&s->Lo, (const float *)s->out.p,
-                                s->want_nobs ? s->nobs.p : nullptr, s->nmiss_bytes,
-                                s->a.kernel.kh * s->a.kernel.kw, dmin, dmax, threshold, d_cand, cap,
-                                d_count, n_host, s->stream());
+    cudaStream_t st = s->stream();
+    const void *nb = s->want_nobs ? s->nobs.p : nullptr;
+    const int nwin = s->a.kernel.kh * s->a.kernel.kw;
+    if (!(s->refined && s->refined_thr == (double)threshold) && !refine_off(s)) {
+        // refinement and thresholding back to back, ONE synchronisation: the length of the
+        // refinement list stays on the device
+        cs_pearson_opts po;
+        RefineArgs R;
+        int rc = refine_args(s, (double)threshold, dmin, dmax, &po, &R);
+        if (rc) return rc;
+        rc = exact_refine_enqueue(R, st);
+        if (rc < 0) return rc;
+        if (rc == 0) {
+            if ((rc = scores_candidates_enqueue(&s->Lo, (const float *)s->out.p, nb, s->nmiss_bytes, nwin, dmin,
+                                                dmax, threshold, d_cand, cap, d_count, st)))
+                return rc;
+            unsigned long long n_ref = 0;
+            CS_CUDA(cudaMemcpyAsync(n_host, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            CS_CUDA(cudaMemcpyAsync(&n_ref, R.d_count, sizeof(n_ref), cudaMemcpyDeviceToHost, st));
+            CS_CUDA(cudaStreamSynchronize(st));
+            if ((long long)n_ref <= R.cap) {
+                refine_done(s, (double)threshold, (long long)n_ref);
+                return CS_OK;
+            }
+            // the list overflowed (nothing was redone): the two-pass form below
+        }
+    }
+    if (int rrc = session_refine(s, (double)threshold, dmin, dmax, st)) return rrc;
+    return cs_scores_candidates(&s->Lo, (const float *)s->out.p, nb, s->nmiss_bytes, nwin, dmin, dmax,
+                                threshold, d_cand, cap, d_count, n_host, st);
 }
 
 // pick_foci (det:387-456) on the scores of the last run; records sorted by first pixel.

@@ -1085,6 +1085,112 @@ __global__ void exact_windows(const PearsonParams P, const ExactArgs A, const in
     }
 }
 
+// The same recomputation, one LANE per window row (kernels of at most 32 rows; 32 / KH windows
+// per warp): the lane finds the first stored column of its row inside the window with one binary
+// search and walks the few entries that follow, instead of one binary search per tap.  The
+// mask sums need no memory at all (geometry).  Used for the geometric mask and without mask.
+template <int MASKMODE>
+__global__ void exact_windows_rows(const PearsonParams P, const ExactArgs A, const int2 *list, long long n,
+                                   const unsigned long long *n_dev, long long cap) {
+    constexpr bool MASK = MASKMODE != MODE_NOMASK;
+    if (n_dev) {
+        // the list length stays on the device (no host round trip between collecting and
+        // redoing); an overflowing list is left to the host's fallback
+        const unsigned long long nd = *n_dev;
+        if (nd > (unsigned long long)cap) return;
+        n = (long long)nd;
+    }
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    const int KH = P.KH, KW = P.KW, kh = (KH - 1) / 2, kw = (KW - 1) / 2;
+    const int wpw = 32 / KH;                    // windows per warp
+    const int sub = lane / KH, i = lane - sub * KH;
+    const long long nwarps = (long long)gridDim.x * wpb;
+    for (long long w0 = (blockIdx.x * (long long)wpb + (threadIdx.x >> 5)) * wpw; w0 < n; w0 += nwarps * wpw) {
+        const long long w = w0 + sub;
+        const bool act = sub < wpw && w < n;
+        int y = 0, x = 0;
+        if (act) {
+            const int2 p = list[w];
+            y = p.x, x = p.y;
+        }
+        const int Y = y + A.pr, X = x + A.pc;   // image coordinates of the window centre
+        const int Yp = Y - kh + i;              // image row of this lane
+        const int r = Yp - A.pr;                // matrix row
+        const int c0 = X - kw - A.pc;           // matrix column of tap j = 0
+        const bool rin = act && r >= 0 && r < A.rows;
+        double h1 = 0.0, h2 = 0.0, q3 = 0.0, sKm = 0.0, sKm2 = 0.0;
+        int nmiss = 0;
+        bool rbit = false;
+        if (MASK && rin) rbit = (P.rbits[Yp >> 5] >> (Yp & 31)) & 1u;
+        if (MASK && act) {
+            // missing taps of this window row (pure geometry)
+            for (int j = 0; j < KW; ++j) {
+                const int Xp = X - kw + j, c = c0 + j;
+                bool cbit = false;
+                if (rin && c >= 0 && c < A.cols) cbit = (P.cbits[Xp >> 5] >> (Xp & 31)) & 1u;
+                const bool inside = rin && c >= 0 && c < A.cols;
+                if (geo_missing(P, Yp, Xp, inside && rbit, cbit)) {
+                    ++nmiss;
+                    sKm += __ldg(P.dK + P.N + i * KW + j);
+                    sKm2 += __ldg(P.dK + 2 * P.N + i * KW + j);
+                }
+            }
+        }
+        if (rin) {
+            const int ca = c0 < 0 ? 0 : c0;
+            const int cb = (c0 + KW - 1 > A.cols - 1) ? A.cols - 1 : c0 + KW - 1;
+            int64_t lo = A.indptr[r];
+            const int64_t end = A.indptr[r + 1];
+            int64_t hi = end;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (A.indices[mid] < ca) lo = mid + 1;
+                else hi = mid;
+            }
+            for (int64_t pos = lo; pos < end; ++pos) {
+                const int c = A.indices[pos];
+                if (c > cb) break;
+                const int j = c - c0;
+                if (MASK) {
+                    const int Xp = c + A.pc;
+                    const bool cbit = (P.cbits[Xp >> 5] >> (Xp & 31)) & 1u;
+                    if (geo_missing(P, Yp, Xp, rbit, cbit)) continue;
+                }
+                const double sv = A.data[pos];
+                h1 += sv;
+                h2 = fma(sv, sv, h2);
+                q3 = fma(sv, __ldg(P.dK + i * KW + j), q3);
+            }
+        }
+        // sum over the KH lanes of the window (segments never cross: lane + o stays inside)
+        for (int o = 16; o > 0; o >>= 1) {
+            const double a1 = __shfl_down_sync(0xffffffffu, h1, o), a2 = __shfl_down_sync(0xffffffffu, h2, o);
+            const double a3 = __shfl_down_sync(0xffffffffu, q3, o);
+            const bool take = i + o < KH;
+            if (take) h1 += a1, h2 += a2, q3 += a3;
+            if (MASK) {
+                const double b1 = __shfl_down_sync(0xffffffffu, sKm, o), b2 = __shfl_down_sync(0xffffffffu, sKm2, o);
+                const int b3 = __shfl_down_sync(0xffffffffu, nmiss, o);
+                if (take) sKm += b1, sKm2 += b2, nmiss += b3;
+            }
+        }
+        if (act && i == 0) {
+            int nmo;
+            const double rx = exact_score_core<MASK>(P, h1, h2, q3, nmiss, sKm, sKm2, nmo);
+            float rr = (float)rx;
+            // keep the side of the threshold the double value is on (pick_foci compares float64)
+            if (rx >= A.thr_pearson && (double)rr < A.thr_pearson) rr = nextafterf(rr, 2.f);
+            if (rx < A.thr_pearson && (double)rr >= A.thr_pearson) rr = nextafterf(rr, -2.f);
+            const long long oi = (long long)y * A.out_pitch + (x - A.out_dlo);
+            A.out[oi] = rr;
+            if (A.nmiss) {
+                if (A.nmiss16) ((unsigned short *)A.nmiss)[oi] = (unsigned short)nmo;
+                else ((unsigned char *)A.nmiss)[oi] = (unsigned char)nmo;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
                                     const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
@@ -1589,12 +1695,10 @@ static int pearson_impl(const cs_layout *Li, const float *d_img, const cs_kernel
 // Pixels of the score image with a score >= threshold - 2e-5 on diagonals dmin..dmax (all
 // candidates of pick_foci plus the borderline ones below the threshold; if they overflow the
 // scratch list, only the borderline band of +-2e-5) are recomputed exactly from the CSR.
-int cs::exact_refine(const RefineArgs &R, cudaStream_t st, long long *n_refined) {
-    *n_refined = 0;
+static int refine_setup(const RefineArgs &R, cudaStream_t st, PearsonParams &P, ExactArgs &A, int &mode) {
     const cs_kernel_desc *K = R.K;
-    PearsonParams P;
     memset(&P, 0, sizeof(P));
-    const int mode = common_params(P, K, R.opts);
+    mode = common_params(P, K, R.opts);
     if (mode) CS_REQUIRE(K->k_mask && K->k2_mask, "mask kernels missing");
     P.mlo = -(1 << 29), P.mhi = 1 << 29;
     P.sdlo = 0, P.sdhi = -1;
@@ -1611,7 +1715,6 @@ int cs::exact_refine(const RefineArgs &R, cudaStream_t st, long long *n_refined)
     const unsigned char *d_f = nullptr;
     int rc = upload_tables(K, mode != 0, nullptr, 0, st, &d_f, &P.dK);
     if (rc) return rc;
-    ExactArgs A;
     memset(&A, 0, sizeof(A));
     A.indptr = R.d_indptr, A.indices = R.d_indices, A.data = R.d_data;
     A.rows = R.rows, A.cols = R.cols, A.pr = R.pr, A.pc = R.pc;
@@ -1625,6 +1728,46 @@ int cs::exact_refine(const RefineArgs &R, cudaStream_t st, long long *n_refined)
     A.out_dlo = R.Lo->dense ? 0 : R.Lo->dlo;
     A.out_dense = R.Lo->dense;
     A.thr_pearson = R.threshold;
+    return CS_OK;
+}
+
+// Enqueue-only variant for the geometric mask / no mask and kernels of at most 32 rows: every
+// pixel >= threshold - 2e-5 is listed and redone with the list length kept on the device.
+// Returns 1 when this form does not apply (pixel mask, tall kernel); the caller then reads
+// *R.d_count with its next synchronisation: a count above R.cap means nothing was redone and
+// exact_refine has to run.
+int cs::exact_refine_enqueue(const RefineArgs &R, cudaStream_t st) {
+    if (R.K->kh > 32 || R.opts->mask_mode == MODE_BITS) return 1;
+    PearsonParams P;
+    ExactArgs A;
+    int mode;
+    int rc = refine_setup(R, st, P, A, mode);
+    if (rc) return rc;
+    const float eps = 2e-5f;
+    int grid = (R.Lo->rows + 7) / 8;
+    if (grid > 148 * 16) grid = 148 * 16;
+    CS_CUDA(cudaMemsetAsync(R.d_count, 0, sizeof(unsigned long long), st));
+    collect_near<<<grid, 256, 0, st>>>(A, R.Lo->rows, R.Lo->cols, R.Lo->dlo, R.Lo->dhi, R.dmin, R.dmax,
+                                       (float)R.threshold - eps, 3.0e38f, R.d_list, R.cap, R.d_count);
+    CS_LAUNCHED();
+    const int blocks = 148 * 8;
+    if (mode == MODE_GEO)
+        exact_windows_rows<MODE_GEO><<<blocks, 256, 0, st>>>(P, A, R.d_list, 0, R.d_count, R.cap);
+    else
+        exact_windows_rows<MODE_NOMASK><<<blocks, 256, 0, st>>>(P, A, R.d_list, 0, R.d_count, R.cap);
+    CS_LAUNCHED();
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+int cs::exact_refine(const RefineArgs &R, cudaStream_t st, long long *n_refined) {
+    *n_refined = 0;
+    const cs_kernel_desc *K = R.K;
+    PearsonParams P;
+    ExactArgs A;
+    int mode;
+    int rc = refine_setup(R, st, P, A, mode);
+    if (rc) return rc;
     const float eps = 2e-5f;
     int grid = (R.Lo->rows + 7) / 8;
     if (grid > 148 * 16) grid = 148 * 16;
@@ -1643,7 +1786,16 @@ int cs::exact_refine(const RefineArgs &R, cudaStream_t st, long long *n_refined)
     if ((long long)n > R.cap || n == 0) return CS_OK;  // nothing to do / too many to redo
     long long blocks = ((long long)n + 7) / 8;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    if (mode == MODE_GEO)
+    static const bool by_tap = getenv("CS_EXACT_BY_TAP") != nullptr;  // the one-search-per-tap kernel
+    if (K->kh <= 32 && mode != MODE_BITS && !by_tap) {
+        const int wpw = 32 / K->kh;
+        blocks = ((long long)n + 8 * wpw - 1) / (8 * wpw);
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        if (mode == MODE_GEO)
+            exact_windows_rows<MODE_GEO><<<(int)blocks, 256, 0, st>>>(P, A, R.d_list, (long long)n, nullptr, 0);
+        else
+            exact_windows_rows<MODE_NOMASK><<<(int)blocks, 256, 0, st>>>(P, A, R.d_list, (long long)n, nullptr, 0);
+    } else if (mode == MODE_GEO)
         exact_windows<MODE_GEO><<<(int)blocks, 256, 0, st>>>(P, A, R.d_list, (long long)n);
     else if (mode == MODE_BITS)
         exact_windows<MODE_BITS><<<(int)blocks, 256, 0, st>>>(P, A, R.d_list, (long long)n);

@@ -159,7 +159,7 @@ __global__ void emit_rows(ScoreView S, const float *__restrict__ sc,
 // float32 on the device anyway and the p-values are evaluated in float32.
 __global__ void emit_rows_narrow(ScoreView S, const float *__restrict__ sc, NmissPlane nobs,
                                  const int64_t *__restrict__ indptr, float *score, float *log10p,
-                                 unsigned char *off, int r0, int r1) {
+                                 unsigned char *off, int r0, int r1, long long limit) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     for (int y = r0 + blockIdx.x * wpb + (threadIdx.x >> 5); y < r1; y += gridDim.x * wpb) {
@@ -176,8 +176,8 @@ __global__ void emit_rows_narrow(ScoreView S, const float *__restrict__ sc, Nmis
                 v = sc[i];
             }
             const unsigned m = __ballot_sync(0xffffffffu, v != 0.f);
-            if (v != 0.f) {
-                const int64_t o = pos + __popc(m & ((1u << lane) - 1u));
+            const int64_t o = pos + __popc(m & ((1u << lane) - 1u));
+            if (v != 0.f && o < limit) {  // (limit: capacity of the arrays when sized from an earlier run)
                 score[o] = v;
                 off[o] = (unsigned char)(x - xbase);
                 if (log10p) log10p[o] = (float)log10_pval(v, nobs_at(nobs, i));
@@ -445,14 +445,14 @@ using namespace cs;
 int cs::scores_emit_rows_narrow(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
                                 int32_t nmiss_bytes, int32_t n_window, const int64_t *d_indptr,
                                 int32_t r0, int32_t r1, float *d_score, float *d_log10p,
-                                uint8_t *d_off, cudaStream_t st) {
+                                uint8_t *d_off, cudaStream_t st, int64_t limit) {
     if (r1 <= r0) return CS_OK;
     CS_REQUIRE(!Lo->dense && Lo->dhi - Lo->dlo < 256, "narrow result format needs a band of <= 256 diagonals");
     ScoreView S = make_view(Lo, -(1 << 30), 1 << 30);
     int grid = (r1 - r0 + 7) / 8;
     if (grid > 148 * 16) grid = 148 * 16;
     emit_rows_narrow<<<grid, 256, 0, st>>>(S, d_out, NmissPlane{d_nmiss, nmiss_bytes, n_window},
-                                           d_indptr, d_score, d_log10p, d_off, r0, r1);
+                                           d_indptr, d_score, d_log10p, d_off, r0, r1, (long long)limit);
     CS_LAUNCHED();
     CS_CUDA(cudaGetLastError());
     return CS_OK;
@@ -485,13 +485,10 @@ extern "C" int cs_scores_emit(const cs_layout *Lo, const float *d_out, const voi
                             d_indices, d_data, d_log10p, (cudaStream_t)stream);
 }
 
-extern "C" int cs_scores_candidates(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
-                                    int32_t nmiss_bytes, int32_t n_window, int32_t dmin,
-                                    int32_t dmax, float threshold,
-                                    cs_candidate *d_cand, int64_t cap, int64_t *d_count,
-                                    int64_t *n_host, void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    CS_REQUIRE(Lo && d_out && d_cand && d_count && n_host, "cs_scores_candidates: null argument");
+int cs::scores_candidates_enqueue(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
+                                  int32_t nmiss_bytes, int32_t n_window, int32_t dmin, int32_t dmax,
+                                  float threshold, cs_candidate *d_cand, int64_t cap, int64_t *d_count,
+                                  cudaStream_t st) {
     ScoreView S = make_view(Lo, dmin, dmax);
     CS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
     int grid = (S.rows + 7) / 8;
@@ -500,6 +497,19 @@ extern "C" int cs_scores_candidates(const cs_layout *Lo, const float *d_out, con
                                           (long long)cap, (unsigned long long *)d_count);
     CS_LAUNCHED();
     CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+extern "C" int cs_scores_candidates(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
+                                    int32_t nmiss_bytes, int32_t n_window, int32_t dmin,
+                                    int32_t dmax, float threshold,
+                                    cs_candidate *d_cand, int64_t cap, int64_t *d_count,
+                                    int64_t *n_host, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CS_REQUIRE(Lo && d_out && d_cand && d_count && n_host, "cs_scores_candidates: null argument");
+    int rc = scores_candidates_enqueue(Lo, d_out, d_nmiss, nmiss_bytes, n_window, dmin, dmax, threshold, d_cand,
+                                       cap, d_count, st);
+    if (rc) return rc;
     CS_CUDA(cudaMemcpyAsync(n_host, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CS_CUDA(cudaStreamSynchronize(st));
     return CS_OK;

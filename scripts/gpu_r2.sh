@@ -55,6 +55,9 @@ tilerows)
     export CS_TILE_ROWS=$tr; echo "== CS_TILE_ROWS=$tr"
     quick loops17; quick borders9 --kernel borders --win-size 9 --pearson 0.15; quick small7 --kernel loops_small --pearson 0.5
   done; unset CS_TILE_ROWS CHROMOSIGHT_B200_LIB;;
+slab)
+  timeout 300 python scripts/dbg_slab.py 4 1 2>&1 | tail -4
+  CHROMOSIGHT_B200_LIB=$PWD/chromosight_b200/libchromosight_b200_ablate.so CS_DEBUG_COUNT=1 timeout 300 python scripts/dbg_slab.py 4 1 2>&1 | grep -i "pearson stats" | sort | uniq -c | tail -3;;
 benchref)
   timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/benchref_$TAG.json 2> gpurun_out/benchref_$TAG.err; echo "benchref rc=$?"; cat gpurun_out/benchref_$TAG.json; nproc;;
 ncu)
