@@ -166,12 +166,22 @@ __device__ __forceinline__ float rcp_fast(float x) {
     return r;
 }
 
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ double thr0(double v, double t) { return fabs(v) < t ? 0.0 : v; }  // [sec:scorefn]
 
 // Squared error amplification above which a window leaves the float32 path: the
 // float32 sums carry ~1e-6 relative error on well-conditioned windows, and the score
 // error grows like amp = rms(S') * rms(K') / (sigma_S * sigma_K).
 constexpr float kAmpLimit2 = 8.0f;
+// ... and the same for the tap products, which are accumulated on the uncentred pixels: their
+// rounding error scales with rms(S) rms(K') / (sigma_S sigma_K) / N, two orders of magnitude
+// below the one of the variance, hence the much wider limit on the squared ratio.
+constexpr float kAmpLimitQ = 1000.0f;
 
 // The reference's formulas (det:1002-1020 no mask, det:1021-1092 masked) in float64 from the
 // raw window sums: h1, h2 = sum S, sum S^2 (missing pixels count as S = 0), s3 = sum S * K_corr,
@@ -455,8 +465,11 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
         if (any)
 #endif
         {                                                                    // [sec:main]
-            const unsigned long long npl2 = pack2(-pl, -pl);
-            // one packed accumulator per window: .lo and .hi collect alternate taps
+            // one packed accumulator per window: .lo and .hi collect alternate taps.  The products
+            // are taken on the pixels as stored: K' sums to ~0, so the pivot enters as one
+            // correction per window (- pl * sum K') and costs no arithmetic in this loop; the
+            // uncentred products only matter for windows with rms(S) >> sigma(S), which the
+            // conditioning test of the score sends to the exact path (kAmpLimitQ).
             unsigned long long acc[RU][RT];
 #pragma unroll
             for (int u = 0; u < RU; ++u)
@@ -468,13 +481,13 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
             for (int iy = 0; iy < nrow; ++iy) {
                 const ulonglong2 *rp =
                     reinterpret_cast<const ulonglong2 *>(tile + (RU * g + iy) * IC + cxa);
-                // xe[q] = (x[2q], x[2q+1]) - block pivot
+                // xe[q] = (x[2q], x[2q+1])
                 unsigned long long xe[2 * NQ];
 #pragma unroll
                 for (int qd = 0; qd < NQ; ++qd) {
                     const ulonglong2 v = rp[qd];
-                    xe[2 * qd] = add2(v.x, npl2);
-                    xe[2 * qd + 1] = add2(v.y, npl2);
+                    xe[2 * qd] = v.x;
+                    xe[2 * qd + 1] = v.y;
                 }
 #pragma unroll
                 for (int u = 0; u < RU; ++u) {
@@ -500,13 +513,14 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     }
                 }
             }
+            const float corr = -pl * P.sumKp;  // sum (S - pl) K' = sum S K' - pl sum K'
 #pragma unroll
             for (int t = 0; t < RT; ++t) {
                 float lo, hi;
                 unpack2(acc[0][t], lo, hi);
-                s3a[t] = lo + hi;
+                s3a[t] = (lo + hi) + corr;
                 unpack2(acc[1][t], lo, hi);
-                s3b[t] = lo + hi;
+                s3b[t] = (lo + hi) + corr;
             }
         }
 
@@ -703,6 +717,13 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                 int nn[RT];
                 const float cm = MASK ? ((MODE == MODE_GEO ? P.fillc : 0.f) - pl) : 0.f;  // S' of a missing pixel
                 const bool raw = P.raw_xcorr != 0;
+                // per-block constants of the per-window formulas
+                const float ncm2 = -cm * cm, pl2 = pl + pl;
+                const float e0 = P.escale * fmaf(pl, pl, 1.f), e1 = P.escale * invN;
+                const float thrN = P.thr * (float)P.N, Nf = (float)P.N;
+                // windows with a missing pixel need min_present pixels and a kernel of non-zero mean
+                const int minp = P.kmean_zero ? 0x7fffffff : max(P.min_present, 1);
+                const int nmsel = (MASK && P.nobs_full) ? -1 : 0;
 #pragma unroll
                 for (int t = 0; t < RT; ++t) {
                     if (t > 0) {
@@ -716,18 +737,17 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     float P1 = g1, P2 = g2, Q3 = s3a[t];
                     if (MASK) {
                         P1 = fmaf(-cm, nf, g1);
-                        P2 = fmaf(-cm * cm, nf, g2);
+                        P2 = fmaf(ncm2, nf, g2);
                         Q3 = fmaf(-cm, sK[t], Q3);
                     }
                     // the three raw correlations xcorr2 thresholds at 1e-4 (det:716), over the
-                    // whole window (missing pixels are zeros)
+                    // whole window (missing pixels are zeros), times N
                     const float kp = MASK ? (P.sumKp - sK[t]) : P.sumKp;  // sum K' over present
-                    const float U1 = fmaf(np, pl, P1);                                   // sum S
-                    const float U2 = fmaf(2.f * pl, P1, fmaf(np * pl, pl, P2));          // sum S^2
-                    const float U3 = fmaf(P.qf, U1, fmaf(pl, kp, Q3));                   // sum S K_corr
-                    const float E = P.escale * (1.f + fmaf(pl, pl, g2 * invN));
-                    const float A1 = fabsf(U1 * invN), A2 = fabsf(U2 * invN), A3 = fabsf(U3 * invN);
-                    const float zone = fmaf(P.thr, 1e-3f, E);
+                    const float U1 = fmaf(np, pl, P1);                    // sum S
+                    const float U2 = fmaf(pl, P1 + U1, P2);               // sum S^2 = P2 + pl (2 P1 + n pl)
+                    const float U3 = fmaf(P.qf, U1, fmaf(pl, kp, Q3));    // sum S K_corr
+                    const float E = fmaf(e1, g2, e0);                     // their float32 error scale
+                    const float zoneN = fmaf(P.thr, 1e-3f, E) * Nf;
                     const float a = MASK ? (P.ksump - sK[t]) : P.ksump;
                     const float b = MASK ? (P.k2sump - sK2[t]) : P.k2sump;
                     const float invn = MASK ? rcp_fast(np) : invN;
@@ -737,24 +757,24 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
                     const float VK = fmaf(-a * invn, a, b);                // n var K
                     const float den2 = VS * VK;
                     bool ok = true;
-                    if (MASK)
-                        ok = nm[t] == 0 || (npres >= P.min_present && npres > 0 && !P.kmean_zero);
+                    if (MASK) ok = nm[t] == 0 || npres >= minp;
                     // det:1088-1091: |sqrt(var S var K)| < 1e-10 -> 0
                     const bool dok = den2 > P.den_floor * np * np;
-                    float r = fminf(1.f, fmaxf(-1.f, C * rsqrtf(den2)));
+                    float r = fminf(1.f, fmaxf(-1.f, C * rsqrt_fast(den2)));
                     // a mean of squares thresholded to 0 makes the variance <= 0: score 0
-                    const bool zero2 = A2 < P.thr - zone;
+                    const bool zero2 = fabsf(U2) < thrN - zoneN;
                     bool hard = !zero2 && ok &&
                                 (!dok ||                                       // flat window
-                                 fminf(fminf(A1, A2), A3) < P.thr + zone ||    // a threshold within rounding distance
-                                 g2 * P.sumKp2 > kAmpLimit2 * den2);           // ill-conditioned float32 sums
+                                 fminf(fminf(fabsf(U1), fabsf(U2)), fabsf(U3)) < thrN + zoneN ||  // a threshold within rounding distance
+                                 g2 * P.sumKp2 > kAmpLimit2 * den2 ||          // ill-conditioned float32 sums
+                                 fabsf(U2) * P.sumKp2 > kAmpLimitQ * den2);    // ... or tap products
                     if (zero2 || !ok || !dok) r = 0.f;
-                    int nmo = (MASK && P.nobs_full && r != 0.f) ? nm[t] : 0;
+                    int nmo = (r != 0.f) ? (nm[t] & nmsel) : 0;
                     if (raw) {
                         // xcorr2: the thresholded raw correlation itself
                         const float au = fabsf(U3);
                         r = au < P.thr ? 0.f : U3;
-                        hard = fabsf(au - P.thr) <= fmaf(P.thr, 1e-3f, E * (float)P.N);
+                        hard = fabsf(au - P.thr) <= fmaf(P.thr, 1e-3f, E * Nf);
                         nmo = 0;
                     }
 #ifdef CS_ABLATE
