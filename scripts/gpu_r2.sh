@@ -58,6 +58,9 @@ tilerows)
 slab)
   timeout 300 python scripts/dbg_slab.py 4 1 2>&1 | tail -4
   CHROMOSIGHT_B200_LIB=$PWD/chromosight_b200/libchromosight_b200_ablate.so CS_DEBUG_COUNT=1 timeout 300 python scripts/dbg_slab.py 4 1 2>&1 | grep -i "pearson stats" | sort | uniq -c | tail -3;;
+ncu7)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:pearson -s 3 -c 1 -o gpurun_out/prof7_$TAG -f \
+      python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --kernel loops_small --pearson 0.5 > gpurun_out/ncu_full7_$TAG.log 2>&1; echo "ncu full 7x7 rc=$?"; tail -2 gpurun_out/ncu_full7_$TAG.log;;
 benchref)
   timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/benchref_$TAG.json 2> gpurun_out/benchref_$TAG.err; echo "benchref rc=$?"; cat gpurun_out/benchref_$TAG.json; nproc;;
 ncu)
