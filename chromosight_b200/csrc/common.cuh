@@ -106,6 +106,12 @@ int scores_candidates_enqueue(const cs_layout *Lo, const float *d_out, const voi
                               int32_t n_window, int32_t dmin, int32_t dmax, float threshold, cs_candidate *d_cand,
                               int64_t cap, int64_t *d_count, cudaStream_t st);
 
+// ... and from the refinement list (device-side length) instead of a pass over the band
+int scores_candidates_from_list(const cs_layout *Lo, const float *d_out, const void *d_nmiss, int32_t nmiss_bytes,
+                                int32_t n_window, int32_t dmin, int32_t dmax, float threshold, const int2 *d_list,
+                                const unsigned long long *d_n, long long list_cap, cs_candidate *d_cand, int64_t cap,
+                                int64_t *d_count, cudaStream_t st);
+
 #define CS_LAUNCHED() (cs::g_launches.fetch_add(1, std::memory_order_relaxed))
 
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }

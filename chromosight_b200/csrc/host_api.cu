@@ -277,6 +277,7 @@ struct cs_session {
     int oy0 = 0, oy1 = 0, ox0 = 0, ox1 = 0, od_lo = 0, od_hi = 0, pr = 0, pc = 0;
     bool want_nobs = false;
     int64_t nnz_in = 0, nnz_m = 0, nnz_out = 0, n_windows = 0;
+    bool planes_zeroed = false;  // score / count planes zeroed since the upload (a run overwrites every window)
     int64_t nnz_hint = -1;   // non-zero scores of the last compaction of this upload (sizes the next one)
     int64_t nnz_async = 0;   // read-back target of a compaction enqueued without synchronisation
     size_t h2d_bytes = 0;
@@ -332,6 +333,7 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
     cudaStream_t st = s->stream();
     s->uploaded = s->ran = false;
     s->nnz_hint = -1;
+    s->planes_zeroed = false;
     s->a = *a;
     const cs_kernel_desc &K = a->kernel;
     CS_REQUIRE(K.kh >= 1 && K.kw >= 1 && K.k_corr, "cs_session_upload: bad kernel");
@@ -635,10 +637,15 @@ static int session_run_impl(cs_session *s, cs_run_stats *stats, bool compact) {
                                &s->geo, a.sym_upper, a.max_dist, a.full ? K.kh : 0,
                                a.full ? K.kw : 0, (int32_t *)s->err.p, st);
     if (rc) return rc;
-    // scores outside the computed set must read as 0
-    CS_CUDA(cudaMemsetAsync(s->out.p, 0, (size_t)s->Lo.n_elems * sizeof(float), st));
-    if (s->want_nobs)  // missing counts: only windows that have one are written by the kernel
-        CS_CUDA(cudaMemsetAsync(s->nobs.p, 0, (size_t)s->Lo.n_elems * (size_t)s->nmiss_bytes, st));
+    // scores outside the computed set must read as 0.  The kernel writes every window of the
+    // region on every run, and missing counts for the same windows of the same mask: the planes
+    // are zeroed once per upload, not per run.
+    if (!s->planes_zeroed) {
+        CS_CUDA(cudaMemsetAsync(s->out.p, 0, (size_t)s->Lo.n_elems * sizeof(float), st));
+        if (s->want_nobs)  // missing counts: only windows that have one are written by the kernel
+            CS_CUDA(cudaMemsetAsync(s->nobs.p, 0, (size_t)s->Lo.n_elems * (size_t)s->nmiss_bytes, st));
+        s->planes_zeroed = true;
+    }
     cs_pearson_opts po;
     session_pearson_opts(s, &po);
     CS_CUDA(cudaEventRecord(s->ev[3], st));
@@ -870,8 +877,11 @@ extern "C" int cs_session_candidates(cs_session *s, float threshold, int32_t dmi
         rc = exact_refine_enqueue(R, st);
         if (rc < 0) return rc;
         if (rc == 0) {
-            if ((rc = scores_candidates_enqueue(&s->Lo, (const float *)s->out.p, nb, s->nmiss_bytes, nwin, dmin,
-                                                dmax, threshold, d_cand, cap, d_count, st)))
+            // every candidate is on the refinement list (score >= threshold - 2e-5 on these
+            // diagonals): thresholding reads the list, not the band a second time
+            if ((rc = scores_candidates_from_list(&s->Lo, (const float *)s->out.p, nb, s->nmiss_bytes, nwin, dmin,
+                                                  dmax, threshold, R.d_list, R.d_count, R.cap, d_cand, cap,
+                                                  d_count, st)))
                 return rc;
             unsigned long long n_ref = 0;
             CS_CUDA(cudaMemcpyAsync(n_host, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, st));

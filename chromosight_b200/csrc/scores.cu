@@ -227,6 +227,34 @@ __global__ void emit_candidates(ScoreView S, const float *__restrict__ sc,
     }
 }
 
+// The same records from a list of pixels (the refinement list of exact_refine_enqueue: every
+// pixel >= threshold - 2e-5 on the scanned diagonals) instead of a second pass over the band.
+// The list length lives on the device; an overflowed list (> list_cap) emits nothing.
+__global__ void emit_candidates_list(ScoreView S, const float *__restrict__ sc, NmissPlane nobs, float threshold,
+                                     const int2 *__restrict__ list, const unsigned long long *n_dev,
+                                     long long list_cap, cs_candidate *out, long long cap,
+                                     unsigned long long *count) {
+    const unsigned long long nd = *n_dev;
+    if (nd > (unsigned long long)list_cap) return;
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < (long long)nd;
+         k += (long long)gridDim.x * blockDim.x) {
+        const int2 p = list[k];
+        const long long i = sidx(S, p.x, p.y);
+        const float v = sc[i];
+        if (v != 0.f && v >= threshold) {
+            const unsigned long long o = atomicAdd(count, 1ull);
+            if ((long long)o < cap) {
+                cs_candidate c;
+                c.row = p.x;
+                c.col = p.y;
+                c.score = v;
+                c.log10p = (float)log10_pval(v, nobs_at(nobs, i));
+                out[o] = c;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // pick_foci on the device (detection.py:387-456, label_foci 459-554, filter_foci 557-592):
 // pixels with score >= threshold form 4-connected foci; foci of at least min_size pixels
@@ -495,6 +523,21 @@ int cs::scores_candidates_enqueue(const cs_layout *Lo, const float *d_out, const
     if (grid > 148 * 16) grid = 148 * 16;
     emit_candidates<<<grid, 256, 0, st>>>(S, d_out, NmissPlane{d_nmiss, nmiss_bytes, n_window}, threshold, d_cand,
                                           (long long)cap, (unsigned long long *)d_count);
+    CS_LAUNCHED();
+    CS_CUDA(cudaGetLastError());
+    return CS_OK;
+}
+
+int cs::scores_candidates_from_list(const cs_layout *Lo, const float *d_out, const void *d_nmiss,
+                                    int32_t nmiss_bytes, int32_t n_window, int32_t dmin, int32_t dmax,
+                                    float threshold, const int2 *d_list, const unsigned long long *d_n,
+                                    long long list_cap, cs_candidate *d_cand, int64_t cap, int64_t *d_count,
+                                    cudaStream_t st) {
+    ScoreView S = make_view(Lo, dmin, dmax);
+    CS_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+    emit_candidates_list<<<148 * 4, 256, 0, st>>>(S, d_out, NmissPlane{d_nmiss, nmiss_bytes, n_window}, threshold,
+                                                  d_list, d_n, list_cap, d_cand, (long long)cap,
+                                                  (unsigned long long *)d_count);
     CS_LAUNCHED();
     CS_CUDA(cudaGetLastError());
     return CS_OK;
