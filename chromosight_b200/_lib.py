@@ -155,6 +155,8 @@ _PROTOS = {
     "cs_pearson_plan": (C.c_int, [C.POINTER(Layout), C.POINTER(KernelDesc), C.POINTER(PearsonOpts),
                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "cs_band_csr_from_pixels": (C.c_int64, [_P, _P, _P, C.c_int32, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int64,
+                                            _P, _P, _P, C.c_int32]),
     "cs_scan_scratch": (C.c_int64, [C.c_int32]),
     "cs_scores_count": (C.c_int, [C.POINTER(Layout), _P, C.c_int32, C.c_int32, _P,
                                    C.POINTER(C.c_int64), _P]),

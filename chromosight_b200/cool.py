@@ -415,19 +415,23 @@ class CoolFile:
         """Diagonals 0..max_diag of the intra block [s:e, s:e] as canonical CSR arrays
         (indptr int64, indices int32, data float64), balanced like `matrix(balance=True)`;
         pixels on masked bins (NaN weight) are dropped.  cooler stores exactly this triangle,
-        sorted: one slice and one filter, no mirroring, no sort.  None when the pixel table
-        is not sorted."""
+        sorted: one slice and one filter, no mirroring, no sort -- done in one fused
+        multi-threaded pass by the library (cs_band_csr_from_pixels), numpy otherwise.
+        None when the pixel table is not sorted."""
         if not self._lex_sorted():
             return None
         off = self._row_offsets()
         lo, hi = int(off[s]), int(off[e])
+        if balance and "weight" not in self._bins.columns:
+            raise ValueError("no 'weight' column: balance the file first")
+        fast = self._band_csr_native(lo, hi, s, e, max_diag, balance)
+        if fast is not None:
+            return fast
         b1 = self._pix.bin1_id.values[lo:hi]
         b2 = self._pix.bin2_id.values[lo:hi]
         keep = (b2 < e) & (b2 - b1 <= max_diag)
         v = self._pix["count"].values[lo:hi].astype(np.float64)
         if balance:
-            if "weight" not in self._bins.columns:
-                raise ValueError("no 'weight' column: balance the file first")
             w = self._bins.weight.values
             v = v * w[b1] * w[b2]
             keep &= np.isfinite(v)
@@ -437,28 +441,64 @@ class CoolFile:
         np.cumsum(np.bincount(rows, minlength=e - s), out=indptr[1:])
         return indptr, (b2[sel] - s).astype(np.int32), v[sel]
 
+    def _band_csr_native(self, lo, hi, s, e, max_diag, balance):
+        """upper_band_csr through libchromosight_b200.so (host code, no GPU needed); None when
+        the library or the column types do not allow it."""
+        try:
+            from . import _lib
+            lib = _lib.load()
+        except Exception:
+            return None
+        b1, b2, cnt = self._pix.bin1_id.values, self._pix.bin2_id.values, self._pix["count"].values
+        code = {np.dtype(np.int32): 0, np.dtype(np.int64): 1, np.dtype(np.float64): 2}.get(cnt.dtype)
+        if code is None or b1.dtype != np.int64 or b2.dtype != np.int64 or not (
+                b1.flags.c_contiguous and b2.flags.c_contiguous and cnt.flags.c_contiguous):
+            return None
+        n = hi - lo
+        indptr = np.empty(e - s + 1, dtype=np.int64)
+        indices = np.empty(max(n, 1), dtype=np.int32)
+        data = np.empty(max(n, 1), dtype=np.float64)
+        w = np.ascontiguousarray(self._bins.weight.values, dtype=np.float64) if balance else None
+        nnz = lib.cs_band_csr_from_pixels(
+            b1.ctypes.data + 8 * lo, b2.ctypes.data + 8 * lo, cnt.ctypes.data + cnt.itemsize * lo, code, n,
+            w.ctypes.data if w is not None else None, s, e, int(max_diag), indptr.ctypes.data,
+            indices.ctypes.data, data.ctypes.data, 0)
+        if nnz < 0:
+            return None
+        return indptr, indices[:nnz], data[:nnz]
+
+    def _inter_index(self):
+        """The inter-chromosomal pixels grouped by (chromosome of bin1, chromosome of bin2), once
+        per file: (order, starts) with the pixels of block (i, j), i < j, at
+        order[starts[i * C + j] : starts[i * C + j + 1]], still sorted by (bin1, bin2)."""
+        if getattr(self, "_inter", None) is None:
+            C = len(self.chromnames)
+            chrom_of = np.repeat(np.arange(C, dtype=np.int16), np.diff(self._chrom_offset))
+            c1 = chrom_of[self._pix.bin1_id.values]
+            c2 = chrom_of[self._pix.bin2_id.values]
+            inter = np.flatnonzero(c1 != c2)
+            key = c1[inter].astype(np.int32) * C + c2[inter]
+            order = np.argsort(key.astype(np.uint16 if C * C < 65536 else np.int32), kind="stable")
+            starts = np.searchsorted(key[order], np.arange(C * C + 1))
+            self._inter = (inter[order], starts)
+        return self._inter
+
     def block_csr(self, s1, e1, s2, e2, balance=True):
-        """The inter block [s1:e1, s2:e2] with s2 >= e1 (stored as is in the upper triangle) as
-        canonical CSR arrays; NaN-weighted pixels are kept (the inter normalisation turns them
-        into zeros, cm:598-601).  The pixels of the rows s1:e1 are grouped by the chromosome
-        of bin2 once and cached, so that the blocks of one chromosome row cost one pass in
-        total.  None when the table is not sorted or the block is below the diagonal."""
+        """The inter block [s1:e1, s2:e2] of two whole chromosomes, the first before the second
+        (stored as is in the upper triangle), as canonical CSR arrays; NaN-weighted pixels are
+        kept (the inter normalisation turns them into zeros, cm:598-601).  The inter pixels of
+        the file are grouped by block once (_inter_index).  None when the table is not sorted
+        or the rectangle is not such a block."""
         if not self._lex_sorted() or s2 < e1:
             return None
-        cache = getattr(self, "_rowslab", None)
-        if cache is None or cache[0] != (s1, e1):
-            off = self._row_offsets()
-            lo, hi = int(off[s1]), int(off[e1])
-            b2 = self._pix.bin2_id.values[lo:hi]
-            cid = np.searchsorted(self._chrom_offset, b2, side="right") - 1
-            order = np.argsort(cid, kind="stable")       # keeps (bin1, bin2) order inside a group
-            starts = np.searchsorted(cid[order], np.arange(len(self._chrom_offset)))
-            cache = self._rowslab = ((s1, e1), lo, order, starts)
-        _, lo, order, starts = cache
+        C = len(self.chromnames)
+        i = int(np.searchsorted(self._chrom_offset, s1, side="right") - 1)
         j = int(np.searchsorted(self._chrom_offset, s2, side="right") - 1)
-        if self._chrom_offset[j] != s2 or self._chrom_offset[j + 1] != e2:
+        if not (0 <= i < j < C) or self._chrom_offset[i] != s1 or self._chrom_offset[i + 1] != e1 or \
+                self._chrom_offset[j] != s2 or self._chrom_offset[j + 1] != e2:
             return None
-        sel = order[starts[j]:starts[j + 1]] + lo
+        order, starts = self._inter_index()
+        sel = order[starts[i * C + j]:starts[i * C + j + 1]]
         b1 = self._pix.bin1_id.values[sel]
         b2 = self._pix.bin2_id.values[sel]
         v = self._pix["count"].values[sel].astype(np.float64)

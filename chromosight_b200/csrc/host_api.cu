@@ -232,6 +232,19 @@ extern "C" int cs_expand_rows(const float *score, const float *log10p, const uin
     return CS_OK;
 }
 
+extern "C" int64_t cs_band_csr_from_pixels(const int64_t *bin1, const int64_t *bin2, const void *count,
+                                           int32_t count_dtype, int64_t n_pix, const double *weight,
+                                           int64_t s, int64_t e, int64_t max_diag, int64_t *indptr,
+                                           int32_t *indices, double *data, int32_t threads) {
+    if (!(bin1 && bin2 && count && indptr && indices && data && e > s && n_pix >= 0 && count_dtype >= 0 &&
+          count_dtype <= 2)) {
+        set_error("cs_band_csr_from_pixels: bad arguments");
+        return CS_ERR_INVALID;
+    }
+    return band_csr_from_pixels(bin1, bin2, count, count_dtype, n_pix, weight, s, e, max_diag, indptr, indices,
+                                data, threads > 0 ? threads : expand_threads_default());
+}
+
 extern "C" void cs_result_free(cs_csr_result *r) {
     if (!r) return;
     pin_release(r->indptr);

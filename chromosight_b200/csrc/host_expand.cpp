@@ -10,6 +10,7 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -284,6 +285,77 @@ void expand_rows(const float *score, const float *log10p, const uint8_t *off,
     parallel_for(nt, [&](int t) {
         if (cut[t + 1] > cut[t]) run(cut[t], cut[t + 1]);
     }, 0);
+}
+
+// Upper band of one chromosome straight out of a .cool pixel table (sorted by bin1, then bin2):
+// the pixels with s <= bin1 < e (n_pix of them, given from the first one on), bin2 < e and
+// bin2 - bin1 <= max_diag become canonical CSR rows; with `weight` the values are balanced
+// (count * w[bin1] * w[bin2]) and pixels on masked bins (non-finite value) are dropped.
+// Two parallel passes over contiguous row ranges: count per row, then write.
+template <typename T>
+static int64_t band_csr_impl(const int64_t *bin1, const int64_t *bin2, const T *count, int64_t n_pix,
+                             const double *weight, int64_t s, int64_t e, int64_t max_diag,
+                             int64_t *indptr, int32_t *indices, double *data, int threads) {
+    const int64_t nrows = e - s;
+    if (nrows <= 0) return 0;
+    int nt = (int)std::min<int64_t>(std::max(threads, 1), std::max<int64_t>(1, n_pix / (1 << 16)));
+    std::vector<int64_t> pcut(nt + 1, n_pix), rcut(nt + 1, nrows);
+    pcut[0] = 0;
+    rcut[0] = 0;
+    for (int t = 1; t < nt; ++t) {
+        // cut between rows: first pixel of the row that holds pixel n_pix * t / nt
+        int64_t p = n_pix * t / nt;
+        const int64_t row = bin1[p];
+        p = std::lower_bound(bin1, bin1 + n_pix, row) - bin1;
+        pcut[t] = std::max(p, pcut[t - 1]);
+        rcut[t] = std::max(row - s, rcut[t - 1]);
+    }
+    auto keep = [&](int64_t k, double &v) {
+        const int64_t b1 = bin1[k], b2 = bin2[k];
+        if (b2 >= e || b2 - b1 > max_diag || b2 < b1) return false;
+        v = (double)count[k];
+        if (weight) {
+            v = v * weight[b1] * weight[b2];
+            if (!std::isfinite(v)) return false;
+        }
+        return true;
+    };
+    indptr[0] = 0;
+    parallel_for(nt, [&](int t) {
+        for (int64_t r = rcut[t]; r < rcut[t + 1]; ++r) indptr[r + 1] = 0;
+        for (int64_t k = pcut[t]; k < pcut[t + 1]; ++k) {
+            double v;
+            if (keep(k, v)) ++indptr[bin1[k] - s + 1];
+        }
+    }, 0);
+    for (int64_t r = 0; r < nrows; ++r) indptr[r + 1] += indptr[r];
+    parallel_for(nt, [&](int t) {
+        int64_t row = -1, o = 0;
+        for (int64_t k = pcut[t]; k < pcut[t + 1]; ++k) {
+            double v;
+            if (!keep(k, v)) continue;
+            const int64_t r = bin1[k] - s;
+            if (r != row) {
+                row = r;
+                o = indptr[r];
+            }
+            indices[o] = (int32_t)(bin2[k] - s);
+            data[o] = v;
+            ++o;
+        }
+    }, 0);
+    return indptr[nrows];
+}
+
+int64_t band_csr_from_pixels(const int64_t *bin1, const int64_t *bin2, const void *count, int count_dtype,
+                             int64_t n_pix, const double *weight, int64_t s, int64_t e, int64_t max_diag,
+                             int64_t *indptr, int32_t *indices, double *data, int threads) {
+    switch (count_dtype) {
+        case 0: return band_csr_impl(bin1, bin2, (const int32_t *)count, n_pix, weight, s, e, max_diag, indptr, indices, data, threads);
+        case 1: return band_csr_impl(bin1, bin2, (const int64_t *)count, n_pix, weight, s, e, max_diag, indptr, indices, data, threads);
+        case 2: return band_csr_impl(bin1, bin2, (const double *)count, n_pix, weight, s, e, max_diag, indptr, indices, data, threads);
+        default: return -1;
+    }
 }
 
 }  // namespace cs

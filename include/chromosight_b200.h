@@ -287,6 +287,22 @@ int cs_expand_rows(const float *score, const float *log10p, const uint8_t *off,
                    int32_t threads);
 
 /* ------------------------------------------------------------------------
+ * HOST function: the upper band of one chromosome straight out of a .cool pixel table
+ * (cooler's pixels/{bin1_id, bin2_id, count}, sorted by bin1 then bin2; what
+ * `clr.matrix(sparse=True, balance=True)[s:e, s:e]` + sp.triu + diag_trim keep of it,
+ * cm:527-624).  `bin1` / `bin2` / `count` point at the first pixel with bin1 >= s, n_pix =
+ * pixels with bin1 < e; count_dtype 0 int32, 1 int64, 2 float64; `weight` = bins/weight of the
+ * whole genome (NULL: raw counts): value = count * w[bin1] * w[bin2], pixels whose value is
+ * not finite (masked bins) are dropped.  Writes canonical CSR rows (indptr[e - s + 1],
+ * indices / data with room for n_pix entries) and returns the number of entries, < 0 on
+ * error.  One fused, multi-threaded pass instead of ~15 numpy passes.
+ * ------------------------------------------------------------------------ */
+int64_t cs_band_csr_from_pixels(const int64_t *bin1, const int64_t *bin2, const void *count,
+                                int32_t count_dtype, int64_t n_pix, const double *weight,
+                                int64_t s, int64_t e, int64_t max_diag, int64_t *indptr,
+                                int32_t *indices, double *data, int32_t threads);
+
+/* ------------------------------------------------------------------------
  * Host-buffer, whole-call entry point: what chromosight.utils.detection.
  * normxcorr2 (det:807-914) does for a sparse signal, from host CSR arrays to
  * host CSR arrays, including host<->device copies through pinned staging.

@@ -83,6 +83,40 @@ def test_genome_model_bookkeeping(fx):
         hg.normalize(norm="force")
 
 
+def test_direct_csr_extraction_matches_the_mirrored_matrix():
+    """CoolFile.upper_band_csr (the library's fused host pass, cs_band_csr_from_pixels, for every
+    count dtype; its numpy twin) and block_csr (inter blocks from the per-file block index)
+    against what `clr.matrix(balance=...)[a:b, c:d]` + triu / diag_trim keep (cm:527-624)."""
+    from chromosight_b200 import synthetic
+    for dtype in (np.float64, np.int32, np.int64):
+        clr = synthetic.genome_cool([900, 700, 400, 250], binsize=10_000, n_diags=117, seed=3, inter_density=2e-3)
+        clr._pix["count"] = clr._pix["count"].values.astype(dtype)
+        off = clr._row_offsets()
+        for ch in clr.chromnames:
+            s, e = clr.extent(ch)
+            for keep in (40, 5000):
+                for balance in (True, False):
+                    ref = clr.matrix(sparse=True, balance=balance)[s:e, s:e].tocsr()
+                    ref = sp.triu(sp.tril(ref, keep)).tocsr()
+                    ref.data[np.isnan(ref.data)] = 0
+                    ref.eliminate_zeros()
+                    nat = clr._band_csr_native(int(off[s]), int(off[e]), s, e, keep, balance)
+                    assert nat is not None
+                    for indptr, idx, v in (nat, clr.upper_band_csr(s, e, keep, balance=balance)):
+                        m = sp.csr_matrix((v, idx, indptr), shape=(e - s, e - s))
+                        assert m.has_canonical_format and m.nnz == ref.nnz and abs(m - ref).max() == 0
+        names = clr.chromnames
+        for i in range(len(names)):
+            for j in range(i + 1, len(names)):
+                (s1, e1), (s2, e2) = clr.extent(names[i]), clr.extent(names[j])
+                indptr, idx, v = clr.block_csr(s1, e1, s2, e2)
+                m = sp.csr_matrix((v, idx, indptr), shape=(e1 - s1, e2 - s2))
+                a, b = m.toarray(), clr.matrix(sparse=True, balance=True)[s1:e1, s2:e2].toarray()
+                assert m.has_canonical_format
+                assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.nan_to_num(a), np.nan_to_num(b))
+        assert clr.block_csr(*clr.extent(names[1]), *clr.extent(names[0])) is None   # below the diagonal
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("fast", [True, False])
 def test_example_cool_detect_loops_matches_reference(fx, fast, monkeypatch):
