@@ -519,8 +519,15 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
             // triangle reaches below it: the two descriptions stay disjoint
             if (g.mask_dlo < 0) g.mask_dlo = 0;
         }
-        // detrended maps have mean 1 on every diagonal; the wide kernel wants NaN sentinels
-        g.fill_value = wide ? __builtin_nanf("") : 1.0f;
+        // The value under the missing pixels: any constant is exact; one near the mean of the
+        // data keeps the float32 sums of masked windows conditioned.  Detrended intra maps have
+        // mean 1 on every diagonal; sparse maps (inter-chromosomal: a stored pixel per ~10^4) have
+        // mean ~0.  The wide kernel wants NaN sentinels.
+        const double area = (double)a->rows * (double)((long long)sig_dmax - sig_dmin + 1 < a->cols
+                                                           ? (long long)sig_dmax - sig_dmin + 1
+                                                           : a->cols);
+        const bool sparse_map = area > 0 && (double)s->nnz_in < 0.2 * area;
+        g.fill_value = wide ? __builtin_nanf("") : (sparse_map ? 0.0f : 1.0f);
     }
     if (a->has_mask == 2) {
         CS_REQUIRE(a->miss_row && a->miss_col, "geometric mask: missing-bin vectors missing");
