@@ -319,10 +319,12 @@ def run_b200(a, kernel):
     gather_cap = 1 << 16   # records exchanged per rank by the final gather (1 MB)
 
     def step():
-        st = sess.run()
+        # the run is enqueued, the candidate thresholding right behind it: ONE host
+        # synchronisation per step (the run's checks are made there)
+        sess.run(wait=False)
         _, nc = sess.candidates(a.pearson, 0, D, out=cand_buf)
         state["ncand"] = nc
-        return st
+        return sess.wait()
 
     def final_gather():
         # the one collective of the path (north_star): the candidate records of every rank, once,
@@ -364,6 +366,8 @@ def run_b200(a, kernel):
         ms_pearson.append(st["ms_pearson"])
         ms_fill.append(st["ms_fill"])
         ms_compact.append(st["ms_compact"])
+    ev_loop = torch.cuda.Event(enable_timing=True)
+    ev_loop.record()          # this rank's own steps, before it meets the others in the gather
     final_gather()
     ev1.record()
     barrier()
@@ -372,14 +376,17 @@ def run_b200(a, kernel):
     launches = _lib.launch_count() - l0
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    per_rank_ms = [ms_total / a.steps]
+    t = torch.tensor([ev0.elapsed_time(ev_loop)], dtype=torch.float64, device=dev)
+    per_rank_ms = [float(t.item()) / a.steps]
     if world > 1:
         # every rank's own device time (the spread between GPUs), then the max the value is quoted on
         allt = torch.zeros(world, dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allt, t)
         per_rank_ms = [float(x) / a.steps for x in allt.tolist()]
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    else:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     ms_step = float(t.item()) / a.steps
     value = (1 if strong else world) * nwin / (ms_step * 1e-3)
     n_eval = int(st["n_windows"])

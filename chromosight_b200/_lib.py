@@ -180,6 +180,8 @@ _PROTOS = {
     "cs_session_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cs_session_upload": (C.c_int, [C.c_void_p, C.POINTER(Normxcorr2Args)]),
     "cs_session_run": (C.c_int, [C.c_void_p, C.POINTER(RunStats)]),
+    "cs_session_run_enqueue": (C.c_int, [_P]),
+    "cs_session_wait": (C.c_int, [_P, C.POINTER(RunStats)]),
     "cs_session_run_scores": (C.c_int, [C.c_void_p, C.POINTER(RunStats)]),
     "cs_session_upload_run_scores": (C.c_int, [C.c_void_p, C.POINTER(Normxcorr2Args), C.POINTER(RunStats)]),
     "cs_foci_work_bytes": (C.c_int64, [C.POINTER(Layout)]),

@@ -293,6 +293,9 @@ struct cs_session {
     bool planes_zeroed = false;  // score / count planes zeroed since the upload (a run overwrites every window)
     int64_t nnz_hint = -1;   // non-zero scores of the last compaction of this upload (sizes the next one)
     int64_t nnz_async = 0;   // read-back target of a compaction enqueued without synchronisation
+    bool pending = false;    // a run was enqueued without synchronisation (cs_session_run_enqueue)
+    int32_t herr_async[2] = {0, 0};
+    long long l0_pending = 0;
     size_t h2d_bytes = 0;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
@@ -343,6 +346,10 @@ static int session_upload_impl(cs_session *s, const cs_normxcorr2_args *a, bool 
     HostCtx *c = s->c;
     std::lock_guard<std::mutex> lk(c->mu);
     CS_CUDA(cudaSetDevice(c->device));
+    if (s->pending) {  // a run nobody waited for: let it drain, its results are replaced
+        cudaStreamSynchronize(s->stream());
+        s->pending = false;
+    }
     cudaStream_t st = s->stream();
     s->uploaded = s->ran = false;
     s->nnz_hint = -1;
@@ -632,12 +639,26 @@ extern "C" int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a) {
 // fill -> Pearson -> CSR compaction, all on the device, inputs already resident.
 static int session_compact(cs_session *s, cudaStream_t st, int64_t *nnz_out, bool *deferred = nullptr);
 
-static int session_run_impl(cs_session *s, cs_run_stats *stats, bool compact) {
+static int session_finish_pending(cs_session *s, cudaStream_t st);
+// an enqueued run is awaited and checked before anything reads its results
+static int session_settle(cs_session *s) {
+    if (!s->pending) return CS_OK;
+    cudaStream_t st = s->stream();
+    CS_CUDA(cudaStreamSynchronize(st));
+    return session_finish_pending(s, st);
+}
+static void session_fill_stats(cs_session *s, cs_run_stats *stats, long long l0);
+
+static int session_run_impl(cs_session *s, cs_run_stats *stats, bool compact, bool enqueue_only = false) {
     CS_REQUIRE(s && s->uploaded, "cs_session_run: nothing uploaded");
     HostCtx *c = s->c;
     std::lock_guard<std::mutex> lk(c->mu);
     CS_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = s->stream();
+    if (s->pending) {
+        CS_CUDA(cudaStreamSynchronize(st));
+        if (int prc = session_finish_pending(s, st)) return prc;
+    }
     if (stats) memset(stats, 0, sizeof(*stats));
     s->ran = false;
     s->refined = false;
@@ -675,13 +696,24 @@ static int session_run_impl(cs_session *s, cs_run_stats *stats, bool compact) {
     if (rc) return rc;
     CS_CUDA(cudaEventRecord(s->ev[4], st));
     int64_t nnz = 0;
-    int32_t herr[2] = {0, 0};
-    CS_CUDA(cudaMemcpyAsync(herr, s->err.p, sizeof(herr), cudaMemcpyDeviceToHost, st));
+    // (a session member, not a local: an enqueue-only run returns before the copy lands)
+    int32_t *herr = s->herr_async;
+    herr[0] = herr[1] = 0;
+    CS_CUDA(cudaMemcpyAsync(herr, s->err.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     s->compacted = false;
+    s->l0_pending = l0;
     bool deferred = false;
     if (compact) {
         if ((rc = session_compact(s, st, &nnz, &deferred))) return rc;
         if (deferred) CS_CUDA(cudaEventRecord(s->ev[5], st));
+    }
+    if (enqueue_only && deferred) {
+        // nothing is awaited: the error counters and the count are checked by the next call that
+        // synchronises (cs_session_candidates, cs_session_wait, ...)
+        s->pending = true;
+        s->nnz_out = s->nnz_hint;
+        s->ran = true;
+        return CS_OK;
     }
     // (the only synchronisation of a re-run; the first compaction of an upload has one more)
     if (!compact || deferred) CS_CUDA(cudaStreamSynchronize(st));
@@ -711,23 +743,76 @@ static int session_run_impl(cs_session *s, cs_run_stats *stats, bool compact) {
     }
     s->nnz_out = nnz;
     s->ran = true;
+    if (stats) session_fill_stats(s, stats, l0);
+    return CS_OK;
+}
+
+static void session_fill_stats(cs_session *s, cs_run_stats *stats, long long l0) {
+    const cs_normxcorr2_args &a = s->a;
+    const int64_t nnz = s->nnz_out;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]);
+    stats->ms_fill = ms;
+    cudaEventElapsedTime(&ms, s->ev[3], s->ev[4]);
+    stats->ms_pearson = ms;
+    cudaEventElapsedTime(&ms, s->ev[4], s->ev[5]);
+    stats->ms_compact = ms;
+    cudaEventElapsedTime(&ms, s->ev[2], s->ev[5]);
+    stats->ms_total = ms;
+    stats->n_windows = s->n_windows;
+    stats->nnz = nnz;
+    stats->launches = g_launches.load() - l0;
+    stats->h2d_bytes = (int64_t)s->h2d_bytes;
+    const size_t per_nz = s->narrow ? (sizeof(float) + 1 + (a.pval ? sizeof(float) : 0))
+                                    : (sizeof(int32_t) + sizeof(double) + (a.pval ? sizeof(double) : 0));
+    stats->d2h_bytes = (int64_t)(((size_t)a.rows + 1) * sizeof(int64_t) + (size_t)nnz * per_nz);
+}
+
+// The checks a run enqueued without synchronisation left open (the stream has been synchronised
+// by the caller): error counters of the fill, capacity of the compacted arrays.
+static int session_finish_pending(cs_session *s, cudaStream_t st) {
+    if (!s->pending) return CS_OK;
+    s->pending = false;
+    const cs_normxcorr2_args &a = s->a;
+    if (s->herr_async[0] > 0 && a.has_mask) {
+        s->ran = false;
+        set_error("There are %d non-zero elements reported as missing.", s->herr_async[0]);
+        return CS_ERR_MASKED_SIGNAL;
+    }
+    if (s->herr_async[1] > 0 && !a.trim_to_max_dist) {
+        s->ran = false;
+        set_error("internal: %d signal pixels fell outside the stored band", s->herr_async[1]);
+        return CS_ERR_INVALID;
+    }
+    if (s->nnz_async > s->nnz_hint) {
+        int64_t nnz = 0;
+        if (int rc = session_compact(s, st, &nnz, nullptr)) return rc;
+    } else {
+        s->nnz_out = s->nnz_hint = s->nnz_async;
+        s->compacted = true;
+    }
+    return CS_OK;
+}
+
+// cs_session_run without waiting for the device (a re-run of the same upload; the first run of
+// an upload, which sizes the result arrays, runs synchronously): the caller goes on enqueueing
+// (cs_session_candidates) and the run's checks are made at the next synchronisation.
+extern "C" int cs_session_run_enqueue(cs_session *s) {
+    return session_run_impl(s, nullptr, true, true);
+}
+
+// Wait for an enqueued run and report its statistics (also valid after a synchronous run).
+extern "C" int cs_session_wait(cs_session *s, cs_run_stats *stats) {
+    CS_REQUIRE(s && s->uploaded, "cs_session_wait: nothing uploaded");
+    HostCtx *c = s->c;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CS_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = s->stream();
+    CS_CUDA(cudaStreamSynchronize(st));
+    if (int rc = session_finish_pending(s, st)) return rc;
     if (stats) {
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]);
-        stats->ms_fill = ms;
-        cudaEventElapsedTime(&ms, s->ev[3], s->ev[4]);
-        stats->ms_pearson = ms;
-        cudaEventElapsedTime(&ms, s->ev[4], s->ev[5]);
-        stats->ms_compact = ms;
-        cudaEventElapsedTime(&ms, s->ev[2], s->ev[5]);
-        stats->ms_total = ms;
-        stats->n_windows = s->n_windows;
-        stats->nnz = nnz;
-        stats->launches = g_launches.load() - l0;
-        stats->h2d_bytes = (int64_t)s->h2d_bytes;
-        const size_t per_nz = s->narrow ? (sizeof(float) + 1 + (a.pval ? sizeof(float) : 0))
-                                        : (sizeof(int32_t) + sizeof(double) + (a.pval ? sizeof(double) : 0));
-        stats->d2h_bytes = (int64_t)(((size_t)a.rows + 1) * sizeof(int64_t) + (size_t)nnz * per_nz);
+        memset(stats, 0, sizeof(*stats));
+        if (!s->empty && s->ran) session_fill_stats(s, stats, s->l0_pending);
     }
     return CS_OK;
 }
@@ -907,12 +992,17 @@ extern "C" int cs_session_candidates(cs_session *s, float threshold, int32_t dmi
             CS_CUDA(cudaMemcpyAsync(n_host, d_count, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
             CS_CUDA(cudaMemcpyAsync(&n_ref, R.d_count, sizeof(n_ref), cudaMemcpyDeviceToHost, st));
             CS_CUDA(cudaStreamSynchronize(st));
+            if (int prc = session_finish_pending(s, st)) return prc;
             if ((long long)n_ref <= R.cap) {
                 refine_done(s, (double)threshold, (long long)n_ref);
                 return CS_OK;
             }
             // the list overflowed (nothing was redone): the two-pass form below
         }
+    }
+    if (s->pending) {
+        CS_CUDA(cudaStreamSynchronize(st));
+        if (int prc = session_finish_pending(s, st)) return prc;
     }
     if (int rrc = session_refine(s, (double)threshold, dmin, dmax, st)) return rrc;
     return cs_scores_candidates(&s->Lo, (const float *)s->out.p, nb, s->nmiss_bytes, nwin, dmin, dmax,
@@ -927,6 +1017,7 @@ extern "C" int cs_session_foci(cs_session *s, double threshold, int32_t dmin, in
     HostCtx *c = s->c;
     std::lock_guard<std::mutex> lk(c->mu);
     CS_CUDA(cudaSetDevice(c->device));
+    if (int src = session_settle(s)) return src;
     *n_host = 0;
     if (s->empty) return CS_OK;
     cudaStream_t st = s->stream();
@@ -960,6 +1051,7 @@ extern "C" int cs_session_download(cs_session *s, cs_csr_result *res) {
     HostCtx *c = s->c;
     std::lock_guard<std::mutex> lk(c->mu);
     CS_CUDA(cudaSetDevice(c->device));
+    if (int src = session_settle(s)) return src;
     cudaStream_t st = s->stream();
     memset(res, 0, sizeof(*res));
     const cs_normxcorr2_args &a = s->a;
@@ -1745,6 +1837,7 @@ extern "C" int cs_session_validate(cs_session *s, const int32_t *host_coords, in
     HostCtx *c = s->c;
     std::lock_guard<std::mutex> lk(c->mu);
     CS_CUDA(cudaSetDevice(c->device));
+    if (int src = session_settle(s)) return src;
     cudaStream_t st = s->stream();
     const cs_normxcorr2_args &a = s->a;
     const int km = a.kernel.kh, kn = a.kernel.kw;

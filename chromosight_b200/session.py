@@ -84,14 +84,27 @@ class Session:
         self.pval = bool(pval)
         return self
 
-    def run(self, compact=True):
+    def run(self, compact=True, wait=True):
         """fill -> Pearson -> CSR compaction (+ p-values of every stored score) on the device;
         returns the run statistics.  compact=False stops after the Pearson kernel: candidates,
-        foci and validate only read the score image (download compacts on demand)."""
+        foci and validate only read the score image (download compacts on demand).
+        wait=False only enqueues the run (re-runs of one upload): the next call that
+        synchronises -- candidates(), wait() -- checks it; returns None."""
         self._bind_stream()
+        if not wait and compact:
+            _lib.check(self._lib.cs_session_run_enqueue(self._h))
+            return None
         st = _lib.RunStats()
         fn = self._lib.cs_session_run if compact else self._lib.cs_session_run_scores
         _lib.check(fn(self._h, C.byref(st)))
+        self.stats = {f: getattr(st, f) for f, _ in _lib.RunStats._fields_}
+        return self.stats
+
+    def wait(self):
+        """Wait for a run enqueued with run(wait=False); the statistics of the last run."""
+        self._bind_stream()
+        st = _lib.RunStats()
+        _lib.check(self._lib.cs_session_wait(self._h, C.byref(st)))
         self.stats = {f: getattr(st, f) for f, _ in _lib.RunStats._fields_}
         return self.stats
 

@@ -384,6 +384,13 @@ void cs_session_destroy(cs_session *s);
 int cs_session_set_stream(cs_session *s, void *stream);
 int cs_session_upload(cs_session *s, const cs_normxcorr2_args *a);
 int cs_session_run(cs_session *s, cs_run_stats *stats);
+/* The same run without waiting for the device (a re-run of the same upload; the first run of an
+ * upload, which sizes the result arrays, is synchronous anyway): the caller keeps enqueueing --
+ * cs_session_candidates right behind it, one synchronisation for both -- and the run's checks
+ * (signal under the mask, capacity of the result arrays) are made by the next call that
+ * synchronises.  cs_session_wait waits and returns the statistics of the last run. */
+int cs_session_run_enqueue(cs_session *s);
+int cs_session_wait(cs_session *s, cs_run_stats *stats);
 /* fill -> Pearson only: the scores stay a float32 image in HBM, which is all that
  * cs_session_candidates / _foci / _validate read (pattern_detector, det:265-345, needs
  * p-values at the foci only); cs_session_download compacts on demand. */

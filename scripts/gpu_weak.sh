@@ -13,5 +13,5 @@ for np in ${@:-1 2}; do
   grep '^{' gpurun_out/weak_n${np}_$TAG.json | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-print('N=%d value %.3e ms/step %.3f breakdown %s launches %s' % (d['n_gpus'], d['value'], d['ms_per_step'], d['step_breakdown_ms'], d['gpu_launches']))"
+print('N=%d value %.3e ms/step %.3f breakdown %s launches %s per-rank %s' % (d['n_gpus'], d['value'], d['ms_per_step'], d['step_breakdown_ms'], d['gpu_launches'], [round(x,3) for x in d['per_rank_ms_per_step']]))"
 done

@@ -553,6 +553,44 @@ def test_device_foci_match_host_pick_foci(thr, presets):
     assert np.array_equal(sizes, foci["size"])
 
 
+def test_enqueued_run_equals_synchronous_run(presets):
+    """Session.run(wait=False) + candidates() + wait() (one host synchronisation per step, what
+    bench.py times) gives the results of the synchronous sequence, run after run."""
+    from chromosight_b200 import synthetic
+    from chromosight_b200.session import Session, records_to_numpy
+    from chromosight_b200.utils import preprocessing as cup
+    kernel = presets.loops["kernels"][0]
+    k, n, D, thr = kernel.shape[0], 6000, 120, 0.3
+    raw, detect = synthetic.band_counts(n, D + k, seed=23, missing_frac=0.03, max_dist=D)
+    mat = cup.detrend(raw, detectable_bins=detect, max_dist=D + k, max_val=10)
+    mat = cup.diag_trim(mat.tocsr(), D + k)
+    mat.data[np.isnan(mat.data)] = 0
+    mat.eliminate_zeros()
+    kw = dict(max_dist=D, sym_upper=True, full=True, missing_tol=0.5, pval=True)
+    s = Session()
+    s.upload(mat, kernel, mask_geometry=cup.missing_geometry(mat.shape, detect, detect, D, True), **kw)
+    st0 = s.run()
+    rec0, n0 = s.candidates(thr, 0, D)
+    rec0 = np.sort(records_to_numpy(rec0, n0).copy(), order=["row", "col"])
+    r0, p0 = s.download()
+    for _ in range(3):
+        assert s.run(wait=False) is None
+        rec, nc = s.candidates(thr, 0, D)
+        st = s.wait()
+        assert st["nnz"] == st0["nnz"] and st["n_windows"] == st0["n_windows"] and st["ms_pearson"] > 0
+        rec = np.sort(records_to_numpy(rec, nc).copy(), order=["row", "col"])
+        assert nc == n0 and np.array_equal(rec, rec0)
+    s.run(wait=False)
+    r1, p1 = s.download()          # download settles the enqueued run itself
+    for a_, b_ in ((r0, r1), (p0, p1)):
+        assert np.array_equal(a_.indptr, b_.indptr) and np.array_equal(a_.indices, b_.indices)
+    # (r0 was downloaded after the refinement at thr: compare with a refined download)
+    s.candidates(thr, 0, D)
+    r2, _ = s.download()
+    assert np.array_equal(r0.data, r2.data)
+    s.close()
+
+
 def test_row_slabs_match_single_run(presets):
     """SURVEY 8e, one chromosome over several GPUs: the row-slab path (rowslab.py; here the
     slabs of a 3-rank plan run one after the other on one device) yields exactly the candidate
