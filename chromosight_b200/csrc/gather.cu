@@ -102,7 +102,9 @@ struct LookupView {
 };
 
 // scores (and log10 p-values) of the score image at UNPADDED coordinates; pixels outside
-// the image, the stored band or dmin..dmax read as 0 (absent from the sparse map)
+// the image or the stored band read as 0 (absent from the sparse map).  dmin..dmax applies to
+// the score only: the reference looks the score up in the diag-trimmed map (det:270, 134) but
+// the p-value in the untrimmed one (det:337-339)
 __global__ void lookup_scores(LookupView S, const float *__restrict__ sc,
                               NmissPlane nobs,
                               const int32_t *__restrict__ coords, long long P,
@@ -112,12 +114,12 @@ __global__ void lookup_scores(LookupView S, const float *__restrict__ sc,
         const int y = coords[2 * p], x = coords[2 * p + 1];
         double v = 0.0, lp = 0.0;
         const int d = x - y;
-        bool in = y >= 0 && y < S.rows && x >= 0 && x < S.cols && d >= S.dmin && d <= S.dmax;
+        bool in = y >= 0 && y < S.rows && x >= 0 && x < S.cols;
         if (in && !S.dense) in = d >= S.dlo && d <= S.dhi;
         if (in) {
             const long long i = (long long)y * S.pitch + (x - (S.dense ? 0 : S.dlo));
             const float vf = sc[i];
-            v = (double)vf;
+            if (d >= S.dmin && d <= S.dmax) v = (double)vf;
             if (vf != 0.f) lp = log10_pval(vf, nobs_at(nobs, i));
         }
         score[p] = v;

@@ -93,6 +93,8 @@ def dense_inter_map(ms, ns, seed, missing_frac=0.04, n_blobs=12):
 
 
 def run_case(name, cmap, cfg, kernel, coords=None, full=True):
+    if len(sys.argv) > 1 and name not in sys.argv[1:]:   # `make_golden_detector.py NAME ...`: only these
+        return
     kernel = np.array(kernel)
     res, windows = cud.pattern_detector(cmap, cfg, kernel, coords=None if coords is None else coords.copy(),
                                         full=full)
@@ -146,6 +148,14 @@ def main():
     coords = np.c_[b1, b2]
     coords[:4] = [[0, 0], [599, 599], [3, 40], [590, 598]]
     run_case("quantify_loops", DummyMap(mat, 60, (det, det)), loops, loops["kernels"][0], coords=coords)
+    # 2b. quantify beyond max_dist and below the diagonal: the score is read from the trimmed
+    # map (0 there, det:270 / det:134), the p-value from the untrimmed one (det:337-339)
+    rng = np.random.default_rng(5)
+    b1 = rng.integers(0, 500, 70)
+    b2 = np.minimum(b1 + rng.integers(40, 95, 70), 599)
+    coords = np.c_[b1, b2]
+    coords[:6] = [[300, 290], [120, 100], [10, 75], [500, 585], [64, 125], [200, 262]]
+    run_case("quantify_far", DummyMap(mat, 60, (det, det)), loops, loops["kernels"][0], coords=coords)
     # 3. borders: 1-D pattern (max_dist = 0 -> scan diagonals 0..1, bin1 := bin2)
     mat2, det2 = intra_map(500, 1, 17, seed=42)
     run_case("detect_borders", DummyMap(mat2, 1, (det2, det2)), borders, borders["kernels"][0])
