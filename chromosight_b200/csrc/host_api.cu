@@ -94,9 +94,13 @@ static int get_ctx(int device, HostCtx **out) {
 
 // memcpy split over the upload pool's threads (up to 4; CS_COPY_THREADS overrides): the staging
 // copy of pageable inputs is on the device's critical path.
+// (g_wide_copy: a scores-only call has no download and no widening competing for the host's
+// memory system and cores -- its staging copies may use the widening pool's threads as well)
+static std::atomic<int> g_wide_copy{0};
 static void memcpy_mt(void *dst, const void *src, size_t n) {
     const size_t kMin = 1u << 20;
-    const int maxt = upload_threads_default();
+    const bool wide = g_wide_copy.load(std::memory_order_relaxed) > 0;
+    const int maxt = wide ? std::max(expand_threads_default(), upload_threads_default()) : upload_threads_default();
     int nt = (int)(n / kMin);
     if (nt > maxt) nt = maxt;
     static const bool plain = getenv("CS_STAGE_PLAIN_MEMCPY") != nullptr;
@@ -114,7 +118,7 @@ static void memcpy_mt(void *dst, const void *src, size_t n) {
         if (o >= n) return;
         const size_t len = (o + per > n) ? n - o : per;
         cp((char *)dst + o, (const char *)src + o, len);
-    }, 1);
+    }, wide ? 0 : 1);
 }
 
 // true when `p` lies in page-locked host memory CUDA knows about (cudaHostAlloc /
@@ -1306,6 +1310,10 @@ static int session_upload_run_pipelined(cs_session *s, const cs_normxcorr2_args 
     // the upload stream must not run ahead of the row pointers (uploaded on `st` by the plan)
     CS_CUDA(cudaEventRecord(s->ev[3], st));
     CS_CUDA(cudaStreamWaitEvent(st_h, s->ev[3], 0));
+    struct WideCopy {  // for the duration of this call
+        WideCopy() { g_wide_copy.fetch_add(1); }
+        ~WideCopy() { g_wide_copy.fetch_sub(1); }
+    } wide_copy;
     SlabUploader upl;
     upl.start(c, st_h, a, s, need_of, ev_up.data(), false);
     int up_end = 0;
