@@ -155,6 +155,8 @@ _PROTOS = {
     "cs_pearson_plan": (C.c_int, [C.POINTER(Layout), C.POINTER(KernelDesc), C.POINTER(PearsonOpts),
                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "cs_pixels_lex_sorted": (C.c_int, [_P, _P, C.c_int64]),
+    "cs_pixels_inter_index": (C.c_int64, [_P, _P, C.c_int64, _P, C.c_int32, _P, _P]),
     "cs_band_csr_from_pixels": (C.c_int64, [_P, _P, _P, C.c_int32, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int64,
                                             _P, _P, _P, C.c_int32]),
     "cs_scan_scratch": (C.c_int64, [C.c_int32]),

@@ -395,10 +395,32 @@ class CoolFile:
 
 
     # ---- direct CSR extraction (what ContactMap.create_mat feeds the device with) -------------
+    def _native(self):
+        """(library, bin1, bin2) when the pixel columns can be handed to the library's host
+        helpers as they are, else None."""
+        if getattr(self, "_nat", 0) == 0:
+            self._nat = None
+            try:
+                from . import _lib
+                lib = _lib.load()
+                b1, b2 = self._pix.bin1_id.values, self._pix.bin2_id.values
+                if b1.dtype == np.int64 and b2.dtype == np.int64 and b1.flags.c_contiguous and b2.flags.c_contiguous:
+                    self._nat = (lib, b1, b2)
+            except Exception:
+                pass
+        return self._nat
+
     def _lex_sorted(self):
         """True when the pixel table is sorted by (bin1, bin2) without duplicates, as cooler
         writes it: row slices of it are canonical CSR rows."""
         if getattr(self, "_lex", None) is None:
+            nat = self._native()
+            if nat is not None:
+                lib, b1, b2 = nat
+                rc = lib.cs_pixels_lex_sorted(b1.ctypes.data, b2.ctypes.data, len(b1))
+                if rc >= 0:
+                    self._lex = bool(rc)
+                    return self._lex
             b1, b2 = self._pix.bin1_id.values, self._pix.bin2_id.values
             d1 = np.diff(b1)
             self._lex = bool(((d1 > 0) | ((d1 == 0) & (np.diff(b2) > 0))).all())
@@ -474,6 +496,17 @@ class CoolFile:
         if getattr(self, "_inter", None) is None:
             C = len(self.chromnames)
             chrom_of = np.repeat(np.arange(C, dtype=np.int16), np.diff(self._chrom_offset))
+            nat = self._native()
+            if nat is not None and C <= 4096:
+                lib, b1, b2 = nat
+                order = np.empty(len(b1), dtype=np.int64)
+                starts = np.empty(C * C + 1, dtype=np.int64)
+                n_inter = lib.cs_pixels_inter_index(b1.ctypes.data, b2.ctypes.data, len(b1),
+                                                    np.ascontiguousarray(chrom_of).ctypes.data, C,
+                                                    order.ctypes.data, starts.ctypes.data)
+                if n_inter >= 0:
+                    self._inter = (order[:n_inter].copy(), starts)
+                    return self._inter
             c1 = chrom_of[self._pix.bin1_id.values]
             c2 = chrom_of[self._pix.bin2_id.values]
             inter = np.flatnonzero(c1 != c2)

@@ -69,6 +69,9 @@ void expand_rows(const float *score, const float *log10p, const uint8_t *off,
                  const int64_t *indptr, int32_t r0, int32_t r1, int32_t dlo, double *data,
                  double *logp, int32_t *indices, int32_t *indices2, int threads);
 int expand_threads_default();
+int pixels_lex_sorted(const int64_t *bin1, const int64_t *bin2, int64_t n, int threads);
+int64_t pixels_inter_index(const int64_t *bin1, const int64_t *bin2, int64_t n, const int16_t *bin_chrom,
+                           int32_t C, int64_t *order, int64_t *starts, int threads);
 int64_t band_csr_from_pixels(const int64_t *bin1, const int64_t *bin2, const void *count, int count_dtype,
                              int64_t n_pix, const double *weight, int64_t s, int64_t e, int64_t max_diag,
                              int64_t *indptr, int32_t *indices, double *data, int threads);

@@ -236,6 +236,24 @@ extern "C" int cs_expand_rows(const float *score, const float *log10p, const uin
     return CS_OK;
 }
 
+extern "C" int cs_pixels_lex_sorted(const int64_t *bin1, const int64_t *bin2, int64_t n_pix) {
+    if (!(bin1 && bin2) || n_pix < 0) {
+        set_error("cs_pixels_lex_sorted: bad arguments");
+        return CS_ERR_INVALID;
+    }
+    return pixels_lex_sorted(bin1, bin2, n_pix, expand_threads_default());
+}
+
+extern "C" int64_t cs_pixels_inter_index(const int64_t *bin1, const int64_t *bin2, int64_t n_pix,
+                                         const int16_t *bin_chrom, int32_t n_chroms, int64_t *order,
+                                         int64_t *starts) {
+    if (!(bin1 && bin2 && bin_chrom && order && starts) || n_pix < 0 || n_chroms < 1 || n_chroms > 4096) {
+        set_error("cs_pixels_inter_index: bad arguments");
+        return CS_ERR_INVALID;
+    }
+    return pixels_inter_index(bin1, bin2, n_pix, bin_chrom, n_chroms, order, starts, expand_threads_default());
+}
+
 extern "C" int64_t cs_band_csr_from_pixels(const int64_t *bin1, const int64_t *bin2, const void *count,
                                            int32_t count_dtype, int64_t n_pix, const double *weight,
                                            int64_t s, int64_t e, int64_t max_diag, int64_t *indptr,

@@ -358,4 +358,62 @@ int64_t band_csr_from_pixels(const int64_t *bin1, const int64_t *bin2, const voi
     }
 }
 
+// 1 when the pixel table is sorted by (bin1, bin2) without duplicates (cooler's invariant)
+int pixels_lex_sorted(const int64_t *bin1, const int64_t *bin2, int64_t n, int threads) {
+    if (n < 2) return 1;
+    const int nt = (int)std::min<int64_t>(std::max(threads, 1), std::max<int64_t>(1, n / (1 << 18)));
+    std::vector<int> okv(nt, 1);
+    parallel_for(nt, [&](int t) {
+        const int64_t a = 1 + (n - 1) * t / nt, b = 1 + (n - 1) * (t + 1) / nt;
+        int ok = 1;
+        for (int64_t k = a; k < b; ++k) {
+            const int64_t d1 = bin1[k] - bin1[k - 1];
+            ok &= (d1 > 0) | ((d1 == 0) & (bin2[k] > bin2[k - 1]));
+        }
+        okv[t] = ok;
+    }, 0);
+    for (int v : okv)
+        if (!v) return 0;
+    return 1;
+}
+
+// The inter-chromosomal pixels grouped by (chromosome of bin1, chromosome of bin2): a stable
+// counting sort by block key c1 * C + c2.  bin_chrom: chromosome of every bin.  Writes the pixel
+// indices, block after block and in table order inside a block, to `order` (room for n) and the
+// block offsets to starts[C * C + 1]; returns the number of inter pixels.
+int64_t pixels_inter_index(const int64_t *bin1, const int64_t *bin2, int64_t n, const int16_t *bin_chrom,
+                           int32_t C, int64_t *order, int64_t *starts, int threads) {
+    const int nb = C * C;
+    const int nt = (int)std::min<int64_t>(std::max(threads, 1), std::max<int64_t>(1, n / (1 << 18)));
+    std::vector<std::vector<int64_t>> hist(nt, std::vector<int64_t>(nb, 0));
+    parallel_for(nt, [&](int t) {
+        const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+        std::vector<int64_t> &h = hist[t];
+        for (int64_t k = a; k < b; ++k) {
+            const int c1 = bin_chrom[bin1[k]], c2 = bin_chrom[bin2[k]];
+            if (c1 != c2) ++h[c1 * C + c2];
+        }
+    }, 0);
+    // offsets: block-major, then thread (keeps table order inside a block)
+    int64_t run = 0;
+    for (int b = 0; b < nb; ++b) {
+        starts[b] = run;
+        for (int t = 0; t < nt; ++t) {
+            const int64_t c = hist[t][b];
+            hist[t][b] = run;
+            run += c;
+        }
+    }
+    starts[nb] = run;
+    parallel_for(nt, [&](int t) {
+        const int64_t a = n * t / nt, b = n * (t + 1) / nt;
+        std::vector<int64_t> &h = hist[t];
+        for (int64_t k = a; k < b; ++k) {
+            const int c1 = bin_chrom[bin1[k]], c2 = bin_chrom[bin2[k]];
+            if (c1 != c2) order[h[c1 * C + c2]++] = k;
+        }
+    }, 0);
+    return run;
+}
+
 }  // namespace cs

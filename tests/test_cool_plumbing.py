@@ -115,6 +115,25 @@ def test_direct_csr_extraction_matches_the_mirrored_matrix():
                 assert m.has_canonical_format
                 assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.nan_to_num(a), np.nan_to_num(b))
         assert clr.block_csr(*clr.extent(names[1]), *clr.extent(names[0])) is None   # below the diagonal
+        # the library's host helpers against their numpy twins
+        assert clr._native() is not None and clr._lex_sorted()
+        order, starts = clr._inter_index()
+        clr._inter, clr._lex, clr._nat = None, None, None          # numpy paths
+        assert clr._lex_sorted()
+        order0, starts0 = clr._inter_index()
+        assert np.array_equal(order, order0) and np.array_equal(starts, starts0)
+    # an unsorted table is recognised as such (both ways) and falls back to the mirrored matrix
+    from chromosight_b200.cool import CoolFile
+    pix = clr._pix.iloc[::-1].reset_index(drop=True)
+    bins = clr._bins
+    for native in (True, False):
+        bad = CoolFile.from_tables(clr.chromnames, clr.chromsizes.values, bins.chrom.cat.codes.values,
+                                   bins.start.values, bins.end.values, bins.weight.values,
+                                   pix.bin1_id.values, pix.bin2_id.values, pix["count"].values, binsize=10_000)
+        if not native:
+            bad._nat = None
+        assert not bad._lex_sorted()
+        assert bad.upper_band_csr(0, 900, 40) is None
 
 
 @pytest.mark.gpu
