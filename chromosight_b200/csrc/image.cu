@@ -335,7 +335,7 @@ int fill_rows(const cs_layout *L, float *d_img, const int64_t *d_sig_indptr,
         const int Y0 = r0 == 0 ? 0 : r0 + row_off;
         const int Y1 = r1 == n_rows ? L->rows : r1 + row_off;
         int g = (Y1 - Y0 + wpb - 1) / wpb;
-        if (g > 148 * 16) g = 148 * 16;
+        if (g > 148 * 64) g = 148 * 64;  // (a row is a few dependent accesses: latency hides in warps)
         if (g > 0) {
             geo_fill<<<g, threads, 0, st>>>(F, Gm, Y0, Y1, d_img, d_err);
             CS_LAUNCHED();

@@ -1021,12 +1021,18 @@ __global__ void collect_near(ExactArgs A, int rows, int cols, int dlo, int dhi, 
         }
         if (a < 0) a = 0;
         if (b > cols - 1) b = cols - 1;
-        for (long long x = a + lane; x <= b; x += 32) {
-            const float v = A.out[(long long)y * A.out_pitch + (x - A.out_dlo)];
-            if (v != 0.f && v >= lo && v <= hi) {
-                const unsigned long long o = atomicAdd(count, 1ull);
-                if ((long long)o < cap) list[o] = make_int2(y, (int)x);
-            }
+        // eight independent loads per lane and pass (a row of <= 256 scores in one pass)
+        const float *row = A.out + (long long)y * A.out_pitch - A.out_dlo;
+        for (long long xb = a + lane; xb <= b; xb += 256) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (xb + 32 * k <= b) ? row[xb + 32 * k] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (v[k] != 0.f && v[k] >= lo && v[k] <= hi) {
+                    const unsigned long long o = atomicAdd(count, 1ull);
+                    if ((long long)o < cap) list[o] = make_int2(y, (int)(xb + 32 * k));
+                }
         }
     }
 }

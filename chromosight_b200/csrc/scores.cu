@@ -34,7 +34,14 @@ __global__ void count_rows(ScoreView S, const float *__restrict__ sc, int64_t *c
         int x0, x1;
         row_range(S, y, x0, x1);
         int c = 0;
-        for (int x = x0 + lane; x < x1; x += 32) c += (sc[sidx(S, y, x)] != 0.f);
+        // eight independent loads per lane and pass (a row of <= 256 scores in one pass)
+        for (int xb = x0 + lane; xb < x1; xb += 256) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = (xb + 32 * k < x1) ? sc[sidx(S, y, xb + 32 * k)] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) c += (v[k] != 0.f);
+        }
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
         if (lane == 0) counts[y + 1] = c;
     }
