@@ -444,20 +444,27 @@ pearson_tiles(const __grid_constant__ CUtensorMap tmap, const PearsonParams P) {
 #pragma unroll
         for (int t = 0; t < RT; ++t) s3a[t] = s3b[t] = 0.f;
         if (any) {                                                           // [sec:pivot]
-            // block pivot: mean of the middle footprint row.  Sums and products are formed on
-            // S - pl (any pivot is algebraically exact; a close one keeps float32 accurate).
-            const float4 *rp4 = reinterpret_cast<const float4 *>(
-                tile + (RU * g + (KH + RU - 1) / 2) * IC + cxa);
+            // block pivot: mean of the middle footprint row (of three rows -- a quarter, the middle
+            // and three quarters down -- for kernels of at most 9 columns, whose single row of
+            // <= 16 pixels is a noisy estimate: fewer windows look ill-conditioned).  The sums of S
+            // and S^2 are formed on S - pl (any pivot is exact; a close one keeps float32 accurate).
+            constexpr int NPR = (KW <= 9) ? 3 : 1;
+            const int fr_ = KH + RU - 1;
             float sacc = 0.f;
 #pragma unroll
-            for (int qd = 0; qd < NQ; ++qd) {
-                const float4 v = rp4[qd];
-                const float vv[4] = {v.x, v.y, v.z, v.w};
+            for (int pr_ = 0; pr_ < NPR; ++pr_) {
+                const int prow = NPR == 1 ? fr_ / 2 : (fr_ * (pr_ + 1)) / 4;
+                const float4 *rp4 = reinterpret_cast<const float4 *>(tile + (RU * g + prow) * IC + cxa);
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (4 * qd + e >= off && 4 * qd + e < off + XW) sacc += vv[e];
+                for (int qd = 0; qd < NQ; ++qd) {
+                    const float4 v = rp4[qd];
+                    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (4 * qd + e >= off && 4 * qd + e < off + XW) sacc += vv[e];
+                }
             }
-            pl = sacc * (1.0f / (float)XW);
+            pl = sacc * (1.0f / (float)(NPR * XW));
         }
 #ifdef CS_ABLATE
         if (any && !(P.dbg & 8))
