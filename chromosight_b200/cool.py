@@ -497,7 +497,7 @@ class CoolFile:
             C = len(self.chromnames)
             chrom_of = np.repeat(np.arange(C, dtype=np.int16), np.diff(self._chrom_offset))
             nat = self._native()
-            if nat is not None and C <= 4096:
+            if nat is not None and C <= 256:   # (one C x C histogram per thread)
                 lib, b1, b2 = nat
                 order = np.empty(len(b1), dtype=np.int64)
                 starts = np.empty(C * C + 1, dtype=np.int64)
